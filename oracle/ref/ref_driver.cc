@@ -1,0 +1,601 @@
+// ORACLE / TEST INFRASTRUCTURE -- NOT PRODUCT CODE.
+//
+// Links the reference's own range coder (compiled IN PLACE from
+// /root/reference/tensorflow_compression/cc/lib/range_coder.cc, see oracle/Makefile)
+// and restates, on the CPU, the TensorFlow-entangled glue that the reference's op
+// kernels put around it (those files need TF headers and cannot be compiled here):
+//
+//   lookup parsing        cc/kernels/range_coder_kernels.cc:110-164  (ScanCDF, IndexCDFVector/Matrix)
+//   channel/index loops   cc/kernels/range_coder_kernels.cc:191-272, 360-429
+//   overflow (Elias-gamma) cc/kernels/range_coder_kernels.cc:290-322, 449-471
+//   finalize              cc/kernels/range_coder_kernels.cc:274-287, 431-446
+//   legacy RangeEncode/RangeDecode addressing
+//                         cc/kernels/range_coding_kernels.cc:60-132, 134-173, 232-269, 345-373
+//                         cc/kernels/range_coding_kernels_util.cc:34-91 (MergeAxes)
+//   PmfToQuantizedCdf     cc/kernels/pmf_to_cdf_kernels.cc:58-101, 104-208
+//
+// Every arithmetic step of the coder itself is executed by the reference's
+// tensorflow_compression::RangeEncoder / RangeDecoder objects.  Streams are sharded
+// over std::thread workers to emulate the reference's ParallelFor over streams
+// (range_coder_kernels.cc:212-218).
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+// legs may load the library built from this file.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <limits>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "tensorflow_compression/cc/lib/range_coder.h"
+
+namespace tfc = tensorflow_compression;
+
+namespace {
+
+thread_local std::string g_error;
+
+int Fail(const std::string& msg) {
+  g_error = msg;
+  return 1;
+}
+
+struct Row {
+  const int32_t* p;  // points at the precision entry
+  int64_t size;      // precision entry + cdf entries (incl. the final 2^|P|)
+};
+
+// Lookup grammar, range_coder_kernels.cc:110-137.
+bool ScanRow(const int32_t* end, const int32_t** cur, std::vector<Row>* rows, std::string* err) {
+  const int32_t* p = *cur;
+  if (end < p + 3) {
+    *err = "CDF ended prematurely.";
+    return false;
+  }
+  const int32_t* first = p;
+  const int64_t aprec = std::abs(static_cast<int64_t>(*first));
+  if (aprec < 1 || aprec >= 17) {
+    *err = "precision=" + std::to_string(aprec) + " not in range [1, 17)";
+    return false;
+  }
+  const int32_t last_value = 1 << aprec;
+  if (*(++p) != 0) {
+    *err = "CDF must start with 0.";
+    return false;
+  }
+  do {
+    if (++p == end) {
+      *err = "CDF must end with 1 << precision.";
+      return false;
+    }
+    if (p[0] < p[-1]) {
+      *err = "CDF must be monotonically increasing.";
+      return false;
+    }
+  } while (*p != last_value);
+  ++p;
+  rows->push_back(Row{first, p - first});
+  while (p != end && *p == last_value) ++p;
+  *cur = p;
+  return true;
+}
+
+bool ParseLookup(const int32_t* lookup, int64_t len, int64_t cols, std::vector<Row>* rows,
+                 std::string* err) {
+  rows->clear();
+  const int32_t* const end = lookup + len;
+  if (cols <= 0) {  // 1-D concatenated form, :139-148
+    for (const int32_t* cur = lookup; cur != end;) {
+      if (!ScanRow(end, &cur, rows, err)) return false;
+    }
+  } else {  // 2-D stacked form, :150-164
+    for (const int32_t* cur = lookup; cur != end;) {
+      const int32_t* row_end = cur + cols;
+      if (!ScanRow(row_end, &cur, rows, err)) return false;
+      if (cur != row_end) {
+        *err = "CDF must end with 1 << precision.";
+        return false;
+      }
+    }
+  }
+  return true;
+}
+
+// range_coder_kernels.cc:290-322
+void OverflowEncode(tfc::RangeEncoder& enc, std::string* sink, const Row& row, int32_t value) {
+  const int32_t max_value = static_cast<int32_t>(row.size) - 3;
+  const int32_t sign = value < 0;
+  int32_t gamma = 0;
+  if (sign) {
+    gamma = -value;
+    value = max_value;
+  } else if (value >= max_value) {
+    gamma = value - max_value + 1;
+    value = max_value;
+  }
+  enc.Encode(row.p[value + 1], row.p[value + 2], -row.p[0], sink);
+  if (value != max_value) return;
+  int32_t n = 1;
+  while (gamma >= (1 << n)) {
+    enc.Encode(0, 1, 1, sink);
+    ++n;
+  }
+  while (--n >= 0) {
+    const int32_t bit = (gamma >> n) & 1;
+    enc.Encode(bit, bit + 1, 1, sink);
+  }
+  enc.Encode(sign, sign + 1, 1, sink);
+}
+
+// range_coder_kernels.cc:449-471
+int32_t OverflowDecode(tfc::RangeDecoder& dec, const Row& row) {
+  static const int32_t kBinary[] = {0, 1, 2};
+  const int32_t max_value = static_cast<int32_t>(row.size) - 3;
+  int32_t value = dec.Decode(absl::Span<const int32_t>(row.p + 1, row.size - 1), -row.p[0]);
+  if (value != max_value) return value;
+  int32_t n = 0;
+  while (dec.DecodeLinearly(absl::Span<const int32_t>(kBinary, 3), 1) == 0) ++n;
+  value = 1 << n;
+  while (--n >= 0) value |= dec.DecodeLinearly(absl::Span<const int32_t>(kBinary, 3), 1) << n;
+  const int32_t sign = dec.DecodeLinearly(absl::Span<const int32_t>(kBinary, 3), 1);
+  return sign ? -value : value + max_value - 1;
+}
+
+void ParallelOverStreams(int64_t n, int threads, const std::function<void(int64_t, int64_t)>& fn) {
+  if (threads <= 1 || n <= 1) {
+    fn(0, n);
+    return;
+  }
+  const int64_t t = std::min<int64_t>(threads, n);
+  std::vector<std::thread> pool;
+  for (int64_t k = 0; k < t; ++k) {
+    const int64_t lo = n * k / t, hi = n * (k + 1) / t;
+    pool.emplace_back([=, &fn] { fn(lo, hi); });
+  }
+  for (auto& th : pool) th.join();
+}
+
+struct Encoder {
+  std::vector<int32_t> lookup;
+  std::vector<Row> rows;
+  std::vector<tfc::RangeEncoder> enc;
+  std::vector<std::string> sink;
+};
+
+struct Decoder {
+  std::vector<int32_t> lookup;
+  std::vector<Row> rows;
+  std::vector<std::string> data;
+  std::vector<tfc::RangeDecoder> dec;
+};
+
+}  // namespace
+
+extern "C" {
+
+const char* tfcref_last_error() { return g_error.c_str(); }
+
+// ---- raw triples: drives RangeEncoder::Encode/Finalize directly (range_coder.cc:37-307) ----
+int64_t tfcref_encode_triples(const int32_t* lower, const int32_t* upper, const int32_t* precision,
+                              int64_t n, uint8_t* out, int64_t out_cap) {
+  tfc::RangeEncoder enc;
+  std::string sink;
+  for (int64_t i = 0; i < n; ++i) enc.Encode(lower[i], upper[i], precision[i], &sink);
+  enc.Finalize(&sink);
+  if (static_cast<int64_t>(sink.size()) > out_cap) return -static_cast<int64_t>(sink.size());
+  std::memcpy(out, sink.data(), sink.size());
+  return static_cast<int64_t>(sink.size());
+}
+
+// ---- CreateRangeEncoder / EntropyEncode{Channel,Index} / EntropyEncodeFinalize ----
+void* tfcref_encoder_create(const int32_t* lookup, int64_t len, int64_t cols, int64_t n_streams) {
+  auto* e = new Encoder;
+  e->lookup.assign(lookup, lookup + len);
+  std::string err;
+  if (!ParseLookup(e->lookup.data(), len, cols, &e->rows, &err)) {
+    g_error = err;
+    delete e;
+    return nullptr;
+  }
+  e->enc.resize(n_streams);
+  e->sink.resize(n_streams);
+  return e;
+}
+
+int tfcref_encoder_encode(void* h, const int32_t* index, const int32_t* value, int64_t n_per_stream,
+                          int threads) {
+  auto* e = static_cast<Encoder*>(h);
+  const int64_t S = static_cast<int64_t>(e->enc.size());
+  const int64_t R = static_cast<int64_t>(e->rows.size());
+  std::mutex mu;
+  std::string err;
+  ParallelOverStreams(S, threads, [&](int64_t lo, int64_t hi) {
+    for (int64_t s = lo; s < hi; ++s) {
+      tfc::RangeEncoder& enc = e->enc[s];
+      std::string* sink = &e->sink[s];
+      const int32_t* pv = value + s * n_per_stream;
+      const int32_t* pi = index ? index + s * n_per_stream : nullptr;
+      for (int64_t ind = 0, j = 0; j < n_per_stream; ++ind, ++j) {
+        const int32_t val = pv[j];
+        int64_t r;
+        if (pi) {
+          r = pi[j];
+          if (r < 0 || r >= R) {
+            std::lock_guard<std::mutex> g(mu);
+            err = "index=" + std::to_string(r) + " not in range [0, " + std::to_string(R) + ")";
+            return;
+          }
+        } else {
+          if (ind >= R) ind = 0;  // :253
+          r = ind;
+        }
+        const Row& row = e->rows[r];
+        if (row.p[0] > 0) {
+          if (val < 0 || val >= row.size - 2) {
+            std::lock_guard<std::mutex> g(mu);
+            err = "value=" + std::to_string(val) + " not in range [0, " +
+                  std::to_string(row.size - 2) + ")";
+            return;
+          }
+          enc.Encode(row.p[val + 1], row.p[val + 2], row.p[0], sink);
+        } else {
+          OverflowEncode(enc, sink, row, val);
+        }
+      }
+    }
+  });
+  if (!err.empty()) return Fail(err);
+  return 0;
+}
+
+// Finalizes every stream (idempotence is NOT provided, as in the reference) and reports sizes.
+int tfcref_encoder_finalize(void* h, int64_t* offsets /* n_streams + 1 */) {
+  auto* e = static_cast<Encoder*>(h);
+  offsets[0] = 0;
+  for (size_t s = 0; s < e->enc.size(); ++s) {
+    e->enc[s].Finalize(&e->sink[s]);
+    offsets[s + 1] = offsets[s] + static_cast<int64_t>(e->sink[s].size());
+  }
+  return 0;
+}
+
+void tfcref_encoder_bytes(void* h, uint8_t* out) {
+  auto* e = static_cast<Encoder*>(h);
+  for (auto& s : e->sink) {
+    std::memcpy(out, s.data(), s.size());
+    out += s.size();
+  }
+}
+
+void tfcref_encoder_free(void* h) { delete static_cast<Encoder*>(h); }
+
+// ---- CreateRangeDecoder / EntropyDecode{Channel,Index} / EntropyDecodeFinalize ----
+void* tfcref_decoder_create(const uint8_t* bytes, const int64_t* offsets, int64_t n_streams,
+                            const int32_t* lookup, int64_t len, int64_t cols) {
+  auto* d = new Decoder;
+  d->lookup.assign(lookup, lookup + len);
+  std::string err;
+  if (!ParseLookup(d->lookup.data(), len, cols, &d->rows, &err)) {
+    g_error = err;
+    delete d;
+    return nullptr;
+  }
+  d->data.resize(n_streams);
+  d->dec.reserve(n_streams);
+  for (int64_t s = 0; s < n_streams; ++s) {
+    d->data[s].assign(reinterpret_cast<const char*>(bytes) + offsets[s], offsets[s + 1] - offsets[s]);
+  }
+  for (int64_t s = 0; s < n_streams; ++s) d->dec.emplace_back(absl::string_view(d->data[s]));
+  return d;
+}
+
+int tfcref_decoder_decode(void* h, const int32_t* index, int32_t* out, int64_t n_per_stream,
+                          int threads) {
+  auto* d = static_cast<Decoder*>(h);
+  const int64_t S = static_cast<int64_t>(d->dec.size());
+  const int64_t R = static_cast<int64_t>(d->rows.size());
+  std::mutex mu;
+  std::string err;
+  ParallelOverStreams(S, threads, [&](int64_t lo, int64_t hi) {
+    for (int64_t s = lo; s < hi; ++s) {
+      tfc::RangeDecoder& dec = d->dec[s];
+      int32_t* po = out + s * n_per_stream;
+      const int32_t* pi = index ? index + s * n_per_stream : nullptr;
+      for (int64_t ind = 0, j = 0; j < n_per_stream; ++ind, ++j) {
+        int64_t r;
+        if (pi) {
+          r = pi[j];
+          if (r < 0 || r >= R) {
+            std::lock_guard<std::mutex> g(mu);
+            err = "index=" + std::to_string(r) + " not in range [0, " + std::to_string(R) + ")";
+            return;
+          }
+        } else {
+          if (R <= ind) ind = 0;
+          r = ind;
+        }
+        const Row& row = d->rows[r];
+        if (row.p[0] > 0) {
+          po[j] = dec.Decode(absl::Span<const int32_t>(row.p + 1, row.size - 1), row.p[0]);
+        } else {
+          po[j] = OverflowDecode(dec, row);
+        }
+      }
+    }
+  });
+  if (!err.empty()) return Fail(err);
+  return 0;
+}
+
+int tfcref_decoder_finalize(void* h, uint8_t* ok /* n_streams */) {
+  auto* d = static_cast<Decoder*>(h);
+  for (size_t s = 0; s < d->dec.size(); ++s) ok[s] = d->dec[s].Finalize() ? 1 : 0;
+  return 0;
+}
+
+void tfcref_decoder_free(void* h) { delete static_cast<Decoder*>(h); }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// Legacy RangeEncode / RangeDecode (one stream, broadcastable N-D CDF).
+// ------------------------------------------------------------------------------------------
+namespace {
+
+// range_coding_kernels_util.cc:34-91
+bool MergeAxes(const std::vector<int64_t>& bshape, const std::vector<int64_t>& sshape,
+               std::vector<int64_t>* mb, std::vector<int64_t>* ms, std::string* err) {
+  auto fmt = [](const std::vector<int64_t>& v) {
+    std::string s = "[";
+    for (size_t i = 0; i < v.size(); ++i) s += (i ? "," : "") + std::to_string(v[i]);
+    return s + "]";
+  };
+  mb->assign(1, 1);
+  ms->assign(1, 1);
+  const int rank = static_cast<int>(bshape.size());
+  for (int i = 0, j = 0; j < rank; ++j) {
+    if (bshape[j] != sshape[j] && sshape[j] != 1) {
+      *err = "Cannot broadcast shape " + fmt(sshape) + " to " + fmt(bshape);
+      return false;
+    }
+    const bool was_b = ((*ms)[i] == 1);
+    const bool is_b = (sshape[j] == 1);
+    const bool merge = (was_b == is_b) || (bshape[j] <= 1) || ((*mb)[i] <= 1);
+    if (merge) {
+      (*mb)[i] *= bshape[j];
+      (*ms)[i] *= sshape[j];
+    } else {
+      mb->push_back(bshape[j]);
+      ms->push_back(sshape[j]);
+      ++i;
+    }
+  }
+  int64_t stride = 1;
+  for (size_t i = bshape.size(); i < sshape.size(); ++i) stride *= sshape[i];
+  ms->push_back(stride);
+  return true;
+}
+
+// Walks data linearly and yields the CDF strip for each element,
+// range_coding_kernels.cc:60-132 (arbitrary N instead of a template).
+struct BroadcastWalk {
+  std::vector<int64_t> dshape, displace, idx;
+  const int32_t* cdf;
+  BroadcastWalk(const std::vector<int64_t>& d, const std::vector<int64_t>& c, const int32_t* p)
+      : dshape(d), displace(d.size(), c.back()), idx(d.size(), 0), cdf(p) {
+    int64_t stride = c.back();
+    for (int i = static_cast<int>(d.size()) - 1; i >= 0; --i) {
+      if (c[i] <= 1) displace[i] -= stride;
+      stride *= c[i];
+    }
+  }
+  const int32_t* Next() {
+    const int32_t* ret = cdf;
+    int i = static_cast<int>(dshape.size()) - 1;
+    for (; i > 0; --i) {
+      if (++idx[i] < dshape[i]) break;
+      idx[i] = 0;
+    }
+    cdf += displace[i];
+    return ret;
+  }
+};
+
+bool CheckLegacy(const std::vector<int64_t>& dshape, const std::vector<int64_t>& cshape,
+                 const int32_t* cdf, int precision, int debug_level, std::string* err) {
+  if (!(0 < precision && precision <= 16)) {
+    *err = "`precision` must be in [1, 16]: " + std::to_string(precision);
+    return false;
+  }
+  if (cshape.size() != dshape.size() + 1) {
+    *err = "`cdf` should have one more axis than `data`";
+    return false;
+  }
+  if (cshape.back() <= 1) {
+    *err = "The last dimension of `cdf` should be > 1";
+    return false;
+  }
+  if (debug_level > 0) {  // CheckCdfValues, :150-173
+    const int64_t size = cshape.back();
+    if (size <= 2) {
+      *err = "CDF size should be > 2: " + std::to_string(size);
+      return false;
+    }
+    int64_t rows = 1;
+    for (size_t i = 0; i + 1 < cshape.size(); ++i) rows *= cshape[i];
+    const int32_t upper = 1 << precision;
+    for (int64_t r = 0; r < rows; ++r) {
+      const int32_t* s = cdf + r * size;
+      if (s[0] != 0 || s[size - 1] != upper) {
+        *err = "CDF should start from 0 and end at " + std::to_string(upper) +
+               ": cdf[0]=" + std::to_string(s[0]) + ", cdf[^1]=" + std::to_string(s[size - 1]);
+        return false;
+      }
+      for (int64_t j = 0; j + 1 < size; ++j) {
+        if (s[j + 1] <= s[j]) {
+          *err = "CDF is not monotonic";
+          return false;
+        }
+      }
+    }
+  }
+  return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+// data int16 with shape dshape[rank]; cdf int32 with shape cshape[rank+1].
+int64_t tfcref_range_encode(const int16_t* data, const int64_t* dshape_, int rank, const int32_t* cdf,
+                            const int64_t* cshape_, int crank, int precision, int debug_level,
+                            uint8_t* out, int64_t out_cap) {
+  std::vector<int64_t> dshape(dshape_, dshape_ + rank), cshape(cshape_, cshape_ + crank);
+  std::string err;
+  if (!CheckLegacy(dshape, cshape, cdf, precision, debug_level, &err)) return -Fail(err);
+  std::vector<int64_t> mb, ms;
+  if (!MergeAxes(dshape, cshape, &mb, &ms, &err)) return -Fail(err);
+  if (mb.size() > 6) return -Fail("Irregular broadcast pattern");
+  int64_t n = 1;
+  for (auto d : dshape) n *= d;
+  const int64_t chip = cshape.back();
+  BroadcastWalk walk(mb, ms, cdf);
+  tfc::RangeEncoder enc;
+  std::string sink;
+  for (int64_t i = 0; i < n; ++i) {
+    const int32_t* strip = walk.Next();
+    const int64_t v = data[i];
+    if (debug_level > 0 && (v < 0 || chip <= v + 1)) {
+      return -Fail("'data' value not in [0, " + std::to_string(chip - 1) + "): value=" +
+                   std::to_string(v));
+    }
+    enc.Encode(strip[v], strip[v + 1], precision, &sink);
+  }
+  enc.Finalize(&sink);
+  if (static_cast<int64_t>(sink.size()) > out_cap) return -Fail("output buffer too small");
+  std::memcpy(out, sink.data(), sink.size());
+  g_error.clear();
+  return static_cast<int64_t>(sink.size());
+}
+
+int tfcref_range_decode(const uint8_t* bytes, int64_t nbytes, const int64_t* dshape_, int rank,
+                        const int32_t* cdf, const int64_t* cshape_, int crank, int precision,
+                        int debug_level, int16_t* out) {
+  std::vector<int64_t> dshape(dshape_, dshape_ + rank), cshape(cshape_, cshape_ + crank);
+  std::string err;
+  if (!CheckLegacy(dshape, cshape, cdf, precision, debug_level, &err)) return Fail(err);
+  std::vector<int64_t> mb, ms;
+  if (!MergeAxes(dshape, cshape, &mb, &ms, &err)) return Fail(err);
+  if (mb.size() > 6) return Fail("Irregular broadcast pattern");
+  int64_t n = 1;
+  for (auto d : dshape) n *= d;
+  const int64_t chip = cshape.back();
+  BroadcastWalk walk(mb, ms, cdf);
+  std::string src(reinterpret_cast<const char*>(bytes), nbytes);
+  tfc::RangeDecoder dec{absl::string_view(src)};
+  for (int64_t i = 0; i < n; ++i) {
+    const int32_t* strip = walk.Next();
+    out[i] = static_cast<int16_t>(dec.Decode(absl::Span<const int32_t>(strip, chip), precision));
+  }
+  return 0;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// PmfToQuantizedCdf, pmf_to_cdf_kernels.cc:58-101,104-208.  Uses std::sort / std::rotate like the
+// reference so that tie order matches what the reference would produce with this libstdc++.
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct Penalty {
+  int32_t* v;
+  double mass, key;
+  double Next() const {
+    if (*v <= 1) return std::numeric_limits<double>::infinity();
+    return mass * (std::log2(*v) - std::log2(*v - 1));
+  }
+  Penalty(int32_t* p, double m) : v(p), mass(m) { key = Next(); }
+  void Step() {
+    --*v;
+    key = Next();
+  }
+  friend bool operator<(const Penalty& a, const Penalty& b) { return a.key < b.key; }
+};
+
+struct Gain {
+  int32_t* v;
+  double mass, key;
+  double Next() const {
+    if (*v < 1) return -std::numeric_limits<double>::infinity();
+    return mass * (std::log2(*v + 1) - std::log2(*v));
+  }
+  Gain(int32_t* p, double m) : v(p), mass(m) { key = Next(); }
+  void Step() {
+    ++*v;
+    key = Next();
+  }
+  friend bool operator>(const Gain& a, const Gain& b) { return a.key > b.key; }
+};
+
+void PmfRow(const float* pmf, int64_t n, int precision, int32_t* cdf /* n+1 */) {
+  const int32_t normalizer = 1 << precision;
+  int32_t* q = cdf + 1;
+  cdf[0] = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    int32_t value = static_cast<int32_t>(std::rint(pmf[i] * normalizer));
+    q[i] = std::max(value, 1);
+  }
+  int32_t sum = std::accumulate(q, q + n, 0);
+  if (sum > normalizer) {
+    std::vector<Penalty> queue;
+    queue.reserve(n);
+    for (int64_t i = 0; i < n; ++i) queue.emplace_back(&q[i], pmf[i]);
+    std::sort(queue.begin(), queue.end());
+    while (sum-- > normalizer) {
+      queue[0].Step();
+      auto it = std::find_if(std::next(queue.begin()), queue.end(),
+                             [&queue](const Penalty& rhs) { return queue[0] < rhs; });
+      std::rotate(queue.begin(), std::next(queue.begin()), it);
+    }
+  } else if (sum < normalizer) {
+    std::vector<Gain> queue;
+    queue.reserve(n);
+    for (int64_t i = 0; i < n; ++i) queue.emplace_back(&q[i], pmf[i]);
+    std::sort(queue.begin(), queue.end(), std::greater<Gain>());
+    while (sum++ < normalizer) {
+      queue[0].Step();
+      auto it = std::find_if(std::next(queue.begin()), queue.end(),
+                             [&queue](const Gain& rhs) { return queue[0] > rhs; });
+      std::rotate(queue.begin(), std::next(queue.begin()), it);
+    }
+  }
+  std::partial_sum(q, q + n, q);
+}
+
+}  // namespace
+
+extern "C" {
+
+int tfcref_pmf_to_cdf(const float* pmf, int64_t rows, int64_t n, int precision, int32_t* cdf) {
+  if (!(0 < precision && precision <= 16))
+    return Fail("`precision` must be in [1, 16]: " + std::to_string(precision));
+  if (n <= 1) return Fail("`pmf` size should be at least 2 in the last axis.");
+  for (int64_t i = 0; i < rows * n; ++i) {
+    if (!(std::isfinite(pmf[i]) && pmf[i] >= 0))
+      return Fail("`pmf` has non-finite or negative element: " + std::to_string(pmf[i]));
+  }
+  for (int64_t r = 0; r < rows; ++r) PmfRow(pmf + r * n, n, precision, cdf + r * (n + 1));
+  return 0;
+}
+
+int tfcref_hardware_threads() { return static_cast<int>(std::thread::hardware_concurrency()); }
+
+}  // extern "C"

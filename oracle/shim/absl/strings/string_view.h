@@ -1,0 +1,4 @@
+// Test-infrastructure shim: absl::string_view == std::string_view.
+#pragma once
+#include <string_view>
+namespace absl { using string_view = std::string_view; }
