@@ -1,0 +1,1469 @@
+// Range coder for sm_100a: one warp per code stream.
+//
+// Replaces (paths relative to /root/reference/tensorflow_compression):
+//   cc/lib/range_coder.cc:37-307, cc/lib/range_coder.h:79-282          the coder
+//   cc/kernels/range_coder_kernels.cc:110-164,168-322,334-471           multi-stream ops
+//   cc/kernels/range_coding_kernels.cc:60-379 (+ _util.cc:34-91)        legacy single-stream ops
+//
+// ENCODER DESIGN.  The reference emits bytes through a delayed-carry state machine.  Its output is
+// exactly the big-number sum  SUM_k a_k * 2^-(16 r_k + 32)  of the per-symbol interval offsets a_k
+// (r_k = number of 16-bit renormalisations before symbol k) followed by a short flush.  Only the
+// recurrence on the interval size is inherently serial.  So per stream (= per warp):
+//   * all 32 lanes cooperatively gather the (lower, upper, precision) triples of the next 32 symbols
+//     (coalesced symbol load + table gather, fused quantisation, Elias-gamma preparation);
+//   * every lane then runs the same serial recurrence (size', base', carry-out) over those triples,
+//     fetched with warp shuffles; a renormalisation appends one *unresolved* 16-bit word plus one
+//     carry bit ("a carry left the 32-bit window while this word was its top half");
+//   * words are staged one per lane and flushed as 64-byte coalesced stores;
+//   * finalize resolves all carries at once with a warp-wide carry-lookahead over 32-word groups,
+//     applies RangeEncoder::Finalize's tail rule and compacts all strings into one buffer.
+// DECODER DESIGN.  Same recurrence; the CDF search is a warp-parallel k-ary search (each lane tests
+// one candidate per round, ballot picks the bracket), the byte window is prefetched 64 B at a time.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace tfcb {
+namespace {
+
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+// ---------------------------------------------------------------------------------------------
+// Lookup tables
+// ---------------------------------------------------------------------------------------------
+struct HostRow {
+  int32_t start;  // index of cdf[0] inside the lookup buffer
+  int32_t ncdf;   // number of cdf entries (bins + 1)
+  int32_t prec;   // signed precision entry
+};
+
+// meta = ncdf | |precision| << 24 | overflow << 31
+__host__ __device__ inline int row_ncdf(int meta) { return meta & 0xFFFFFF; }
+__host__ __device__ inline int row_prec(int meta) { return (meta >> 24) & 0x1F; }
+__host__ __device__ inline bool row_ovf(int meta) { return meta < 0; }
+
+// Grammar of range_coder_kernels.cc:110-137 (one row) and :139-164 (1-D / 2-D containers).
+int scan_row(const int32_t* base, const int32_t* end, const int32_t** cur, std::vector<HostRow>* rows) {
+  const int32_t* p = *cur;
+  if (end - p < 3) return fail(TFCB_INVALID_ARGUMENT, "CDF ended prematurely.");
+  const int64_t ap = p[0] < 0 ? -(int64_t)p[0] : (int64_t)p[0];
+  if (ap < 1 || ap >= 17)
+    return fail(TFCB_INVALID_ARGUMENT, "precision=%lld not in range [1, 17)", (long long)ap);
+  const int32_t last = 1 << ap;
+  const int32_t* first = p;
+  if (p[1] != 0) return fail(TFCB_INVALID_ARGUMENT, "CDF must start with 0.");
+  p += 1;
+  for (;;) {
+    ++p;
+    if (p == end) return fail(TFCB_INVALID_ARGUMENT, "CDF must end with 1 << precision.");
+    if (p[0] < p[-1]) return fail(TFCB_INVALID_ARGUMENT, "CDF must be monotonically increasing.");
+    if (*p == last) break;
+  }
+  ++p;
+  rows->push_back(HostRow{(int32_t)(first + 1 - base), (int32_t)(p - first - 1), first[0]});
+  while (p != end && *p == last) ++p;
+  *cur = p;
+  return TFCB_OK;
+}
+
+int parse_lookup(const int32_t* lookup, int64_t len, int64_t cols, std::vector<HostRow>* rows) {
+  rows->clear();
+  if (len < 0 || (len > 0 && lookup == nullptr))
+    return fail(TFCB_INVALID_ARGUMENT, "`lookup` is null");
+  if (len >= (1ll << 31)) return fail(TFCB_INVALID_ARGUMENT, "`lookup` too large");
+  if (cols < 0 || (cols > 0 && len % cols != 0))
+    return fail(TFCB_INVALID_ARGUMENT, "`lookup` must be rank 1 or 2");
+  const int32_t* end = lookup + len;
+  for (const int32_t* cur = lookup; cur != end;) {
+    const int32_t* row_end = cols > 0 ? cur + cols : end;
+    TFCB_TRY(scan_row(lookup, row_end, &cur, rows));
+    if (cols > 0 && cur != row_end)
+      return fail(TFCB_INVALID_ARGUMENT, "CDF must end with 1 << precision.");
+  }
+  return TFCB_OK;
+}
+
+struct DeviceLookup {
+  int32_t* lookup = nullptr;  // device copy of the raw table
+  int2* rows = nullptr;       // {start, meta}
+  int n_rows = 0;
+  bool any_overflow = false;
+  int max_prec = 0;
+
+  int upload(const int32_t* lookup_host, int64_t len, int64_t cols, cudaStream_t s) {
+    std::vector<HostRow> hr;
+    TFCB_TRY(parse_lookup(lookup_host, len, cols, &hr));
+    n_rows = (int)hr.size();
+    std::vector<int2> meta(std::max<size_t>(hr.size(), 1));
+    for (size_t i = 0; i < hr.size(); ++i) {
+      const int ap = hr[i].prec < 0 ? -hr[i].prec : hr[i].prec;
+      any_overflow |= hr[i].prec < 0;
+      max_prec = std::max(max_prec, ap);
+      meta[i].x = hr[i].start;
+      meta[i].y = hr[i].ncdf | (ap << 24) | (hr[i].prec < 0 ? (int)0x80000000 : 0);
+    }
+    TFCB_TRY(dev_alloc((void**)&lookup, std::max<int64_t>(len, 1) * sizeof(int32_t), s));
+    TFCB_TRY(dev_alloc((void**)&rows, meta.size() * sizeof(int2), s));
+    if (len > 0)
+      TFCB_CUDA_TRY(cudaMemcpyAsync(lookup, lookup_host, len * sizeof(int32_t),
+                                    cudaMemcpyHostToDevice, s));
+    TFCB_CUDA_TRY(cudaMemcpyAsync(rows, meta.data(), meta.size() * sizeof(int2),
+                                  cudaMemcpyHostToDevice, s));
+    // the host vectors die at return: make sure the copies have been staged
+    TFCB_CUDA_TRY(cudaStreamSynchronize(s));
+    return TFCB_OK;
+  }
+  void release(cudaStream_t s) {
+    dev_free(lookup, s);
+    dev_free(rows, s);
+    lookup = nullptr;
+    rows = nullptr;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Encoder state and serial recurrence
+// ---------------------------------------------------------------------------------------------
+struct EncState {
+  uint32_t base;   // low end of the interval (32-bit window, wraps)
+  uint32_t span;   // size - 1
+  uint32_t cnt;    // 16-bit words appended so far
+  uint32_t carry;  // a carry left the window at the current position (belongs to word cnt-1)
+  uint32_t run;    // length of the run of 0xFFFF words immediately left of the window
+  uint32_t pad[3];
+};
+
+struct EncChain {
+  uint32_t base, span, cnt, carry, run;
+  uint32_t word;   // this lane's staged word (word index (cnt & ~31) + lane)
+  uint32_t cmask;  // carry bits of the staged group
+  uint16_t* words;
+  uint32_t* cbits;
+  uint32_t cap;  // capacity in words (multiple of 32)
+  bool overflowed;
+};
+
+__device__ __forceinline__ void enc_flush_group(EncChain& c, int lane) {
+  // called with (c.cnt & 31) == 0 right after the 32nd word of a group was staged
+  const uint32_t g0 = c.cnt - 32;
+  if (c.cnt <= c.cap) {
+    c.words[g0 + lane] = (uint16_t)c.word;
+    if (lane == 0) c.cbits[g0 >> 5] = c.cmask;
+  } else {
+    c.overflowed = true;
+  }
+  c.cmask = 0;
+}
+
+// One Encode(lower, upper, precision) of range_coder.cc:37-264 in the big-number formulation.
+__device__ __forceinline__ void enc_step(EncChain& c, uint32_t lo, uint32_t hi, uint32_t p, int lane) {
+  const uint32_t a = scale_cum(c.span, lo, p);
+  const uint32_t b = scale_cum(c.span, hi, p);  // 2^32 truncates to 0, b - 1 wraps as in the reference
+  const uint32_t nb = c.base + a;
+  c.carry |= (nb < a) ? 1u : 0u;
+  c.base = nb;
+  c.span = b - a - 1u;
+  if (c.span < 65536u) {
+    const uint32_t top = nb >> 16;
+    const uint32_t slot = c.cnt & 31u;
+    if ((uint32_t)lane == slot) c.word = top;
+    c.cmask |= c.carry << slot;
+    c.carry = 0;
+    c.run = (top == 0xFFFFu) ? c.run + 1u : 0u;
+    c.base = nb << 16;
+    c.span = (c.span << 16) | 0xFFFFu;
+    c.cnt += 1;
+    if ((c.cnt & 31u) == 0) enc_flush_group(c, lane);
+  }
+}
+
+// Escape tail of OverflowEncode (range_coder_kernels.cc:306-321): Elias-gamma code of g, then sign,
+// every bit coded with the uniform binary CDF {0,1,2} at precision 1.
+__device__ __forceinline__ void enc_gamma(EncChain& c, uint32_t g, uint32_t sign, int lane) {
+  const int n = 32 - __clz(g);  // g >= 1
+  for (int i = 1; i < n; ++i) enc_step(c, 0, 1, 1, lane);
+  for (int i = n - 1; i >= 0; --i) {
+    const uint32_t bit = (g >> i) & 1u;
+    enc_step(c, bit, bit + 1, 1, lane);
+  }
+  enc_step(c, sign, sign + 1, 1, lane);
+}
+
+enum : int { kModeIndex = 1, kModeF32 = 2 };
+
+struct EncParams {
+  const int32_t* lookup;
+  const int2* rows;
+  int n_rows;
+  const void* value;       // int32 or float [S, n]
+  const int32_t* index;    // [S, n] or null
+  const float* qoff;       // channel+f32: [n_rows] or null; index+f32: loc [S, n] or null
+  const int32_t* coff;     // f32 modes: cdf_offset [n_rows]
+  long long n;
+  long long n_streams;
+  EncState* state;
+  uint16_t* words;
+  uint32_t* cbits;
+  long long cap;  // words per stream
+  DevError* err;
+};
+
+struct Gathered {
+  uint32_t pack;   // lower | (upper - 1) << 16
+  uint32_t prec;
+  uint32_t gamma;  // escape payload (0 = none)
+  uint32_t sign;
+};
+
+template <int MODE>
+__device__ __forceinline__ Gathered enc_gather(const EncParams& P, long long s, long long j,
+                                               uint32_t chan_row, bool valid) {
+  Gathered g;
+  g.pack = 0;  // lower=0, upper=1 at precision 1 would still consume range: use prec 0 marker
+  g.prec = 0;
+  g.gamma = 0;
+  g.sign = 0;
+  if (!valid) return g;
+  const long long at = s * P.n + j;
+  int row;
+  if (MODE & kModeIndex) {
+    row = __ldg(P.index + at);
+    if (row < 0 || row >= P.n_rows) {
+      report(P.err, kErrIndex, s, j, row, P.n_rows);
+      return g;
+    }
+  } else {
+    row = (int)chan_row;
+  }
+  const int2 ri = __ldg(P.rows + row);
+  int v;
+  if (MODE & kModeF32) {
+    float y = __ldg(reinterpret_cast<const float*>(P.value) + at);
+    if (MODE & kModeIndex) {
+      if (P.qoff) y -= __ldg(P.qoff + at);  // loc
+    } else {
+      if (P.qoff) y -= __ldg(P.qoff + row);
+    }
+    v = (int)rintf(y) - __ldg(P.coff + row);
+  } else {
+    v = __ldg(reinterpret_cast<const int32_t*>(P.value) + at);
+  }
+  const int ncdf = row_ncdf(ri.y);
+  if (!row_ovf(ri.y)) {
+    if (v < 0 || v >= ncdf - 1) {
+      report(P.err, kErrValue, s, j, v, ncdf - 1);
+      return g;
+    }
+  } else {
+    const int esc = ncdf - 2;
+    if (v < 0) {
+      g.gamma = (uint32_t)(-(long long)v);
+      g.sign = 1;
+      v = esc;
+    } else if (v >= esc) {
+      g.gamma = (uint32_t)(v - esc + 1);
+      v = esc;
+    }
+  }
+  const uint32_t lower = (uint32_t)__ldg(P.lookup + ri.x + v);
+  const uint32_t upper = (uint32_t)__ldg(P.lookup + ri.x + v + 1);
+  g.pack = lower | ((upper - 1u) << 16);
+  g.prec = (uint32_t)row_prec(ri.y);
+  return g;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(32) encode_kernel(const EncParams P) {
+  const long long s = blockIdx.x;
+  const int lane = threadIdx.x;
+  if (s >= P.n_streams) return;
+
+  EncChain c;
+  {
+    const EncState st = P.state[s];
+    c.base = st.base;
+    c.span = st.span;
+    c.cnt = st.cnt;
+    c.carry = st.carry;
+    c.run = st.run;
+  }
+  c.words = P.words + s * P.cap;
+  c.cbits = P.cbits + s * (P.cap >> 5);
+  c.cap = (uint32_t)P.cap;
+  c.overflowed = false;
+  // reload the partially filled group left by a previous call
+  {
+    const uint32_t g0 = c.cnt & ~31u;
+    const uint32_t fill = c.cnt & 31u;
+    c.word = ((uint32_t)lane < fill) ? c.words[g0 + lane] : 0u;
+    c.cmask = fill ? c.cbits[g0 >> 5] : 0u;
+  }
+
+  uint32_t chan_row = 0, chan_step = 0;
+  if (!(MODE & kModeIndex)) {
+    chan_row = (uint32_t)lane % (uint32_t)P.n_rows;
+    chan_step = 32u % (uint32_t)P.n_rows;
+  }
+
+  Gathered cur = enc_gather<MODE>(P, s, lane, chan_row, lane < P.n);
+  for (long long g0 = 0; g0 < P.n; g0 += 32) {
+    // prefetch the next group's triples while this group runs through the serial chain
+    uint32_t next_row = chan_row + chan_step;
+    if (!(MODE & kModeIndex) && next_row >= (uint32_t)P.n_rows) next_row -= (uint32_t)P.n_rows;
+    const long long jn = g0 + 32 + lane;
+    const Gathered nxt = enc_gather<MODE>(P, s, jn, next_row, jn < P.n);
+    chan_row = next_row;
+
+    const int count = (int)min(32ll, P.n - g0);
+    const unsigned esc_mask = __ballot_sync(kFull, cur.gamma != 0);
+    const unsigned bad_mask = __ballot_sync(kFull, cur.prec == 0 && lane < count);
+    if (bad_mask) break;  // argument error already recorded; stop this stream
+    if (count == 32 && esc_mask == 0) {
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const uint32_t pk = __shfl_sync(kFull, cur.pack, k);
+        const uint32_t pr = __shfl_sync(kFull, cur.prec, k);
+        enc_step(c, pk & 0xFFFFu, (pk >> 16) + 1u, pr, lane);
+      }
+    } else {
+      for (int k = 0; k < count; ++k) {
+        const uint32_t pk = __shfl_sync(kFull, cur.pack, k);
+        const uint32_t pr = __shfl_sync(kFull, cur.prec, k);
+        enc_step(c, pk & 0xFFFFu, (pk >> 16) + 1u, pr, lane);
+        if ((esc_mask >> k) & 1u) {
+          const uint32_t gm = __shfl_sync(kFull, cur.gamma, k);
+          const uint32_t sg = __shfl_sync(kFull, cur.sign, k);
+          enc_gamma(c, gm, sg, lane);
+        }
+      }
+    }
+    cur = nxt;
+  }
+
+  // spill the partially filled group and the scalar state
+  {
+    const uint32_t g0 = c.cnt & ~31u;
+    const uint32_t fill = c.cnt & 31u;
+    if (fill) {
+      if (g0 + 32 <= c.cap) {
+        if ((uint32_t)lane < fill) c.words[g0 + lane] = (uint16_t)c.word;
+        if (lane == 0) c.cbits[g0 >> 5] = c.cmask;
+      } else {
+        c.overflowed = true;
+      }
+    }
+    if (c.overflowed) report(P.err, kErrCapacity, s, c.cnt, c.cnt, c.cap);
+    if (lane == 0) {
+      EncState st;
+      st.base = c.base;
+      st.span = c.span;
+      st.cnt = c.cnt;
+      st.carry = c.carry;
+      st.run = c.run;
+      st.pad[0] = st.pad[1] = st.pad[2] = 0;
+      P.state[s] = st;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Encoder finalize
+// ---------------------------------------------------------------------------------------------
+__global__ void enc_init_state_kernel(EncState* st, long long n) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) {
+    EncState s;
+    s.base = 0;
+    s.span = 0xFFFFFFFFu;
+    s.cnt = 0;
+    s.carry = 0;
+    s.run = 0;
+    s.pad[0] = s.pad[1] = s.pad[2] = 0;
+    st[i] = s;
+  }
+}
+
+// Tail rule of RangeEncoder::Finalize (range_coder.cc:266-307) expressed on (words, state).
+// Returns the string length; `straddle` = the interval still contains 2^32 ("state 1").
+__device__ __forceinline__ long long enc_final_length(const EncState& st, const uint16_t* words,
+                                                      bool* straddle, uint32_t* tail, int* ntail) {
+  const uint32_t top_end = st.base + st.span;
+  *ntail = 0;
+  *tail = 0;
+  if (top_end < st.base) {
+    // pick 2^32: +1 ripples through `run` 0xFFFF words into word d, everything right of d is zero
+    // and dropped, and so is the low byte of word d when it is zero.
+    *straddle = true;
+    const uint32_t d = st.cnt - 1u - st.run;
+    const uint32_t wd = ((uint32_t)words[d] + 1u) & 0xFFFFu;
+    return 2ll * d + 1 + ((wd & 0xFFu) ? 1 : 0);
+  }
+  *straddle = false;
+  if (st.base != 0) {
+    const uint32_t r24 = ((st.base - 1u) >> 24) + 1u;
+    if (r24 <= (top_end >> 24)) {
+      *tail = r24 << 8;
+      *ntail = 1;
+    } else {
+      const uint32_t r16 = ((st.base - 1u) >> 16) + 1u;
+      *tail = r16;
+      *ntail = (r16 & 0xFFu) ? 2 : 1;
+    }
+  }
+  return 2ll * st.cnt + *ntail;
+}
+
+__global__ void enc_lengths_kernel(const EncState* state, const uint16_t* words, long long cap,
+                                   long long n_streams, long long* lens) {
+  const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (s >= n_streams) return;
+  bool straddle;
+  uint32_t tail;
+  int ntail;
+  lens[s] = enc_final_length(state[s], words + s * cap, &straddle, &tail, &ntail);
+}
+
+// Single-block exclusive scan: offsets[0..n] from lens[0..n-1].
+__global__ void exclusive_scan_kernel(const long long* lens, long long n, long long* offsets) {
+  __shared__ long long warp_sums[32];
+  __shared__ long long carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (long long base = 0; base < n; base += blockDim.x) {
+    const long long i = base + tid;
+    long long v = (i < n) ? lens[i] : 0;
+    long long x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const long long y = __shfl_up_sync(kFull, x, d);
+      if (lane >= d) x += y;
+    }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      long long w = (lane < (int)(blockDim.x >> 5)) ? warp_sums[lane] : 0;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const long long y = __shfl_up_sync(kFull, w, d);
+        if (lane >= d) w += y;
+      }
+      warp_sums[lane] = w;  // inclusive
+    }
+    __syncthreads();
+    const long long before = carry_s + (wid ? warp_sums[wid - 1] : 0) + (x - v);
+    if (i < n) offsets[i] = before;
+    __syncthreads();
+    if (tid == blockDim.x - 1) carry_s = before + v;
+    __syncthreads();
+  }
+  if (tid == 0) offsets[n] = carry_s;
+}
+
+// One warp per stream: resolve carries right-to-left, 32 words per step, and write the bytes.
+__global__ void __launch_bounds__(128) enc_write_kernel(const EncState* state, const uint16_t* words,
+                                                        const uint32_t* cbits, long long cap,
+                                                        long long n_streams,
+                                                        const long long* offsets, uint8_t* out) {
+  const long long s = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (s >= n_streams) return;
+  const EncState st = state[s];
+  const uint16_t* w = words + s * cap;
+  const uint32_t* cb = cbits + s * (cap >> 5);
+  uint8_t* dst = out + offsets[s];
+  bool straddle;
+  uint32_t tail;
+  int ntail;
+  const long long len = enc_final_length(st, w, &straddle, &tail, &ntail);
+  const long long body = straddle ? len : 2ll * st.cnt;  // bytes that come from resolved words
+
+  // carry entering the right-most word (index cnt-1)
+  uint32_t x = straddle ? 1u : st.carry;
+  const long long n_groups = ((long long)st.cnt + 31) >> 5;
+  for (long long g = n_groups - 1; g >= 0; --g) {
+    const uint32_t idx = (uint32_t)(g << 5) + lane;
+    const bool live = idx < st.cnt;
+    const uint32_t word = live ? (uint32_t)w[idx] : 0u;
+    uint32_t F = cb[g];
+    const uint32_t fill = st.cnt - (uint32_t)(g << 5);
+    if (fill < 32u) F &= (1u << fill) - 1u;
+    // P: word propagates a carry.  Dead lanes right of the last word must pass `x` through.
+    const uint32_t Pm = __ballot_sync(kFull, live ? (word == 0xFFFFu) : true);
+    // position j = 31 - i (bit 0 = right-most word); c[j+1] = F[31-j] | (P[31-j] & c[j])
+    const uint32_t G = __brev(F);
+    const uint32_t A = G | __brev(Pm);
+    const unsigned long long sum = (unsigned long long)A + G + x;
+    const uint32_t cin = (uint32_t)sum ^ A ^ G;  // bit j = carry into position j
+    const uint32_t my_c = (cin >> (31 - lane)) & 1u;
+    x = (uint32_t)(sum >> 32) & 1u;
+    if (live) {
+      const uint32_t r = (word + my_c) & 0xFFFFu;
+      const long long b0 = 2ll * idx;
+      if (b0 < body) dst[b0] = (uint8_t)(r >> 8);
+      if (b0 + 1 < body) dst[b0 + 1] = (uint8_t)r;
+    }
+  }
+  if (!straddle && lane == 0) {
+    if (ntail >= 1) dst[body] = (uint8_t)(tail >> 8);
+    if (ntail == 2) dst[body + 1] = (uint8_t)tail;
+  }
+}
+
+__global__ void enc_grow_kernel(const uint16_t* src, const uint32_t* src_cb, long long src_cap,
+                                uint16_t* dst, uint32_t* dst_cb, long long dst_cap,
+                                const EncState* state) {
+  const long long s = blockIdx.x;
+  const uint32_t used = (state[s].cnt + 31u) & ~31u;
+  for (uint32_t i = threadIdx.x; i < used; i += blockDim.x) dst[s * dst_cap + i] = src[s * src_cap + i];
+  for (uint32_t i = threadIdx.x; i < (used >> 5); i += blockDim.x)
+    dst_cb[s * (dst_cap >> 5) + i] = src_cb[s * (src_cap >> 5) + i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Decoder
+// ---------------------------------------------------------------------------------------------
+struct DecState {
+  uint32_t base, span, value;
+  uint32_t pos;  // 16-bit words consumed (starts at 2)
+};
+
+struct DecParams {
+  const int32_t* lookup;
+  const int2* rows;
+  int n_rows;
+  const uint8_t* bytes;
+  const long long* offsets;
+  const int32_t* index;
+  void* out;               // int32 or float [S, n]
+  const float* qoff;       // channel: [n_rows]; index: loc [S, n]
+  const int32_t* coff;     // [n_rows]
+  long long n;
+  long long n_streams;
+  DecState* state;
+  DevError* err;
+};
+
+struct ByteWindow {
+  const uint8_t* p;
+  long long len;
+  uint32_t lane_word;  // word (pos & ~31) + lane
+  uint32_t next;       // word at index pos
+};
+
+__device__ __forceinline__ uint32_t bw_fetch(const ByteWindow& w, long long word_idx) {
+  const long long b = 2 * word_idx;
+  uint32_t hi = 0, lo = 0;
+  if (b < w.len) hi = w.p[b];
+  if (b + 1 < w.len) lo = w.p[b + 1];
+  return (hi << 8) | lo;
+}
+
+__device__ __forceinline__ void bw_seek(ByteWindow& w, uint32_t pos, int lane) {
+  w.lane_word = bw_fetch(w, (long long)(pos & ~31u) + lane);
+  w.next = __shfl_sync(kFull, w.lane_word, pos & 31u);
+}
+
+struct DecChain {
+  uint32_t base, span, value, pos;
+};
+
+__device__ __forceinline__ void dec_update(DecChain& c, ByteWindow& w, uint32_t a, uint32_t b, int lane) {
+  c.base += a;
+  c.span = b - a - 1u;
+  if (c.span < 65536u) {
+    c.base <<= 16;
+    c.span = (c.span << 16) | 0xFFFFu;
+    c.value = (c.value << 16) | w.next;
+    c.pos += 1;
+    if ((c.pos & 31u) == 0) {
+      bw_seek(w, c.pos, lane);
+    } else {
+      w.next = __shfl_sync(kFull, w.lane_word, c.pos & 31u);
+    }
+  }
+}
+
+// Smallest i in [1, ncdf-1] with scale(cdf[i]) > value - base; identical to the reference's binary
+// search (range_coder.h:204-222,241-251) for every monotone CDF.  Clamped for corrupt streams.
+__device__ __forceinline__ int dec_symbol(DecChain& c, ByteWindow& w, const int32_t* cdf, int ncdf,
+                                          uint32_t p, int lane) {
+  const uint32_t v = c.value - c.base;
+  int lo_i = 1;
+  int n = ncdf - 1;
+  int i;
+  for (;;) {
+    const int stride = (n + 31) >> 5;
+    int off = (lane + 1) * stride - 1;
+    if (off > n - 1) off = n - 1;
+    const uint32_t cv = (uint32_t)__ldg(cdf + lo_i + off);
+    const bool pred = v < scale_cum(c.span, cv, p);
+    // scale_cum truncates 2^32 to 0; that only happens for cv == 2^p with span == 2^32-1, where the
+    // true value 2^32 exceeds every v.
+    const bool full = (cv == (1u << p)) && (c.span == 0xFFFFFFFFu);
+    const unsigned m = __ballot_sync(kFull, pred || full);
+    const int f = m ? (__ffs(m) - 1) : 31;
+    if (stride == 1) {
+      i = lo_i + min(f, n - 1);
+      break;
+    }
+    const int skip = min(f * stride, n - 1);
+    lo_i += skip;
+    n = min(stride, n - skip);
+  }
+  const uint32_t ca = (uint32_t)__ldg(cdf + i - 1);
+  const uint32_t cb = (uint32_t)__ldg(cdf + i);
+  dec_update(c, w, scale_cum(c.span, ca, p), scale_cum(c.span, cb, p), lane);
+  return i - 1;
+}
+
+// DecodeLinearly({0,1,2}, 1), range_coder_kernels.cc:450,461-469.
+__device__ __forceinline__ uint32_t dec_bit(DecChain& c, ByteWindow& w, int lane) {
+  const uint32_t v = c.value - c.base;
+  const uint32_t half = scale_cum(c.span, 1, 1);
+  const uint32_t whole = scale_cum(c.span, 2, 1);  // size, truncated
+  // bit = 0 iff v < half  (half = floor(size/2) <= 2^31 never truncates)
+  const uint32_t bit = (v < half) ? 0u : 1u;
+  dec_update(c, w, bit ? half : 0u, bit ? whole : half, lane);
+  return bit;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(32) decode_kernel(const DecParams P) {
+  const long long s = blockIdx.x;
+  const int lane = threadIdx.x;
+  if (s >= P.n_streams) return;
+  DecChain c;
+  {
+    const DecState st = P.state[s];
+    c.base = st.base;
+    c.span = st.span;
+    c.value = st.value;
+    c.pos = st.pos;
+  }
+  ByteWindow w;
+  w.p = P.bytes + P.offsets[s];
+  w.len = P.offsets[s + 1] - P.offsets[s];
+  if (c.pos == 0) {  // fresh stream: the constructor reads four bytes (range_coder.h:79-83)
+    const uint32_t w0 = bw_fetch(w, 0), w1 = bw_fetch(w, 1);
+    c.value = (w0 << 16) | w1;
+    c.pos = 2;
+  }
+  bw_seek(w, c.pos, lane);
+
+  uint32_t chan_row = 0;
+  bool stop = false;
+  for (long long g0 = 0; g0 < P.n && !stop; g0 += 32) {
+    const int count = (int)min(32ll, P.n - g0);
+    const long long at = s * P.n + g0 + lane;
+    int my_row = 0;
+    if (MODE & kModeIndex) {
+      if (lane < count) {
+        my_row = __ldg(P.index + at);
+        if (my_row < 0 || my_row >= P.n_rows) {
+          report(P.err, kErrIndex, s, g0 + lane, my_row, P.n_rows);
+          my_row = -1;
+        }
+      }
+      if (__ballot_sync(kFull, my_row < 0)) {
+        stop = true;
+        break;
+      }
+    }
+    int my_sym = 0;
+    for (int k = 0; k < count; ++k) {
+      int row;
+      if (MODE & kModeIndex) {
+        row = __shfl_sync(kFull, my_row, k);
+      } else {
+        row = (int)chan_row;
+        chan_row = (chan_row + 1 == (uint32_t)P.n_rows) ? 0u : chan_row + 1;
+      }
+      const int2 ri = __ldg(P.rows + row);
+      const int ncdf = row_ncdf(ri.y);
+      const uint32_t p = (uint32_t)row_prec(ri.y);
+      int sym = dec_symbol(c, w, P.lookup + ri.x, ncdf, p, lane);
+      if (row_ovf(ri.y) && sym == ncdf - 2) {
+        const int esc = ncdf - 2;
+        int nb = 0;
+        while (dec_bit(c, w, lane) == 0 && nb < 64) ++nb;
+        uint32_t val = (nb < 32) ? (1u << nb) : 0u;
+        int t = nb;
+        while (--t >= 0) {
+          const uint32_t bit = dec_bit(c, w, lane);
+          if (t < 32) val |= bit << t;
+        }
+        const uint32_t sg = dec_bit(c, w, lane);
+        sym = sg ? -(int)val : (int)val + esc - 1;
+      }
+      if (lane == k) my_sym = sym;
+    }
+    if (lane < count) {
+      if (MODE & kModeF32) {
+        int row;
+        if (MODE & kModeIndex) {
+          row = my_row;
+        } else {
+          row = (int)((g0 + lane) % P.n_rows);
+        }
+        float y = (float)(my_sym + __ldg(P.coff + row));
+        if (P.qoff) y += (MODE & kModeIndex) ? __ldg(P.qoff + at) : __ldg(P.qoff + row);
+        reinterpret_cast<float*>(P.out)[at] = y;
+      } else {
+        reinterpret_cast<int32_t*>(P.out)[at] = my_sym;
+      }
+    }
+  }
+  if (lane == 0) {
+    DecState st;
+    st.base = c.base;
+    st.span = c.span;
+    st.value = c.value;
+    st.pos = c.pos;
+    P.state[s] = st;
+  }
+}
+
+__global__ void dec_init_state_kernel(DecState* st, long long n) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) {
+    DecState s;
+    s.base = 0;
+    s.span = 0xFFFFFFFFu;
+    s.value = 0;
+    s.pos = 0;
+    st[i] = s;
+  }
+}
+
+// RangeDecoder::Finalize, range_coder.h:144-169.
+__global__ void dec_finalize_kernel(const DecState* state, const uint8_t* bytes, const long long* offsets,
+                                    long long n, uint8_t* ok) {
+  const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  DecState st = state[s];
+  const long long len = offsets[s + 1] - offsets[s];
+  if (st.pos == 0) {  // never decoded from: only the constructor ran (four bytes, zero padded)
+    const uint8_t* p = bytes + offsets[s];
+    uint32_t v = 0;
+    for (int i = 0; i < 4; ++i) v = (v << 8) | (i < len ? (uint32_t)p[i] : 0u);
+    st.value = v;
+    st.pos = 2;
+  }
+  bool good;
+  if (2ll * st.pos < len) {
+    good = false;  // did not read to the end
+  } else {
+    const uint32_t top_end = st.base + st.span;
+    if (st.base == 0 || top_end < st.base) {
+      good = (st.value == 0);
+    } else {
+      const int shift = (((st.base - 1u) >> 24) < (top_end >> 24)) ? 24 : 16;
+      const uint32_t mid = ((st.base - 1u) >> shift) + 1u;
+      good = ((mid << shift) == st.value);
+    }
+  }
+  ok[s] = good ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Legacy single-stream ops
+// ---------------------------------------------------------------------------------------------
+struct LegacyDims {
+  int rank;               // merged rank (<= 6)
+  long long data[6];      // merged data shape
+  long long cdfd[6];      // merged cdf shape
+  long long chip;         // strip length
+};
+
+__device__ __forceinline__ long long legacy_strip(const LegacyDims& d, long long lin) {
+  long long off = 0, stride = d.chip;
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+    if (i < d.rank) {
+      const long long coord = lin % d.data[i];
+      lin /= d.data[i];
+      if (d.cdfd[i] > 1) off += coord * stride;
+      stride *= d.cdfd[i];
+    }
+  }
+  return off;
+}
+
+// CheckCdfValues, range_coding_kernels.cc:150-173.
+__global__ void legacy_check_cdf_kernel(const int32_t* cdf, long long rows, long long size, int precision,
+                                        DevError* err) {
+  const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const int32_t* s = cdf + r * size;
+  const int32_t top = 1 << precision;
+  if (s[0] != 0 || s[size - 1] != top) {
+    report(err, kErrCdf, r, 0, s[0], s[size - 1], 1);
+    return;
+  }
+  for (long long j = 0; j + 1 < size; ++j) {
+    if (s[j + 1] <= s[j]) {
+      report(err, kErrCdf, r, j, s[j], s[j + 1], 2);
+      return;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(32) legacy_encode_kernel(const int16_t* data, long long n,
+                                                           const int32_t* cdf, LegacyDims dims,
+                                                           int precision, int debug, EncState* state,
+                                                           uint16_t* words, uint32_t* cbits,
+                                                           long long cap, DevError* err) {
+  const int lane = threadIdx.x;
+  EncChain c;
+  c.base = 0;
+  c.span = 0xFFFFFFFFu;
+  c.cnt = 0;
+  c.carry = 0;
+  c.run = 0;
+  c.word = 0;
+  c.cmask = 0;
+  c.words = words;
+  c.cbits = cbits;
+  c.cap = (uint32_t)cap;
+  c.overflowed = false;
+  for (long long g0 = 0; g0 < n; g0 += 32) {
+    const int count = (int)min(32ll, n - g0);
+    uint32_t pack = 0;
+    bool bad = false;
+    if (lane < count) {
+      const long long j = g0 + lane;
+      const long long v = data[j];
+      if (v < 0 || dims.chip <= v + 1) {
+        if (debug > 0) report(err, kErrValue, 0, j, v, dims.chip - 1);
+        bad = true;  // without debug the reference has undefined behaviour; we stop instead
+      } else {
+        const int32_t* strip = cdf + legacy_strip(dims, j);
+        const uint32_t lower = (uint32_t)strip[v], upper = (uint32_t)strip[v + 1];
+        if (!(lower < upper) || upper > (1u << precision)) {
+          bad = true;  // zero-probability symbol / invalid strip: UB in the reference
+          report(err, kErrCdf, 0, j, lower, upper, 3);
+        }
+        pack = lower | ((upper - 1u) << 16);
+      }
+    }
+    if (__ballot_sync(kFull, bad)) break;
+    for (int k = 0; k < count; ++k) {
+      const uint32_t pk = __shfl_sync(kFull, pack, k);
+      enc_step(c, pk & 0xFFFFu, (pk >> 16) + 1u, (uint32_t)precision, lane);
+    }
+  }
+  const uint32_t g0 = c.cnt & ~31u, fill = c.cnt & 31u;
+  if (fill) {
+    if (g0 + 32 <= c.cap) {
+      if ((uint32_t)lane < fill) c.words[g0 + lane] = (uint16_t)c.word;
+      if (lane == 0) c.cbits[g0 >> 5] = c.cmask;
+    } else {
+      c.overflowed = true;
+    }
+  }
+  if (c.overflowed) report(err, kErrCapacity, 0, c.cnt, c.cnt, c.cap);
+  if (lane == 0) {
+    EncState st;
+    st.base = c.base;
+    st.span = c.span;
+    st.cnt = c.cnt;
+    st.carry = c.carry;
+    st.run = c.run;
+    st.pad[0] = st.pad[1] = st.pad[2] = 0;
+    state[0] = st;
+  }
+}
+
+__global__ void __launch_bounds__(32) legacy_decode_kernel(const uint8_t* bytes, long long len,
+                                                           long long n, const int32_t* cdf,
+                                                           LegacyDims dims, int precision,
+                                                           int16_t* out) {
+  const int lane = threadIdx.x;
+  DecChain c;
+  c.base = 0;
+  c.span = 0xFFFFFFFFu;
+  ByteWindow w;
+  w.p = bytes;
+  w.len = len;
+  c.value = (bw_fetch(w, 0) << 16) | bw_fetch(w, 1);
+  c.pos = 2;
+  bw_seek(w, c.pos, lane);
+  for (long long g0 = 0; g0 < n; g0 += 32) {
+    const int count = (int)min(32ll, n - g0);
+    long long my_off = 0;
+    if (lane < count) my_off = legacy_strip(dims, g0 + lane);
+    int my_sym = 0;
+    for (int k = 0; k < count; ++k) {
+      const long long off = __shfl_sync(kFull, my_off, k);
+      const int sym = dec_symbol(c, w, cdf + off, (int)dims.chip, (uint32_t)precision, lane);
+      if (lane == k) my_sym = sym;
+    }
+    if (lane < count) out[g0 + lane] = (int16_t)my_sym;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host-side handles
+// ---------------------------------------------------------------------------------------------
+int fetch_error(DevError* d_err, cudaStream_t s, const char* what) {
+  DevError e;
+  TFCB_CUDA_TRY(cudaMemcpyAsync(&e, d_err, sizeof e, cudaMemcpyDeviceToHost, s));
+  TFCB_CUDA_TRY(cudaStreamSynchronize(s));
+  switch (e.code) {
+    case kErrNone:
+      return TFCB_OK;
+    case kErrIndex:
+      return fail(TFCB_INVALID_ARGUMENT, "index=%lld not in range [0, %lld) (stream %lld, element %lld)",
+                  e.value, e.limit, e.stream, e.pos);
+    case kErrValue:
+      if (std::strcmp(what, "legacy") == 0)
+        return fail(TFCB_INVALID_ARGUMENT, "'data' value not in [0, %lld): value=%lld", e.limit, e.value);
+      return fail(TFCB_INVALID_ARGUMENT, "value=%lld not in range [0, %lld) (stream %lld, element %lld)",
+                  e.value, e.limit, e.stream, e.pos);
+    case kErrCapacity:
+      return fail(TFCB_CUDA_ERROR, "internal: output arena too small (stream %lld needs > %lld words)",
+                  e.stream, e.limit);
+    case kErrCdf:
+      if (e.aux == 1)
+        return fail(TFCB_INVALID_ARGUMENT, "CDF should start from 0 and end at 2^precision: cdf[0]=%lld, cdf[^1]=%lld",
+                    e.value, e.limit);
+      if (e.aux == 2) return fail(TFCB_INVALID_ARGUMENT, "CDF is not monotonic");
+      return fail(TFCB_INVALID_ARGUMENT,
+                  "symbol with zero probability or invalid CDF strip at element %lld: lower=%lld upper=%lld",
+                  e.pos, e.value, e.limit);
+  }
+  return fail(TFCB_CUDA_ERROR, "unknown device error %d", e.code);
+}
+
+}  // namespace
+}  // namespace tfcb
+
+using namespace tfcb;
+
+struct tfcb_encoder {
+  DeviceLookup lut;
+  long long n_streams = 0;
+  EncState* state = nullptr;
+  uint16_t* words = nullptr;
+  uint32_t* cbits = nullptr;
+  long long cap = 0;    // words per stream (multiple of 32)
+  long long bound = 0;  // worst-case words emitted so far per stream
+  DevError* err = nullptr;
+  long long* lens = nullptr;
+  long long* offsets = nullptr;
+  uint8_t* out = nullptr;
+  long long total = 0;
+  bool finalized = false;
+  cudaStream_t home = nullptr;
+};
+
+namespace {
+
+// Worst-case 16-bit words one call can append per stream: every Encode(.., p) shrinks the interval by
+// at most 2^p, i.e. consumes at most p bits; an escape adds at most 65 one-bit symbols.
+long long words_bound(const tfcb_encoder* h, long long n) {
+  const long long bits = h->lut.max_prec + (h->lut.any_overflow ? 65 : 0);
+  return (n * bits + 15) / 16 + 2;
+}
+
+int ensure_capacity(tfcb_encoder* h, long long extra_words, cudaStream_t s) {
+  const long long need = h->bound + extra_words + 32;
+  if (need <= h->cap) return TFCB_OK;
+  if (need >= (1ll << 31) - 64)
+    return fail(TFCB_INVALID_ARGUMENT, "a single code stream may not exceed 2^31 16-bit words");
+  const long long new_cap = (std::max(need, h->cap * 2) + 31) & ~31ll;
+  uint16_t* nw = nullptr;
+  uint32_t* nc = nullptr;
+  const long long S = std::max<long long>(h->n_streams, 1);
+  TFCB_TRY(dev_alloc((void**)&nw, (size_t)S * new_cap * sizeof(uint16_t), s));
+  TFCB_TRY(dev_alloc((void**)&nc, (size_t)S * (new_cap >> 5) * sizeof(uint32_t), s));
+  if (h->cap > 0 && h->bound > 0 && h->n_streams > 0) {
+    enc_grow_kernel<<<(unsigned)h->n_streams, 128, 0, s>>>(h->words, h->cbits, h->cap, nw, nc, new_cap,
+                                                           h->state);
+    TFCB_LAUNCHED();
+    TFCB_CUDA_TRY(cudaGetLastError());
+  }
+  dev_free(h->words, s);
+  dev_free(h->cbits, s);
+  h->words = nw;
+  h->cbits = nc;
+  h->cap = new_cap;
+  return TFCB_OK;
+}
+
+template <int MODE>
+int launch_encode(tfcb_encoder* h, const void* value, const int32_t* index, const float* qoff,
+                  const int32_t* coff, long long n, cudaStream_t s) {
+  if (h->finalized) return fail(TFCB_INVALID_ARGUMENT, "encoder handle was already finalized");
+  if (n < 0) return fail(TFCB_INVALID_ARGUMENT, "negative element count");
+  if (h->n_streams == 0 || n == 0) return TFCB_OK;
+  if (h->lut.n_rows == 0) return fail(TFCB_INVALID_ARGUMENT, "index=0 not in range [0, 0)");
+  if (value == nullptr) return fail(TFCB_INVALID_ARGUMENT, "`value` is null");
+  if ((MODE & kModeIndex) && index == nullptr) return fail(TFCB_INVALID_ARGUMENT, "`index` is null");
+  if ((MODE & kModeF32) && coff == nullptr) return fail(TFCB_INVALID_ARGUMENT, "`cdf_offset` is null");
+  const long long extra = words_bound(h, n);
+  TFCB_TRY(ensure_capacity(h, extra, s));
+  h->bound += extra;
+  EncParams P;
+  P.lookup = h->lut.lookup;
+  P.rows = h->lut.rows;
+  P.n_rows = h->lut.n_rows;
+  P.value = value;
+  P.index = index;
+  P.qoff = qoff;
+  P.coff = coff;
+  P.n = n;
+  P.n_streams = h->n_streams;
+  P.state = h->state;
+  P.words = h->words;
+  P.cbits = h->cbits;
+  P.cap = h->cap;
+  P.err = h->err;
+  if (h->n_streams > 0x7FFFFFFFll) return fail(TFCB_INVALID_ARGUMENT, "too many streams");
+  encode_kernel<MODE><<<(unsigned)h->n_streams, 32, 0, s>>>(P);
+  TFCB_LAUNCHED();
+  TFCB_CUDA_TRY(cudaGetLastError());
+  return TFCB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tfcb_encoder_create(const int32_t* lookup_host, int64_t lookup_len, int64_t lookup_cols,
+                        int64_t n_streams, void* stream, tfcb_encoder** out) {
+  if (!out) return fail(TFCB_INVALID_ARGUMENT, "null output handle");
+  *out = nullptr;
+  if (n_streams < 0) return fail(TFCB_INVALID_ARGUMENT, "negative stream count");
+  cudaStream_t s = as_stream(stream);
+  tfcb_encoder* h = new tfcb_encoder;
+  h->home = s;
+  h->n_streams = n_streams;
+  int rc = h->lut.upload(lookup_host, lookup_len, lookup_cols, s);
+  if (rc == TFCB_OK) rc = dev_alloc((void**)&h->state, std::max<int64_t>(n_streams, 1) * sizeof(EncState), s);
+  if (rc == TFCB_OK) rc = dev_alloc((void**)&h->err, sizeof(DevError), s);
+  if (rc != TFCB_OK) {
+    tfcb_encoder_destroy(h);
+    return rc;
+  }
+  cudaMemsetAsync(h->err, 0, sizeof(DevError), s);
+  if (n_streams > 0) {
+    enc_init_state_kernel<<<(unsigned)((n_streams + 255) / 256), 256, 0, s>>>(h->state, n_streams);
+    TFCB_LAUNCHED();
+  }
+  if (cudaGetLastError() != cudaSuccess) {
+    tfcb_encoder_destroy(h);
+    return fail(TFCB_CUDA_ERROR, "encoder state initialisation failed");
+  }
+  *out = h;
+  return TFCB_OK;
+}
+
+int tfcb_encode_channel(tfcb_encoder* h, const int32_t* value_dev, int64_t n, void* stream) {
+  if (!h) return fail(TFCB_INVALID_ARGUMENT, "'handle' is not an encoder");
+  return launch_encode<0>(h, value_dev, nullptr, nullptr, nullptr, n, as_stream(stream));
+}
+
+int tfcb_encode_index(tfcb_encoder* h, const int32_t* index_dev, const int32_t* value_dev, int64_t n,
+                      void* stream) {
+  if (!h) return fail(TFCB_INVALID_ARGUMENT, "'handle' is not an encoder");
+  return launch_encode<kModeIndex>(h, value_dev, index_dev, nullptr, nullptr, n, as_stream(stream));
+}
+
+int tfcb_encode_channel_f32(tfcb_encoder* h, const float* y_dev, const float* quant_offset_dev,
+                            const int32_t* cdf_offset_dev, int64_t n, void* stream) {
+  if (!h) return fail(TFCB_INVALID_ARGUMENT, "'handle' is not an encoder");
+  return launch_encode<kModeF32>(h, y_dev, nullptr, quant_offset_dev, cdf_offset_dev, n, as_stream(stream));
+}
+
+int tfcb_encode_index_f32(tfcb_encoder* h, const int32_t* index_dev, const float* y_dev,
+                          const float* loc_dev, const int32_t* cdf_offset_dev, int64_t n, void* stream) {
+  if (!h) return fail(TFCB_INVALID_ARGUMENT, "'handle' is not an encoder");
+  return launch_encode<kModeIndex | kModeF32>(h, y_dev, index_dev, loc_dev, cdf_offset_dev, n,
+                                              as_stream(stream));
+}
+
+int tfcb_encoder_check(tfcb_encoder* h, void* stream) {
+  if (!h) return fail(TFCB_INVALID_ARGUMENT, "'handle' is not an encoder");
+  return fetch_error(h->err, as_stream(stream), "encode");
+}
+
+int tfcb_encode_finalize(tfcb_encoder* h, void* stream, int64_t* total_bytes_host) {
+  if (!h) return fail(TFCB_INVALID_ARGUMENT, "'handle' is not an encoder");
+  if (h->finalized) return fail(TFCB_INVALID_ARGUMENT, "encoder handle was already finalized");
+  cudaStream_t s = as_stream(stream);
+  TFCB_TRY(fetch_error(h->err, s, "encode"));
+  const long long S = h->n_streams;
+  TFCB_TRY(dev_alloc((void**)&h->lens, std::max<long long>(S, 1) * sizeof(long long), s));
+  TFCB_TRY(dev_alloc((void**)&h->offsets, (S + 1) * sizeof(long long), s));
+  if (h->cap == 0) TFCB_TRY(ensure_capacity(h, 0, s));
+  if (S > 0) {
+    enc_lengths_kernel<<<(unsigned)((S + 127) / 128), 128, 0, s>>>(h->state, h->words, h->cap, S, h->lens);
+    TFCB_LAUNCHED();
+  }
+  exclusive_scan_kernel<<<1, 1024, 0, s>>>(h->lens, S, h->offsets);
+  TFCB_LAUNCHED();
+  TFCB_CUDA_TRY(cudaGetLastError());
+  long long total = 0;
+  TFCB_CUDA_TRY(cudaMemcpyAsync(&total, h->offsets + S, sizeof total, cudaMemcpyDeviceToHost, s));
+  TFCB_CUDA_TRY(cudaStreamSynchronize(s));
+  h->total = total;
+  TFCB_TRY(dev_alloc((void**)&h->out, (size_t)std::max<long long>(total, 1), s));
+  if (S > 0) {
+    enc_write_kernel<<<(unsigned)((S + 3) / 4), 128, 0, s>>>(h->state, h->words, h->cbits, h->cap, S,
+                                                             h->offsets, h->out);
+    TFCB_LAUNCHED();
+    TFCB_CUDA_TRY(cudaGetLastError());
+  }
+  // the word arena is no longer needed
+  dev_free(h->words, s);
+  dev_free(h->cbits, s);
+  h->words = nullptr;
+  h->cbits = nullptr;
+  h->finalized = true;
+  if (total_bytes_host) *total_bytes_host = total;
+  return TFCB_OK;
+}
+
+int tfcb_encoder_output(tfcb_encoder* h, const uint8_t** bytes_dev, const int64_t** offsets_dev) {
+  if (!h || !h->finalized) return fail(TFCB_INVALID_ARGUMENT, "encoder handle is not finalized");
+  if (bytes_dev) *bytes_dev = h->out;
+  if (offsets_dev) *offsets_dev = reinterpret_cast<const int64_t*>(h->offsets);
+  return TFCB_OK;
+}
+
+int tfcb_encoder_copy_output(tfcb_encoder* h, uint8_t* bytes_host, int64_t* offsets_host, void* stream) {
+  if (!h || !h->finalized) return fail(TFCB_INVALID_ARGUMENT, "encoder handle is not finalized");
+  cudaStream_t s = as_stream(stream);
+  if (bytes_host && h->total > 0)
+    TFCB_CUDA_TRY(cudaMemcpyAsync(bytes_host, h->out, (size_t)h->total, cudaMemcpyDeviceToHost, s));
+  if (offsets_host)
+    TFCB_CUDA_TRY(cudaMemcpyAsync(offsets_host, h->offsets, (h->n_streams + 1) * sizeof(long long),
+                                  cudaMemcpyDeviceToHost, s));
+  TFCB_CUDA_TRY(cudaStreamSynchronize(s));
+  return TFCB_OK;
+}
+
+void tfcb_encoder_destroy(tfcb_encoder* h) {
+  if (!h) return;
+  cudaStream_t s = h->home;
+  h->lut.release(s);
+  dev_free(h->state, s);
+  dev_free(h->words, s);
+  dev_free(h->cbits, s);
+  dev_free(h->err, s);
+  dev_free(h->lens, s);
+  dev_free(h->offsets, s);
+  dev_free(h->out, s);
+  delete h;
+}
+
+}  // extern "C"
+
+struct tfcb_decoder {
+  DeviceLookup lut;
+  long long n_streams = 0;
+  const uint8_t* bytes = nullptr;
+  const long long* offsets = nullptr;
+  DecState* state = nullptr;
+  DevError* err = nullptr;
+  uint8_t* ok = nullptr;
+  cudaStream_t home = nullptr;
+};
+
+namespace {
+
+template <int MODE>
+int launch_decode(tfcb_decoder* h, const int32_t* index, void* out, const float* qoff,
+                  const int32_t* coff, long long n, cudaStream_t s) {
+  if (n < 0) return fail(TFCB_INVALID_ARGUMENT, "negative element count");
+  if (h->n_streams == 0 || n == 0) return TFCB_OK;
+  if (h->lut.n_rows == 0) return fail(TFCB_INVALID_ARGUMENT, "index=0 not in range [0, 0)");
+  if (out == nullptr) return fail(TFCB_INVALID_ARGUMENT, "output is null");
+  if ((MODE & kModeIndex) && index == nullptr) return fail(TFCB_INVALID_ARGUMENT, "`index` is null");
+  if ((MODE & kModeF32) && coff == nullptr) return fail(TFCB_INVALID_ARGUMENT, "`cdf_offset` is null");
+  DecParams P;
+  P.lookup = h->lut.lookup;
+  P.rows = h->lut.rows;
+  P.n_rows = h->lut.n_rows;
+  P.bytes = h->bytes;
+  P.offsets = h->offsets;
+  P.index = index;
+  P.out = out;
+  P.qoff = qoff;
+  P.coff = coff;
+  P.n = n;
+  P.n_streams = h->n_streams;
+  P.state = h->state;
+  P.err = h->err;
+  decode_kernel<MODE><<<(unsigned)h->n_streams, 32, 0, s>>>(P);
+  TFCB_LAUNCHED();
+  TFCB_CUDA_TRY(cudaGetLastError());
+  return TFCB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tfcb_decoder_create(const uint8_t* bytes_dev, const int64_t* offsets_dev, int64_t n_streams,
+                        const int32_t* lookup_host, int64_t lookup_len, int64_t lookup_cols,
+                        void* stream, tfcb_decoder** out) {
+  if (!out) return fail(TFCB_INVALID_ARGUMENT, "null output handle");
+  *out = nullptr;
+  if (n_streams <= 0) return fail(TFCB_INVALID_ARGUMENT, "`encoded` is empty");
+  if (!offsets_dev) return fail(TFCB_INVALID_ARGUMENT, "`offsets` is null");
+  cudaStream_t s = as_stream(stream);
+  tfcb_decoder* h = new tfcb_decoder;
+  h->home = s;
+  h->n_streams = n_streams;
+  h->bytes = bytes_dev;
+  h->offsets = reinterpret_cast<const long long*>(offsets_dev);
+  int rc = h->lut.upload(lookup_host, lookup_len, lookup_cols, s);
+  if (rc == TFCB_OK) rc = dev_alloc((void**)&h->state, n_streams * sizeof(DecState), s);
+  if (rc == TFCB_OK) rc = dev_alloc((void**)&h->err, sizeof(DevError), s);
+  if (rc == TFCB_OK) rc = dev_alloc((void**)&h->ok, n_streams, s);
+  if (rc != TFCB_OK) {
+    tfcb_decoder_destroy(h);
+    return rc;
+  }
+  cudaMemsetAsync(h->err, 0, sizeof(DevError), s);
+  dec_init_state_kernel<<<(unsigned)((n_streams + 255) / 256), 256, 0, s>>>(h->state, n_streams);
+  TFCB_LAUNCHED();
+  if (cudaGetLastError() != cudaSuccess) {
+    tfcb_decoder_destroy(h);
+    return fail(TFCB_CUDA_ERROR, "decoder state initialisation failed");
+  }
+  *out = h;
+  return TFCB_OK;
+}
+
+int tfcb_decode_channel(tfcb_decoder* h, int32_t* out_dev, int64_t n, void* stream) {
+  if (!h) return fail(TFCB_INVALID_ARGUMENT, "'handle' is not a decoder");
+  return launch_decode<0>(h, nullptr, out_dev, nullptr, nullptr, n, as_stream(stream));
+}
+
+int tfcb_decode_index(tfcb_decoder* h, const int32_t* index_dev, int32_t* out_dev, int64_t n, void* stream) {
+  if (!h) return fail(TFCB_INVALID_ARGUMENT, "'handle' is not a decoder");
+  return launch_decode<kModeIndex>(h, index_dev, out_dev, nullptr, nullptr, n, as_stream(stream));
+}
+
+int tfcb_decode_channel_f32(tfcb_decoder* h, float* out_dev, const float* quant_offset_dev,
+                            const int32_t* cdf_offset_dev, int64_t n, void* stream) {
+  if (!h) return fail(TFCB_INVALID_ARGUMENT, "'handle' is not a decoder");
+  return launch_decode<kModeF32>(h, nullptr, out_dev, quant_offset_dev, cdf_offset_dev, n, as_stream(stream));
+}
+
+int tfcb_decode_index_f32(tfcb_decoder* h, const int32_t* index_dev, float* out_dev, const float* loc_dev,
+                          const int32_t* cdf_offset_dev, int64_t n, void* stream) {
+  if (!h) return fail(TFCB_INVALID_ARGUMENT, "'handle' is not a decoder");
+  return launch_decode<kModeIndex | kModeF32>(h, index_dev, out_dev, loc_dev, cdf_offset_dev, n,
+                                              as_stream(stream));
+}
+
+int tfcb_decode_finalize(tfcb_decoder* h, uint8_t* ok_host, void* stream) {
+  if (!h) return fail(TFCB_INVALID_ARGUMENT, "'handle' is not a decoder");
+  cudaStream_t s = as_stream(stream);
+  TFCB_TRY(fetch_error(h->err, s, "decode"));
+  dec_finalize_kernel<<<(unsigned)((h->n_streams + 127) / 128), 128, 0, s>>>(h->state, h->bytes, h->offsets,
+                                                                             h->n_streams, h->ok);
+  TFCB_LAUNCHED();
+  TFCB_CUDA_TRY(cudaGetLastError());
+  if (ok_host) TFCB_CUDA_TRY(cudaMemcpyAsync(ok_host, h->ok, h->n_streams, cudaMemcpyDeviceToHost, s));
+  TFCB_CUDA_TRY(cudaStreamSynchronize(s));
+  return TFCB_OK;
+}
+
+void tfcb_decoder_destroy(tfcb_decoder* h) {
+  if (!h) return;
+  cudaStream_t s = h->home;
+  h->lut.release(s);
+  dev_free(h->state, s);
+  dev_free(h->err, s);
+  dev_free(h->ok, s);
+  delete h;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Legacy ops: host side
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+// MergeAxes of range_coding_kernels_util.cc:34-91 plus the argument checks of
+// range_coding_kernels.cc:134-148,179-185.
+int legacy_prepare(const int64_t* dshape, int rank, const int64_t* cshape, int crank, int precision,
+                   int debug_level, LegacyDims* dims, long long* n_elems, long long* n_rows) {
+  if (!(0 < precision && precision <= 16))
+    return fail(TFCB_INVALID_ARGUMENT, "`precision` must be in [1, 16]: %d", precision);
+  if (!(debug_level == 0 || debug_level == 1))
+    return fail(TFCB_INVALID_ARGUMENT, "`debug_level` must be 0 or 1: %d", debug_level);
+  if (rank < 0 || crank != rank + 1)
+    return fail(TFCB_INVALID_ARGUMENT, "`cdf` should have one more axis than `data`: data rank=%d, cdf rank=%d",
+                rank, crank);
+  if (cshape[rank] <= 1)
+    return fail(TFCB_INVALID_ARGUMENT, "The last dimension of `cdf` should be > 1: %lld",
+                (long long)cshape[rank]);
+  if (debug_level > 0 && cshape[rank] <= 2)
+    return fail(TFCB_INVALID_ARGUMENT, "CDF size should be > 2: %lld", (long long)cshape[rank]);
+  std::vector<long long> md(1, 1), mc(1, 1);
+  long long n = 1, rows = 1;
+  for (int j = 0; j < rank; ++j) {
+    if (dshape[j] < 0) return fail(TFCB_INVALID_ARGUMENT, "negative dimension");
+    if (dshape[j] != cshape[j] && cshape[j] != 1)
+      return fail(TFCB_INVALID_ARGUMENT, "Cannot broadcast shape of `cdf` to the shape of `data` at axis %d (%lld vs %lld)",
+                  j, (long long)cshape[j], (long long)dshape[j]);
+    const bool was_b = mc.back() == 1, is_b = cshape[j] == 1;
+    if (was_b == is_b || dshape[j] <= 1 || md.back() <= 1) {
+      md.back() *= dshape[j];
+      mc.back() *= cshape[j];
+    } else {
+      md.push_back(dshape[j]);
+      mc.push_back(cshape[j]);
+    }
+    n *= dshape[j];
+    rows *= cshape[j];
+  }
+  if (md.size() > 6)
+    return fail(TFCB_INVALID_ARGUMENT, "Irregular broadcast pattern: more than 6 merged axis groups");
+  dims->rank = (int)md.size();
+  for (int i = 0; i < 6; ++i) {
+    dims->data[i] = i < dims->rank ? md[i] : 1;
+    dims->cdfd[i] = i < dims->rank ? mc[i] : 1;
+  }
+  dims->chip = cshape[rank];
+  *n_elems = n;
+  *n_rows = rows;
+  return TFCB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tfcb_range_encode(const int16_t* data_dev, const int64_t* data_shape_host, int rank,
+                      const int32_t* cdf_dev, const int64_t* cdf_shape_host, int cdf_rank, int precision,
+                      int debug_level, uint8_t* out_host, int64_t out_cap, int64_t* n_bytes_host,
+                      void* stream) {
+  cudaStream_t s = as_stream(stream);
+  LegacyDims dims;
+  long long n = 0, rows = 0;
+  TFCB_TRY(legacy_prepare(data_shape_host, rank, cdf_shape_host, cdf_rank, precision, debug_level, &dims,
+                          &n, &rows));
+  const long long cap = (((n * precision + 15) / 16 + 2 + 32) + 31) & ~31ll;
+  if (cap >= (1ll << 31) - 64) return fail(TFCB_INVALID_ARGUMENT, "input too large for one code stream");
+  EncState* state = nullptr;
+  uint16_t* words = nullptr;
+  uint32_t* cbits = nullptr;
+  DevError* err = nullptr;
+  long long* lens = nullptr;
+  uint8_t* out = nullptr;
+  int rc = dev_alloc((void**)&state, sizeof(EncState), s);
+  if (rc == TFCB_OK) rc = dev_alloc((void**)&words, cap * sizeof(uint16_t), s);
+  if (rc == TFCB_OK) rc = dev_alloc((void**)&cbits, (cap >> 5) * sizeof(uint32_t), s);
+  if (rc == TFCB_OK) rc = dev_alloc((void**)&err, sizeof(DevError), s);
+  if (rc == TFCB_OK) rc = dev_alloc((void**)&lens, 3 * sizeof(long long), s);
+  if (rc == TFCB_OK) rc = dev_alloc((void**)&out, (size_t)(2 * cap + 8), s);
+  auto cleanup = [&]() {
+    dev_free(state, s);
+    dev_free(words, s);
+    dev_free(cbits, s);
+    dev_free(err, s);
+    dev_free(lens, s);
+    dev_free(out, s);
+  };
+  if (rc != TFCB_OK) {
+    cleanup();
+    return rc;
+  }
+  cudaMemsetAsync(err, 0, sizeof(DevError), s);
+  if (debug_level > 0 && rows > 0) {
+    legacy_check_cdf_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, s>>>(cdf_dev, rows, dims.chip,
+                                                                          precision, err);
+    TFCB_LAUNCHED();
+    rc = fetch_error(err, s, "legacy");
+    if (rc != TFCB_OK) {
+      cleanup();
+      return rc;
+    }
+  }
+  legacy_encode_kernel<<<1, 32, 0, s>>>(data_dev, n, cdf_dev, dims, precision, debug_level, state, words,
+                                        cbits, cap, err);
+  TFCB_LAUNCHED();
+  rc = fetch_error(err, s, "legacy");
+  if (rc != TFCB_OK) {
+    cleanup();
+    return rc;
+  }
+  enc_lengths_kernel<<<1, 32, 0, s>>>(state, words, cap, 1, lens);
+  exclusive_scan_kernel<<<1, 32, 0, s>>>(lens, 1, lens + 1);
+  enc_write_kernel<<<1, 128, 0, s>>>(state, words, cbits, cap, 1, lens + 1, out);
+  TFCB_LAUNCHED();
+  TFCB_LAUNCHED();
+  TFCB_LAUNCHED();
+  long long total = 0;
+  cudaMemcpyAsync(&total, lens, sizeof total, cudaMemcpyDeviceToHost, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) {
+    cleanup();
+    return fail(TFCB_CUDA_ERROR, "CUDA error '%s' in tfcb_range_encode", cudaGetErrorString(e));
+  }
+  if (n_bytes_host) *n_bytes_host = total;
+  if (total > out_cap) {
+    cleanup();
+    return fail(TFCB_INVALID_ARGUMENT, "output buffer too small: need %lld bytes", total);
+  }
+  if (total > 0) cudaMemcpyAsync(out_host, out, (size_t)total, cudaMemcpyDeviceToHost, s);
+  e = cudaStreamSynchronize(s);
+  cleanup();
+  if (e != cudaSuccess) return fail(TFCB_CUDA_ERROR, "CUDA error '%s' in tfcb_range_encode", cudaGetErrorString(e));
+  return TFCB_OK;
+}
+
+int tfcb_range_decode(const uint8_t* encoded_host, int64_t n_bytes, const int64_t* shape_host, int rank,
+                      const int32_t* cdf_dev, const int64_t* cdf_shape_host, int cdf_rank, int precision,
+                      int debug_level, int16_t* out_dev, void* stream) {
+  cudaStream_t s = as_stream(stream);
+  LegacyDims dims;
+  long long n = 0, rows = 0;
+  TFCB_TRY(legacy_prepare(shape_host, rank, cdf_shape_host, cdf_rank, precision, debug_level, &dims, &n, &rows));
+  if (n_bytes < 0) return fail(TFCB_INVALID_ARGUMENT, "negative string length");
+  uint8_t* bytes = nullptr;
+  DevError* err = nullptr;
+  int rc = dev_alloc((void**)&bytes, (size_t)std::max<int64_t>(n_bytes, 1), s);
+  if (rc == TFCB_OK) rc = dev_alloc((void**)&err, sizeof(DevError), s);
+  auto cleanup = [&]() {
+    dev_free(bytes, s);
+    dev_free(err, s);
+  };
+  if (rc != TFCB_OK) {
+    cleanup();
+    return rc;
+  }
+  cudaMemsetAsync(err, 0, sizeof(DevError), s);
+  if (n_bytes > 0) cudaMemcpyAsync(bytes, encoded_host, (size_t)n_bytes, cudaMemcpyHostToDevice, s);
+  if (debug_level > 0 && rows > 0) {
+    legacy_check_cdf_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, s>>>(cdf_dev, rows, dims.chip,
+                                                                          precision, err);
+    TFCB_LAUNCHED();
+    rc = fetch_error(err, s, "legacy");
+    if (rc != TFCB_OK) {
+      cleanup();
+      return rc;
+    }
+  }
+  if (n > 0) {
+    legacy_decode_kernel<<<1, 32, 0, s>>>(bytes, n_bytes, n, cdf_dev, dims, precision, out_dev);
+    TFCB_LAUNCHED();
+  }
+  cudaError_t e = cudaStreamSynchronize(s);
+  cleanup();
+  if (e != cudaSuccess) return fail(TFCB_CUDA_ERROR, "CUDA error '%s' in tfcb_range_decode", cudaGetErrorString(e));
+  return TFCB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,109 @@
+"""GPU parity for GDN/IGDN: closed forms of the reference's tests (layers/gdn_test.py:42-88, atol 1e-6) and
+random-parameter parity against the fp64 oracle (north-star tolerance: 1e-5 relative)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gdn_oracle
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5  # BASELINE.json north_star: "GDN within 1e-5 relative of the reference fp32 path"
+
+
+@pytest.fixture(scope="module")
+def F():
+  from compression_b200 import functional
+  return functional
+
+
+def _params(C, seed):
+  g = torch.Generator().manual_seed(seed)
+  gamma = 0.1 * torch.eye(C) + (0.02 * torch.randn(C, C, generator=g)).abs()
+  beta = 1.0 + 0.5 * torch.rand(C, generator=g)
+  return gamma, beta
+
+
+def _x(n_pix, C, seed):
+  g = torch.Generator().manual_seed(seed)
+  scale = 0.05 + 3.95 * torch.rand(C, generator=g)
+  return torch.randn(n_pix, C, generator=g) * scale
+
+
+def _relerr(got, want):
+  want = want.double()
+  return ((got.double().cpu() - want).abs() / (want.abs() + 1e-30)).max().item()
+
+
+@pytest.mark.parametrize("C", [3, 5, 32, 128, 192])
+def test_closed_forms(F, C):
+  x = torch.rand(77, C).cuda() - 0.5
+  eye = (0.1 * torch.eye(C)).cuda()
+  ones = torch.ones(C).cuda()
+  xc = x.cpu()
+  y = F.gdn_forward(x, eye, ones).cpu()
+  assert torch.allclose(y, xc / (1 + 0.1 * xc.abs()), rtol=0, atol=1e-6)
+  y = F.gdn_forward(x, eye, ones, inverse=True).cpu()
+  assert torch.allclose(y, xc * (1 + 0.1 * xc.abs()), rtol=0, atol=1e-6)
+  y = F.gdn_forward(x, eye, ones, rectify=True).cpu()
+  xr = torch.relu(xc)
+  assert torch.allclose(y, xr / (1 + 0.1 * xr), rtol=0, atol=1e-6)
+  y = F.gdn_forward(x, eye, ones, alpha=2, epsilon=0.5).cpu()
+  assert torch.allclose(y, xc / torch.sqrt(1 + 0.1 * xc**2), rtol=0, atol=1e-6)
+  # fixed gamma = all ones, beta = 0 (gdn_test.py:80-88)
+  y = F.gdn_forward(x.abs() + 0.1, torch.ones(C, C).cuda(), torch.zeros(C).cuda()).cpu()
+  xa = xc.abs() + 0.1
+  assert torch.allclose(y, xa / xa.sum(-1, keepdim=True), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("C,n_pix", [(128, 4099), (192, 2500), (64, 333), (7, 129)])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_forward_vs_fp64_oracle(F, C, n_pix, inverse):
+  gamma, beta = _params(C, 4)
+  x = _x(n_pix, C, 6)
+  want = gdn_oracle.gdn_reference(x, gamma, beta, inverse=inverse)
+  got = F.gdn_forward(x.cuda(), gamma.cuda(), beta.cuda(), inverse=inverse)
+  assert _relerr(got, want) < RTOL
+
+
+@pytest.mark.parametrize("alpha,epsilon,rectify", [(1, 1, True), (2, 0.5, False), (1.5, 0.7, True), (2, 1, False),
+                                                   (1, 0.5, False)])
+def test_forward_variants(F, alpha, epsilon, rectify):
+  C = 64
+  gamma, beta = _params(C, 5)
+  x = _x(1000, C, 8)
+  for inverse in (False, True):
+    want = gdn_oracle.gdn_reference(x, gamma, beta, inverse, rectify, alpha, epsilon)
+    got = F.gdn_forward(x.cuda(), gamma.cuda(), beta.cuda(), inverse, rectify, alpha, epsilon)
+    mask = torch.isfinite(want)
+    err = ((got.double().cpu() - want)[mask].abs() / (want[mask].abs() + 1e-6)).max().item()
+    assert err < 2e-5
+
+
+@pytest.mark.parametrize("C,n_pix", [(128, 3000), (192, 1111), (5, 257)])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_backward_vs_fp64_oracle(F, C, n_pix, inverse):
+  gamma, beta = _params(C, 14)
+  x = _x(n_pix, C, 16)
+  dy = torch.randn(n_pix, C, generator=torch.Generator().manual_seed(1))
+  wx, wg, wb = gdn_oracle.gdn_reference_grads(x, gamma, beta, dy, inverse=inverse)
+  dx, dg, db = F.gdn_backward(x.cuda(), gamma.cuda(), beta.cuda(), dy.cuda(), inverse=inverse)
+
+  def close(got, want, tol):
+    scale = want.abs().max().item()
+    return ((got.double().cpu() - want).abs().max().item() / scale) < tol
+
+  assert close(dx, wx, 2e-5)
+  assert close(dg, wg, 2e-5)
+  assert close(db, wb, 2e-5)
+
+
+def test_autograd_wrapper(F):
+  C = 32
+  gamma, beta = _params(C, 2)
+  x = _x(100, C, 3).cuda().requires_grad_(True)
+  g = gamma.cuda().requires_grad_(True)
+  b = beta.cuda().requires_grad_(True)
+  y = F.gdn(x, g, b)
+  y.square().sum().backward()
+  assert x.grad is not None and g.grad.shape == (C, C) and b.grad.shape == (C,)
