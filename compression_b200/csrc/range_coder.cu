@@ -89,13 +89,16 @@ struct DeviceLookup {
   int32_t* lookup = nullptr;  // device copy of the raw table
   int2* rows = nullptr;       // {start, meta}
   int n_rows = 0;
+  long long len = 0;
   bool any_overflow = false;
   int max_prec = 0;
 
-  int upload(const int32_t* lookup_host, int64_t len, int64_t cols, cudaStream_t s) {
+  int upload(const int32_t* lookup_host, int64_t len_, int64_t cols, cudaStream_t s) {
+    const int64_t len = len_;
     std::vector<HostRow> hr;
     TFCB_TRY(parse_lookup(lookup_host, len, cols, &hr));
     n_rows = (int)hr.size();
+    this->len = len_;
     std::vector<int2> meta(std::max<size_t>(hr.size(), 1));
     for (size_t i = 0; i < hr.size(); ++i) {
       const int ap = hr[i].prec < 0 ? -hr[i].prec : hr[i].prec;
@@ -158,25 +161,25 @@ __device__ __forceinline__ void enc_flush_group(EncChain& c, int lane) {
 }
 
 // One Encode(lower, upper, precision) of range_coder.cc:37-264 in the big-number formulation.
+// Written with selects so that the only branch is the (1-in-32-words) group flush: a single warp
+// per stream has nobody to hide a taken-branch bubble behind.
 __device__ __forceinline__ void enc_step(EncChain& c, uint32_t lo, uint32_t hi, uint32_t p, int lane) {
   const uint32_t a = scale_cum(c.span, lo, p);
   const uint32_t b = scale_cum(c.span, hi, p);  // 2^32 truncates to 0, b - 1 wraps as in the reference
   const uint32_t nb = c.base + a;
-  c.carry |= (nb < a) ? 1u : 0u;
-  c.base = nb;
-  c.span = b - a - 1u;
-  if (c.span < 65536u) {
-    const uint32_t top = nb >> 16;
-    const uint32_t slot = c.cnt & 31u;
-    if ((uint32_t)lane == slot) c.word = top;
-    c.cmask |= c.carry << slot;
-    c.carry = 0;
-    c.run = (top == 0xFFFFu) ? c.run + 1u : 0u;
-    c.base = nb << 16;
-    c.span = (c.span << 16) | 0xFFFFu;
-    c.cnt += 1;
-    if ((c.cnt & 31u) == 0) enc_flush_group(c, lane);
-  }
+  const uint32_t s = b - a - 1u;
+  const bool renorm = s < 65536u;
+  const uint32_t carry = c.carry | ((nb < a) ? 1u : 0u);
+  const uint32_t top = nb >> 16;
+  const uint32_t slot = c.cnt & 31u;
+  c.word = (renorm && (uint32_t)lane == slot) ? top : c.word;
+  c.cmask |= renorm ? (carry << slot) : 0u;
+  c.carry = renorm ? 0u : carry;
+  c.run = renorm ? ((top == 0xFFFFu) ? c.run + 1u : 0u) : c.run;
+  c.base = renorm ? (nb << 16) : nb;
+  c.span = renorm ? ((s << 16) | 0xFFFFu) : s;
+  c.cnt += renorm ? 1u : 0u;
+  if (renorm && (c.cnt & 31u) == 0) enc_flush_group(c, lane);
 }
 
 // Escape tail of OverflowEncode (range_coder_kernels.cc:306-321): Elias-gamma code of g, then sign,
@@ -320,17 +323,27 @@ __global__ void __launch_bounds__(32) encode_kernel(const EncParams P) {
     const unsigned esc_mask = __ballot_sync(kFull, cur.gamma != 0);
     const unsigned bad_mask = __ballot_sync(kFull, cur.prec == 0 && lane < count);
     if (bad_mask) break;  // argument error already recorded; stop this stream
-    if (count == 32 && esc_mask == 0) {
-#pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        const uint32_t pk = __shfl_sync(kFull, cur.pack, k);
-        const uint32_t pr = __shfl_sync(kFull, cur.prec, k);
+    // The triples travel by warp shuffle; they are requested two symbols ahead so that the shuffle
+    // latency never sits on the serial span recurrence.
+    uint32_t pk0 = __shfl_sync(kFull, cur.pack, 0), pr0 = __shfl_sync(kFull, cur.prec, 0);
+    uint32_t pk1 = __shfl_sync(kFull, cur.pack, 1), pr1 = __shfl_sync(kFull, cur.prec, 1);
+    if (esc_mask == 0) {
+#pragma unroll 4
+      for (int k = 0; k < count; ++k) {
+        const uint32_t pk = pk0, pr = pr0;
+        pk0 = pk1;
+        pr0 = pr1;
+        pk1 = __shfl_sync(kFull, cur.pack, (k + 2) & 31);
+        pr1 = __shfl_sync(kFull, cur.prec, (k + 2) & 31);
         enc_step(c, pk & 0xFFFFu, (pk >> 16) + 1u, pr, lane);
       }
     } else {
       for (int k = 0; k < count; ++k) {
-        const uint32_t pk = __shfl_sync(kFull, cur.pack, k);
-        const uint32_t pr = __shfl_sync(kFull, cur.prec, k);
+        const uint32_t pk = pk0, pr = pr0;
+        pk0 = pk1;
+        pr0 = pr1;
+        pk1 = __shfl_sync(kFull, cur.pack, (k + 2) & 31);
+        pr1 = __shfl_sync(kFull, cur.prec, (k + 2) & 31);
         enc_step(c, pk & 0xFFFFu, (pk >> 16) + 1u, pr, lane);
         if ((esc_mask >> k) & 1u) {
           const uint32_t gm = __shfl_sync(kFull, cur.gamma, k);
@@ -534,6 +547,7 @@ struct DecParams {
   const int32_t* lookup;
   const int2* rows;
   int n_rows;
+  long long lookup_len;
   const uint8_t* bytes;
   const long long* offsets;
   const int32_t* index;
@@ -598,7 +612,7 @@ __device__ __forceinline__ int dec_symbol(DecChain& c, ByteWindow& w, const int3
     const int stride = (n + 31) >> 5;
     int off = (lane + 1) * stride - 1;
     if (off > n - 1) off = n - 1;
-    const uint32_t cv = (uint32_t)__ldg(cdf + lo_i + off);
+    const uint32_t cv = (uint32_t)cdf[lo_i + off];
     const bool pred = v < scale_cum(c.span, cv, p);
     // scale_cum truncates 2^32 to 0; that only happens for cv == 2^p with span == 2^32-1, where the
     // true value 2^32 exceeds every v.
@@ -613,8 +627,8 @@ __device__ __forceinline__ int dec_symbol(DecChain& c, ByteWindow& w, const int3
     lo_i += skip;
     n = min(stride, n - skip);
   }
-  const uint32_t ca = (uint32_t)__ldg(cdf + i - 1);
-  const uint32_t cb = (uint32_t)__ldg(cdf + i);
+  const uint32_t ca = (uint32_t)cdf[i - 1];
+  const uint32_t cb = (uint32_t)cdf[i];
   dec_update(c, w, scale_cum(c.span, ca, p), scale_cum(c.span, cb, p), lane);
   return i - 1;
 }
@@ -630,11 +644,89 @@ __device__ __forceinline__ uint32_t dec_bit(DecChain& c, ByteWindow& w, int lane
   return bit;
 }
 
-template <int MODE>
+// Candidate positions of one search round over cdf indices [lo_i, hi_i] (invariant:
+// scale(cdf[lo_i]) <= v < scale(cdf[hi_i])).  Every lane owns two candidates m = lane, lane + 32.
+//   len <= 63 : final round, candidate m -> index lo_i + m (valid while <= hi_i)
+//   else      : coarse round, stride s = ceil(len / 64), candidate m -> min(lo_i + (m+1) s, hi_i)
+struct Round {
+  int stride;  // 0 = final round
+  int idx0, idx1;
+  bool v0, v1;
+};
+
+__device__ __forceinline__ Round plan_round(int lo_i, int hi_i, int lane) {
+  Round r;
+  const int len = hi_i - lo_i;
+  if (len <= 63) {
+    r.stride = 0;
+    r.idx0 = lo_i + lane;
+    r.idx1 = lo_i + lane + 32;
+    r.v0 = r.idx0 <= hi_i;
+    r.v1 = r.idx1 <= hi_i;
+    if (!r.v0) r.idx0 = hi_i;
+    if (!r.v1) r.idx1 = hi_i;
+  } else {
+    r.stride = (len + 63) >> 6;
+    r.idx0 = min(lo_i + (lane + 1) * r.stride, hi_i);
+    r.idx1 = min(lo_i + (lane + 33) * r.stride, hi_i);
+    r.v0 = r.v1 = true;
+  }
+  return r;
+}
+
+// Decodes one symbol given the (possibly prefetched) candidates of the first round.
+// Equivalent to RangeDecoder::DecodeInternal<BinarySearch> (range_coder.h:224-271): smallest i >= 1
+// with scale(cdf[i]) > value - base.  span == 2^32-1 (where scale(2^p) wraps) takes the slow path.
+__device__ __forceinline__ int dec_symbol_fast(DecChain& c, ByteWindow& w, const int32_t* cdf, int ncdf,
+                                               uint32_t p, Round r, uint32_t c0, uint32_t c1, int lane) {
+  if (c.span == 0xFFFFFFFFu) return dec_symbol(c, w, cdf, ncdf, p, lane);
+  const uint32_t v = c.value - c.base;
+  int lo_i = 0, hi_i = ncdf - 1;
+  for (;;) {
+    const uint32_t t0 = scale_cum(c.span, c0, p);
+    const uint32_t t1 = scale_cum(c.span, c1, p);
+    const bool le0 = r.v0 && t0 <= v;
+    const bool le1 = r.v1 && t1 <= v;
+    const int below = __popc(__ballot_sync(kFull, le0)) + __popc(__ballot_sync(kFull, le1));
+    if (r.stride == 0) {
+      const uint32_t amax = max(le0 ? t0 : 0u, le1 ? t1 : 0u);
+      const uint32_t bmin = min((r.v0 && !le0) ? t0 : 0xFFFFFFFFu, (r.v1 && !le1) ? t1 : 0xFFFFFFFFu);
+      const uint32_t a = __reduce_max_sync(kFull, amax);
+      const uint32_t b = __reduce_min_sync(kFull, bmin);
+      dec_update(c, w, a, b, lane);
+      // `below` counts the indices lo_i .. with scale <= v; lo_i itself always qualifies
+      int i = lo_i + max(below, 1);
+      i = min(i, ncdf - 1);
+      return i - 1;
+    }
+    const int f = min(below, 63);
+    const int nlo = (f == 0) ? lo_i : min(lo_i + f * r.stride, hi_i);
+    const int nhi = min(lo_i + (f + 1) * r.stride, hi_i);
+    lo_i = min(nlo, nhi - 1);
+    hi_i = nhi;
+    r = plan_round(lo_i, hi_i, lane);
+    c0 = (uint32_t)cdf[r.idx0];
+    c1 = (uint32_t)cdf[r.idx1];
+  }
+}
+
+template <int MODE, bool SMEM>
 __global__ void __launch_bounds__(32) decode_kernel(const DecParams P) {
+  extern __shared__ __align__(16) int32_t s_tab[];
   const long long s = blockIdx.x;
   const int lane = threadIdx.x;
   if (s >= P.n_streams) return;
+  const int32_t* tab = P.lookup;
+  const int2* rows = P.rows;
+  if (SMEM) {
+    const int ntab = (int)((P.lookup_len + 1) & ~1ll);
+    for (int i = lane; i < (int)P.lookup_len; i += 32) s_tab[i] = P.lookup[i];
+    int2* srows = reinterpret_cast<int2*>(s_tab + ntab);
+    for (int i = lane; i < P.n_rows; i += 32) srows[i] = P.rows[i];
+    __syncwarp();
+    tab = s_tab;
+    rows = srows;
+  }
   DecChain c;
   {
     const DecState st = P.state[s];
@@ -653,13 +745,15 @@ __global__ void __launch_bounds__(32) decode_kernel(const DecParams P) {
   }
   bw_seek(w, c.pos, lane);
 
-  uint32_t chan_row = 0;
-  bool stop = false;
-  for (long long g0 = 0; g0 < P.n && !stop; g0 += 32) {
+  uint32_t chan_row = (uint32_t)lane % (uint32_t)P.n_rows;
+  const uint32_t chan_step = 32u % (uint32_t)P.n_rows;
+  for (long long g0 = 0; g0 < P.n; g0 += 32) {
     const int count = (int)min(32ll, P.n - g0);
     const long long at = s * P.n + g0 + lane;
-    int my_row = 0;
+    // per-lane row descriptor of symbol g0 + lane
+    int my_row = (int)chan_row;
     if (MODE & kModeIndex) {
+      my_row = 0;
       if (lane < count) {
         my_row = __ldg(P.index + at);
         if (my_row < 0 || my_row >= P.n_rows) {
@@ -667,25 +761,36 @@ __global__ void __launch_bounds__(32) decode_kernel(const DecParams P) {
           my_row = -1;
         }
       }
-      if (__ballot_sync(kFull, my_row < 0)) {
-        stop = true;
-        break;
-      }
+      if (__ballot_sync(kFull, my_row < 0)) break;
+    } else {
+      chan_row += chan_step;
+      if (chan_row >= (uint32_t)P.n_rows) chan_row -= (uint32_t)P.n_rows;
     }
+    const int2 my_ri = rows[my_row];
+
+    // software pipeline: descriptor of symbol k+2 by shuffle, candidates of symbol k+1 by load,
+    // arithmetic of symbol k.
+    int st1 = __shfl_sync(kFull, my_ri.x, 0), mt1 = __shfl_sync(kFull, my_ri.y, 0);
+    int st2 = __shfl_sync(kFull, my_ri.x, 1), mt2 = __shfl_sync(kFull, my_ri.y, 1);
+    Round r1 = plan_round(0, row_ncdf(mt1) - 1, lane);
+    uint32_t c0n = (uint32_t)tab[st1 + r1.idx0], c1n = (uint32_t)tab[st1 + r1.idx1];
     int my_sym = 0;
     for (int k = 0; k < count; ++k) {
-      int row;
-      if (MODE & kModeIndex) {
-        row = __shfl_sync(kFull, my_row, k);
-      } else {
-        row = (int)chan_row;
-        chan_row = (chan_row + 1 == (uint32_t)P.n_rows) ? 0u : chan_row + 1;
-      }
-      const int2 ri = __ldg(P.rows + row);
-      const int ncdf = row_ncdf(ri.y);
-      const uint32_t p = (uint32_t)row_prec(ri.y);
-      int sym = dec_symbol(c, w, P.lookup + ri.x, ncdf, p, lane);
-      if (row_ovf(ri.y) && sym == ncdf - 2) {
+      const int st0 = st1, mt0 = mt1;
+      const Round r0 = r1;
+      const uint32_t c0 = c0n, c1 = c1n;
+      st1 = st2;
+      mt1 = mt2;
+      st2 = __shfl_sync(kFull, my_ri.x, (k + 2) & 31);
+      mt2 = __shfl_sync(kFull, my_ri.y, (k + 2) & 31);
+      r1 = plan_round(0, row_ncdf(mt1) - 1, lane);
+      c0n = (uint32_t)tab[st1 + r1.idx0];
+      c1n = (uint32_t)tab[st1 + r1.idx1];
+
+      const int ncdf = row_ncdf(mt0);
+      const uint32_t p = (uint32_t)row_prec(mt0);
+      int sym = dec_symbol_fast(c, w, tab + st0, ncdf, p, r0, c0, c1, lane);
+      if (row_ovf(mt0) && sym == ncdf - 2) {
         const int esc = ncdf - 2;
         int nb = 0;
         while (dec_bit(c, w, lane) == 0 && nb < 64) ++nb;
@@ -702,14 +807,8 @@ __global__ void __launch_bounds__(32) decode_kernel(const DecParams P) {
     }
     if (lane < count) {
       if (MODE & kModeF32) {
-        int row;
-        if (MODE & kModeIndex) {
-          row = my_row;
-        } else {
-          row = (int)((g0 + lane) % P.n_rows);
-        }
-        float y = (float)(my_sym + __ldg(P.coff + row));
-        if (P.qoff) y += (MODE & kModeIndex) ? __ldg(P.qoff + at) : __ldg(P.qoff + row);
+        float y = (float)(my_sym + __ldg(P.coff + my_row));
+        if (P.qoff) y += (MODE & kModeIndex) ? __ldg(P.qoff + at) : __ldg(P.qoff + my_row);
         reinterpret_cast<float*>(P.out)[at] = y;
       } else {
         reinterpret_cast<int32_t*>(P.out)[at] = my_sym;
@@ -1189,6 +1288,7 @@ int launch_decode(tfcb_decoder* h, const int32_t* index, void* out, const float*
   P.lookup = h->lut.lookup;
   P.rows = h->lut.rows;
   P.n_rows = h->lut.n_rows;
+  P.lookup_len = h->lut.len;
   P.bytes = h->bytes;
   P.offsets = h->offsets;
   P.index = index;
@@ -1199,7 +1299,15 @@ int launch_decode(tfcb_decoder* h, const int32_t* index, void* out, const float*
   P.n_streams = h->n_streams;
   P.state = h->state;
   P.err = h->err;
-  decode_kernel<MODE><<<(unsigned)h->n_streams, 32, 0, s>>>(P);
+  // Tables live in shared memory when two CTAs per SM still fit (every stream is its own CTA).
+  const size_t smem = (size_t)(((h->lut.len + 1) & ~1ll) * sizeof(int32_t) + (size_t)h->lut.n_rows * sizeof(int2));
+  if (smem <= 100 * 1024) {
+    TFCB_CUDA_TRY(cudaFuncSetAttribute(decode_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+    decode_kernel<MODE, true><<<(unsigned)h->n_streams, 32, smem, s>>>(P);
+  } else {
+    decode_kernel<MODE, false><<<(unsigned)h->n_streams, 32, 0, s>>>(P);
+  }
   TFCB_LAUNCHED();
   TFCB_CUDA_TRY(cudaGetLastError());
   return TFCB_OK;

@@ -32,6 +32,29 @@ def enc():
 t, tm = timeit(enc)
 nbytes = box["s"].nbytes()
 print(f"encode cfg2: {t:.3f} ms best / {tm:.3f} med -> {S*N/t/1e3:.1f} Msym/s, {8*nbytes/(S*N):.3f} bit/sym")
+# kernel-only timing (handle creation / finalize outside the timed region)
+def enc_only():
+  hs = [gen_ops.create_range_encoder([S], lookup) for _ in range(6)]
+  torch.cuda.synchronize()
+  ts = []
+  for h in hs:
+    a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+    a.record(); gen_ops.entropy_encode_channel(h, v); b.record(); torch.cuda.synchronize()
+    ts.append(a.elapsed_time(b))
+  return min(ts)
+t = enc_only()
+print(f"encode kernel only: {t:.3f} ms -> {S*N/t/1e3:.1f} Msym/s")
+def dec_only():
+  hs = [gen_ops.create_range_decoder(box["s"], lookup) for _ in range(6)]
+  torch.cuda.synchronize()
+  ts = []
+  for h in hs:
+    a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+    a.record(); gen_ops.entropy_decode_channel(h, [N]); b.record(); torch.cuda.synchronize()
+    ts.append(a.elapsed_time(b))
+  return min(ts)
+t = dec_only()
+print(f"decode kernel only: {t:.3f} ms -> {S*N/t/1e3:.1f} Msym/s")
 def dec():
   h = gen_ops.create_range_decoder(box["s"], lookup)
   h, out = gen_ops.entropy_decode_channel(h, [N])
