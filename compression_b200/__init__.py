@@ -10,9 +10,18 @@ from compression_b200._lib import InvalidArgumentError
 
 def __getattr__(name):  # lazy: importing the package must not require torch / the built library
   import importlib
-  lazy = {
-      "gen_ops": "compression_b200.gen_ops",
+  modules = ("gen_ops", "functional", "math_ops", "distributions", "entropy_models", "gdn")
+  if name in modules:
+    return importlib.import_module("compression_b200." + name)
+  exported = {
+      "GDN": "gdn", "GDNParameter": "gdn",
+      "ContinuousBatchedEntropyModel": "entropy_models", "ContinuousIndexedEntropyModel": "entropy_models",
+      "LocationScaleIndexedEntropyModel": "entropy_models", "EntropyBottleneck": "entropy_models",
+      "NoisyDeepFactorized": "distributions", "DeepFactorized": "distributions", "NoisyNormal": "distributions",
+      "NoisyLaplace": "distributions", "NoisyLogistic": "distributions",
+      "round_st": "math_ops", "lower_bound": "math_ops", "upper_bound": "math_ops",
+      "perturb_and_apply": "math_ops",
   }
-  if name in lazy:
-    return importlib.import_module(lazy[name])
+  if name in exported:
+    return getattr(importlib.import_module("compression_b200." + exported[name]), name)
   raise AttributeError(name)

@@ -1,0 +1,356 @@
+"""Priors used to derive range-coding tables, mirroring tensorflow_compression/python/distributions:
+helpers.py:29-219 (tail / offset estimation), deep_factorized.py:50-267 and uniform_noise.py:50-262.
+TensorFlow Probability is replaced by a minimal scalar-distribution protocol on PyTorch:
+``cdf / survival_function / log_cdf / log_survival_function / quantile / batch_shape / dtype``."""
+import math
+
+import torch
+from torch import nn
+
+__all__ = [
+    "estimate_tails", "quantization_offset", "lower_tail", "upper_tail", "DeepFactorized",
+    "NoisyDeepFactorized", "UniformNoiseAdapter", "Normal", "Laplace", "Logistic", "NoisyNormal",
+    "NoisyLaplace", "NoisyLogistic",
+]
+
+
+# ------------------------------------------------------------------------------------------------
+# helpers.py
+# ------------------------------------------------------------------------------------------------
+def estimate_tails(func, target, shape, dtype=torch.float32, device=None):
+  """Adam-style root finding of func(x) == target (helpers.py:29-102), vectorised over `shape`."""
+  shape = tuple(int(s) for s in shape)
+  target = torch.as_tensor(target, dtype=dtype, device=device)
+  tails = torch.zeros(shape, dtype=dtype, device=device)
+  m = torch.zeros_like(tails)
+  v = torch.ones_like(tails)
+  loss = torch.full_like(tails, torch.finfo(dtype).max)
+  count = torch.zeros(shape, dtype=torch.int32, device=device)
+  best_tails, best_loss = tails.clone(), loss.clone()
+  while bool(loss.max() > 1e-8) and bool(count.min() < 100):
+    t = tails.detach().requires_grad_(True)
+    with torch.enable_grad():
+      loss = (func(t) - target).abs()
+      grad, = torch.autograd.grad(loss.sum(), t)
+    loss = loss.detach()
+    better = loss < best_loss
+    best_tails = torch.where(better, tails, best_tails)
+    best_loss = torch.where(better, loss, best_loss)
+    prev_m = m
+    m = (prev_m + grad) / 2
+    v = (v + grad.square()) / 2
+    k = torch.sqrt((count + 1).to(dtype))
+    tails = tails - 0.1 * m / (k * torch.sqrt(v) + 1e-20)
+    count = torch.where((count > 0) | (prev_m * grad < 0), count + 1, count)
+  return best_tails
+
+
+def quantization_offset(distribution):
+  """helpers.py:104-147: offset - round(offset) of the best available location statistic."""
+  offset = None
+  for name in ("_quantization_offset", "mode", "median", "mean"):
+    fn = getattr(distribution, name, None)
+    if fn is None:
+      continue
+    try:
+      offset = fn()
+      break
+    except NotImplementedError:
+      continue
+  if offset is None:
+    offset = torch.zeros((), dtype=distribution.dtype)
+  offset = torch.as_tensor(offset).detach()
+  return offset - torch.round(offset)
+
+
+def _tail(distribution, tail_mass, lower):
+  own = getattr(distribution, "_lower_tail" if lower else "_upper_tail", None)
+  if own is not None:
+    try:
+      return own(tail_mass).detach()
+    except NotImplementedError:
+      pass
+  try:
+    q = tail_mass / 2 if lower else 1 - tail_mass / 2
+    return distribution.quantile(q).detach()
+  except NotImplementedError:
+    pass
+  fn = getattr(distribution, "log_cdf" if lower else "log_survival_function", None)
+  if fn is None:
+    raise NotImplementedError(
+        "`distribution` must implement `_lower_tail()`/`_upper_tail()`, `quantile()`, or "
+        "`log_cdf()`/`log_survival_function()` so that the tails can be located.")
+  target = math.log(tail_mass / 2)
+  return estimate_tails(fn, target, distribution.batch_shape, distribution.dtype,
+                        getattr(distribution, "device", None)).detach()
+
+
+def lower_tail(distribution, tail_mass):
+  """helpers.py:150-183."""
+  return _tail(distribution, tail_mass, True)
+
+
+def upper_tail(distribution, tail_mass):
+  """helpers.py:186-219."""
+  return _tail(distribution, tail_mass, False)
+
+
+# ------------------------------------------------------------------------------------------------
+# deep_factorized.py
+# ------------------------------------------------------------------------------------------------
+def _log_expm1(x):
+  x = torch.as_tensor(x, dtype=torch.float64)
+  return torch.where(x < 15.0, torch.log(torch.expm1(torch.clamp(x, max=15.0))), x)
+
+
+class DeepFactorized(nn.Module):
+  """Fully factorized density with a small monotone MLP per channel as CDF logits
+  (deep_factorized.py:50-260)."""
+
+  def __init__(self, batch_shape=(), num_filters=(3, 3), init_scale=10, dtype=torch.float32, device=None):
+    super().__init__()
+    self._batch_shape = tuple(int(s) for s in batch_shape)
+    self.num_filters = tuple(int(f) for f in num_filters)
+    self.init_scale = float(init_scale)
+    self.dtype = dtype
+    channels = 1
+    for s in self._batch_shape:
+      channels *= s
+    self._channels = channels
+    filters = (1,) + self.num_filters + (1,)
+    scale = self.init_scale**(1 / (len(self.num_filters) + 1))
+    self.matrices = nn.ParameterList()
+    self.biases = nn.ParameterList()
+    self.factors = nn.ParameterList()
+    for i in range(len(self.num_filters) + 1):
+      init = float(_log_expm1(1 / scale / filters[i + 1]))
+      self.matrices.append(nn.Parameter(
+          torch.full((channels, filters[i + 1], filters[i]), init, dtype=dtype, device=device)))
+      self.biases.append(nn.Parameter(
+          torch.rand((channels, filters[i + 1], 1), dtype=dtype, device=device) - 0.5))
+      if i < len(self.num_filters):
+        self.factors.append(nn.Parameter(torch.zeros((channels, filters[i + 1], 1), dtype=dtype, device=device)))
+
+  @property
+  def batch_shape(self):
+    return self._batch_shape
+
+  @property
+  def device(self):
+    return self.matrices[0].device
+
+  def _broadcast(self, inputs):
+    inputs = torch.as_tensor(inputs, dtype=self.dtype, device=self.device)
+    shape = torch.broadcast_shapes(tuple(inputs.shape), self._batch_shape)
+    return inputs.expand(shape)
+
+  def _logits_cumulative(self, inputs):
+    """deep_factorized.py:166-193."""
+    inputs = self._broadcast(inputs)
+    shape = inputs.shape
+    x = inputs.reshape(-1, 1, self._channels).permute(2, 1, 0)  # (channels, 1, batch)
+    logits = x
+    for i in range(len(self.num_filters) + 1):
+      logits = torch.matmul(torch.nn.functional.softplus(self.matrices[i]), logits) + self.biases[i]
+      if i < len(self.num_filters):
+        logits = logits + torch.tanh(self.factors[i]) * torch.tanh(logits)
+    return logits.permute(2, 1, 0).reshape(shape)
+
+  def log_cdf(self, x):
+    return torch.nn.functional.logsigmoid(self._logits_cumulative(x))
+
+  def log_survival_function(self, x):
+    return torch.nn.functional.logsigmoid(-self._logits_cumulative(x))
+
+  def cdf(self, x):
+    return torch.sigmoid(self._logits_cumulative(x))
+
+  def survival_function(self, x):
+    return torch.sigmoid(-self._logits_cumulative(x))
+
+  def prob(self, x):
+    x = self._broadcast(x).detach().requires_grad_(True)
+    with torch.enable_grad():
+      c = self.cdf(x)
+      p, = torch.autograd.grad(c.sum(), x, create_graph=torch.is_grad_enabled())
+    return p
+
+  def log_prob(self, x):
+    x = self._broadcast(x)
+    xr = x.detach().requires_grad_(True)
+    with torch.enable_grad():
+      logits = self._logits_cumulative(xr)
+      dlogits, = torch.autograd.grad(logits.sum(), xr, create_graph=torch.is_grad_enabled())
+    lg = self._logits_cumulative(x)
+    return torch.nn.functional.logsigmoid(lg) + torch.nn.functional.logsigmoid(-lg) + torch.log(dlogits)
+
+  def quantile(self, q):
+    raise NotImplementedError
+
+  def _quantization_offset(self):
+    return estimate_tails(self._logits_cumulative, 0., self._batch_shape, self.dtype, self.device)
+
+  def _lower_tail(self, tail_mass):
+    logits = math.log(tail_mass / 2 / (1. - tail_mass / 2))
+    return estimate_tails(self._logits_cumulative, logits, self._batch_shape, self.dtype, self.device)
+
+  def _upper_tail(self, tail_mass):
+    logits = -math.log(tail_mass / 2 / (1. - tail_mass / 2))
+    return estimate_tails(self._logits_cumulative, logits, self._batch_shape, self.dtype, self.device)
+
+
+# ------------------------------------------------------------------------------------------------
+# Closed-form location-scale bases (stand-ins for tfp.distributions.{Normal,Laplace,Logistic})
+# ------------------------------------------------------------------------------------------------
+class _LocScale:
+
+  def __init__(self, loc, scale, dtype=torch.float32):
+    loc = torch.as_tensor(loc, dtype=dtype)
+    scale = torch.as_tensor(scale, dtype=dtype, device=loc.device if loc.dim() else None)
+    if scale.device != loc.device:
+      loc = loc.to(scale.device)
+    self.loc, self.scale = torch.broadcast_tensors(loc, scale)
+    self.dtype = self.loc.dtype
+
+  @property
+  def batch_shape(self):
+    return tuple(self.loc.shape)
+
+  @property
+  def device(self):
+    return self.loc.device
+
+  def _z(self, x):
+    x = torch.as_tensor(x, dtype=self.dtype, device=self.device)
+    return (x - self.loc) / self.scale
+
+  def mean(self):
+    return self.loc
+
+  def mode(self):
+    return self.loc
+
+  def survival_function(self, x):
+    return self._std_cdf(-self._z(x))
+
+  def cdf(self, x):
+    return self._std_cdf(self._z(x))
+
+  def log_cdf(self, x):
+    return self._std_log_cdf(self._z(x))
+
+  def log_survival_function(self, x):
+    return self._std_log_cdf(-self._z(x))
+
+  def quantile(self, q):
+    q = torch.as_tensor(q, dtype=self.dtype, device=self.device)
+    return self.loc + self.scale * self._std_quantile(q)
+
+
+class Normal(_LocScale):
+  _std_cdf = staticmethod(torch.special.ndtr)
+  _std_log_cdf = staticmethod(torch.special.log_ndtr)
+  _std_quantile = staticmethod(torch.special.ndtri)
+
+
+class Logistic(_LocScale):
+  _std_cdf = staticmethod(torch.sigmoid)
+  _std_log_cdf = staticmethod(torch.nn.functional.logsigmoid)
+  _std_quantile = staticmethod(torch.logit)
+
+
+class Laplace(_LocScale):
+
+  @staticmethod
+  def _std_cdf(z):
+    return 0.5 - 0.5 * torch.sign(z) * torch.expm1(-z.abs())
+
+  @staticmethod
+  def _std_log_cdf(z):
+    return torch.where(z < 0, math.log(0.5) + z, torch.log1p(-0.5 * torch.exp(-z.abs())))
+
+  @staticmethod
+  def _std_quantile(q):
+    return torch.where(q < 0.5, torch.log(2 * q), -torch.log(2 * (1 - q)))
+
+
+# ------------------------------------------------------------------------------------------------
+# uniform_noise.py
+# ------------------------------------------------------------------------------------------------
+def _logsum_expbig_minus_expsmall(big, small):
+  return torch.where(torch.isinf(big), big, torch.log1p(-torch.exp(small - big)) + big)
+
+
+class UniformNoiseAdapter(nn.Module):
+  """p(y) = c(y + .5) - c(y - .5) of a base density (uniform_noise.py:50-191)."""
+
+  def __init__(self, base):
+    super().__init__()
+    self.base = base
+
+  @property
+  def dtype(self):
+    return self.base.dtype
+
+  @property
+  def batch_shape(self):
+    return self.base.batch_shape
+
+  @property
+  def device(self):
+    return self.base.device
+
+  def log_prob(self, y):
+    """uniform_noise.py:128-151 (the log-sf / log-cdf select)."""
+    b = self.base
+    logsf_p, logsf_m = b.log_survival_function(y + .5), b.log_survival_function(y - .5)
+    logcdf_p, logcdf_m = b.log_cdf(y + .5), b.log_cdf(y - .5)
+    right = logsf_p < logcdf_p
+    big = torch.where(right, logsf_m, logcdf_p)
+    small = torch.where(right, logsf_p, logcdf_m)
+    return _logsum_expbig_minus_expsmall(big, small)
+
+  def prob(self, y):
+    """uniform_noise.py:171-183."""
+    b = self.base
+    sf_p, sf_m = b.survival_function(y + .5), b.survival_function(y - .5)
+    cdf_p, cdf_m = b.cdf(y + .5), b.cdf(y - .5)
+    return torch.where(sf_p < cdf_p, sf_m - sf_p, cdf_p - cdf_m)
+
+  def mean(self):
+    return self.base.mean()
+
+  def _quantization_offset(self):
+    return quantization_offset(self.base)
+
+  def _lower_tail(self, tail_mass):
+    return lower_tail(self.base, tail_mass)
+
+  def _upper_tail(self, tail_mass):
+    return upper_tail(self.base, tail_mass)
+
+
+class NoisyDeepFactorized(UniformNoiseAdapter):
+  """deep_factorized.py:263-267."""
+
+  def __init__(self, **kwargs):
+    super().__init__(DeepFactorized(**kwargs))
+
+
+class NoisyNormal(UniformNoiseAdapter):
+  """uniform_noise.py:257-262."""
+
+  def __init__(self, loc, scale, dtype=torch.float32):
+    super().__init__(Normal(loc, scale, dtype))
+
+
+class NoisyLogistic(UniformNoiseAdapter):
+
+  def __init__(self, loc, scale, dtype=torch.float32):
+    super().__init__(Logistic(loc, scale, dtype))
+
+
+class NoisyLaplace(UniformNoiseAdapter):
+
+  def __init__(self, loc, scale, dtype=torch.float32):
+    super().__init__(Laplace(loc, scale, dtype))

@@ -78,3 +78,72 @@ class _GDNFunction(torch.autograd.Function):
 def gdn(x, gamma, beta, inverse=False, rectify=False, alpha=1.0, epsilon=1.0):
   """Differentiable GDN/IGDN on channels-last float32 CUDA tensors."""
   return _GDNFunction.apply(x, gamma, beta, bool(inverse), bool(rectify), float(alpha), float(epsilon))
+
+
+# ------------------------------------------------------------------------------------------------
+# Fused quantise + encode / decode + dequantise (K3 fused into K4/K5 and K6)
+# ------------------------------------------------------------------------------------------------
+def _f32(t, device):
+  return None if t is None else t.to(device=device, dtype=torch.float32).contiguous()
+
+
+def _i32(t, device):
+  return None if t is None else t.to(device=device, dtype=torch.int32).contiguous()
+
+
+def encode_channel_f32(handle, y, quant_offset, cdf_offset):
+  """symbols = int32(rint(y - quant_offset[c])) - cdf_offset[c] range-coded in channel mode, without
+  materialising the int32 tensor (continuous_batched.py:375-382)."""
+  handle._require()
+  y = _f32(y, y.device)
+  n = y.numel() // handle.n_streams
+  check(_lib.lib().tfcb_encode_channel_f32(handle._h, _p(y), _p(_f32(quant_offset, y.device)),
+                                           _p(_i32(cdf_offset, y.device)), n, _stream()))
+  return handle
+
+
+def encode_index_f32(handle, index, y, loc, cdf_offset):
+  """symbols = int32(rint(y - loc)) - cdf_offset[index], index mode (continuous_indexed.py:378-385)."""
+  handle._require()
+  y = _f32(y, y.device)
+  n = y.numel() // handle.n_streams
+  check(_lib.lib().tfcb_encode_index_f32(handle._h, _p(_i32(index, y.device)), _p(y), _p(_f32(loc, y.device)),
+                                         _p(_i32(cdf_offset, y.device)), n, _stream()))
+  return handle
+
+
+def decode_channel_f32(handle, out_shape, quant_offset, cdf_offset):
+  """Decodes and dequantises: float(sym + cdf_offset[c]) + quant_offset[c] (continuous_batched.py:416-421)."""
+  dev = handle._encoded.bytes_dev.device
+  out = torch.empty(tuple(out_shape), dtype=torch.float32, device=dev)
+  n = out.numel() // handle.n_streams
+  check(_lib.lib().tfcb_decode_channel_f32(handle._h, _p(out), _p(_f32(quant_offset, dev)),
+                                           _p(_i32(cdf_offset, dev)), n, _stream()))
+  return out
+
+
+def decode_index_f32(handle, index, loc, cdf_offset):
+  """Decodes and dequantises in index mode (continuous_indexed.py:409-416)."""
+  dev = handle._encoded.bytes_dev.device
+  index = _i32(index, dev)
+  out = torch.empty(tuple(index.shape), dtype=torch.float32, device=dev)
+  n = out.numel() // handle.n_streams
+  check(_lib.lib().tfcb_decode_index_f32(handle._h, _p(index), _p(out), _p(_f32(loc, dev)),
+                                         _p(_i32(cdf_offset, dev)), n, _stream()))
+  return out
+
+
+def build_lookup(pmf, pmf_length, precision):
+  """The per-row PMF -> CDF loop of _build_tables in one launch (continuous_base.py:282-294):
+  pmf float32 [rows, max_len] (CUDA), pmf_length int [rows] -> 1-D int32 lookup [-p, cdf...]*rows."""
+  import numpy as np
+  pmf = pmf.to(dtype=torch.float32).contiguous()
+  assert pmf.is_cuda and pmf.dim() == 2
+  lens = np.ascontiguousarray(np.asarray(pmf_length.cpu() if isinstance(pmf_length, torch.Tensor) else pmf_length,
+                                         dtype=np.int32).reshape(-1))
+  assert lens.shape[0] == pmf.shape[0]
+  total = int(lens.astype(np.int64).sum() + 3 * lens.shape[0])
+  lookup = torch.empty(total, dtype=torch.int32, device=pmf.device)
+  check(_lib.lib().tfcb_build_lookup(_p(pmf), pmf.shape[0], pmf.shape[1], lens.ctypes.data_as(C.c_void_p),
+                                     int(precision), _p(lookup), _stream()))
+  return lookup

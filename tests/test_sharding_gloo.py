@@ -1,0 +1,73 @@
+"""CPU, world_size 2 over gloo: the N>1 path of the hot path = batch sharding + one table broadcast."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import util
+
+
+def _free_port():
+  with socket.socket() as s:
+    s.bind(("127.0.0.1", 0))
+    return s.getsockname()[1]
+
+
+def _tables():
+  rng = np.random.default_rng(3)
+  cdfs = [util.random_cdf(rng, 10 + c, 12) for c in range(5)]
+  lookup = util.make_lookup_1d(cdfs, [12] * 5, [True] * 5)
+  return torch.from_numpy(lookup), torch.arange(-3, 2, dtype=torch.int32), torch.linspace(-.4, .4, 5)
+
+
+def _worker(rank, world, port, q):
+  os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  try:
+    from compression_b200 import entropy_models as em
+    from compression_b200 import sharding
+    if rank == 0:
+      cdf, coff, qoff = _tables()
+      model = em.ContinuousBatchedEntropyModel(prior_shape=(5,), coding_rank=3, compression=True, cdf=cdf,
+                                               cdf_offset=coff, quantization_offset=qoff)
+    else:
+      model = em.ContinuousBatchedEntropyModel(prior_shape=(5,), coding_rank=3, compression=True,
+                                               cdf_shapes=(1, 1), quantization_offset=True)
+    sharding.broadcast_tables(model, src=0)
+    lo, hi = sharding.shard_range(257, rank, world)
+    q.put((rank, model.cdf.clone(), model.cdf_offset.clone(), model.quantization_offset.clone(), lo, hi))
+  finally:
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_table_broadcast_and_batch_shards():
+  world, port = 2, _free_port()
+  ctx = mp.get_context("spawn")
+  q = ctx.Queue()
+  procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+  for p in procs:
+    p.start()
+  got = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+  for p in procs:
+    p.join(timeout=60)
+    assert p.exitcode == 0
+  cdf, coff, qoff = _tables()
+  for rank, c, o, qo, lo, hi in got:
+    assert torch.equal(c, cdf.to(torch.int32)) and torch.equal(o, coff) and torch.allclose(qo, qoff)
+  assert got[0][4] == 0 and got[0][5] == got[1][4] and got[1][5] == 257
+  assert abs((got[0][5] - got[0][4]) - (got[1][5] - got[1][4])) <= 1
+
+
+def test_shard_range_partitions_everything():
+  from compression_b200 import sharding
+  for n in (0, 1, 7, 256, 2048):
+    for world in (1, 2, 3, 8):
+      pieces = [sharding.shard_range(n, r, world) for r in range(world)]
+      assert pieces[0][0] == 0 and pieces[-1][1] == n
+      assert all(a[1] == b[0] for a, b in zip(pieces, pieces[1:]))
+      sizes = [hi - lo for lo, hi in pieces]
+      assert max(sizes) - min(sizes) <= 1
