@@ -178,7 +178,7 @@ def run_reference(args):
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
-  ap.add_argument("--steps", type=int, default=20)
+  ap.add_argument("--steps", type=int, default=200)
   ap.add_argument("--warmup", type=int, default=5)
   ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
   ap.add_argument("--no-extras", action="store_true", help="skip the decode / GDN / CPU-baseline side measurements")

@@ -92,6 +92,7 @@ struct DeviceLookup {
   long long len = 0;
   bool any_overflow = false;
   int max_prec = 0;
+  int uniform_prec = 0;  // > 0 when every row shares one precision
 
   int upload(const int32_t* lookup_host, int64_t len_, int64_t cols, cudaStream_t s) {
     const int64_t len = len_;
@@ -104,9 +105,11 @@ struct DeviceLookup {
       const int ap = hr[i].prec < 0 ? -hr[i].prec : hr[i].prec;
       any_overflow |= hr[i].prec < 0;
       max_prec = std::max(max_prec, ap);
+      uniform_prec = (i == 0 || uniform_prec == ap) ? ap : -1;
       meta[i].x = hr[i].start;
       meta[i].y = hr[i].ncdf | (ap << 24) | (hr[i].prec < 0 ? (int)0x80000000 : 0);
     }
+    if (uniform_prec < 0) uniform_prec = 0;
     TFCB_TRY(dev_alloc((void**)&lookup, std::max<int64_t>(len, 1) * sizeof(int32_t), s));
     TFCB_TRY(dev_alloc((void**)&rows, meta.size() * sizeof(int2), s));
     if (len > 0)
@@ -129,70 +132,127 @@ struct DeviceLookup {
 // ---------------------------------------------------------------------------------------------
 // Encoder state and serial recurrence
 // ---------------------------------------------------------------------------------------------
+// Per stream the arena holds the UNRESOLVED 16-bit words (`words`) and one carry bit per word
+// (`cbits`, bit w = "a carry left the 32-bit window while word w was its top half", i.e. +1 into
+// word w-1; bit `cnt` is the pending carry of the not yet emitted top word).
 struct EncState {
-  uint32_t base;   // low end of the interval (32-bit window, wraps)
-  uint32_t span;   // size - 1
-  uint32_t cnt;    // 16-bit words appended so far
-  uint32_t carry;  // a carry left the window at the current position (belongs to word cnt-1)
-  uint32_t run;    // length of the run of 0xFFFF words immediately left of the window
-  uint32_t pad[3];
+  uint32_t base;  // low end of the interval (32-bit window, wraps)
+  uint32_t span;  // size - 1
+  uint32_t cnt;   // 16-bit words appended so far
+  uint32_t pad;
+};
+
+// Pre-scaled operands of one Encode(lower, upper, p): {lower', 0, upper', addend_hi}.
+//   lower' = lower << (32 - p);  a  = hi32(span * lower' + {lower', 0})          = floor(size*lower/2^p)
+//   upper' = upper << (32 - p);  b1 = hi32(span * upper' + {upper', 0xFFFFFFFF}) = floor(size*upper/2^p) - 1
+//   upper == 2^p (does not fit 32 bits): upper' = 0xFFFFFFFF, addend_hi = 0      -> b1 = span = size - 1
+// (exact for every span in [2^16 - 1, 2^32 - 1]; checked exhaustively against the reference formula.)
+__device__ __forceinline__ uint4 enc_operands(uint32_t lower, uint32_t upper, uint32_t p) {
+  const uint32_t sh = 32u - p;
+  const bool full = upper == (1u << p);
+  return make_uint4(lower << sh, 0u, full ? 0xFFFFFFFFu : (upper << sh), full ? 0u : 0xFFFFFFFFu);
+}
+
+// A single warp per stream is LATENCY bound by the serial recurrence (measured: IMAD.HI ~10 cycles,
+// ISETP->SEL ~7; ~37 cycles per symbol for the 4-instruction dependent chain), so everything that is
+// not the recurrence is moved off that warp:
+//   chain warp   : span / base / word-count recurrence; leaves one {base after the add, word count}
+//                  entry per Encode() in shared memory (EncChain);
+//   drain warp   : reconstructs carries, 16-bit words and carry bits from 32 entries at a time, all
+//                  lanes in parallel (EncDrain);
+//   gather warp  : symbol loads, quantisation, table lookups, operand pre-scaling (encode_kernel).
+struct ChunkInfo {
+  uint32_t n;         // entries in this chunk (<= 32)
+  uint32_t cnt_end;   // word count after the last entry
+  uint32_t last;      // nonzero: no further chunk follows
+  uint32_t pad;
 };
 
 struct EncChain {
-  uint32_t base, span, cnt, carry, run;
-  uint32_t word;   // this lane's staged word (word index (cnt & ~31) + lane)
-  uint32_t cmask;  // carry bits of the staged group
+  uint32_t base, span, cnt;
+  uint2* ent;  // current entry buffer (shared, 32 entries)
+
+  // One Encode(lower, upper, precision) of range_coder.cc:37-264; `slot` is where its entry goes.
+  // Operands come pre-scaled (see enc_operands): with c' = c << (32 - p) the reference's
+  // floor(size * c / 2^p) is the HIGH word of  span * c' + c'  -- one IMAD.HI, no shift -- and the
+  // upper bound's "- 1" (and the c == 2^p corner) is folded into the 64-bit addend.
+  __device__ __forceinline__ void step(uint4 o, int slot) { step(make_uint2(o.x, o.y), make_uint2(o.z, o.w), slot); }
+  __device__ __forceinline__ void step(uint2 ol, uint2 oh, int slot) {
+    const unsigned long long ta = (unsigned long long)span * ol.x + (((unsigned long long)ol.y << 32) | ol.x);
+    const unsigned long long tb = (unsigned long long)span * oh.x + (((unsigned long long)oh.y << 32) | oh.x);
+    const uint32_t a = (uint32_t)(ta >> 32);   // floor(size * lower / 2^p)
+    const uint32_t b1 = (uint32_t)(tb >> 32);  // floor(size * upper / 2^p) - 1
+    const uint32_t nb = base + a;
+    const uint32_t s = b1 - a;
+    ent[slot] = make_uint2(nb, cnt);
+    const bool renorm = s < 65536u;
+    span = renorm ? ((s << 16) | 0xFFFFu) : s;
+    base = renorm ? (nb << 16) : nb;
+    cnt += renorm ? 1u : 0u;
+  }
+};
+
+struct EncDrain {
+  uint32_t dbase;   // base before the first entry of the next chunk
+  uint32_t cb_cur;  // carry bits of word group (cnt >> 5) accumulated so far
   uint16_t* words;
   uint32_t* cbits;
   uint32_t cap;  // capacity in words (multiple of 32)
   bool overflowed;
+  int lane;
+
+  __device__ __forceinline__ void begin(const EncState& st, uint16_t* w, uint32_t* cb, uint32_t cap_, int lane_) {
+    dbase = st.base;
+    words = w;
+    cbits = cb;
+    cap = cap_;
+    overflowed = false;
+    lane = lane_;
+    cb_cur = (st.cnt == 0) ? 0u : cb[st.cnt >> 5];
+  }
+
+  // Resolves entries [0, n) of `ent` (32 per pass): emits the word of every renormalising entry and ORs
+  // the carry bits into the per-32-words carry masks.
+  __device__ __forceinline__ void drain(const uint2* ent, int n, uint32_t cnt_end) {
+    for (int e0 = 0; e0 < n; e0 += 32) {
+      const int m = min(32, n - e0);
+      const uint2* en = ent + e0;
+      const bool act = lane < m;
+      const uint2 me = en[act ? lane : 0];
+      const uint2 pv = en[(act && lane > 0) ? lane - 1 : 0];
+      const uint32_t pass_end = (e0 + 32 < n) ? en[32].y : cnt_end;  // word count after this pass
+      const uint32_t cnt_next = (lane + 1 < m) ? en[lane + 1].y : pass_end;
+      const uint32_t before = (lane == 0) ? dbase : ((me.y != pv.y) ? (pv.x << 16) : pv.x);
+      const bool carry = act && (me.x < before);
+      const bool ren = act && cnt_next != me.y;
+      if (ren) {
+        if (me.y < cap) words[me.y] = (uint16_t)(me.x >> 16);
+        else overflowed = true;
+      }
+      const uint32_t g0 = en[0].y >> 5;
+      const uint32_t bit = 1u << (me.y & 31u);
+      const uint32_t m0 = __reduce_or_sync(kFull, (carry && (me.y >> 5) == g0) ? bit : 0u);
+      const uint32_t m1 = __reduce_or_sync(kFull, (carry && (me.y >> 5) != g0) ? bit : 0u);
+      cb_cur |= m0;
+      if ((pass_end >> 5) != g0) {
+        if (lane == 0 && g0 < (cap >> 5)) cbits[g0] = cb_cur;
+        cb_cur = m1;
+      }
+      // base after the last entry of this pass = the next pass's "before"
+      const uint2 lastent = en[m - 1];
+      dbase = (pass_end != lastent.y) ? (lastent.x << 16) : lastent.x;
+    }
+  }
+
+  __device__ __forceinline__ void end(uint32_t cnt_end, DevError* err, long long stream) {
+    if ((cnt_end >> 5) < (cap >> 5)) {
+      if (lane == 0) cbits[cnt_end >> 5] = cb_cur;
+    } else {
+      overflowed = true;
+    }
+    if (__any_sync(kFull, overflowed)) report(err, kErrCapacity, stream, cnt_end, cnt_end, cap);
+  }
 };
-
-__device__ __forceinline__ void enc_flush_group(EncChain& c, int lane) {
-  // called with (c.cnt & 31) == 0 right after the 32nd word of a group was staged
-  const uint32_t g0 = c.cnt - 32;
-  if (c.cnt <= c.cap) {
-    c.words[g0 + lane] = (uint16_t)c.word;
-    if (lane == 0) c.cbits[g0 >> 5] = c.cmask;
-  } else {
-    c.overflowed = true;
-  }
-  c.cmask = 0;
-}
-
-// One Encode(lower, upper, precision) of range_coder.cc:37-264 in the big-number formulation.
-// Written with selects so that the only branch is the (1-in-32-words) group flush: a single warp
-// per stream has nobody to hide a taken-branch bubble behind.
-__device__ __forceinline__ void enc_step(EncChain& c, uint32_t lo, uint32_t hi, uint32_t p, int lane) {
-  const uint32_t a = scale_cum(c.span, lo, p);
-  const uint32_t b = scale_cum(c.span, hi, p);  // 2^32 truncates to 0, b - 1 wraps as in the reference
-  const uint32_t nb = c.base + a;
-  const uint32_t s = b - a - 1u;
-  const bool renorm = s < 65536u;
-  const uint32_t carry = c.carry | ((nb < a) ? 1u : 0u);
-  const uint32_t top = nb >> 16;
-  const uint32_t slot = c.cnt & 31u;
-  c.word = (renorm && (uint32_t)lane == slot) ? top : c.word;
-  c.cmask |= renorm ? (carry << slot) : 0u;
-  c.carry = renorm ? 0u : carry;
-  c.run = renorm ? ((top == 0xFFFFu) ? c.run + 1u : 0u) : c.run;
-  c.base = renorm ? (nb << 16) : nb;
-  c.span = renorm ? ((s << 16) | 0xFFFFu) : s;
-  c.cnt += renorm ? 1u : 0u;
-  if (renorm && (c.cnt & 31u) == 0) enc_flush_group(c, lane);
-}
-
-// Escape tail of OverflowEncode (range_coder_kernels.cc:306-321): Elias-gamma code of g, then sign,
-// every bit coded with the uniform binary CDF {0,1,2} at precision 1.
-__device__ __forceinline__ void enc_gamma(EncChain& c, uint32_t g, uint32_t sign, int lane) {
-  const int n = 32 - __clz(g);  // g >= 1
-  for (int i = 1; i < n; ++i) enc_step(c, 0, 1, 1, lane);
-  for (int i = n - 1; i >= 0; --i) {
-    const uint32_t bit = (g >> i) & 1u;
-    enc_step(c, bit, bit + 1, 1, lane);
-  }
-  enc_step(c, sign, sign + 1, 1, lane);
-}
 
 enum : int { kModeIndex = 1, kModeF32 = 2 };
 
@@ -200,6 +260,8 @@ struct EncParams {
   const int32_t* lookup;
   const int2* rows;
   int n_rows;
+  int uniform_prec;        // > 0: every row has this precision
+  int n_sms;
   const void* value;       // int32 or float [S, n]
   const int32_t* index;    // [S, n] or null
   const float* qoff;       // channel+f32: [n_rows] or null; index+f32: loc [S, n] or null
@@ -213,48 +275,79 @@ struct EncParams {
   DevError* err;
 };
 
+// The gather of one group of 32 symbols is split in two stages so that no global-memory latency is
+// ever exposed to the (in-order) warp:
+//   stage A, two groups ahead : the symbol itself (y / value, index, loc) and, in channel mode, the row
+//                               descriptor and the per-row offsets -- all independent loads;
+//   stage B, one group ahead  : quantise, range-check, escape mapping, then the two table loads;
+//   (current group)           : the table values are written to shared memory for the serial chain.
+struct Fetched {
+  float y;
+  int v;
+  float loc_or_q;
+  int coff;
+  int row;
+  int2 ri;
+  bool valid;
+};
+
 struct Gathered {
-  uint32_t pack;   // lower | (upper - 1) << 16
-  uint32_t prec;
+  uint4 ops;       // pre-scaled operands (enc_operands)
+  uint32_t prec;   // 0 = invalid / out of range
   uint32_t gamma;  // escape payload (0 = none)
   uint32_t sign;
 };
 
 template <int MODE>
-__device__ __forceinline__ Gathered enc_gather(const EncParams& P, long long s, long long j,
-                                               uint32_t chan_row, bool valid) {
+__device__ __forceinline__ Fetched enc_fetch(const EncParams& P, long long s, long long j, uint32_t chan_row) {
+  Fetched f;
+  f.y = 0.f;
+  f.v = 0;
+  f.loc_or_q = 0.f;
+  f.coff = 0;
+  f.row = (int)chan_row;
+  f.ri = make_int2(0, 0);
+  f.valid = j < P.n;
+  if (!f.valid) return f;
+  const long long at = s * P.n + j;
+  if (MODE & kModeF32) {
+    f.y = __ldg(reinterpret_cast<const float*>(P.value) + at);
+  } else {
+    f.v = __ldg(reinterpret_cast<const int32_t*>(P.value) + at);
+  }
+  if (MODE & kModeIndex) {
+    f.row = __ldg(P.index + at);
+    if ((MODE & kModeF32) && P.qoff) f.loc_or_q = __ldg(P.qoff + at);
+  } else {
+    f.ri = __ldg(P.rows + f.row);
+    if (MODE & kModeF32) {
+      if (P.qoff) f.loc_or_q = __ldg(P.qoff + f.row);
+      f.coff = __ldg(P.coff + f.row);
+    }
+  }
+  return f;
+}
+
+template <int MODE>
+__device__ __forceinline__ Gathered enc_gather(const EncParams& P, long long s, long long j, Fetched f) {
   Gathered g;
-  g.pack = 0;  // lower=0, upper=1 at precision 1 would still consume range: use prec 0 marker
+  g.ops = make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);
   g.prec = 0;
   g.gamma = 0;
   g.sign = 0;
-  if (!valid) return g;
-  const long long at = s * P.n + j;
-  int row;
+  if (!f.valid) return g;
   if (MODE & kModeIndex) {
-    row = __ldg(P.index + at);
-    if (row < 0 || row >= P.n_rows) {
-      report(P.err, kErrIndex, s, j, row, P.n_rows);
+    if (f.row < 0 || f.row >= P.n_rows) {
+      report(P.err, kErrIndex, s, j, f.row, P.n_rows);
       return g;
     }
-  } else {
-    row = (int)chan_row;
+    f.ri = __ldg(P.rows + f.row);
+    if (MODE & kModeF32) f.coff = __ldg(P.coff + f.row);
   }
-  const int2 ri = __ldg(P.rows + row);
-  int v;
-  if (MODE & kModeF32) {
-    float y = __ldg(reinterpret_cast<const float*>(P.value) + at);
-    if (MODE & kModeIndex) {
-      if (P.qoff) y -= __ldg(P.qoff + at);  // loc
-    } else {
-      if (P.qoff) y -= __ldg(P.qoff + row);
-    }
-    v = (int)rintf(y) - __ldg(P.coff + row);
-  } else {
-    v = __ldg(reinterpret_cast<const int32_t*>(P.value) + at);
-  }
-  const int ncdf = row_ncdf(ri.y);
-  if (!row_ovf(ri.y)) {
+  int v = f.v;
+  if (MODE & kModeF32) v = (int)rintf(f.y - f.loc_or_q) - f.coff;
+  const int ncdf = row_ncdf(f.ri.y);
+  if (!row_ovf(f.ri.y)) {
     if (v < 0 || v >= ncdf - 1) {
       report(P.err, kErrValue, s, j, v, ncdf - 1);
       return g;
@@ -270,114 +363,239 @@ __device__ __forceinline__ Gathered enc_gather(const EncParams& P, long long s, 
       v = esc;
     }
   }
-  const uint32_t lower = (uint32_t)__ldg(P.lookup + ri.x + v);
-  const uint32_t upper = (uint32_t)__ldg(P.lookup + ri.x + v + 1);
-  g.pack = lower | ((upper - 1u) << 16);
-  g.prec = (uint32_t)row_prec(ri.y);
+  const uint32_t lower = (uint32_t)__ldg(P.lookup + f.ri.x + v);
+  const uint32_t upper = (uint32_t)__ldg(P.lookup + f.ri.x + v + 1);
+  g.prec = (uint32_t)row_prec(f.ri.y);
+  g.ops = enc_operands(lower, upper, g.prec);
   return g;
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(32) encode_kernel(const EncParams P) {
-  const long long s = blockIdx.x;
-  const int lane = threadIdx.x;
-  if (s >= P.n_streams) return;
+// Named barriers (bar.sync / bar.arrive) for the warp-to-warp hand-offs.
+__device__ __forceinline__ void bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
 
+struct GroupMeta {
+  unsigned esc_mask;   // lanes whose symbol escapes
+  unsigned sign_mask;  // sign bits of the escapes
+  unsigned bad;        // an argument error was recorded: stop
+  unsigned pad;
+};
+
+// Shared state of one code stream's CTA (three warps on three SM sub-partitions).  A hand-off unit is a
+// GROUP of kGroup symbols (kGroup / 32 gather passes); one barrier round trip per group and direction.
+constexpr int kGroup = 128;
+constexpr int kSub = kGroup / 32;
+
+struct EncShared {
+  uint4 ops[2][kGroup + 2];  // gather -> chain: pre-scaled operands, double buffered per group (+2: prefetch overrun)
+  uint32_t gamma[2][kGroup];
+  GroupMeta meta[2][kSub];
+  uint2 ent[2][kGroup + 1];  // chain -> drain: entries, double buffered per chunk (+1: drain reads en[32])
+  ChunkInfo chunk[2];
+};
+
+enum : int { kBarOpsFull = 1, kBarOpsEmpty = 3, kBarEntFull = 5, kBarEntEmpty = 7 };
+
+// Chain-warp helper: publishes the current entry buffer as a chunk and switches to the other one.
+struct ChunkWriter {
+  EncShared* sh;
+  long long chunks;
+  int n;  // entries in the current buffer
+
+  __device__ __forceinline__ void begin(EncShared* sh_, EncChain& c) {
+    sh = sh_;
+    chunks = 0;
+    n = 0;
+    c.ent = sh->ent[0];
+  }
+  __device__ __forceinline__ void publish(EncChain& c, bool last) {
+    const int b = (int)(chunks & 1);
+    if ((threadIdx.x & 31) == 0) {
+      ChunkInfo ci;
+      ci.n = (uint32_t)n;
+      ci.cnt_end = c.cnt;
+      ci.last = last ? 1u : 0u;
+      ci.pad = 0;
+      sh->chunk[b] = ci;
+    }
+    bar_arrive(kBarEntFull + b, 64);  // arrive orders the preceding shared-memory writes
+    ++chunks;
+    n = 0;
+    if (!last) {
+      const int nb = (int)(chunks & 1);
+      if (chunks >= 2) bar_sync(kBarEntEmpty + nb, 64);  // the drain warp is done with that buffer
+      c.ent = sh->ent[nb];
+    }
+  }
+  // slow path: append one step, hand over when the buffer is full
+  __device__ __forceinline__ void step(EncChain& c, uint4 o) {
+    c.step(o, n);
+    if (++n == kGroup) publish(c, false);
+  }
+  // Escape tail of OverflowEncode (range_coder_kernels.cc:306-321): Elias-gamma code of g, then the
+  // sign, every bit coded with the uniform binary CDF {0,1,2} at precision 1.
+  __device__ __forceinline__ void gamma(EncChain& c, uint32_t g, uint32_t sign) {
+    const int nb = 32 - __clz(g);  // g >= 1
+    for (int i = 1; i < nb; ++i) step(c, enc_operands(0, 1, 1));
+    for (int i = nb - 1; i >= 0; --i) {
+      const uint32_t bit = (g >> i) & 1u;
+      step(c, enc_operands(bit, bit + 1, 1));
+    }
+    step(c, enc_operands(sign, sign + 1, 1));
+  }
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(96) encode_kernel(const EncParams P) {
+  __shared__ __align__(16) EncShared sh;
+  const long long s = blockIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;  // role: 0 chain, 1 gather, 2 drain
+  const long long n_groups = (P.n + kGroup - 1) / kGroup;
+
+  if (warp == 1) {
+    // ------------------------------- gather warp -------------------------------
+    uint32_t row_a = 0, chan_step = 0;
+    if (!(MODE & kModeIndex)) {
+      row_a = (uint32_t)lane % (uint32_t)P.n_rows;
+      chan_step = 32u % (uint32_t)P.n_rows;
+    }
+    auto advance_row = [&]() {
+      if (!(MODE & kModeIndex)) {
+        row_a += chan_step;
+        if (row_a >= (uint32_t)P.n_rows) row_a -= (uint32_t)P.n_rows;
+      }
+    };
+    // stage A (symbol loads) runs three 32-symbol passes ahead of stage B: no global latency is waited for
+    Fetched f0 = enc_fetch<MODE>(P, s, lane, row_a);
+    advance_row();
+    Fetched f1 = enc_fetch<MODE>(P, s, 32 + lane, row_a);
+    advance_row();
+    Fetched f2 = enc_fetch<MODE>(P, s, 64 + lane, row_a);
+    advance_row();
+    long long pass = 0;
+    for (long long g = 0; g < n_groups; ++g) {
+      const int b = (int)(g & 1);
+      if (g >= 2) bar_sync(kBarOpsEmpty + b, 64);  // the chain warp is done with this buffer
+      unsigned any_bad = 0;
+#pragma unroll
+      for (int sub = 0; sub < kSub; ++sub, ++pass) {
+        const Fetched fcur = f0;
+        f0 = f1;
+        f1 = f2;
+        f2 = enc_fetch<MODE>(P, s, (pass + 3) * 32 + lane, row_a);
+        advance_row();
+        const long long j0 = pass * 32;
+        const Gathered cur = enc_gather<MODE>(P, s, j0 + lane, fcur);
+        const int count = (int)max(0ll, min(32ll, P.n - j0));
+        const unsigned esc_mask = __ballot_sync(kFull, cur.gamma != 0);
+        const unsigned sign_mask = __ballot_sync(kFull, cur.sign != 0);
+        const unsigned bad_mask = __ballot_sync(kFull, cur.prec == 0 && lane < count);
+        sh.ops[b][sub * 32 + lane] = cur.ops;
+        sh.gamma[b][sub * 32 + lane] = cur.gamma;
+        if (lane == 0) {
+          GroupMeta m;
+          m.esc_mask = esc_mask;
+          m.sign_mask = sign_mask;
+          m.bad = bad_mask;
+          m.pad = 0;
+          sh.meta[b][sub] = m;
+        }
+        any_bad |= bad_mask;
+      }
+      bar_arrive(kBarOpsFull + b, 64);
+      if (any_bad) break;
+    }
+    return;
+  }
+
+  if (warp == 2) {
+    // ------------------------------- drain warp -------------------------------
+    EncDrain d;
+    d.begin(P.state[s], P.words + s * P.cap, P.cbits + s * (P.cap >> 5), (uint32_t)P.cap, lane);
+    for (long long k = 0;; ++k) {
+      const int b = (int)(k & 1);
+      bar_sync(kBarEntFull + b, 64);
+      const ChunkInfo ci = sh.chunk[b];
+      d.drain(sh.ent[b], (int)ci.n, ci.cnt_end);
+      if (ci.last) {
+        d.end(ci.cnt_end, P.err, s);
+        break;
+      }
+      bar_arrive(kBarEntEmpty + b, 64);
+    }
+    return;
+  }
+
+  // --------------------------------- chain warp ---------------------------------
   EncChain c;
   {
     const EncState st = P.state[s];
     c.base = st.base;
     c.span = st.span;
     c.cnt = st.cnt;
-    c.carry = st.carry;
-    c.run = st.run;
   }
-  c.words = P.words + s * P.cap;
-  c.cbits = P.cbits + s * (P.cap >> 5);
-  c.cap = (uint32_t)P.cap;
-  c.overflowed = false;
-  // reload the partially filled group left by a previous call
-  {
-    const uint32_t g0 = c.cnt & ~31u;
-    const uint32_t fill = c.cnt & 31u;
-    c.word = ((uint32_t)lane < fill) ? c.words[g0 + lane] : 0u;
-    c.cmask = fill ? c.cbits[g0 >> 5] : 0u;
-  }
-
-  uint32_t chan_row = 0, chan_step = 0;
-  if (!(MODE & kModeIndex)) {
-    chan_row = (uint32_t)lane % (uint32_t)P.n_rows;
-    chan_step = 32u % (uint32_t)P.n_rows;
-  }
-
-  Gathered cur = enc_gather<MODE>(P, s, lane, chan_row, lane < P.n);
-  for (long long g0 = 0; g0 < P.n; g0 += 32) {
-    // prefetch the next group's triples while this group runs through the serial chain
-    uint32_t next_row = chan_row + chan_step;
-    if (!(MODE & kModeIndex) && next_row >= (uint32_t)P.n_rows) next_row -= (uint32_t)P.n_rows;
-    const long long jn = g0 + 32 + lane;
-    const Gathered nxt = enc_gather<MODE>(P, s, jn, next_row, jn < P.n);
-    chan_row = next_row;
-
-    const int count = (int)min(32ll, P.n - g0);
-    const unsigned esc_mask = __ballot_sync(kFull, cur.gamma != 0);
-    const unsigned bad_mask = __ballot_sync(kFull, cur.prec == 0 && lane < count);
-    if (bad_mask) break;  // argument error already recorded; stop this stream
-    // The triples travel by warp shuffle; they are requested two symbols ahead so that the shuffle
-    // latency never sits on the serial span recurrence.
-    uint32_t pk0 = __shfl_sync(kFull, cur.pack, 0), pr0 = __shfl_sync(kFull, cur.prec, 0);
-    uint32_t pk1 = __shfl_sync(kFull, cur.pack, 1), pr1 = __shfl_sync(kFull, cur.prec, 1);
-    if (esc_mask == 0) {
-#pragma unroll 4
-      for (int k = 0; k < count; ++k) {
-        const uint32_t pk = pk0, pr = pr0;
-        pk0 = pk1;
-        pr0 = pr1;
-        pk1 = __shfl_sync(kFull, cur.pack, (k + 2) & 31);
-        pr1 = __shfl_sync(kFull, cur.prec, (k + 2) & 31);
-        enc_step(c, pk & 0xFFFFu, (pk >> 16) + 1u, pr, lane);
+  ChunkWriter w;
+  w.begin(&sh, c);
+  bool stop = false;
+  for (long long g = 0; g < n_groups && !stop; ++g) {
+    const int b = (int)(g & 1);
+    bar_sync(kBarOpsFull + b, 64);
+    for (int sub = 0; sub < kSub; ++sub) {
+      const GroupMeta meta = sh.meta[b][sub];
+      if (meta.bad) {  // argument error already recorded; stop this stream
+        stop = true;
+        break;
       }
-    } else {
-      for (int k = 0; k < count; ++k) {
-        const uint32_t pk = pk0, pr = pr0;
-        pk0 = pk1;
-        pr0 = pr1;
-        pk1 = __shfl_sync(kFull, cur.pack, (k + 2) & 31);
-        pr1 = __shfl_sync(kFull, cur.prec, (k + 2) & 31);
-        enc_step(c, pk & 0xFFFFu, (pk >> 16) + 1u, pr, lane);
-        if ((esc_mask >> k) & 1u) {
-          const uint32_t gm = __shfl_sync(kFull, cur.gamma, k);
-          const uint32_t sg = __shfl_sync(kFull, cur.sign, k);
-          enc_gamma(c, gm, sg, lane);
+      const int count = (int)max(0ll, min(32ll, P.n - (g * kGroup + sub * 32)));
+      const uint4* ops = sh.ops[b] + sub * 32;
+      if (count == 32 && meta.esc_mask == 0 && w.n + 32 <= kGroup) {
+        // static slots; operands are fetched two symbols ahead so that the shared-memory latency stays
+        // off the chain
+        uint2* const ent_save = c.ent;
+        c.ent = ent_save + w.n;
+        // two 64-bit loads per symbol (not one 128-bit one): each multiply-add gets its addend in a
+        // register pair of its own, which keeps ptxas from inserting pair-copy MOVs on the chain warp
+        const uint2* q = reinterpret_cast<const uint2*>(ops);
+        uint2 l0 = q[0], h0 = q[1];
+#pragma unroll 1
+        for (int kk = 0; kk < 32; kk += 8) {
+          const uint2* p = q + 2 * kk;
+          uint2* const e = c.ent;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {  // immediates only; the prefetch may run 1 entry past the group (padded)
+            const uint2 ol = l0, oh = h0;
+            l0 = p[2 * j + 2];
+            h0 = p[2 * j + 3];
+            c.step(ol, oh, j);
+          }
+          c.ent = e + 8;
+        }
+        c.ent = ent_save;
+        w.n += 32;
+        if (w.n == kGroup) w.publish(c, false);
+      } else {
+        for (int k = 0; k < count; ++k) {
+          w.step(c, ops[k]);
+          if ((meta.esc_mask >> k) & 1u) w.gamma(c, sh.gamma[b][sub * 32 + k], (meta.sign_mask >> k) & 1u);
         }
       }
     }
-    cur = nxt;
+    if (w.n > 0) w.publish(c, false);  // one chunk per group in the common case
+    if (g + 2 < n_groups) bar_arrive(kBarOpsEmpty + b, 64);
   }
-
-  // spill the partially filled group and the scalar state
-  {
-    const uint32_t g0 = c.cnt & ~31u;
-    const uint32_t fill = c.cnt & 31u;
-    if (fill) {
-      if (g0 + 32 <= c.cap) {
-        if ((uint32_t)lane < fill) c.words[g0 + lane] = (uint16_t)c.word;
-        if (lane == 0) c.cbits[g0 >> 5] = c.cmask;
-      } else {
-        c.overflowed = true;
-      }
-    }
-    if (c.overflowed) report(P.err, kErrCapacity, s, c.cnt, c.cnt, c.cap);
-    if (lane == 0) {
-      EncState st;
-      st.base = c.base;
-      st.span = c.span;
-      st.cnt = c.cnt;
-      st.carry = c.carry;
-      st.run = c.run;
-      st.pad[0] = st.pad[1] = st.pad[2] = 0;
-      P.state[s] = st;
-    }
+  w.publish(c, true);  // (possibly empty) final chunk: lets the drain warp finish
+  if (lane == 0) {
+    EncState st;
+    st.base = c.base;
+    st.span = c.span;
+    st.cnt = c.cnt;
+    st.pad = 0;
+    P.state[s] = st;
   }
 }
 
@@ -391,9 +609,7 @@ __global__ void enc_init_state_kernel(EncState* st, long long n) {
     s.base = 0;
     s.span = 0xFFFFFFFFu;
     s.cnt = 0;
-    s.carry = 0;
-    s.run = 0;
-    s.pad[0] = s.pad[1] = s.pad[2] = 0;
+    s.pad = 0;
     st[i] = s;
   }
 }
@@ -406,10 +622,12 @@ __device__ __forceinline__ long long enc_final_length(const EncState& st, const 
   *ntail = 0;
   *tail = 0;
   if (top_end < st.base) {
-    // pick 2^32: +1 ripples through `run` 0xFFFF words into word d, everything right of d is zero
-    // and dropped, and so is the low byte of word d when it is zero.
+    // The reference picks 2^32: +1 ripples through the run of 0xFFFF words left of the window into
+    // word d (the delayed word, < 0xFFFF); everything right of d becomes zero and is dropped, and so
+    // is the low byte of word d when it is zero.
     *straddle = true;
-    const uint32_t d = st.cnt - 1u - st.run;
+    uint32_t d = st.cnt - 1u;
+    while (d > 0 && words[d] == 0xFFFFu) --d;
     const uint32_t wd = ((uint32_t)words[d] + 1u) & 0xFFFFu;
     return 2ll * d + 1 + ((wd & 0xFFu) ? 1 : 0);
   }
@@ -494,7 +712,7 @@ __global__ void __launch_bounds__(128) enc_write_kernel(const EncState* state, c
   const long long body = straddle ? len : 2ll * st.cnt;  // bytes that come from resolved words
 
   // carry entering the right-most word (index cnt-1)
-  uint32_t x = straddle ? 1u : st.carry;
+  uint32_t x = straddle ? 1u : ((cb[st.cnt >> 5] >> (st.cnt & 31u)) & 1u);
   const long long n_groups = ((long long)st.cnt + 31) >> 5;
   for (long long g = n_groups - 1; g >= 0; --g) {
     const uint32_t idx = (uint32_t)(g << 5) + lane;
@@ -531,7 +749,7 @@ __global__ void enc_grow_kernel(const uint16_t* src, const uint32_t* src_cb, lon
   const long long s = blockIdx.x;
   const uint32_t used = (state[s].cnt + 31u) & ~31u;
   for (uint32_t i = threadIdx.x; i < used; i += blockDim.x) dst[s * dst_cap + i] = src[s * src_cap + i];
-  for (uint32_t i = threadIdx.x; i < (used >> 5); i += blockDim.x)
+  for (uint32_t i = threadIdx.x; i <= (state[s].cnt >> 5); i += blockDim.x)
     dst_cb[s * (dst_cap >> 5) + i] = src_cb[s * (src_cap >> 5) + i];
 }
 
@@ -915,22 +1133,23 @@ __global__ void __launch_bounds__(32) legacy_encode_kernel(const int16_t* data, 
                                                            int precision, int debug, EncState* state,
                                                            uint16_t* words, uint32_t* cbits,
                                                            long long cap, DevError* err) {
+  __shared__ __align__(8) uint2 s_ent[32];
   const int lane = threadIdx.x;
+  EncState st0;
+  st0.base = 0;
+  st0.span = 0xFFFFFFFFu;
+  st0.cnt = 0;
+  st0.pad = 0;
   EncChain c;
-  c.base = 0;
-  c.span = 0xFFFFFFFFu;
+  c.base = st0.base;
+  c.span = st0.span;
   c.cnt = 0;
-  c.carry = 0;
-  c.run = 0;
-  c.word = 0;
-  c.cmask = 0;
-  c.words = words;
-  c.cbits = cbits;
-  c.cap = (uint32_t)cap;
-  c.overflowed = false;
+  c.ent = s_ent;
+  EncDrain d;
+  d.begin(st0, words, cbits, (uint32_t)cap, lane);
   for (long long g0 = 0; g0 < n; g0 += 32) {
     const int count = (int)min(32ll, n - g0);
-    uint32_t pack = 0;
+    uint32_t lower = 0, upper = 1;
     bool bad = false;
     if (lane < count) {
       const long long j = g0 + lane;
@@ -940,38 +1159,29 @@ __global__ void __launch_bounds__(32) legacy_encode_kernel(const int16_t* data, 
         bad = true;  // without debug the reference has undefined behaviour; we stop instead
       } else {
         const int32_t* strip = cdf + legacy_strip(dims, j);
-        const uint32_t lower = (uint32_t)strip[v], upper = (uint32_t)strip[v + 1];
+        lower = (uint32_t)strip[v];
+        upper = (uint32_t)strip[v + 1];
         if (!(lower < upper) || upper > (1u << precision)) {
           bad = true;  // zero-probability symbol / invalid strip: UB in the reference
           report(err, kErrCdf, 0, j, lower, upper, 3);
         }
-        pack = lower | ((upper - 1u) << 16);
       }
     }
     if (__ballot_sync(kFull, bad)) break;
     for (int k = 0; k < count; ++k) {
-      const uint32_t pk = __shfl_sync(kFull, pack, k);
-      enc_step(c, pk & 0xFFFFu, (pk >> 16) + 1u, (uint32_t)precision, lane);
+      const uint32_t lo = __shfl_sync(kFull, lower, k);
+      const uint32_t hi = __shfl_sync(kFull, upper, k);
+      c.step(enc_operands(lo, hi, (uint32_t)precision), k);
     }
+    d.drain(s_ent, count, c.cnt);
   }
-  const uint32_t g0 = c.cnt & ~31u, fill = c.cnt & 31u;
-  if (fill) {
-    if (g0 + 32 <= c.cap) {
-      if ((uint32_t)lane < fill) c.words[g0 + lane] = (uint16_t)c.word;
-      if (lane == 0) c.cbits[g0 >> 5] = c.cmask;
-    } else {
-      c.overflowed = true;
-    }
-  }
-  if (c.overflowed) report(err, kErrCapacity, 0, c.cnt, c.cnt, c.cap);
+  d.end(c.cnt, err, 0);
   if (lane == 0) {
     EncState st;
     st.base = c.base;
     st.span = c.span;
     st.cnt = c.cnt;
-    st.carry = c.carry;
-    st.run = c.run;
-    st.pad[0] = st.pad[1] = st.pad[2] = 0;
+    st.pad = 0;
     state[0] = st;
   }
 }
@@ -1007,6 +1217,17 @@ __global__ void __launch_bounds__(32) legacy_decode_kernel(const uint8_t* bytes,
 // ---------------------------------------------------------------------------------------------
 // Host-side handles
 // ---------------------------------------------------------------------------------------------
+int device_sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
 int fetch_error(DevError* d_err, cudaStream_t s, const char* what) {
   DevError e;
   TFCB_CUDA_TRY(cudaMemcpyAsync(&e, d_err, sizeof e, cudaMemcpyDeviceToHost, s));
@@ -1110,6 +1331,8 @@ int launch_encode(tfcb_encoder* h, const void* value, const int32_t* index, cons
   P.lookup = h->lut.lookup;
   P.rows = h->lut.rows;
   P.n_rows = h->lut.n_rows;
+  P.uniform_prec = h->lut.uniform_prec;
+  P.n_sms = device_sm_count();
   P.value = value;
   P.index = index;
   P.qoff = qoff;
@@ -1122,7 +1345,7 @@ int launch_encode(tfcb_encoder* h, const void* value, const int32_t* index, cons
   P.cap = h->cap;
   P.err = h->err;
   if (h->n_streams > 0x7FFFFFFFll) return fail(TFCB_INVALID_ARGUMENT, "too many streams");
-  encode_kernel<MODE><<<(unsigned)h->n_streams, 32, 0, s>>>(P);
+  encode_kernel<MODE><<<(unsigned)h->n_streams, 96, 0, s>>>(P);
   TFCB_LAUNCHED();
   TFCB_CUDA_TRY(cudaGetLastError());
   return TFCB_OK;

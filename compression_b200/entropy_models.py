@@ -36,7 +36,7 @@ class ContinuousEntropyModelBase(nn.Module):
   def __init__(self, coding_rank=None, compression=False, stateless=False, expected_grads=False,
                tail_mass=2**-8, bottleneck_dtype=None, laplace_tail_mass=0):
     super().__init__()
-    self._prior = None
+    object.__setattr__(self, "_prior", None)  # never a registered submodule: tables, not priors, are state
     self._coding_rank = int(coding_rank)
     self._compression = bool(compression)
     self._stateless = bool(stateless)
@@ -64,7 +64,7 @@ class ContinuousEntropyModelBase(nn.Module):
 
   @prior.deleter
   def prior(self):
-    self._prior = None
+    object.__setattr__(self, "_prior", None)
 
   @property
   def cdf(self):
@@ -211,7 +211,7 @@ class ContinuousBatchedEntropyModel(ContinuousEntropyModelBase):
     super().__init__(coding_rank=coding_rank, compression=compression, stateless=stateless,
                      expected_grads=expected_grads, tail_mass=tail_mass, bottleneck_dtype=bottleneck_dtype,
                      laplace_tail_mass=laplace_tail_mass)
-    self._prior = prior
+    object.__setattr__(self, "_prior", prior)
     self._offset_heuristic = bool(offset_heuristic)
     self._prior_shape = tuple(int(s) for s in (prior_shape if prior is None else prior.batch_shape))
     if self.coding_rank < len(self.prior_shape):
@@ -389,7 +389,7 @@ class ContinuousIndexedEntropyModel(ContinuousEntropyModelBase):
       else:
         grids = torch.meshgrid(*[torch.arange(r, dtype=torch.int32) for r in self.index_ranges], indexing="ij")
         indexes = torch.stack(grids, dim=self.channel_axis)
-      self._prior = self._make_prior(indexes)
+      object.__setattr__(self, "_prior", self._make_prior(indexes))
       cdf, cdf_offset = self._build_tables(self.prior, range_coder_precision)
       self._init_compression(cdf, cdf_offset, None)
 
