@@ -714,27 +714,45 @@ __global__ void __launch_bounds__(128) enc_write_kernel(const EncState* state, c
   // carry entering the right-most word (index cnt-1)
   uint32_t x = straddle ? 1u : ((cb[st.cnt >> 5] >> (st.cnt & 31u)) & 1u);
   const long long n_groups = ((long long)st.cnt + 31) >> 5;
-  for (long long g = n_groups - 1; g >= 0; --g) {
-    const uint32_t idx = (uint32_t)(g << 5) + lane;
-    const bool live = idx < st.cnt;
-    const uint32_t word = live ? (uint32_t)w[idx] : 0u;
-    uint32_t F = cb[g];
-    const uint32_t fill = st.cnt - (uint32_t)(g << 5);
-    if (fill < 32u) F &= (1u << fill) - 1u;
-    // P: word propagates a carry.  Dead lanes right of the last word must pass `x` through.
-    const uint32_t Pm = __ballot_sync(kFull, live ? (word == 0xFFFFu) : true);
-    // position j = 31 - i (bit 0 = right-most word); c[j+1] = F[31-j] | (P[31-j] & c[j])
-    const uint32_t G = __brev(F);
-    const uint32_t A = G | __brev(Pm);
-    const unsigned long long sum = (unsigned long long)A + G + x;
-    const uint32_t cin = (uint32_t)sum ^ A ^ G;  // bit j = carry into position j
-    const uint32_t my_c = (cin >> (31 - lane)) & 1u;
-    x = (uint32_t)(sum >> 32) & 1u;
-    if (live) {
-      const uint32_t r = (word + my_c) & 0xFFFFu;
-      const long long b0 = 2ll * idx;
-      if (b0 < body) dst[b0] = (uint8_t)(r >> 8);
-      if (b0 + 1 < body) dst[b0 + 1] = (uint8_t)r;
+  const bool even = ((reinterpret_cast<uintptr_t>(dst)) & 1) == 0;
+  constexpr int kBatch = 8;  // groups whose (independent) loads are in flight together
+  for (long long gt = n_groups; gt > 0; gt -= kBatch) {
+    uint32_t word[kBatch], F[kBatch];
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i) {
+      const long long g = gt - 1 - i;
+      const uint32_t idx = (uint32_t)(g << 5) + lane;
+      word[i] = (g >= 0 && idx < st.cnt) ? (uint32_t)w[idx] : 0u;
+      F[i] = (g >= 0) ? cb[g] : 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i) {
+      const long long g = gt - 1 - i;
+      if (g < 0) break;
+      const uint32_t idx = (uint32_t)(g << 5) + lane;
+      const bool live = idx < st.cnt;
+      uint32_t Fm = F[i];
+      const uint32_t fill = st.cnt - (uint32_t)(g << 5);
+      if (fill < 32u) Fm &= (1u << fill) - 1u;
+      // P: word propagates a carry.  Dead lanes right of the last word must pass `x` through.
+      const uint32_t Pm = __ballot_sync(kFull, live ? (word[i] == 0xFFFFu) : true);
+      // position j = 31 - lane (bit 0 = right-most word); c[j+1] = F[31-j] | (P[31-j] & c[j])
+      const uint32_t G = __brev(Fm);
+      const uint32_t A = G | __brev(Pm);
+      const unsigned long long sum = (unsigned long long)A + G + x;
+      const uint32_t cin = (uint32_t)sum ^ A ^ G;  // bit j = carry into position j
+      const uint32_t my_c = (cin >> (31 - lane)) & 1u;
+      x = (uint32_t)(sum >> 32) & 1u;
+      if (live) {
+        const uint32_t r = (word[i] + my_c) & 0xFFFFu;
+        const long long b0 = 2ll * idx;
+        if (even && b0 + 1 < body) {
+          *reinterpret_cast<uint16_t*>(dst + b0) = (uint16_t)((r >> 8) | ((r & 0xFFu) << 8));  // big endian
+        } else {
+          if (b0 < body) dst[b0] = (uint8_t)(r >> 8);
+          if (b0 + 1 < body) dst[b0 + 1] = (uint8_t)r;
+        }
+      }
     }
   }
   if (!straddle && lane == 0) {
