@@ -1,14 +1,350 @@
-// GDN forward on the 5th-generation tensor cores (tcgen05 + TMEM) -- see DESIGN.md.
-// Placeholder until the tcgen05 kernel lands: reports "not handled" so that tfcb_gdn_forward uses the
-// fp32 CUDA-core kernel of gdn.cu.
+// GDN / IGDN forward on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//
+//   n[pix, i] = sum_j p[pix, j] * gamma[j, i]      p = |x|, x^2 or relu(x) variants (py/layers/gdn.py:377-398)
+//
+// is a [n_pix x C] x [C x C] GEMM with 2*C^2 FLOP per 8*C bytes of HBM traffic: on fp32 CUDA cores it is
+// compute bound at ~1/3 of the HBM roofline.  Here the contraction runs as  tcgen05.mma kind::f16  on an
+// error-compensated bf16 split (3 products: hi*hi + lo*hi + hi*lo, fp32 accumulation in TMEM), which keeps the
+// result within ~4e-6 of fp32 (the contract is 1e-5) at bf16 tensor throughput.
+//
+// One CTA per SM, persistent over 128-pixel tiles.  gamma's hi/lo planes live in shared memory for the whole
+// launch in the UMMA "K-major, no swizzle" core-matrix layout ([K/8][N][8] bf16, LBO = N*16 B, SBO = 128 B).
+// Per tile, K is consumed in chunks of 64 channels:
+//   cp.async x[128, 64] fp32 -> staging  ->  threads split |x| into bf16 hi/lo operand planes
+//   ([8][128][8] bf16 each, LBO = 2048 B, SBO = 128 B)  ->  fence.proxy.async  ->  one thread issues 4 K-steps x
+//   3 MMAs (M=128, N=C, K=16)  ->  tcgen05.commit -> mbarrier.
+// Epilogue, 64 output channels at a time: tcgen05.ld (warp w owns TMEM lanes 32*(w%4)..) -> staging ->
+// coalesced pass  y = x / (beta + n)  with x re-read from L2.
+//
+// Everything outside {C in {128, 192}, alpha in {1, 2}, eps in {1, 0.5}} falls back to the fp32 kernels in gdn.cu.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace tfcb {
+namespace {
 
-int gdn_tc_forward(const float*, const float*, const float*, float*, long long, int, int, float, float,
-                   cudaStream_t, bool* handled) {
-  *handled = false;
+constexpr int kTileM = 128;    // pixels per tile (UMMA M)
+constexpr int kChunkK = 64;    // input channels per operand chunk
+constexpr int kStageLd = 68;   // staging row stride in floats (64 + 4: conflict-free 128-bit row access)
+constexpr int kTcThreads = 256;
+
+struct TcFlags {
+  int inverse, rectify, alpha_mode, eps_mode;  // alpha_mode: 1 |u|, 2 u^2; eps_mode: 1 identity, 2 sqrt
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+// bits [0,14) start >> 4, [16,30) leading byte offset >> 4 (between the two 8-element K chunks of one MMA),
+// [32,46) stride byte offset >> 4 (between 8-row groups), [46,48) version = 1, [61,64) layout = 0.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+
+// Instruction descriptor for kind::f16: D = f32 (bits [4,6) = 1), A = B = bf16 ([7,10) = [10,13) = 1), both
+// K-major ([15], [16] = 0), N >> 3 at [17,23), M >> 4 at [24,29).
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint32_t mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+}
+
+__device__ __forceinline__ bool mbar_wait(uint32_t mbar, uint32_t parity) {
+  for (int spin = 0; spin < (1 << 24); ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(mbar), "r"(parity)
+        : "memory");
+    if (done) return true;
+  }
+  return false;  // never spin forever on a bad descriptor: the host reports an error instead of hanging
+}
+
+__device__ __forceinline__ float tc_pool(float x, const TcFlags& f) {
+  const float u = f.rectify ? fmaxf(x, 0.f) : x;
+  if (f.alpha_mode == 2) return u * u;
+  return f.rectify ? u : fabsf(u);
+}
+
+__device__ __forceinline__ float tc_out(float x, float n, const TcFlags& f) {
+  const float u = f.rectify ? fmaxf(x, 0.f) : x;
+  const float m = (f.eps_mode == 2) ? sqrtf(n) : n;
+  return f.inverse ? u * m : u / m;
+}
+
+// bf16 split of 8 consecutive values -> two 16-byte rows of the hi / lo operand planes
+__device__ __forceinline__ void split8(const float (&v)[8], uint4* hi, uint4* lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * i] - __bfloat162float(h0));
+    const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h1));
+    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  }
+  *hi = make_uint4(h[0], h[1], h[2], h[3]);
+  *lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// gamma [C, C] fp32 (gamma[j, i]) -> hi / lo bf16 planes in the B-operand layout [j / 8][i][j % 8].
+__global__ void gdn_tc_prep_kernel(const float* __restrict__ gamma, int C, __nv_bfloat16* __restrict__ planes) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over (j / 8, i)
+  if (idx >= (C / 8) * C) return;
+  const int jc = idx / C, i = idx % C;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = gamma[(jc * 8 + e) * C + i];
+  uint4 hi, lo;
+  split8(v, &hi, &lo);
+  reinterpret_cast<uint4*>(planes)[idx] = hi;
+  reinterpret_cast<uint4*>(planes + (size_t)C * C)[idx] = lo;
+}
+
+template <int C>
+struct TcSmem {
+  static constexpr int kPlaneB = C * C * 2;                 // one gamma plane
+  static constexpr int kPlaneA = kTileM * kChunkK * 2;      // one operand-chunk plane (16 KB)
+  static constexpr int kStage = kTileM * kStageLd * 4;      // fp32 staging (34 KB)
+  static constexpr int kOffBh = 0;
+  static constexpr int kOffBl = kOffBh + kPlaneB;
+  static constexpr int kOffAh = kOffBl + kPlaneB;
+  static constexpr int kOffAl = kOffAh + kPlaneA;
+  static constexpr int kOffStage = kOffAl + kPlaneA;
+  static constexpr int kOffBeta = kOffStage + kStage;
+  static constexpr int kOffBar = kOffBeta + C * 4;
+  static constexpr int kBytes = kOffBar + 64;
+};
+
+template <int C>
+__global__ void __launch_bounds__(kTcThreads, 1)
+gdn_tc_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ planes,
+                  const float* __restrict__ beta, float* __restrict__ y, long long n_pix, TcFlags f) {
+  using L = TcSmem<C>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float* stage = reinterpret_cast<float*>(smem + L::kOffStage);
+  float* beta_s = reinterpret_cast<float*>(smem + L::kOffBeta);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffBar + 8);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  constexpr int kTmemCols = (C <= 128) ? 128 : 256;
+  constexpr uint32_t kIdesc = umma_idesc(kTileM, C);
+
+  // ---- one-time setup: gamma planes -> smem, beta, mbarrier, TMEM ----
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(planes);
+    uint4* dst = reinterpret_cast<uint4*>(smem + L::kOffBh);
+    for (int i = tid; i < 2 * L::kPlaneB / 16; i += kTcThreads) dst[i] = src[i];
+    for (int i = tid; i < C; i += kTcThreads) beta_s[i] = beta[i];
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // plane stores -> visible to the tensor core
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t mbar_addr = smem_u32(mbar);
+  const uint32_t a_hi = smem_u32(smem + L::kOffAh), a_lo = smem_u32(smem + L::kOffAl);
+  const uint32_t b_hi = smem_u32(smem + L::kOffBh), b_lo = smem_u32(smem + L::kOffBl);
+  uint32_t parity = 0;
+
+  const long long n_tiles = (n_pix + kTileM - 1) / kTileM;
+  for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const long long p0 = t * kTileM;
+    // ================= mainloop over K chunks =================
+    for (int kc = 0; kc < C / kChunkK; ++kc) {
+      // (1) x[p0 .. p0+127, kc*64 .. +63] -> staging, 16 B per cp.async
+#pragma unroll
+      for (int it = 0; it < (kTileM * kChunkK / 4) / kTcThreads; ++it) {
+        const int idx = it * kTcThreads + tid;
+        const int row = idx >> 4, c4 = idx & 15;
+        float* dst = stage + row * kStageLd + c4 * 4;
+        if (p0 + row < n_pix) {
+          const float* src = x + (p0 + row) * C + kc * kChunkK + c4 * 4;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+        } else {
+          *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+      // (2) pool + bf16 split -> operand planes ([kchunk][row][8] bf16)
+      {
+        const int row = tid & (kTileM - 1), half = tid >> 7;  // 2 threads per row, 32 channels each
+        const float* src = stage + row * kStageLd + half * 32;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 v0 = *reinterpret_cast<const float4*>(src + q * 8);
+          const float4 v1 = *reinterpret_cast<const float4*>(src + q * 8 + 4);
+          float v[8] = {tc_pool(v0.x, f), tc_pool(v0.y, f), tc_pool(v0.z, f), tc_pool(v0.w, f),
+                        tc_pool(v1.x, f), tc_pool(v1.y, f), tc_pool(v1.z, f), tc_pool(v1.w, f)};
+          uint4 hi, lo;
+          split8(v, &hi, &lo);
+          const int kchunk = half * 4 + q;
+          *reinterpret_cast<uint4*>(smem + L::kOffAh + kchunk * (kTileM * 16) + row * 16) = hi;
+          *reinterpret_cast<uint4*>(smem + L::kOffAl + kchunk * (kTileM * 16) + row * 16) = lo;
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      // (3) one thread issues the MMAs of this chunk: 4 K-steps x (hi*hi + lo*hi + hi*lo)
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int s = 0; s < kChunkK / 16; ++s) {
+          const uint32_t a_off = (uint32_t)(2 * s) * (kTileM * 16);
+          const uint32_t b_off = (uint32_t)(kc * (kChunkK / 8) + 2 * s) * (C * 16);
+          const uint64_t dah = umma_desc(a_hi + a_off, kTileM * 16, 128);
+          const uint64_t dal = umma_desc(a_lo + a_off, kTileM * 16, 128);
+          const uint64_t dbh = umma_desc(b_hi + b_off, C * 16, 128);
+          const uint64_t dbl = umma_desc(b_lo + b_off, C * 16, 128);
+          umma_bf16(tmem_base, dah, dbh, kIdesc, (kc | s) ? 1u : 0u);
+          umma_bf16(tmem_base, dal, dbh, kIdesc, 1u);
+          umma_bf16(tmem_base, dah, dbl, kIdesc, 1u);
+        }
+        umma_commit(mbar_addr);  // arrives when every MMA issued so far has read its operands and written D
+      }
+      // (4) operand planes / staging are reused by the next chunk: wait for the tensor core
+      if (!mbar_wait(mbar_addr, parity)) __trap();  // a descriptor bug must fail loudly, never hang the GPU
+      parity ^= 1u;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    // ================= epilogue: 64 output channels at a time =================
+    for (int cc = 0; cc < C / 64; ++cc) {
+      {
+        const int q = warp & 3, h = warp >> 2;  // TMEM lane quarter, 32-column half
+        const int row = q * 32 + (tid & 31);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 64 + h * 32);
+        uint32_t r[32];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+              "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+              "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float* dst = stage + row * kStageLd + h * 32;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<float4*>(dst + 4 * i) =
+              make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                          __uint_as_float(r[4 * i + 3]));
+      }
+      __syncthreads();
+#pragma unroll
+      for (int it = 0; it < (kTileM * 64 / 4) / kTcThreads; ++it) {
+        const int idx = it * kTcThreads + tid;
+        const int row = idx >> 4, c4 = idx & 15;
+        if (p0 + row < n_pix) {
+          const long long g = (p0 + row) * C + cc * 64 + c4 * 4;
+          const float4 xv = __ldg(reinterpret_cast<const float4*>(x + g));
+          const float4 nv = *reinterpret_cast<const float4*>(stage + row * kStageLd + c4 * 4);
+          const float4 bv = *reinterpret_cast<const float4*>(beta_s + cc * 64 + c4 * 4);
+          float4 o;
+          o.x = tc_out(xv.x, bv.x + nv.x, f);
+          o.y = tc_out(xv.y, bv.y + nv.y, f);
+          o.z = tc_out(xv.z, bv.z + nv.z, f);
+          o.w = tc_out(xv.w, bv.w + nv.w, f);
+          *reinterpret_cast<float4*>(y + g) = o;
+        }
+      }
+      __syncthreads();
+    }
+    // TMEM is overwritten by the next tile's first MMA: order the tcgen05.ld's before it
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+  }
+}
+
+template <int C>
+int launch_tc(const float* x, const float* gamma, const float* beta, float* y, long long n_pix, TcFlags f,
+              cudaStream_t s) {
+  using L = TcSmem<C>;
+  __nv_bfloat16* planes = nullptr;
+  TFCB_TRY(dev_alloc((void**)&planes, (size_t)2 * C * C * sizeof(__nv_bfloat16), s));
+  gdn_tc_prep_kernel<<<((C / 8) * C + 255) / 256, 256, 0, s>>>(gamma, C, planes);
+  TFCB_LAUNCHED();
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gdn_tc_fwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      dev_free(planes, s);
+      return fail(TFCB_CUDA_ERROR, "cannot reserve %d bytes of shared memory: %s", L::kBytes, cudaGetErrorString(e));
+    }
+    attr_set = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long n_tiles = (n_pix + kTileM - 1) / kTileM;
+  const int grid = (int)std::min<long long>(n_tiles, sms);
+  gdn_tc_fwd_kernel<C><<<grid, kTcThreads, L::kBytes, s>>>(x, planes, beta, y, n_pix, f);
+  TFCB_LAUNCHED();
+  cudaError_t e = cudaGetLastError();
+  dev_free(planes, s);  // stream ordered: released after the kernel
+  if (e != cudaSuccess) return fail(TFCB_CUDA_ERROR, "GDN tensor-core kernel launch failed: %s", cudaGetErrorString(e));
   return TFCB_OK;
+}
+
+}  // namespace
+
+int gdn_tc_forward(const float* x, const float* gamma, const float* beta, float* y, long long n_pix, int C,
+                   int flags, float alpha, float eps, cudaStream_t s, bool* handled) {
+  *handled = false;
+  if (!(C == 128 || C == 192)) return TFCB_OK;
+  if (!(alpha == 1.f || alpha == 2.f) || !(eps == 1.f || eps == 0.5f)) return TFCB_OK;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) return TFCB_OK;  // 16-byte rows
+  if (const char* env = getenv("TFCB_GDN_FP32")) {
+    if (env[0] == '1') return TFCB_OK;  // debugging aid: force the CUDA-core kernels
+  }
+  TcFlags f;
+  f.inverse = (flags & TFCB_GDN_INVERSE) ? 1 : 0;
+  f.rectify = (flags & TFCB_GDN_RECTIFY) ? 1 : 0;
+  f.alpha_mode = (alpha == 2.f) ? 2 : 1;
+  f.eps_mode = (eps == 0.5f) ? 2 : 1;
+  *handled = true;
+  if (C == 128) return launch_tc<128>(x, gamma, beta, y, n_pix, f, s);
+  return launch_tc<192>(x, gamma, beta, y, n_pix, f, s);
 }
 
 }  // namespace tfcb
