@@ -25,8 +25,8 @@ namespace tfcb {
 namespace {
 
 constexpr int kTileM = 128;    // pixels per tile (UMMA M)
-constexpr int kChunkK = 64;    // input channels per operand chunk
-constexpr int kStageLd = 68;   // staging row stride in floats (64 + 4: conflict-free 128-bit row access)
+constexpr int kChunkK = 32;    // input channels per operand chunk
+constexpr int kStageLd = 36;   // staging row stride in floats (32 + 4: conflict-free 128-bit row access)
 constexpr int kTcThreads = 256;
 
 struct TcFlags {
@@ -82,28 +82,43 @@ __device__ __forceinline__ bool mbar_wait(uint32_t mbar, uint32_t parity) {
   return false;  // never spin forever on a bad descriptor: the host reports an error instead of hanging
 }
 
+// FAST = the default GDN / IGDN of bls2017 / bmshj2018 (alpha = 1, epsilon = 1, no rectification): no
+// per-element branches.  Otherwise the runtime flags are honoured.
+template <bool FAST>
 __device__ __forceinline__ float tc_pool(float x, const TcFlags& f) {
+  if (FAST) return fabsf(x);
   const float u = f.rectify ? fmaxf(x, 0.f) : x;
   if (f.alpha_mode == 2) return u * u;
   return f.rectify ? u : fabsf(u);
 }
 
+// y = u / m (GDN) or u * m (IGDN).  The quotient uses the hardware reciprocal (MUFU.RCP, <= 2 ulp): an IEEE
+// divide costs ~20 instructions per element, which made the whole kernel ALU bound (ncu, profiles/), and
+// 2.4e-7 is far inside the 1e-5 contract.
+template <bool FAST>
 __device__ __forceinline__ float tc_out(float x, float n, const TcFlags& f) {
+  if (FAST) return f.inverse ? x * n : __fdividef(x, n);
   const float u = f.rectify ? fmaxf(x, 0.f) : x;
   const float m = (f.eps_mode == 2) ? sqrtf(n) : n;
-  return f.inverse ? u * m : u / m;
+  return f.inverse ? u * m : __fdividef(u, m);
 }
 
-// bf16 split of 8 consecutive values -> two 16-byte rows of the hi / lo operand planes
+// bf16 split of 8 consecutive values -> two 16-byte rows of the hi / lo operand planes.
+// Packed conversions (cvt.rn.bf16x2.f32) and integer re-expansion of the hi part keep this at ~3
+// instructions per element.
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
+}
+
 __device__ __forceinline__ void split8(const float (&v)[8], uint4* hi, uint4* lo) {
   uint32_t h[4], l[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * i] - __bfloat162float(h0));
-    const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h1));
-    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    h[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+    const float h0 = __uint_as_float(h[i] << 16), h1 = __uint_as_float(h[i] & 0xFFFF0000u);
+    l[i] = pack_bf16x2(v[2 * i] - h0, v[2 * i + 1] - h1);
   }
   *hi = make_uint4(h[0], h[1], h[2], h[3]);
   *lo = make_uint4(l[0], l[1], l[2], l[3]);
@@ -123,36 +138,54 @@ __global__ void gdn_tc_prep_kernel(const float* __restrict__ gamma, int C, __nv_
   reinterpret_cast<uint4*>(planes + (size_t)C * C)[idx] = lo;
 }
 
-template <int C>
+// G independent thread groups per CTA (each runs the tile pipeline on its own tiles with its own staging,
+// operand planes, TMEM columns and mbarriers); they share gamma's planes.  Two groups per CTA give the same
+// latency overlap as two CTAs per SM would, which the 64-147 KB of gamma planes rules out.
+//
+// Inside a group the K chunks (32 channels) of all its tiles form one software pipeline with double-buffered
+// staging and operand planes:
+//   step i :  cp.async(chunk i+1)  |  wait chunk i  |  (planes[b] free <- MMAs of chunk i-2 done)  |
+//             convert chunk i -> planes[b]  |  issue MMAs(chunk i), commit -> mbar[b]
+//   last chunk of a tile: wait mbar[b], epilogue through staging[b] (staging[b^1] is receiving chunk i+1).
+template <int C, int G>
 struct TcSmem {
   static constexpr int kPlaneB = C * C * 2;                 // one gamma plane
-  static constexpr int kPlaneA = kTileM * kChunkK * 2;      // one operand-chunk plane (16 KB)
-  static constexpr int kStage = kTileM * kStageLd * 4;      // fp32 staging (34 KB)
+  static constexpr int kPlaneA = kTileM * kChunkK * 2;      // one operand-chunk plane (8 KB)
+  static constexpr int kStage = kTileM * kStageLd * 4;      // fp32 staging (18 KB)
+  static constexpr int kBuf = 2 * kPlaneA + kStage;         // one pipeline buffer: hi plane, lo plane, staging
+  static constexpr int kGroup = 2 * kBuf;                   // double buffered
   static constexpr int kOffBh = 0;
   static constexpr int kOffBl = kOffBh + kPlaneB;
-  static constexpr int kOffAh = kOffBl + kPlaneB;
-  static constexpr int kOffAl = kOffAh + kPlaneA;
-  static constexpr int kOffStage = kOffAl + kPlaneA;
-  static constexpr int kOffBeta = kOffStage + kStage;
+  static constexpr int kOffGroups = kOffBl + kPlaneB;
+  static constexpr int kOffBeta = kOffGroups + G * kGroup;
   static constexpr int kOffBar = kOffBeta + C * 4;
   static constexpr int kBytes = kOffBar + 64;
 };
 
-template <int C>
+__device__ __forceinline__ void group_sync(int g, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(count) : "memory");
+}
+
+template <int C, int G, bool FAST>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gdn_tc_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ planes,
                   const float* __restrict__ beta, float* __restrict__ y, long long n_pix, TcFlags f) {
-  using L = TcSmem<C>;
+  using L = TcSmem<C, G>;
+  constexpr int TPG = kTcThreads / G;         // threads per group
+  constexpr int TPR = TPG / kTileM;           // threads per pixel row in the convert stage (1 or 2)
+  constexpr int CPT = kChunkK / TPR;          // input channels per convert thread and chunk (32 or 16)
+  constexpr int NCH = C / kChunkK;            // K chunks per tile
+  constexpr int LDS_PER_T = (kTileM * kChunkK / 4) / TPG;  // float4 per thread for one [128 x 32] block
   extern __shared__ __align__(1024) uint8_t smem[];
-  float* stage = reinterpret_cast<float*>(smem + L::kOffStage);
   float* beta_s = reinterpret_cast<float*>(smem + L::kOffBeta);
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffBar + 8);
-  const int tid = threadIdx.x, warp = tid >> 5;
-  constexpr int kTmemCols = (C <= 128) ? 128 : 256;
+  uint64_t* mbars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);  // [G][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffBar + 48);
+  const int tid = threadIdx.x;
+  const int g = tid / TPG, gtid = tid % TPG, gwarp = gtid >> 5;
+  constexpr int kTmemCols = (G * C <= 128) ? 128 : ((G * C <= 256) ? 256 : 512);
   constexpr uint32_t kIdesc = umma_idesc(kTileM, C);
 
-  // ---- one-time setup: gamma planes -> smem, beta, mbarrier, TMEM ----
+  // ---- one-time setup: gamma planes -> smem, beta, mbarriers, TMEM ----
   {
     const uint4* src = reinterpret_cast<const uint4*>(planes);
     uint4* dst = reinterpret_cast<uint4*>(smem + L::kOffBh);
@@ -160,10 +193,11 @@ gdn_tc_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__
     for (int i = tid; i < C; i += kTcThreads) beta_s[i] = beta[i];
   }
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
+    for (int i = 0; i < 2 * G; ++i)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbars + i)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {
+  if (tid < 32) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"(kTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -172,80 +206,135 @@ gdn_tc_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t mbar_addr = smem_u32(mbar);
-  const uint32_t a_hi = smem_u32(smem + L::kOffAh), a_lo = smem_u32(smem + L::kOffAl);
+  const uint32_t tmem_base = *tmem_slot + (uint32_t)(g * C);  // this group's accumulator columns
+  uint8_t* gbuf = smem + L::kOffGroups + g * L::kGroup;
   const uint32_t b_hi = smem_u32(smem + L::kOffBh), b_lo = smem_u32(smem + L::kOffBl);
-  uint32_t parity = 0;
+  uint32_t par[2] = {0u, 0u};  // phase parity of mbar[0], mbar[1]
+  uint32_t pending[2] = {0u, 0u};  // a commit on mbar[b] has not been waited for yet
 
   const long long n_tiles = (n_pix + kTileM - 1) / kTileM;
-  for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    const long long p0 = t * kTileM;
-    // ================= mainloop over K chunks =================
-    for (int kc = 0; kc < C / kChunkK; ++kc) {
-      // (1) x[p0 .. p0+127, kc*64 .. +63] -> staging, 16 B per cp.async
+  const long long t_step = (long long)gridDim.x * G;
+  const long long t_first = (long long)blockIdx.x * G + g;
+  const long long my_tiles = (t_first < n_tiles) ? (n_tiles - t_first + t_step - 1) / t_step : 0;
+  const long long n_steps = my_tiles * NCH;
+
+  auto issue_load = [&](long long step) {
+    const long long tile = t_first + (step / NCH) * t_step;
+    const int kc = (int)(step % NCH), b = (int)(step & 1);
+    const long long p0 = tile * kTileM;
+    float* stage = reinterpret_cast<float*>(gbuf + b * L::kBuf + 2 * L::kPlaneA);
 #pragma unroll
-      for (int it = 0; it < (kTileM * kChunkK / 4) / kTcThreads; ++it) {
-        const int idx = it * kTcThreads + tid;
-        const int row = idx >> 4, c4 = idx & 15;
-        float* dst = stage + row * kStageLd + c4 * 4;
-        if (p0 + row < n_pix) {
-          const float* src = x + (p0 + row) * C + kc * kChunkK + c4 * 4;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-        } else {
-          *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+    for (int it = 0; it < LDS_PER_T; ++it) {
+      const int idx = it * TPG + gtid;
+      const int row = idx >> 3, c4 = idx & 7;
+      float* dst = stage + row * kStageLd + c4 * 4;
+      if (p0 + row < n_pix) {
+        const float* src = x + (p0 + row) * C + kc * kChunkK + c4 * 4;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+      } else {
+        *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      __syncthreads();
-      // (2) pool + bf16 split -> operand planes ([kchunk][row][8] bf16)
-      {
-        const int row = tid & (kTileM - 1), half = tid >> 7;  // 2 threads per row, 32 channels each
-        const float* src = stage + row * kStageLd + half * 32;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 v0 = *reinterpret_cast<const float4*>(src + q * 8);
-          const float4 v1 = *reinterpret_cast<const float4*>(src + q * 8 + 4);
-          float v[8] = {tc_pool(v0.x, f), tc_pool(v0.y, f), tc_pool(v0.z, f), tc_pool(v0.w, f),
-                        tc_pool(v1.x, f), tc_pool(v1.y, f), tc_pool(v1.z, f), tc_pool(v1.w, f)};
-          uint4 hi, lo;
-          split8(v, &hi, &lo);
-          const int kchunk = half * 4 + q;
-          *reinterpret_cast<uint4*>(smem + L::kOffAh + kchunk * (kTileM * 16) + row * 16) = hi;
-          *reinterpret_cast<uint4*>(smem + L::kOffAl + kchunk * (kTileM * 16) + row * 16) = lo;
-        }
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncthreads();
-      // (3) one thread issues the MMAs of this chunk: 4 K-steps x (hi*hi + lo*hi + hi*lo)
-      if (tid == 0) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-        for (int s = 0; s < kChunkK / 16; ++s) {
-          const uint32_t a_off = (uint32_t)(2 * s) * (kTileM * 16);
-          const uint32_t b_off = (uint32_t)(kc * (kChunkK / 8) + 2 * s) * (C * 16);
-          const uint64_t dah = umma_desc(a_hi + a_off, kTileM * 16, 128);
-          const uint64_t dal = umma_desc(a_lo + a_off, kTileM * 16, 128);
-          const uint64_t dbh = umma_desc(b_hi + b_off, C * 16, 128);
-          const uint64_t dbl = umma_desc(b_lo + b_off, C * 16, 128);
-          umma_bf16(tmem_base, dah, dbh, kIdesc, (kc | s) ? 1u : 0u);
-          umma_bf16(tmem_base, dal, dbh, kIdesc, 1u);
-          umma_bf16(tmem_base, dah, dbl, kIdesc, 1u);
-        }
-        umma_commit(mbar_addr);  // arrives when every MMA issued so far has read its operands and written D
-      }
-      // (4) operand planes / staging are reused by the next chunk: wait for the tensor core
-      if (!mbar_wait(mbar_addr, parity)) __trap();  // a descriptor bug must fail loudly, never hang the GPU
-      parity ^= 1u;
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
-    // ================= epilogue: 64 output channels at a time =================
-    for (int cc = 0; cc < C / 64; ++cc) {
-      {
-        const int q = warp & 3, h = warp >> 2;  // TMEM lane quarter, 32-column half
-        const int row = q * 32 + (tid & 31);
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 64 + h * 32);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  if (n_steps > 0) issue_load(0);
+  for (long long step = 0; step < n_steps; ++step) {
+    const long long tile = t_first + (step / NCH) * t_step;
+    const int kc = (int)(step % NCH), b = (int)(step & 1);
+    const long long p0 = tile * kTileM;
+    uint8_t* ah_p = gbuf + b * L::kBuf;
+    uint8_t* al_p = ah_p + L::kPlaneA;
+    float* stage = reinterpret_cast<float*>(ah_p + 2 * L::kPlaneA);
+    const uint32_t mbar_addr = smem_u32(mbars + 2 * g + b);
+
+    // (0) next chunk's load goes out first; at the start of a tile also pull the group's next tile into L2
+    if (step + 1 < n_steps) {
+      issue_load(step + 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");  // chunk `step` has landed, `step + 1` is in flight
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    if (kc == 0) {
+      const long long pn = (tile + t_step) * kTileM;
+      const long long rows = min((long long)kTileM, n_pix - pn);
+      if (rows > 0) {
+        const char* base = reinterpret_cast<const char*>(x + pn * C);
+        const long long bytes = rows * C * 4;
+        for (long long off = (long long)gtid * 128; off < bytes; off += (long long)TPG * 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+      }
+    }
+    // (1) the operand planes of this buffer were read by the MMAs of chunk step-2: wait for them
+    if (pending[b]) {
+      if (!mbar_wait(mbar_addr, par[b])) __trap();  // a descriptor bug must fail loudly, never hang the GPU
+      par[b] ^= 1u;
+      pending[b] = 0u;
+    }
+    group_sync(g, TPG);  // every thread's cp.async of this chunk is visible
+    // (2) pool + bf16 split -> operand planes ([kchunk][row][8] bf16)
+    {
+      const int row = gtid & (kTileM - 1), part = gtid >> 7;
+      const float* src = stage + row * kStageLd + part * CPT;
+#pragma unroll
+      for (int q = 0; q < CPT / 8; ++q) {
+        const float4 v0 = *reinterpret_cast<const float4*>(src + q * 8);
+        const float4 v1 = *reinterpret_cast<const float4*>(src + q * 8 + 4);
+        float v[8] = {tc_pool<FAST>(v0.x, f), tc_pool<FAST>(v0.y, f), tc_pool<FAST>(v0.z, f), tc_pool<FAST>(v0.w, f),
+                      tc_pool<FAST>(v1.x, f), tc_pool<FAST>(v1.y, f), tc_pool<FAST>(v1.z, f), tc_pool<FAST>(v1.w, f)};
+        uint4 hi, lo;
+        split8(v, &hi, &lo);
+        const int kchunk = part * (CPT / 8) + q;
+        *reinterpret_cast<uint4*>(ah_p + kchunk * (kTileM * 16) + row * 16) = hi;
+        *reinterpret_cast<uint4*>(al_p + kchunk * (kTileM * 16) + row * 16) = lo;
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    group_sync(g, TPG);
+    // (3) one thread issues the MMAs of this chunk: 2 K-steps x (hi*hi + lo*hi + hi*lo)
+    if (gtid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a_hi = smem_u32(ah_p), a_lo = smem_u32(al_p);
+#pragma unroll
+      for (int s = 0; s < kChunkK / 16; ++s) {
+        const uint32_t a_off = (uint32_t)(2 * s) * (kTileM * 16);
+        const uint32_t b_off = (uint32_t)(kc * (kChunkK / 8) + 2 * s) * (C * 16);
+        const uint64_t dah = umma_desc(a_hi + a_off, kTileM * 16, 128);
+        const uint64_t dal = umma_desc(a_lo + a_off, kTileM * 16, 128);
+        const uint64_t dbh = umma_desc(b_hi + b_off, C * 16, 128);
+        const uint64_t dbl = umma_desc(b_lo + b_off, C * 16, 128);
+        umma_bf16(tmem_base, dah, dbh, kIdesc, (kc | s) ? 1u : 0u);
+        umma_bf16(tmem_base, dal, dbh, kIdesc, 1u);
+        umma_bf16(tmem_base, dah, dbl, kIdesc, 1u);
+      }
+      umma_commit(mbar_addr);  // arrives when every MMA issued so far has completed
+    }
+    pending[b] = 1u;
+    if (kc != NCH - 1) continue;
+
+    // ================= end of tile: epilogue, 32 output channels at a time =================
+    if (!mbar_wait(mbar_addr, par[b])) __trap();
+    par[b] ^= 1u;
+    pending[b] = 0u;
+    if (pending[b ^ 1]) {  // the commit of chunk step-1 completed earlier (commits complete in order): consume its phase
+      if (!mbar_wait(smem_u32(mbars + 2 * g + (b ^ 1)), par[b ^ 1])) __trap();
+      par[b ^ 1] ^= 1u;
+      pending[b ^ 1] = 0u;
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    for (int cc = 0; cc < C / 32; ++cc) {
+      // x of this column block: coalesced re-read (L2 hits), issued before the TMEM round trip
+      float4 xv[LDS_PER_T];
+#pragma unroll
+      for (int it = 0; it < LDS_PER_T; ++it) {
+        const int idx = it * TPG + gtid;
+        const int row = idx >> 3, c4 = idx & 7;
+        xv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p0 + row < n_pix) xv[it] = __ldg(reinterpret_cast<const float4*>(x + (p0 + row) * C + cc * 32 + c4 * 4));
+      }
+      if (gwarp < 4) {  // one warp per TMEM lane quarter
+        const int row = gwarp * 32 + (gtid & 31);
+        const uint32_t taddr = tmem_base + ((uint32_t)(gwarp * 32) << 16) + (uint32_t)(cc * 32);
         uint32_t r[32];
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -258,54 +347,53 @@ gdn_tc_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__
               "=r"(r[30]), "=r"(r[31])
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        float* dst = stage + row * kStageLd + h * 32;
+        float* dst = stage + row * kStageLd;
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           *reinterpret_cast<float4*>(dst + 4 * i) =
               make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
                           __uint_as_float(r[4 * i + 3]));
       }
-      __syncthreads();
+      group_sync(g, TPG);
 #pragma unroll
-      for (int it = 0; it < (kTileM * 64 / 4) / kTcThreads; ++it) {
-        const int idx = it * kTcThreads + tid;
-        const int row = idx >> 4, c4 = idx & 15;
+      for (int it = 0; it < LDS_PER_T; ++it) {
+        const int idx = it * TPG + gtid;
+        const int row = idx >> 3, c4 = idx & 7;
         if (p0 + row < n_pix) {
-          const long long g = (p0 + row) * C + cc * 64 + c4 * 4;
-          const float4 xv = __ldg(reinterpret_cast<const float4*>(x + g));
           const float4 nv = *reinterpret_cast<const float4*>(stage + row * kStageLd + c4 * 4);
-          const float4 bv = *reinterpret_cast<const float4*>(beta_s + cc * 64 + c4 * 4);
+          const float4 bv = *reinterpret_cast<const float4*>(beta_s + cc * 32 + c4 * 4);
           float4 o;
-          o.x = tc_out(xv.x, bv.x + nv.x, f);
-          o.y = tc_out(xv.y, bv.y + nv.y, f);
-          o.z = tc_out(xv.z, bv.z + nv.z, f);
-          o.w = tc_out(xv.w, bv.w + nv.w, f);
-          *reinterpret_cast<float4*>(y + g) = o;
+          o.x = tc_out<FAST>(xv[it].x, bv.x + nv.x, f);
+          o.y = tc_out<FAST>(xv[it].y, bv.y + nv.y, f);
+          o.z = tc_out<FAST>(xv[it].z, bv.z + nv.z, f);
+          o.w = tc_out<FAST>(xv[it].w, bv.w + nv.w, f);
+          *reinterpret_cast<float4*>(y + (p0 + row) * C + cc * 32 + c4 * 4) = o;
         }
       }
-      __syncthreads();
+      group_sync(g, TPG);
     }
     // TMEM is overwritten by the next tile's first MMA: order the tcgen05.ld's before it
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    group_sync(g, TPG);
   }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+  if (tid < 32) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "r"(kTmemCols));
   }
 }
 
-template <int C>
+template <int C, int G, bool FAST>
 int launch_tc(const float* x, const float* gamma, const float* beta, float* y, long long n_pix, TcFlags f,
               cudaStream_t s) {
-  using L = TcSmem<C>;
+  using L = TcSmem<C, G>;
   __nv_bfloat16* planes = nullptr;
   TFCB_TRY(dev_alloc((void**)&planes, (size_t)2 * C * C * sizeof(__nv_bfloat16), s));
   gdn_tc_prep_kernel<<<((C / 8) * C + 255) / 256, 256, 0, s>>>(gamma, C, planes);
   TFCB_LAUNCHED();
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gdn_tc_fwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes);
+    cudaError_t e = cudaFuncSetAttribute(gdn_tc_fwd_kernel<C, G, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes);
     if (e != cudaSuccess) {
       (void)cudaGetLastError();
       dev_free(planes, s);
@@ -317,8 +405,8 @@ int launch_tc(const float* x, const float* gamma, const float* beta, float* y, l
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long n_tiles = (n_pix + kTileM - 1) / kTileM;
-  const int grid = (int)std::min<long long>(n_tiles, sms);
-  gdn_tc_fwd_kernel<C><<<grid, kTcThreads, L::kBytes, s>>>(x, planes, beta, y, n_pix, f);
+  const int grid = (int)std::min<long long>((n_tiles + G - 1) / G, sms);
+  gdn_tc_fwd_kernel<C, G, FAST><<<grid, kTcThreads, L::kBytes, s>>>(x, planes, beta, y, n_pix, f);
   TFCB_LAUNCHED();
   cudaError_t e = cudaGetLastError();
   dev_free(planes, s);  // stream ordered: released after the kernel
@@ -343,8 +431,14 @@ int gdn_tc_forward(const float* x, const float* gamma, const float* beta, float*
   f.alpha_mode = (alpha == 2.f) ? 2 : 1;
   f.eps_mode = (eps == 0.5f) ? 2 : 1;
   *handled = true;
-  if (C == 128) return launch_tc<128>(x, gamma, beta, y, n_pix, f, s);
-  return launch_tc<192>(x, gamma, beta, y, n_pix, f, s);
+  const bool fast = (alpha == 1.f) && (eps == 1.f) && !f.rectify;
+  if (C == 128) {  // 198 KB of shared memory: two tile pipelines per CTA
+    return fast ? launch_tc<128, 2, true>(x, gamma, beta, y, n_pix, f, s)
+                : launch_tc<128, 2, false>(x, gamma, beta, y, n_pix, f, s);
+  }
+  // C == 192: 216 KB, gamma's planes leave room for one pipeline
+  return fast ? launch_tc<192, 1, true>(x, gamma, beta, y, n_pix, f, s)
+              : launch_tc<192, 1, false>(x, gamma, beta, y, n_pix, f, s);
 }
 
 }  // namespace tfcb
