@@ -88,13 +88,15 @@ int parse_lookup(const int32_t* lookup, int64_t len, int64_t cols, std::vector<H
 struct DeviceLookup {
   int32_t* lookup = nullptr;  // device copy of the raw table
   int2* rows = nullptr;       // {start, meta}
+  uint2* pairs = nullptr;     // decoder: per cdf entry {c', addend_hi} so that hi32(span*c' + {c',addend_hi}) = T(c) - 1
+  int4* rows4 = nullptr;      // decoder: {start, meta, window_lo, 0}
   int n_rows = 0;
   long long len = 0;
   bool any_overflow = false;
   int max_prec = 0;
   int uniform_prec = 0;  // > 0 when every row shares one precision
 
-  int upload(const int32_t* lookup_host, int64_t len_, int64_t cols, cudaStream_t s) {
+  int upload(const int32_t* lookup_host, int64_t len_, int64_t cols, cudaStream_t s, bool for_decoder = false) {
     const int64_t len = len_;
     std::vector<HostRow> hr;
     TFCB_TRY(parse_lookup(lookup_host, len, cols, &hr));
@@ -117,6 +119,33 @@ struct DeviceLookup {
                                     cudaMemcpyHostToDevice, s));
     TFCB_CUDA_TRY(cudaMemcpyAsync(rows, meta.data(), meta.size() * sizeof(int2),
                                   cudaMemcpyHostToDevice, s));
+    std::vector<uint2> hp;
+    std::vector<int4> hr4;
+    if (for_decoder) {
+      // Pre-scaled search keys (see dec2): B'(c) = floor(size*c/2^p) - 1 = hi32(span*c' + {c', 0xFFFFFFFF}) with
+      // c' = c << (32-p); c == 2^p -> {0xFFFFFFFF, 0} (B' = span); c == 0 -> c' = 0 marks "never an upper bound".
+      // window_lo: first index of the 64-entry search window centred on the row's median.
+      hp.assign(std::max<int64_t>(len, 1), make_uint2(0u, 0u));
+      hr4.resize(meta.size());
+      for (size_t i = 0; i < hr.size(); ++i) {
+        const int ap = hr[i].prec < 0 ? -hr[i].prec : hr[i].prec;
+        const int n = hr[i].ncdf - 1;
+        int median = n;
+        for (int e = 0; e < hr[i].ncdf; ++e) {
+          const uint32_t c = (uint32_t)lookup_host[hr[i].start + e];
+          hp[hr[i].start + e] = (c == (1u << ap)) ? make_uint2(0xFFFFFFFFu, 0u) : make_uint2(c << (32 - ap), 0xFFFFFFFFu);
+          if (e >= 1 && median == n && c >= (1u << ap) / 2) median = e;
+        }
+        int wlo = median - 32;
+        if (wlo > n - 63) wlo = n - 63;
+        if (wlo < 0) wlo = 0;
+        hr4[i] = make_int4(meta[i].x, meta[i].y, wlo, 0);
+      }
+      TFCB_TRY(dev_alloc((void**)&pairs, hp.size() * sizeof(uint2), s));
+      TFCB_TRY(dev_alloc((void**)&rows4, hr4.size() * sizeof(int4), s));
+      TFCB_CUDA_TRY(cudaMemcpyAsync(pairs, hp.data(), hp.size() * sizeof(uint2), cudaMemcpyHostToDevice, s));
+      TFCB_CUDA_TRY(cudaMemcpyAsync(rows4, hr4.data(), hr4.size() * sizeof(int4), cudaMemcpyHostToDevice, s));
+    }
     // the host vectors die at return: make sure the copies have been staged
     TFCB_CUDA_TRY(cudaStreamSynchronize(s));
     return TFCB_OK;
@@ -124,8 +153,12 @@ struct DeviceLookup {
   void release(cudaStream_t s) {
     dev_free(lookup, s);
     dev_free(rows, s);
+    dev_free(pairs, s);
+    dev_free(rows4, s);
     lookup = nullptr;
     rows = nullptr;
+    pairs = nullptr;
+    rows4 = nullptr;
   }
 };
 
@@ -782,6 +815,8 @@ struct DecState {
 struct DecParams {
   const int32_t* lookup;
   const int2* rows;
+  const uint2* pairs;
+  const int4* rows4;
   int n_rows;
   long long lookup_len;
   const uint8_t* bytes;
@@ -946,24 +981,242 @@ __device__ __forceinline__ int dec_symbol_fast(DecChain& c, ByteWindow& w, const
   }
 }
 
-template <int MODE, bool SMEM>
-__global__ void __launch_bounds__(32) decode_kernel(const DecParams P) {
-  extern __shared__ __align__(16) int32_t s_tab[];
-  const long long s = blockIdx.x;
-  const int lane = threadIdx.x;
-  if (s >= P.n_streams) return;
-  const int32_t* tab = P.lookup;
-  const int2* rows = P.rows;
-  if (SMEM) {
-    const int ntab = (int)((P.lookup_len + 1) & ~1ll);
-    for (int i = lane; i < (int)P.lookup_len; i += 32) s_tab[i] = P.lookup[i];
-    int2* srows = reinterpret_cast<int2*>(s_tab + ntab);
-    for (int i = lane; i < P.n_rows; i += 32) srows[i] = P.rows[i];
-    __syncwarp();
-    tab = s_tab;
-    rows = srows;
+// ---------------------------------------------------------------------------------------------
+// Decoder v2: three warps per stream (prepare / chain / resolve), pre-scaled search keys
+// ---------------------------------------------------------------------------------------------
+// The decoder has the encoder's recurrence plus a search per symbol.  As in the encoder everything that
+// is not the recurrence leaves the latency-critical warp:
+//   prepare warp : per symbol the row's search window (64 pre-scaled keys around the row's median);
+//   chain warp   : every lane evaluates two keys B'(c) = T(c) - 1 = hi32(span*c' + addend) (one IMAD.HI
+//                  each), two warp reductions give the bracketing pair (a, b1) and the new interval; the
+//                  SYMBOL INDEX is not needed to continue -- only {value - base, span} are recorded;
+//   resolve warp : recovers the symbol index of 32 recorded symbols at a time by binary search over the
+//                  window, applies cdf_offset / de-quantisation and writes the output coalesced.
+// Rare cases (escape symbols, symbols outside the window, rows wider than the window) are handled on the
+// chain warp by a generic warp-parallel search and hand the finished symbol to the resolve warp.
+constexpr int kDecGroup = 128;
+
+struct DecDesc {      // one symbol's search window, prepared ahead of the chain
+  int wbase;          // entry index (into pairs) of the window's first key
+  int end;            // entry index of the row's last cdf entry (c == 2^p)
+  int start;          // entry index of cdf[0]
+  int flags;          // bit 0: overflow row, bit 1: window does not start at cdf[0]; bits 8.. : n = ncdf - 1
+};
+
+struct DecShared {
+  DecDesc desc[2][kDecGroup + 2];
+  uint2 ent[2][kDecGroup];        // {value - base, span} before the symbol's update
+  int ovr[2][kDecGroup];          // symbols finished on the chain warp (escapes, window misses)
+  unsigned ovr_mask[2][kDecGroup / 32];
+  unsigned bad[2];
+  unsigned count[2];
+  unsigned rbad[2];    // chain -> resolve copies (the prepare warp may already be two groups ahead)
+  unsigned rcount[2];
+};
+
+enum : int { kBarDescFull = 1, kBarDescEmpty = 3, kBarDecEntFull = 5, kBarDecEntEmpty = 7 };
+
+__device__ __forceinline__ uint32_t key_bound(uint32_t span, uint2 q) {  // B'(c) = floor(size*c/2^p) - 1
+  return (uint32_t)(((unsigned long long)span * q.x + (((unsigned long long)q.y << 32) | q.x)) >> 32);
+}
+
+struct Dec2 {
+  uint32_t base, span, value, pos;
+  uint32_t w0, w1;  // lane l holds stream words (pos & ~31) + l and (pos & ~31) + 32 + l
+  uint32_t next;    // word at index pos
+  ByteWindow bw;
+  int lane;
+
+  __device__ __forceinline__ void seek() {
+    const long long g0 = (long long)(pos & ~31u);
+    w0 = bw_fetch(bw, g0 + lane);
+    w1 = bw_fetch(bw, g0 + 32 + lane);
+    next = __shfl_sync(kFull, w0, pos & 31u);
   }
-  DecChain c;
+  // new interval [base + a, base + b1] and 16-bit renormalisation (range_coder.h:255-268)
+  __device__ __forceinline__ void update(uint32_t a, uint32_t b1) {
+    const uint32_t nb = base + a;
+    const uint32_t s = b1 - a;
+    const bool renorm = s < 65536u;
+    span = renorm ? ((s << 16) | 0xFFFFu) : s;
+    base = renorm ? (nb << 16) : nb;
+    value = renorm ? ((value << 16) | next) : value;
+    pos += renorm ? 1u : 0u;
+    if (renorm && (pos & 31u) == 0) {  // crossed into the prefetched window: rotate and prefetch the next one
+      w0 = w1;
+      w1 = bw_fetch(bw, (long long)pos + 32 + lane);
+    }
+    next = __shfl_sync(kFull, w0, pos & 31u);
+  }
+  // DecodeLinearly({0,1,2}, 1), range_coder_kernels.cc:450,461-469
+  __device__ __forceinline__ uint32_t bit() {
+    const uint32_t v = value - base;
+    const uint32_t half = key_bound(span, make_uint2(0x80000000u, 0u)) ;  // floor(size / 2) ... see below
+    // key_bound with addend_hi = 0 returns hi32(span*c' + c') = floor(size * 1 / 2) exactly (no "-1")
+    const uint32_t b = (v < half) ? 0u : 1u;
+    update(b ? half : 0u, b ? span : half - 1u);
+    return b;
+  }
+  // Generic warp-parallel search over the whole row (pairs[start .. start + n]); returns the symbol.
+  __device__ __forceinline__ int search_row(const uint2* pairs, int start, int n, uint32_t* a_out, uint32_t* b_out) {
+    const uint32_t v = value - base;
+    int lo_i = 0, hi_i = n;
+    for (;;) {
+      const int len = hi_i - lo_i;
+      const bool final_round = len <= 63;
+      const int stride = final_round ? 1 : ((len + 63) >> 6);
+      int i0, i1;
+      if (final_round) {
+        i0 = lo_i + lane;
+        i1 = lo_i + lane + 32;
+      } else {
+        i0 = lo_i + (lane + 1) * stride;
+        i1 = lo_i + (lane + 33) * stride;
+      }
+      i0 = min(i0, hi_i);
+      i1 = min(i1, hi_i);
+      const uint2 q0 = pairs[start + i0], q1 = pairs[start + i1];
+      const uint32_t B0 = key_bound(span, q0), B1 = key_bound(span, q1);
+      const bool ge0 = (v <= B0) && q0.x != 0u, ge1 = (v <= B1) && q1.x != 0u;
+      // distinct candidates below v (clamped duplicates sit at hi_i, which is never below)
+      const int below = __popc(__ballot_sync(kFull, !ge0)) + __popc(__ballot_sync(kFull, !ge1));
+      if (final_round) {
+        const uint32_t m = ge0 ? B0 : (ge1 ? B1 : 0xFFFFFFFFu);
+        const uint32_t am = ge1 ? (ge0 ? 0u : B0 + 1u) : B1 + 1u;
+        *b_out = __reduce_min_sync(kFull, m);
+        *a_out = __reduce_max_sync(kFull, am);
+        int i = lo_i + below;  // smallest index whose bound is >= v
+        i = max(1, min(i, n));
+        return i - 1;
+      }
+      const int f = min(below, 63);
+      const int nlo = (f == 0) ? lo_i : min(lo_i + f * stride, hi_i - 1);
+      const int nhi = min(lo_i + (f + 1) * stride, hi_i);
+      lo_i = nlo;
+      hi_i = max(nhi, nlo + 1);
+    }
+  }
+};
+
+template <int MODE, bool SMEM>
+__global__ void __launch_bounds__(96) decode_kernel(const DecParams P) {
+  extern __shared__ __align__(16) uint8_t s_dyn[];
+  __shared__ __align__(16) DecShared sh;
+  const long long s = blockIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const long long n_groups = (P.n + kDecGroup - 1) / kDecGroup;
+
+  // tables: shared memory when they fit (loaded by all three warps), global (L1/L2) otherwise
+  const uint2* pairs = P.pairs;
+  const int4* rows4 = P.rows4;
+  if (SMEM) {
+    uint2* sp = reinterpret_cast<uint2*>(s_dyn);
+    int4* sr = reinterpret_cast<int4*>(s_dyn + ((P.lookup_len * 8 + 15) & ~15ll));
+    for (int i = threadIdx.x; i < (int)P.lookup_len; i += 96) sp[i] = P.pairs[i];
+    for (int i = threadIdx.x; i < P.n_rows; i += 96) sr[i] = P.rows4[i];
+    __syncthreads();
+    pairs = sp;
+    rows4 = sr;
+  }
+
+  if (warp == 1) {
+    // ------------------------------- prepare warp -------------------------------
+    uint32_t chan_row = (uint32_t)lane % (uint32_t)P.n_rows;
+    const uint32_t chan_step = 32u % (uint32_t)P.n_rows;
+    for (long long g = 0; g < n_groups; ++g) {
+      const int b = (int)(g & 1);
+      if (g >= 2) bar_sync(kBarDescEmpty + b, 64);
+      unsigned bad = 0;
+#pragma unroll
+      for (int sub = 0; sub < kDecGroup / 32; ++sub) {
+        const long long j = g * kDecGroup + sub * 32 + lane;
+        int row = (int)chan_row;
+        if (MODE & kModeIndex) {
+          row = 0;
+          if (j < P.n) {
+            row = __ldg(P.index + s * P.n + j);
+            if (row < 0 || row >= P.n_rows) {
+              report(P.err, kErrIndex, s, j, row, P.n_rows);
+              row = -1;
+            }
+          }
+          bad |= __ballot_sync(kFull, row < 0);
+          if (row < 0) row = 0;
+        } else {
+          chan_row += chan_step;
+          if (chan_row >= (uint32_t)P.n_rows) chan_row -= (uint32_t)P.n_rows;
+        }
+        const int4 r4 = rows4[row];
+        const int n = row_ncdf(r4.y) - 1;
+        DecDesc d;
+        d.wbase = r4.x + r4.z;
+        d.end = r4.x + n;
+        d.start = r4.x;
+        d.flags = (row_ovf(r4.y) ? 1 : 0) | (r4.z != 0 ? 2 : 0) | (n << 8);
+        sh.desc[b][sub * 32 + lane] = d;
+        if (sub == kDecGroup / 32 - 1 && lane < 2) sh.desc[b][kDecGroup + lane] = d;  // pipeline overrun slots
+      }
+      if (lane == 0) {
+        sh.bad[b] = bad;
+        sh.count[b] = (unsigned)min((long long)kDecGroup, P.n - g * kDecGroup);
+      }
+      bar_arrive(kBarDescFull + b, 64);
+      if (bad) break;
+    }
+    return;
+  }
+
+  if (warp == 2) {
+    // ------------------------------- resolve warp -------------------------------
+    for (long long g = 0; g < n_groups; ++g) {
+      const int b = (int)(g & 1);
+      bar_sync(kBarDecEntFull + b, 64);
+      const int count = (int)sh.rcount[b];
+      if (sh.rbad[b]) break;
+      for (int sub = 0; sub * 32 < count; ++sub) {
+        const int k = sub * 32 + lane;
+        const long long j = g * kDecGroup + k;
+        if (k < count) {
+          const long long at = s * P.n + j;
+          int row;
+          if (MODE & kModeIndex) row = __ldg(P.index + at);
+          else row = (int)(j % P.n_rows);
+          int sym;
+          if ((sh.ovr_mask[b][sub] >> lane) & 1u) {
+            sym = sh.ovr[b][k];
+          } else {
+            // binary search inside the window: smallest index whose bound is >= v
+            const int4 r4 = rows4[row];
+            const int n = row_ncdf(r4.y) - 1;
+            const uint2 e = sh.ent[b][k];
+            int lo = r4.z, hi = min(r4.z + 63, n);  // bound(lo) < v <= bound(hi) is known
+            while (hi - lo > 1) {
+              const int mid = (lo + hi) >> 1;
+              const uint2 q = pairs[r4.x + mid];
+              const bool ge = (e.x <= key_bound(e.y, q)) && q.x != 0u;
+              if (ge) hi = mid; else lo = mid;
+            }
+            // lo may itself be the answer's predecessor or (lo == window start == 0) cdf[0]
+            sym = hi - 1;
+          }
+          if (MODE & kModeF32) {
+            float yv = (float)(sym + __ldg(P.coff + row));
+            if (P.qoff) yv += (MODE & kModeIndex) ? __ldg(P.qoff + at) : __ldg(P.qoff + row);
+            reinterpret_cast<float*>(P.out)[at] = yv;
+          } else {
+            reinterpret_cast<int32_t*>(P.out)[at] = sym;
+          }
+        }
+      }
+      if (g + 2 < n_groups) bar_arrive(kBarDecEntEmpty + b, 64);
+    }
+    return;
+  }
+
+  // --------------------------------- chain warp ---------------------------------
+  Dec2 c;
+  c.lane = lane;
   {
     const DecState st = P.state[s];
     c.base = st.base;
@@ -971,85 +1224,85 @@ __global__ void __launch_bounds__(32) decode_kernel(const DecParams P) {
     c.value = st.value;
     c.pos = st.pos;
   }
-  ByteWindow w;
-  w.p = P.bytes + P.offsets[s];
-  w.len = P.offsets[s + 1] - P.offsets[s];
+  c.bw.p = P.bytes + P.offsets[s];
+  c.bw.len = P.offsets[s + 1] - P.offsets[s];
   if (c.pos == 0) {  // fresh stream: the constructor reads four bytes (range_coder.h:79-83)
-    const uint32_t w0 = bw_fetch(w, 0), w1 = bw_fetch(w, 1);
-    c.value = (w0 << 16) | w1;
+    const uint32_t x0 = bw_fetch(c.bw, 0), x1 = bw_fetch(c.bw, 1);
+    c.value = (x0 << 16) | x1;
     c.pos = 2;
   }
-  bw_seek(w, c.pos, lane);
+  c.seek();
 
-  uint32_t chan_row = (uint32_t)lane % (uint32_t)P.n_rows;
-  const uint32_t chan_step = 32u % (uint32_t)P.n_rows;
-  for (long long g0 = 0; g0 < P.n; g0 += 32) {
-    const int count = (int)min(32ll, P.n - g0);
-    const long long at = s * P.n + g0 + lane;
-    // per-lane row descriptor of symbol g0 + lane
-    int my_row = (int)chan_row;
-    if (MODE & kModeIndex) {
-      my_row = 0;
-      if (lane < count) {
-        my_row = __ldg(P.index + at);
-        if (my_row < 0 || my_row >= P.n_rows) {
-          report(P.err, kErrIndex, s, g0 + lane, my_row, P.n_rows);
-          my_row = -1;
-        }
-      }
-      if (__ballot_sync(kFull, my_row < 0)) break;
-    } else {
-      chan_row += chan_step;
-      if (chan_row >= (uint32_t)P.n_rows) chan_row -= (uint32_t)P.n_rows;
-    }
-    const int2 my_ri = rows[my_row];
-
-    // software pipeline: descriptor of symbol k+2 by shuffle, candidates of symbol k+1 by load,
-    // arithmetic of symbol k.
-    int st1 = __shfl_sync(kFull, my_ri.x, 0), mt1 = __shfl_sync(kFull, my_ri.y, 0);
-    int st2 = __shfl_sync(kFull, my_ri.x, 1), mt2 = __shfl_sync(kFull, my_ri.y, 1);
-    Round r1 = plan_round(0, row_ncdf(mt1) - 1, lane);
-    uint32_t c0n = (uint32_t)tab[st1 + r1.idx0], c1n = (uint32_t)tab[st1 + r1.idx1];
-    int my_sym = 0;
+  for (long long g = 0; g < n_groups; ++g) {
+    const int b = (int)(g & 1);
+    bar_sync(kBarDescFull + b, 64);
+    const bool bad = sh.bad[b] != 0;
+    const int count = bad ? 0 : (int)sh.count[b];
+    if (g >= 2) bar_sync(kBarDecEntEmpty + b, 64);  // the resolve warp is done with this entry buffer
+    const DecDesc* desc = sh.desc[b];
+    unsigned omask[kDecGroup / 32];
+#pragma unroll
+    for (int i = 0; i < kDecGroup / 32; ++i) omask[i] = 0u;
+    // software pipeline: descriptor two symbols ahead, candidate keys one symbol ahead
+    DecDesc d1 = desc[0];
+    DecDesc d2 = desc[1];
+    uint2 q0n = pairs[min(d1.wbase + lane, d1.end)], q1n = pairs[min(d1.wbase + lane + 32, d1.end)];
     for (int k = 0; k < count; ++k) {
-      const int st0 = st1, mt0 = mt1;
-      const Round r0 = r1;
-      const uint32_t c0 = c0n, c1 = c1n;
-      st1 = st2;
-      mt1 = mt2;
-      st2 = __shfl_sync(kFull, my_ri.x, (k + 2) & 31);
-      mt2 = __shfl_sync(kFull, my_ri.y, (k + 2) & 31);
-      r1 = plan_round(0, row_ncdf(mt1) - 1, lane);
-      c0n = (uint32_t)tab[st1 + r1.idx0];
-      c1n = (uint32_t)tab[st1 + r1.idx1];
+      const DecDesc d = d1;
+      const uint2 q0 = q0n, q1 = q1n;
+      d1 = d2;
+      d2 = desc[k + 2];
+      q0n = pairs[min(d1.wbase + lane, d1.end)];
+      q1n = pairs[min(d1.wbase + lane + 32, d1.end)];
 
-      const int ncdf = row_ncdf(mt0);
-      const uint32_t p = (uint32_t)row_prec(mt0);
-      int sym = dec_symbol_fast(c, w, tab + st0, ncdf, p, r0, c0, c1, lane);
-      if (row_ovf(mt0) && sym == ncdf - 2) {
-        const int esc = ncdf - 2;
+      const uint32_t v = c.value - c.base;
+      const uint32_t span0 = c.span;
+      const uint32_t B0 = key_bound(span0, q0), B1 = key_bound(span0, q1);
+      const bool ge0 = (v <= B0) && q0.x != 0u, ge1 = (v <= B1) && q1.x != 0u;
+      const uint32_t m = ge0 ? B0 : (ge1 ? B1 : 0xFFFFFFFFu);
+      const uint32_t am = ge1 ? (ge0 ? 0u : B0 + 1u) : B1 + 1u;
+      uint32_t b1 = __reduce_min_sync(kFull, m);
+      uint32_t a = __reduce_max_sync(kFull, am);
+      sh.ent[b][k] = make_uint2(v, span0);
+      const bool miss = (b1 == 0xFFFFFFFFu) || (a == 0u && (d.flags & 2));
+      const bool esc = (d.flags & 1) && (b1 == span0);
+      if (!(miss || esc)) {
+        c.update(a, b1);
+        continue;
+      }
+      // ---- rare path: finish the symbol here ----
+      const int n = d.flags >> 8;
+      int sym;
+      if (miss) {
+        sym = c.search_row(pairs, d.start, n, &a, &b1);
+      } else {
+        sym = n - 1;
+      }
+      c.update(a, b1);
+      if ((d.flags & 1) && sym == n - 1) {  // OverflowDecode, range_coder_kernels.cc:449-471
         int nb = 0;
-        while (dec_bit(c, w, lane) == 0 && nb < 64) ++nb;
+        while (c.bit() == 0 && nb < 64) ++nb;
         uint32_t val = (nb < 32) ? (1u << nb) : 0u;
         int t = nb;
         while (--t >= 0) {
-          const uint32_t bit = dec_bit(c, w, lane);
-          if (t < 32) val |= bit << t;
+          const uint32_t bitv = c.bit();
+          if (t < 32) val |= bitv << t;
         }
-        const uint32_t sg = dec_bit(c, w, lane);
-        sym = sg ? -(int)val : (int)val + esc - 1;
+        const uint32_t sg = c.bit();
+        sym = sg ? -(int)val : (int)val + (n - 1) - 1;
       }
-      if (lane == k) my_sym = sym;
+      sh.ovr[b][k] = sym;
+      omask[k >> 5] |= 1u << (k & 31);
     }
-    if (lane < count) {
-      if (MODE & kModeF32) {
-        float y = (float)(my_sym + __ldg(P.coff + my_row));
-        if (P.qoff) y += (MODE & kModeIndex) ? __ldg(P.qoff + at) : __ldg(P.qoff + my_row);
-        reinterpret_cast<float*>(P.out)[at] = y;
-      } else {
-        reinterpret_cast<int32_t*>(P.out)[at] = my_sym;
-      }
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < kDecGroup / 32; ++i) sh.ovr_mask[b][i] = omask[i];
+      sh.rbad[b] = bad ? 1u : 0u;
+      sh.rcount[b] = (unsigned)count;
     }
+    bar_arrive(kBarDecEntFull + b, 64);
+    if (bad) break;
+    if (g + 2 < n_groups) bar_arrive(kBarDescEmpty + b, 64);
   }
   if (lane == 0) {
     DecState st;
@@ -1528,6 +1781,8 @@ int launch_decode(tfcb_decoder* h, const int32_t* index, void* out, const float*
   DecParams P;
   P.lookup = h->lut.lookup;
   P.rows = h->lut.rows;
+  P.pairs = h->lut.pairs;
+  P.rows4 = h->lut.rows4;
   P.n_rows = h->lut.n_rows;
   P.lookup_len = h->lut.len;
   P.bytes = h->bytes;
@@ -1540,14 +1795,14 @@ int launch_decode(tfcb_decoder* h, const int32_t* index, void* out, const float*
   P.n_streams = h->n_streams;
   P.state = h->state;
   P.err = h->err;
-  // Tables live in shared memory when two CTAs per SM still fit (every stream is its own CTA).
-  const size_t smem = (size_t)(((h->lut.len + 1) & ~1ll) * sizeof(int32_t) + (size_t)h->lut.n_rows * sizeof(int2));
-  if (smem <= 100 * 1024) {
+  // Search keys live in shared memory when two CTAs per SM still fit (every stream is its own CTA).
+  const size_t smem = (size_t)((h->lut.len * 8 + 15) & ~15ll) + (size_t)h->lut.n_rows * sizeof(int4);
+  if (smem <= 96 * 1024) {
     TFCB_CUDA_TRY(cudaFuncSetAttribute(decode_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
-    decode_kernel<MODE, true><<<(unsigned)h->n_streams, 32, smem, s>>>(P);
+    decode_kernel<MODE, true><<<(unsigned)h->n_streams, 96, smem, s>>>(P);
   } else {
-    decode_kernel<MODE, false><<<(unsigned)h->n_streams, 32, 0, s>>>(P);
+    decode_kernel<MODE, false><<<(unsigned)h->n_streams, 96, 0, s>>>(P);
   }
   TFCB_LAUNCHED();
   TFCB_CUDA_TRY(cudaGetLastError());
@@ -1571,7 +1826,7 @@ int tfcb_decoder_create(const uint8_t* bytes_dev, const int64_t* offsets_dev, in
   h->n_streams = n_streams;
   h->bytes = bytes_dev;
   h->offsets = reinterpret_cast<const long long*>(offsets_dev);
-  int rc = h->lut.upload(lookup_host, lookup_len, lookup_cols, s);
+  int rc = h->lut.upload(lookup_host, lookup_len, lookup_cols, s, /*for_decoder=*/true);
   if (rc == TFCB_OK) rc = dev_alloc((void**)&h->state, n_streams * sizeof(DecState), s);
   if (rc == TFCB_OK) rc = dev_alloc((void**)&h->err, sizeof(DevError), s);
   if (rc == TFCB_OK) rc = dev_alloc((void**)&h->ok, n_streams, s);
