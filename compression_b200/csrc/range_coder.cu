@@ -89,7 +89,8 @@ struct DeviceLookup {
   int32_t* lookup = nullptr;  // device copy of the raw table
   int2* rows = nullptr;       // {start, meta}
   uint2* pairs = nullptr;     // decoder: per cdf entry {c', addend_hi} so that hi32(span*c' + {c',addend_hi}) = T(c) - 1
-  int4* rows4 = nullptr;      // decoder: {start, meta, window_lo, 0}
+  int4* rows4 = nullptr;      // decoder: {key segment start, meta, first window index, irregular}
+  long long n_pairs = 0;
   int n_rows = 0;
   long long len = 0;
   bool any_overflow = false;
@@ -122,25 +123,31 @@ struct DeviceLookup {
     std::vector<uint2> hp;
     std::vector<int4> hr4;
     if (for_decoder) {
-      // Pre-scaled search keys (see dec2): B'(c) = floor(size*c/2^p) - 1 = hi32(span*c' + {c', 0xFFFFFFFF}) with
-      // c' = c << (32-p); c == 2^p -> {0xFFFFFFFF, 0} (B' = span); c == 0 -> c' = 0 marks "never an upper bound".
-      // window_lo: first index of the 64-entry search window centred on the row's median.
-      hp.assign(std::max<int64_t>(len, 1), make_uint2(0u, 0u));
+      // Pre-scaled search keys: B'(c) = floor(size*c/2^p) - 1 = hi32(span*c' + {c', 0xFFFFFFFF}) with
+      // c' = c << (32-p); c == 2^p -> {0xFFFFFFFF, 0} (B' = span = size - 1).  Every row gets its own padded
+      // segment: keys of cdf[0..n], then "full" keys up to index 64, so that the 64-key search window
+      // [wfirst, wfirst + 63] (centred on the row's median, wfirst >= 1) never needs clamping.
+      // Rows with a zero key at index >= 1 (leading zero-width bins) are marked irregular: slow path only.
       hr4.resize(meta.size());
       for (size_t i = 0; i < hr.size(); ++i) {
         const int ap = hr[i].prec < 0 ? -hr[i].prec : hr[i].prec;
         const int n = hr[i].ncdf - 1;
-        int median = n;
-        for (int e = 0; e < hr[i].ncdf; ++e) {
+        const int pstart = (int)hp.size();
+        int median = n, irregular = 0;
+        for (int e = 0; e <= n; ++e) {
           const uint32_t c = (uint32_t)lookup_host[hr[i].start + e];
-          hp[hr[i].start + e] = (c == (1u << ap)) ? make_uint2(0xFFFFFFFFu, 0u) : make_uint2(c << (32 - ap), 0xFFFFFFFFu);
+          hp.push_back((c == (1u << ap)) ? make_uint2(0xFFFFFFFFu, 0u) : make_uint2(c << (32 - ap), 0xFFFFFFFFu));
+          if (e >= 1 && c == 0u) irregular = 1;
           if (e >= 1 && median == n && c >= (1u << ap) / 2) median = e;
         }
-        int wlo = median - 32;
-        if (wlo > n - 63) wlo = n - 63;
-        if (wlo < 0) wlo = 0;
-        hr4[i] = make_int4(meta[i].x, meta[i].y, wlo, 0);
+        for (int e = n + 1; e <= 64; ++e) hp.push_back(make_uint2(0xFFFFFFFFu, 0u));
+        int wfirst = median - 31;
+        if (wfirst > n - 63) wfirst = n - 63;
+        if (wfirst < 1) wfirst = 1;
+        hr4[i] = make_int4(pstart, meta[i].y, wfirst, irregular);
       }
+      if (hp.empty()) hp.push_back(make_uint2(0u, 0u));
+      n_pairs = (long long)hp.size();
       TFCB_TRY(dev_alloc((void**)&pairs, hp.size() * sizeof(uint2), s));
       TFCB_TRY(dev_alloc((void**)&rows4, hr4.size() * sizeof(int4), s));
       TFCB_CUDA_TRY(cudaMemcpyAsync(pairs, hp.data(), hp.size() * sizeof(uint2), cudaMemcpyHostToDevice, s));
@@ -819,6 +826,7 @@ struct DecParams {
   const int4* rows4;
   int n_rows;
   long long lookup_len;
+  long long n_pairs;
   const uint8_t* bytes;
   const long long* offsets;
   const int32_t* index;
@@ -995,12 +1003,14 @@ __device__ __forceinline__ int dec_symbol_fast(DecChain& c, ByteWindow& w, const
 // Rare cases (escape symbols, symbols outside the window, rows wider than the window) are handled on the
 // chain warp by a generic warp-parallel search and hand the finished symbol to the resolve warp.
 constexpr int kDecGroup = 128;
+constexpr int kRing = 2048;       // words; the prepare warp keeps [pos, pos + kRingAhead) valid
+constexpr int kRingAhead = 1536;  // > words two groups can consume even if every symbol escapes (256 * 5.1)
 
 struct DecDesc {      // one symbol's search window, prepared ahead of the chain
-  int wbase;          // entry index (into pairs) of the window's first key
-  int end;            // entry index of the row's last cdf entry (c == 2^p)
-  int start;          // entry index of cdf[0]
-  int flags;          // bit 0: overflow row, bit 1: window does not start at cdf[0]; bits 8.. : n = ncdf - 1
+  int win;            // key index of the window's first key (segment start + wfirst)
+  int flags;          // bit 0: overflow row, bit 1: wfirst > 1, bit 2: irregular row (slow path only)
+  int seg;            // key index of cdf[0]
+  int n;              // ncdf - 1
 };
 
 struct DecShared {
@@ -1012,28 +1022,40 @@ struct DecShared {
   unsigned count[2];
   unsigned rbad[2];    // chain -> resolve copies (the prepare warp may already be two groups ahead)
   unsigned rcount[2];
+  unsigned pos_pub[2]; // chain -> prepare: stream position (16-bit words) after the group that used buffer b
+  uint16_t ring[kRing]; // the stream's next words, big-endian decoded, filled ahead by the prepare warp
 };
 
 enum : int { kBarDescFull = 1, kBarDescEmpty = 3, kBarDecEntFull = 5, kBarDecEntEmpty = 7 };
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ uint32_t key_bound(uint32_t span, uint2 q) {  // B'(c) = floor(size*c/2^p) - 1
   return (uint32_t)(((unsigned long long)span * q.x + (((unsigned long long)q.y << 32) | q.x)) >> 32);
 }
 
+__device__ __forceinline__ uint2 lds_v2(uint32_t addr) {
+  uint2 r;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t x, uint32_t y) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+  uint32_t r;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(r) : "r"(addr));
+  return r;
+}
+
 struct Dec2 {
   uint32_t base, span, value, pos;
-  uint32_t w0, w1;  // lane l holds stream words (pos & ~31) + l and (pos & ~31) + 32 + l
-  uint32_t next;    // word at index pos
-  ByteWindow bw;
+  uint32_t next;       // word at index pos
+  uint32_t ring_addr;  // shared address of DecShared::ring
   int lane;
 
-  __device__ __forceinline__ void seek() {
-    const long long g0 = (long long)(pos & ~31u);
-    w0 = bw_fetch(bw, g0 + lane);
-    w1 = bw_fetch(bw, g0 + 32 + lane);
-    next = __shfl_sync(kFull, w0, pos & 31u);
-  }
-  // new interval [base + a, base + b1] and 16-bit renormalisation (range_coder.h:255-268)
+  __device__ __forceinline__ void seek() { next = lds_u16(ring_addr + ((pos & (kRing - 1)) << 1)); }
+  // new interval [base + a, base + b1] and 16-bit renormalisation (range_coder.h:255-268); branch free
   __device__ __forceinline__ void update(uint32_t a, uint32_t b1) {
     const uint32_t nb = base + a;
     const uint32_t s = b1 - a;
@@ -1042,11 +1064,7 @@ struct Dec2 {
     base = renorm ? (nb << 16) : nb;
     value = renorm ? ((value << 16) | next) : value;
     pos += renorm ? 1u : 0u;
-    if (renorm && (pos & 31u) == 0) {  // crossed into the prefetched window: rotate and prefetch the next one
-      w0 = w1;
-      w1 = bw_fetch(bw, (long long)pos + 32 + lane);
-    }
-    next = __shfl_sync(kFull, w0, pos & 31u);
+    next = lds_u16(ring_addr + ((pos & (kRing - 1)) << 1));  // consumed at the next renormalisation, not before
   }
   // DecodeLinearly({0,1,2}, 1), range_coder_kernels.cc:450,461-469
   __device__ __forceinline__ uint32_t bit() {
@@ -1112,8 +1130,8 @@ __global__ void __launch_bounds__(96) decode_kernel(const DecParams P) {
   const int4* rows4 = P.rows4;
   if (SMEM) {
     uint2* sp = reinterpret_cast<uint2*>(s_dyn);
-    int4* sr = reinterpret_cast<int4*>(s_dyn + ((P.lookup_len * 8 + 15) & ~15ll));
-    for (int i = threadIdx.x; i < (int)P.lookup_len; i += 96) sp[i] = P.pairs[i];
+    int4* sr = reinterpret_cast<int4*>(s_dyn + ((P.n_pairs * 8 + 15) & ~15ll));
+    for (int i = threadIdx.x; i < (int)P.n_pairs; i += 96) sp[i] = P.pairs[i];
     for (int i = threadIdx.x; i < P.n_rows; i += 96) sr[i] = P.rows4[i];
     __syncthreads();
     pairs = sp;
@@ -1124,9 +1142,21 @@ __global__ void __launch_bounds__(96) decode_kernel(const DecParams P) {
     // ------------------------------- prepare warp -------------------------------
     uint32_t chan_row = (uint32_t)lane % (uint32_t)P.n_rows;
     const uint32_t chan_step = 32u % (uint32_t)P.n_rows;
+    ByteWindow bw;
+    bw.p = P.bytes + P.offsets[s];
+    bw.len = P.offsets[s + 1] - P.offsets[s];
+    long long filled = (long long)P.state[s].pos;  // ring holds words [.., filled)
+    auto fill_ring = [&](long long upto) {
+      for (long long wi = filled + lane; wi < upto; wi += 32) sh.ring[wi & (kRing - 1)] = (uint16_t)bw_fetch(bw, wi);
+      filled = max(filled, upto);
+    };
+    fill_ring(filled + kRingAhead);
     for (long long g = 0; g < n_groups; ++g) {
       const int b = (int)(g & 1);
-      if (g >= 2) bar_sync(kBarDescEmpty + b, 64);
+      if (g >= 2) {
+        bar_sync(kBarDescEmpty + b, 64);
+        fill_ring((long long)sh.pos_pub[b] + kRingAhead);  // pos after group g-2; two groups consume < kRingAhead
+      }
       unsigned bad = 0;
 #pragma unroll
       for (int sub = 0; sub < kDecGroup / 32; ++sub) {
@@ -1148,12 +1178,11 @@ __global__ void __launch_bounds__(96) decode_kernel(const DecParams P) {
           if (chan_row >= (uint32_t)P.n_rows) chan_row -= (uint32_t)P.n_rows;
         }
         const int4 r4 = rows4[row];
-        const int n = row_ncdf(r4.y) - 1;
         DecDesc d;
-        d.wbase = r4.x + r4.z;
-        d.end = r4.x + n;
-        d.start = r4.x;
-        d.flags = (row_ovf(r4.y) ? 1 : 0) | (r4.z != 0 ? 2 : 0) | (n << 8);
+        d.win = r4.x + r4.z;
+        d.flags = (row_ovf(r4.y) ? 1 : 0) | (r4.z > 1 ? 2 : 0) | (r4.w ? 4 : 0);
+        d.seg = r4.x;
+        d.n = row_ncdf(r4.y) - 1;
         sh.desc[b][sub * 32 + lane] = d;
         if (sub == kDecGroup / 32 - 1 && lane < 2) sh.desc[b][kDecGroup + lane] = d;  // pipeline overrun slots
       }
@@ -1186,18 +1215,19 @@ __global__ void __launch_bounds__(96) decode_kernel(const DecParams P) {
           if ((sh.ovr_mask[b][sub] >> lane) & 1u) {
             sym = sh.ovr[b][k];
           } else {
-            // binary search inside the window: smallest index whose bound is >= v
+            // binary search inside the window: smallest key index whose bound is >= v.  The key just left of
+            // the window is known to be below (cdf[0] = 0, or a below-candidate existed), the last one >= v.
             const int4 r4 = rows4[row];
-            const int n = row_ncdf(r4.y) - 1;
             const uint2 e = sh.ent[b][k];
-            int lo = r4.z, hi = min(r4.z + 63, n);  // bound(lo) < v <= bound(hi) is known
-            while (hi - lo > 1) {
-              const int mid = (lo + hi) >> 1;
-              const uint2 q = pairs[r4.x + mid];
-              const bool ge = (e.x <= key_bound(e.y, q)) && q.x != 0u;
-              if (ge) hi = mid; else lo = mid;
+            const uint2* keys = pairs + r4.x;
+            int lo = r4.z - 1, hi = r4.z + 63;
+#pragma unroll
+            for (int it = 0; it < 6; ++it) {
+              const int mid = (lo + hi + 1) >> 1;
+              const bool ge = e.x <= key_bound(e.y, keys[mid]);
+              hi = ge ? mid : hi;
+              lo = ge ? lo : mid;
             }
-            // lo may itself be the answer's predecessor or (lo == window start == 0) cdf[0]
             sym = hi - 1;
           }
           if (MODE & kModeF32) {
@@ -1224,62 +1254,76 @@ __global__ void __launch_bounds__(96) decode_kernel(const DecParams P) {
     c.value = st.value;
     c.pos = st.pos;
   }
-  c.bw.p = P.bytes + P.offsets[s];
-  c.bw.len = P.offsets[s + 1] - P.offsets[s];
-  if (c.pos == 0) {  // fresh stream: the constructor reads four bytes (range_coder.h:79-83)
-    const uint32_t x0 = bw_fetch(c.bw, 0), x1 = bw_fetch(c.bw, 1);
-    c.value = (x0 << 16) | x1;
-    c.pos = 2;
-  }
-  c.seek();
+  c.ring_addr = smem_addr(sh.ring);
+  bool started = false;
 
   for (long long g = 0; g < n_groups; ++g) {
     const int b = (int)(g & 1);
     bar_sync(kBarDescFull + b, 64);
+    if (!started) {  // the ring is valid from here on
+      started = true;
+      if (c.pos == 0) {  // fresh stream: the constructor reads four bytes (range_coder.h:79-83)
+        c.value = ((uint32_t)sh.ring[0] << 16) | (uint32_t)sh.ring[1];
+        c.pos = 2;
+      }
+      c.seek();
+    }
     const bool bad = sh.bad[b] != 0;
     const int count = bad ? 0 : (int)sh.count[b];
     if (g >= 2) bar_sync(kBarDecEntEmpty + b, 64);  // the resolve warp is done with this entry buffer
     const DecDesc* desc = sh.desc[b];
-    unsigned omask[kDecGroup / 32];
-#pragma unroll
-    for (int i = 0; i < kDecGroup / 32; ++i) omask[i] = 0u;
+    unsigned om0 = 0, om1 = 0, om2 = 0, om3 = 0;  // symbols finished on this warp (bit per symbol)
+    const uint32_t desc_addr = smem_addr(sh.desc[b]);
+    const uint32_t ent_addr = smem_addr(sh.ent[b]);
+    const uint2* lkeys = pairs + lane;  // this lane's two candidates: lkeys[win], lkeys[win + 32]
+    const uint32_t lkeys_addr = SMEM ? smem_addr(lkeys) : 0u;
+    auto load_keys = [&](int win, uint2* q0, uint2* q1) {
+      if (SMEM) {
+        *q0 = lds_v2(lkeys_addr + (uint32_t)win * 8u);
+        *q1 = lds_v2(lkeys_addr + (uint32_t)win * 8u + 256u);
+      } else {
+        *q0 = __ldg(lkeys + win);
+        *q1 = __ldg(lkeys + win + 32);
+      }
+    };
     // software pipeline: descriptor two symbols ahead, candidate keys one symbol ahead
-    DecDesc d1 = desc[0];
-    DecDesc d2 = desc[1];
-    uint2 q0n = pairs[min(d1.wbase + lane, d1.end)], q1n = pairs[min(d1.wbase + lane + 32, d1.end)];
+    uint2 d1 = lds_v2(desc_addr);
+    uint2 d2 = lds_v2(desc_addr + 16u);
+    uint2 q0n, q1n;
+    load_keys((int)d1.x, &q0n, &q1n);
+#pragma unroll 4
     for (int k = 0; k < count; ++k) {
-      const DecDesc d = d1;
+      const int2 d = make_int2((int)d1.x, (int)d1.y);
       const uint2 q0 = q0n, q1 = q1n;
       d1 = d2;
-      d2 = desc[k + 2];
-      q0n = pairs[min(d1.wbase + lane, d1.end)];
-      q1n = pairs[min(d1.wbase + lane + 32, d1.end)];
+      d2 = lds_v2(desc_addr + (uint32_t)(k + 2) * 16u);
+      load_keys((int)d1.x, &q0n, &q1n);
 
       const uint32_t v = c.value - c.base;
       const uint32_t span0 = c.span;
       const uint32_t B0 = key_bound(span0, q0), B1 = key_bound(span0, q1);
-      const bool ge0 = (v <= B0) && q0.x != 0u, ge1 = (v <= B1) && q1.x != 0u;
+      const bool ge0 = v <= B0, ge1 = v <= B1;
       const uint32_t m = ge0 ? B0 : (ge1 ? B1 : 0xFFFFFFFFu);
       const uint32_t am = ge1 ? (ge0 ? 0u : B0 + 1u) : B1 + 1u;
       uint32_t b1 = __reduce_min_sync(kFull, m);
       uint32_t a = __reduce_max_sync(kFull, am);
-      sh.ent[b][k] = make_uint2(v, span0);
-      const bool miss = (b1 == 0xFFFFFFFFu) || (a == 0u && (d.flags & 2));
-      const bool esc = (d.flags & 1) && (b1 == span0);
-      if (!(miss || esc)) {
+      sts_v2(ent_addr + (uint32_t)k * 8u, v, span0);
+      // fast path unless: no key >= v in the window, nothing below although the window starts inside the row,
+      // an irregular row, or the escape bin of an overflow row
+      const bool rare = (b1 == 0xFFFFFFFFu) || (a == 0u && (d.y & 2)) || (d.y & 4) || ((d.y & 1) && b1 == span0);
+      if (!rare) {
         c.update(a, b1);
         continue;
       }
       // ---- rare path: finish the symbol here ----
-      const int n = d.flags >> 8;
-      int sym;
-      if (miss) {
-        sym = c.search_row(pairs, d.start, n, &a, &b1);
-      } else {
-        sym = n - 1;
-      }
+      const DecDesc df = desc[k];
+      const int n = df.n;
+      int sym = n - 1;
+      const bool in_window = !((b1 == 0xFFFFFFFFu) || (a == 0u && (d.y & 2)) || (d.y & 4));
+      if (!in_window) sym = c.search_row(pairs, df.seg, n, &a, &b1);
+      else if (!((d.y & 1) && b1 == span0)) sym = -1;  // unreachable
       c.update(a, b1);
-      if ((d.flags & 1) && sym == n - 1) {  // OverflowDecode, range_coder_kernels.cc:449-471
+      if ((d.y & 1) && sym == n - 1) {  // OverflowDecode, range_coder_kernels.cc:449-471
         int nb = 0;
         while (c.bit() == 0 && nb < 64) ++nb;
         uint32_t val = (nb < 32) ? (1u << nb) : 0u;
@@ -1292,8 +1336,13 @@ __global__ void __launch_bounds__(96) decode_kernel(const DecParams P) {
         sym = sg ? -(int)val : (int)val + (n - 1) - 1;
       }
       sh.ovr[b][k] = sym;
-      omask[k >> 5] |= 1u << (k & 31);
+      const unsigned bitk = 1u << (k & 31);
+      om0 |= (k >> 5) == 0 ? bitk : 0u;
+      om1 |= (k >> 5) == 1 ? bitk : 0u;
+      om2 |= (k >> 5) == 2 ? bitk : 0u;
+      om3 |= (k >> 5) == 3 ? bitk : 0u;
     }
+    const unsigned omask[kDecGroup / 32] = {om0, om1, om2, om3};
     if (lane == 0) {
 #pragma unroll
       for (int i = 0; i < kDecGroup / 32; ++i) sh.ovr_mask[b][i] = omask[i];
@@ -1302,7 +1351,10 @@ __global__ void __launch_bounds__(96) decode_kernel(const DecParams P) {
     }
     bar_arrive(kBarDecEntFull + b, 64);
     if (bad) break;
-    if (g + 2 < n_groups) bar_arrive(kBarDescEmpty + b, 64);
+    if (g + 2 < n_groups) {
+      if (lane == 0) sh.pos_pub[b] = c.pos;
+      bar_arrive(kBarDescEmpty + b, 64);
+    }
   }
   if (lane == 0) {
     DecState st;
@@ -1783,6 +1835,7 @@ int launch_decode(tfcb_decoder* h, const int32_t* index, void* out, const float*
   P.rows = h->lut.rows;
   P.pairs = h->lut.pairs;
   P.rows4 = h->lut.rows4;
+  P.n_pairs = h->lut.n_pairs;
   P.n_rows = h->lut.n_rows;
   P.lookup_len = h->lut.len;
   P.bytes = h->bytes;
@@ -1796,7 +1849,7 @@ int launch_decode(tfcb_decoder* h, const int32_t* index, void* out, const float*
   P.state = h->state;
   P.err = h->err;
   // Search keys live in shared memory when two CTAs per SM still fit (every stream is its own CTA).
-  const size_t smem = (size_t)((h->lut.len * 8 + 15) & ~15ll) + (size_t)h->lut.n_rows * sizeof(int4);
+  const size_t smem = (size_t)((h->lut.n_pairs * 8 + 15) & ~15ll) + (size_t)h->lut.n_rows * sizeof(int4);
   if (smem <= 96 * 1024) {
     TFCB_CUDA_TRY(cudaFuncSetAttribute(decode_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
