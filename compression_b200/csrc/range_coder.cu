@@ -91,6 +91,7 @@ struct DeviceLookup {
   uint2* pairs = nullptr;     // decoder: per cdf entry {c', addend_hi} so that hi32(span*c' + {c',addend_hi}) = T(c) - 1
   int4* rows4 = nullptr;      // decoder: {key segment start, meta, first window index, irregular}
   long long n_pairs = 0;
+  int zero_win = 0;  // key index of the all-zero window (decoder tables only)
   int n_rows = 0;
   long long len = 0;
   bool any_overflow = false;
@@ -127,7 +128,7 @@ struct DeviceLookup {
       // c' = c << (32-p); c == 2^p -> {0xFFFFFFFF, 0} (B' = span = size - 1).  Every row gets its own padded
       // segment: keys of cdf[0..n], then "full" keys up to index 64, so that the 64-key search window
       // [wfirst, wfirst + 63] (centred on the row's median, wfirst >= 1) never needs clamping.
-      // Rows with a zero key at index >= 1 (leading zero-width bins) are marked irregular: slow path only.
+      // Rows with zero-width bins at either end are marked irregular: slow path only.
       hr4.resize(meta.size());
       for (size_t i = 0; i < hr.size(); ++i) {
         const int ap = hr[i].prec < 0 ? -hr[i].prec : hr[i].prec;
@@ -138,6 +139,7 @@ struct DeviceLookup {
           const uint32_t c = (uint32_t)lookup_host[hr[i].start + e];
           hp.push_back((c == (1u << ap)) ? make_uint2(0xFFFFFFFFu, 0u) : make_uint2(c << (32 - ap), 0xFFFFFFFFu));
           if (e >= 1 && c == 0u) irregular = 1;
+          if (e >= 1 && e < n && c == (1u << ap)) irregular = 1;  // trailing zero-width bins
           if (e >= 1 && median == n && c >= (1u << ap) / 2) median = e;
         }
         for (int e = n + 1; e <= 64; ++e) hp.push_back(make_uint2(0xFFFFFFFFu, 0u));
@@ -146,7 +148,9 @@ struct DeviceLookup {
         if (wfirst < 1) wfirst = 1;
         hr4[i] = make_int4(pstart, meta[i].y, wfirst, irregular);
       }
-      if (hp.empty()) hp.push_back(make_uint2(0u, 0u));
+      // window of keys whose bound is 0: used for irregular rows so that the chain always takes the slow path
+      zero_win = (int)hp.size();
+      for (int e = 0; e < 64; ++e) hp.push_back(make_uint2(0u, 0u));
       n_pairs = (long long)hp.size();
       TFCB_TRY(dev_alloc((void**)&pairs, hp.size() * sizeof(uint2), s));
       TFCB_TRY(dev_alloc((void**)&rows4, hr4.size() * sizeof(int4), s));
@@ -827,6 +831,7 @@ struct DecParams {
   int n_rows;
   long long lookup_len;
   long long n_pairs;
+  int zero_win;
   const uint8_t* bytes;
   const long long* offsets;
   const int32_t* index;
@@ -1007,10 +1012,10 @@ constexpr int kRing = 2048;       // words; the prepare warp keeps [pos, pos + k
 constexpr int kRingAhead = 1536;  // > words two groups can consume even if every symbol escapes (256 * 5.1)
 
 struct DecDesc {      // one symbol's search window, prepared ahead of the chain
-  int win;            // key index of the window's first key (segment start + wfirst)
-  int flags;          // bit 0: overflow row, bit 1: wfirst > 1, bit 2: irregular row (slow path only)
+  int win;            // key index of the window's first key (segment start + wfirst; the zero window if irregular)
+  uint32_t thr;       // the window's answer needs a candidate below v unless it starts the row: slow if a < thr
   int seg;            // key index of cdf[0]
-  int n;              // ncdf - 1
+  int n;              // ncdf - 1, bit 31: overflow row
 };
 
 struct DecShared {
@@ -1023,12 +1028,16 @@ struct DecShared {
   unsigned rbad[2];    // chain -> resolve copies (the prepare warp may already be two groups ahead)
   unsigned rcount[2];
   unsigned pos_pub[2]; // chain -> prepare: stream position (16-bit words) after the group that used buffer b
-  uint16_t ring[kRing]; // the stream's next words, big-endian decoded, filled ahead by the prepare warp
 };
 
 enum : int { kBarDescFull = 1, kBarDescEmpty = 3, kBarDecEntFull = 5, kBarDecEntEmpty = 7 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint32_t opaque(uint32_t x) {
+  asm volatile("mov.u32 %0, %0;" : "+r"(x));
+  return x;
+}
 
 __device__ __forceinline__ uint32_t key_bound(uint32_t span, uint2 q) {  // B'(c) = floor(size*c/2^p) - 1
   return (uint32_t)(((unsigned long long)span * q.x + (((unsigned long long)q.y << 32) | q.x)) >> 32);
@@ -1049,22 +1058,25 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
 }
 
 struct Dec2 {
-  uint32_t base, span, value, pos;
-  uint32_t next;       // word at index pos
-  uint32_t ring_addr;  // shared address of DecShared::ring
+  uint32_t base, span, value;
+  uint32_t pos2;       // stream position in BYTES (2 * word index)
+  uint32_t next;       // word at that position
+  uint32_t ring_addr;  // shared address of the word ring (4096-byte aligned)
   int lane;
 
-  __device__ __forceinline__ void seek() { next = lds_u16(ring_addr + ((pos & (kRing - 1)) << 1)); }
-  // new interval [base + a, base + b1] and 16-bit renormalisation (range_coder.h:255-268); branch free
+  __device__ __forceinline__ void seek() { next = lds_u16(ring_addr | (pos2 & (2 * kRing - 2))); }
+  // new interval [base + a, base + b1] and 16-bit renormalisation (range_coder.h:255-268); branch free:
+  // all three 16-bit shifts are one byte permute with a shared selector
   __device__ __forceinline__ void update(uint32_t a, uint32_t b1) {
     const uint32_t nb = base + a;
     const uint32_t s = b1 - a;
     const bool renorm = s < 65536u;
-    span = renorm ? ((s << 16) | 0xFFFFu) : s;
-    base = renorm ? (nb << 16) : nb;
-    value = renorm ? ((value << 16) | next) : value;
-    pos += renorm ? 1u : 0u;
-    next = lds_u16(ring_addr + ((pos & (kRing - 1)) << 1));  // consumed at the next renormalisation, not before
+    const uint32_t sel = renorm ? 0x1054u : 0x3210u;  // {x.b1, x.b0, y.b1, y.b0} : x
+    span = __byte_perm(s, 0xFFFFFFFFu, sel);
+    base = __byte_perm(nb, 0u, sel);
+    value = __byte_perm(value, next, sel);
+    pos2 += renorm ? 2u : 0u;
+    next = lds_u16(ring_addr | (pos2 & (2 * kRing - 2)));  // consumed at the next renormalisation, not before
   }
   // DecodeLinearly({0,1,2}, 1), range_coder_kernels.cc:450,461-469
   __device__ __forceinline__ uint32_t bit() {
@@ -1120,6 +1132,11 @@ template <int MODE, bool SMEM>
 __global__ void __launch_bounds__(96) decode_kernel(const DecParams P) {
   extern __shared__ __align__(16) uint8_t s_dyn[];
   __shared__ __align__(16) DecShared sh;
+  // The stream's next words, filled ahead by the prepare warp.  The chain warp addresses the ring as
+  // base | offset, so its ABSOLUTE shared address must be 4096-byte aligned (static alignment is relative to the
+  // CTA's window, which starts after the reserved 1 KB): carve an aligned ring out of a buffer twice the size.
+  __shared__ __align__(16) uint16_t ring_buf[2 * kRing];
+  uint16_t* const ring = ring_buf + (((4096u - (smem_addr(ring_buf) & 4095u)) & 4095u) >> 1);
   const long long s = blockIdx.x;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -1147,7 +1164,7 @@ __global__ void __launch_bounds__(96) decode_kernel(const DecParams P) {
     bw.len = P.offsets[s + 1] - P.offsets[s];
     long long filled = (long long)P.state[s].pos;  // ring holds words [.., filled)
     auto fill_ring = [&](long long upto) {
-      for (long long wi = filled + lane; wi < upto; wi += 32) sh.ring[wi & (kRing - 1)] = (uint16_t)bw_fetch(bw, wi);
+      for (long long wi = filled + lane; wi < upto; wi += 32) ring[wi & (kRing - 1)] = (uint16_t)bw_fetch(bw, wi);
       filled = max(filled, upto);
     };
     fill_ring(filled + kRingAhead);
@@ -1179,10 +1196,10 @@ __global__ void __launch_bounds__(96) decode_kernel(const DecParams P) {
         }
         const int4 r4 = rows4[row];
         DecDesc d;
-        d.win = r4.x + r4.z;
-        d.flags = (row_ovf(r4.y) ? 1 : 0) | (r4.z > 1 ? 2 : 0) | (r4.w ? 4 : 0);
+        d.win = r4.w ? P.zero_win : r4.x + r4.z;
+        d.thr = (r4.z > 1 || r4.w) ? 1u : 0u;
         d.seg = r4.x;
-        d.n = row_ncdf(r4.y) - 1;
+        d.n = (row_ncdf(r4.y) - 1) | (row_ovf(r4.y) ? (int)0x80000000 : 0);
         sh.desc[b][sub * 32 + lane] = d;
         if (sub == kDecGroup / 32 - 1 && lane < 2) sh.desc[b][kDecGroup + lane] = d;  // pipeline overrun slots
       }
@@ -1252,9 +1269,9 @@ __global__ void __launch_bounds__(96) decode_kernel(const DecParams P) {
     c.base = st.base;
     c.span = st.span;
     c.value = st.value;
-    c.pos = st.pos;
+    c.pos2 = st.pos << 1;
   }
-  c.ring_addr = smem_addr(sh.ring);
+  c.ring_addr = opaque(smem_addr(ring));
   bool started = false;
 
   for (long long g = 0; g < n_groups; ++g) {
@@ -1262,9 +1279,9 @@ __global__ void __launch_bounds__(96) decode_kernel(const DecParams P) {
     bar_sync(kBarDescFull + b, 64);
     if (!started) {  // the ring is valid from here on
       started = true;
-      if (c.pos == 0) {  // fresh stream: the constructor reads four bytes (range_coder.h:79-83)
-        c.value = ((uint32_t)sh.ring[0] << 16) | (uint32_t)sh.ring[1];
-        c.pos = 2;
+      if (c.pos2 == 0) {  // fresh stream: the constructor reads four bytes (range_coder.h:79-83)
+        c.value = ((uint32_t)ring[0] << 16) | (uint32_t)ring[1];
+        c.pos2 = 4;
       }
       c.seek();
     }
@@ -1273,75 +1290,88 @@ __global__ void __launch_bounds__(96) decode_kernel(const DecParams P) {
     if (g >= 2) bar_sync(kBarDecEntEmpty + b, 64);  // the resolve warp is done with this entry buffer
     const DecDesc* desc = sh.desc[b];
     unsigned om0 = 0, om1 = 0, om2 = 0, om3 = 0;  // symbols finished on this warp (bit per symbol)
-    const uint32_t desc_addr = smem_addr(sh.desc[b]);
-    const uint32_t ent_addr = smem_addr(sh.ent[b]);
+    // opaque shared addresses: keeps them in registers instead of being re-derived every symbol
+    const uint32_t desc_addr = opaque(smem_addr(sh.desc[b]));
+    const uint32_t ent_addr = opaque(smem_addr(sh.ent[b]));
     const uint2* lkeys = pairs + lane;  // this lane's two candidates: lkeys[win], lkeys[win + 32]
-    const uint32_t lkeys_addr = SMEM ? smem_addr(lkeys) : 0u;
-    auto load_keys = [&](int win, uint2* q0, uint2* q1) {
+    const uint32_t lkeys_addr = SMEM ? opaque(smem_addr(lkeys)) : 0u;
+    auto load_keys = [&](uint32_t win, uint2& q0, uint2& q1) {
       if (SMEM) {
-        *q0 = lds_v2(lkeys_addr + (uint32_t)win * 8u);
-        *q1 = lds_v2(lkeys_addr + (uint32_t)win * 8u + 256u);
+        q0 = lds_v2(lkeys_addr + win * 8u);
+        q1 = lds_v2(lkeys_addr + win * 8u + 256u);
       } else {
-        *q0 = __ldg(lkeys + win);
-        *q1 = __ldg(lkeys + win + 32);
+        q0 = __ldg(lkeys + win);
+        q1 = __ldg(lkeys + win + 32);
       }
     };
-    // software pipeline: descriptor two symbols ahead, candidate keys one symbol ahead
-    uint2 d1 = lds_v2(desc_addr);
-    uint2 d2 = lds_v2(desc_addr + 16u);
-    uint2 q0n, q1n;
-    load_keys((int)d1.x, &q0n, &q1n);
-#pragma unroll 4
-    for (int k = 0; k < count; ++k) {
-      const int2 d = make_int2((int)d1.x, (int)d1.y);
-      const uint2 q0 = q0n, q1 = q1n;
-      d1 = d2;
-      d2 = lds_v2(desc_addr + (uint32_t)(k + 2) * 16u);
-      load_keys((int)d1.x, &q0n, &q1n);
-
+    // One symbol.  dc = descriptor of this symbol (reloaded with the one two ahead once used), dn = the next
+    // symbol's; qc* = this symbol's candidate keys, qn* = receives the next symbol's.  Called with the roles
+    // swapped on alternate symbols so that the software pipeline needs no register moves.
+    uint32_t daddr = desc_addr + 32u;  // descriptor two symbols ahead
+    uint32_t eaddr = ent_addr;         // this symbol's entry
+    auto step = [&](uint2& dc, const uint2& dn, const uint2& qc0, const uint2& qc1, uint2& qn0, uint2& qn1) {
+      load_keys(dn.x, qn0, qn1);
+      const uint32_t thr = dc.y;
+      dc = lds_v2(daddr);
+      daddr += 16u;
       const uint32_t v = c.value - c.base;
       const uint32_t span0 = c.span;
-      const uint32_t B0 = key_bound(span0, q0), B1 = key_bound(span0, q1);
+      const uint32_t B0 = key_bound(span0, qc0), B1 = key_bound(span0, qc1);
       const bool ge0 = v <= B0, ge1 = v <= B1;
       const uint32_t m = ge0 ? B0 : (ge1 ? B1 : 0xFFFFFFFFu);
       const uint32_t am = ge1 ? (ge0 ? 0u : B0 + 1u) : B1 + 1u;
       uint32_t b1 = __reduce_min_sync(kFull, m);
       uint32_t a = __reduce_max_sync(kFull, am);
-      sts_v2(ent_addr + (uint32_t)k * 8u, v, span0);
-      // fast path unless: no key >= v in the window, nothing below although the window starts inside the row,
-      // an irregular row, or the escape bin of an overflow row
-      const bool rare = (b1 == 0xFFFFFFFFu) || (a == 0u && (d.y & 2)) || (d.y & 4) || ((d.y & 1) && b1 == span0);
-      if (!rare) {
+      sts_v2(eaddr, v, span0);
+      eaddr += 8u;
+      // Fast path: the window holds a key >= v that is not the row's last one, and (unless the window starts
+      // the row) a key below v.  b1 >= span0 covers "no key" (~0) and the last bin (escape of overflow rows).
+      if (b1 < span0 && a >= thr) {
         c.update(a, b1);
-        continue;
-      }
-      // ---- rare path: finish the symbol here ----
-      const DecDesc df = desc[k];
-      const int n = df.n;
-      int sym = n - 1;
-      const bool in_window = !((b1 == 0xFFFFFFFFu) || (a == 0u && (d.y & 2)) || (d.y & 4));
-      if (!in_window) sym = c.search_row(pairs, df.seg, n, &a, &b1);
-      else if (!((d.y & 1) && b1 == span0)) sym = -1;  // unreachable
-      c.update(a, b1);
-      if ((d.y & 1) && sym == n - 1) {  // OverflowDecode, range_coder_kernels.cc:449-471
-        int nb = 0;
-        while (c.bit() == 0 && nb < 64) ++nb;
-        uint32_t val = (nb < 32) ? (1u << nb) : 0u;
-        int t = nb;
-        while (--t >= 0) {
-          const uint32_t bitv = c.bit();
-          if (t < 32) val |= bitv << t;
+      } else {
+        // ---- rare path ----
+        const int k = (int)((eaddr - 8u - ent_addr) >> 3);
+        const DecDesc df = desc[k];
+        const int n = df.n & 0x7FFFFFFF;
+        const bool ovf = df.n < 0;
+        const bool miss = (b1 == 0xFFFFFFFFu) || (a < thr);
+        int sym = n - 1;  // in-window hit with b1 == span: the row's last bin (regular rows)
+        if (miss) sym = c.search_row(pairs, df.seg, n, &a, &b1);
+        c.update(a, b1);
+        bool finished = miss;
+        if (ovf && sym == n - 1) {  // OverflowDecode, range_coder_kernels.cc:449-471
+          int nb = 0;
+          while (c.bit() == 0 && nb < 64) ++nb;
+          uint32_t val = (nb < 32) ? (1u << nb) : 0u;
+          int t = nb;
+          while (--t >= 0) {
+            const uint32_t bitv = c.bit();
+            if (t < 32) val |= bitv << t;
+          }
+          const uint32_t sg = c.bit();
+          sym = sg ? -(int)val : (int)val + (n - 1) - 1;
+          finished = true;
         }
-        const uint32_t sg = c.bit();
-        sym = sg ? -(int)val : (int)val + (n - 1) - 1;
+        if (finished) {  // otherwise the resolve warp finds the (last) bin like any other
+          sh.ovr[b][k] = sym;
+          const unsigned bitk = 1u << (k & 31);
+          om0 |= (k >> 5) == 0 ? bitk : 0u;
+          om1 |= (k >> 5) == 1 ? bitk : 0u;
+          om2 |= (k >> 5) == 2 ? bitk : 0u;
+          om3 |= (k >> 5) == 3 ? bitk : 0u;
+        }
       }
-      sh.ovr[b][k] = sym;
-      const unsigned bitk = 1u << (k & 31);
-      om0 |= (k >> 5) == 0 ? bitk : 0u;
-      om1 |= (k >> 5) == 1 ? bitk : 0u;
-      om2 |= (k >> 5) == 2 ? bitk : 0u;
-      om3 |= (k >> 5) == 3 ? bitk : 0u;
+    };
+    uint2 da = lds_v2(desc_addr), db = lds_v2(desc_addr + 16u);
+    uint2 qa0, qa1, qb0, qb1;
+    load_keys(da.x, qa0, qa1);
+    const uint32_t eend = ent_addr + (uint32_t)(count & ~1) * 8u;
+#pragma unroll 2
+    while (eaddr != eend) {
+      step(da, db, qa0, qa1, qb0, qb1);
+      step(db, da, qb0, qb1, qa0, qa1);
     }
+    if (count & 1) step(da, db, qa0, qa1, qb0, qb1);
     const unsigned omask[kDecGroup / 32] = {om0, om1, om2, om3};
     if (lane == 0) {
 #pragma unroll
@@ -1352,7 +1382,7 @@ __global__ void __launch_bounds__(96) decode_kernel(const DecParams P) {
     bar_arrive(kBarDecEntFull + b, 64);
     if (bad) break;
     if (g + 2 < n_groups) {
-      if (lane == 0) sh.pos_pub[b] = c.pos;
+      if (lane == 0) sh.pos_pub[b] = c.pos2 >> 1;
       bar_arrive(kBarDescEmpty + b, 64);
     }
   }
@@ -1361,7 +1391,7 @@ __global__ void __launch_bounds__(96) decode_kernel(const DecParams P) {
     st.base = c.base;
     st.span = c.span;
     st.value = c.value;
-    st.pos = c.pos;
+    st.pos = c.pos2 >> 1;
     P.state[s] = st;
   }
 }
@@ -1836,6 +1866,7 @@ int launch_decode(tfcb_decoder* h, const int32_t* index, void* out, const float*
   P.pairs = h->lut.pairs;
   P.rows4 = h->lut.rows4;
   P.n_pairs = h->lut.n_pairs;
+  P.zero_win = h->lut.zero_win;
   P.n_rows = h->lut.n_rows;
   P.lookup_len = h->lut.len;
   P.bytes = h->bytes;
