@@ -1057,6 +1057,13 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
   return r;
 }
 
+// volatile: keeps the interval update ahead of the branch that follows it in program order
+__device__ __forceinline__ uint32_t prmt(uint32_t x, uint32_t y, uint32_t sel) {
+  uint32_t r;
+  asm volatile("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(y), "r"(sel));
+  return r;
+}
+
 struct Dec2 {
   uint32_t base, span, value;
   uint32_t pos2;       // stream position in BYTES (2 * word index)
@@ -1072,9 +1079,9 @@ struct Dec2 {
     const uint32_t s = b1 - a;
     const bool renorm = s < 65536u;
     const uint32_t sel = renorm ? 0x1054u : 0x3210u;  // {x.b1, x.b0, y.b1, y.b0} : x
-    span = __byte_perm(s, 0xFFFFFFFFu, sel);
-    base = __byte_perm(nb, 0u, sel);
-    value = __byte_perm(value, next, sel);
+    span = prmt(s, 0xFFFFFFFFu, sel);
+    base = prmt(nb, 0u, sel);
+    value = prmt(value, next, sel);
     pos2 += renorm ? 2u : 0u;
     next = lds_u16(ring_addr | (pos2 & (2 * kRing - 2)));  // consumed at the next renormalisation, not before
   }
@@ -1304,12 +1311,16 @@ __global__ void __launch_bounds__(96) decode_kernel(const DecParams P) {
         q1 = __ldg(lkeys + win + 32);
       }
     };
-    // One symbol.  dc = descriptor of this symbol (reloaded with the one two ahead once used), dn = the next
-    // symbol's; qc* = this symbol's candidate keys, qn* = receives the next symbol's.  Called with the roles
-    // swapped on alternate symbols so that the software pipeline needs no register moves.
+    // One symbol of the fast path.  dc = descriptor of this symbol (reloaded with the one two ahead once
+    // used), dn = the next symbol's; qc* = this symbol's candidate keys, qn* = receives the next symbol's.
+    // Called with the roles swapped on alternate symbols so that the software pipeline needs no register
+    // moves.  The interval update is issued BEFORE the "is this symbol special" branch so that the branch
+    // latency is off the serial chain; a special symbol restores the state and leaves the loop.
     uint32_t daddr = desc_addr + 32u;  // descriptor two symbols ahead
     uint32_t eaddr = ent_addr;         // this symbol's entry
-    auto step = [&](uint2& dc, const uint2& dn, const uint2& qc0, const uint2& qc1, uint2& qn0, uint2& qn1) {
+    const uint32_t eend = ent_addr + (uint32_t)count * 8u;
+    uint32_t ra = 0, rb1 = 0, rthr = 0;  // the special symbol's window answer
+    auto step = [&](uint2& dc, const uint2& dn, const uint2& qc0, const uint2& qc1, uint2& qn0, uint2& qn1) -> bool {
       load_keys(dn.x, qn0, qn1);
       const uint32_t thr = dc.y;
       dc = lds_v2(daddr);
@@ -1320,58 +1331,82 @@ __global__ void __launch_bounds__(96) decode_kernel(const DecParams P) {
       const bool ge0 = v <= B0, ge1 = v <= B1;
       const uint32_t m = ge0 ? B0 : (ge1 ? B1 : 0xFFFFFFFFu);
       const uint32_t am = ge1 ? (ge0 ? 0u : B0 + 1u) : B1 + 1u;
-      uint32_t b1 = __reduce_min_sync(kFull, m);
-      uint32_t a = __reduce_max_sync(kFull, am);
+      const uint32_t b1 = __reduce_min_sync(kFull, m);
+      const uint32_t a = __reduce_max_sync(kFull, am);
       sts_v2(eaddr, v, span0);
       eaddr += 8u;
       // Fast path: the window holds a key >= v that is not the row's last one, and (unless the window starts
       // the row) a key below v.  b1 >= span0 covers "no key" (~0) and the last bin (escape of overflow rows).
-      if (b1 < span0 && a >= thr) {
-        c.update(a, b1);
-      } else {
-        // ---- rare path ----
-        const int k = (int)((eaddr - 8u - ent_addr) >> 3);
-        const DecDesc df = desc[k];
-        const int n = df.n & 0x7FFFFFFF;
-        const bool ovf = df.n < 0;
-        const bool miss = (b1 == 0xFFFFFFFFu) || (a < thr);
-        int sym = n - 1;  // in-window hit with b1 == span: the row's last bin (regular rows)
-        if (miss) sym = c.search_row(pairs, df.seg, n, &a, &b1);
-        c.update(a, b1);
-        bool finished = miss;
-        if (ovf && sym == n - 1) {  // OverflowDecode, range_coder_kernels.cc:449-471
-          int nb = 0;
-          while (c.bit() == 0 && nb < 64) ++nb;
-          uint32_t val = (nb < 32) ? (1u << nb) : 0u;
-          int t = nb;
-          while (--t >= 0) {
-            const uint32_t bitv = c.bit();
-            if (t < 32) val |= bitv << t;
-          }
-          const uint32_t sg = c.bit();
-          sym = sg ? -(int)val : (int)val + (n - 1) - 1;
-          finished = true;
-        }
-        if (finished) {  // otherwise the resolve warp finds the (last) bin like any other
-          sh.ovr[b][k] = sym;
-          const unsigned bitk = 1u << (k & 31);
-          om0 |= (k >> 5) == 0 ? bitk : 0u;
-          om1 |= (k >> 5) == 1 ? bitk : 0u;
-          om2 |= (k >> 5) == 2 ? bitk : 0u;
-          om3 |= (k >> 5) == 3 ? bitk : 0u;
-        }
+      const bool special = !(b1 < span0 && a >= thr);
+      const uint32_t base0 = c.base, value0 = c.value, pos0 = c.pos2, next0 = c.next;
+      c.update(a, b1);
+      if (special) {
+        c.base = base0;
+        c.span = span0;
+        c.value = value0;
+        c.pos2 = pos0;
+        c.next = next0;
+        ra = a;
+        rb1 = b1;
+        rthr = thr;
       }
+      return special;
     };
-    uint2 da = lds_v2(desc_addr), db = lds_v2(desc_addr + 16u);
-    uint2 qa0, qa1, qb0, qb1;
-    load_keys(da.x, qa0, qa1);
-    const uint32_t eend = ent_addr + (uint32_t)(count & ~1) * 8u;
-#pragma unroll 2
-    while (eaddr != eend) {
-      step(da, db, qa0, qa1, qb0, qb1);
-      step(db, da, qb0, qb1, qa0, qa1);
+    uint2 da, db, qa0, qa1, qb0, qb1;
+    auto prime = [&](uint32_t k) {  // restart the software pipeline at symbol k
+      daddr = desc_addr + k * 16u;
+      da = lds_v2(daddr);
+      db = lds_v2(daddr + 16u);
+      daddr += 32u;
+      load_keys(da.x, qa0, qa1);
+    };
+    prime(0u);
+    for (;;) {
+      bool special = false;
+      for (;;) {
+        if (eaddr == eend) break;
+        special = step(da, db, qa0, qa1, qb0, qb1);
+        if (special) break;
+        if (eaddr == eend) break;
+        special = step(db, da, qb0, qb1, qa0, qa1);
+        if (special) break;
+      }
+      if (!special) break;
+      // ---- special symbol k: its entry is stored, the coder state is the one before it ----
+      const int k = (int)((eaddr - 8u - ent_addr) >> 3);
+      uint32_t a = ra, b1 = rb1;
+      const DecDesc df = desc[k];
+      const int n = df.n & 0x7FFFFFFF;
+      const bool ovf = df.n < 0;
+      const bool miss = (b1 == 0xFFFFFFFFu) || (a < rthr);
+      int sym = n - 1;  // in-window hit with b1 == span: the row's last bin (regular rows)
+      if (miss) sym = c.search_row(pairs, df.seg, n, &a, &b1);
+      c.update(a, b1);
+      bool finished = miss;
+      if (ovf && sym == n - 1) {  // OverflowDecode, range_coder_kernels.cc:449-471
+        int nb = 0;
+        while (c.bit() == 0 && nb < 64) ++nb;
+        uint32_t val = (nb < 32) ? (1u << nb) : 0u;
+        int t = nb;
+        while (--t >= 0) {
+          const uint32_t bitv = c.bit();
+          if (t < 32) val |= bitv << t;
+        }
+        const uint32_t sg = c.bit();
+        sym = sg ? -(int)val : (int)val + (n - 1) - 1;
+        finished = true;
+      }
+      if (finished) {  // otherwise the resolve warp finds the (last) bin like any other
+        sh.ovr[b][k] = sym;
+        const unsigned bitk = 1u << (k & 31);
+        om0 |= (k >> 5) == 0 ? bitk : 0u;
+        om1 |= (k >> 5) == 1 ? bitk : 0u;
+        om2 |= (k >> 5) == 2 ? bitk : 0u;
+        om3 |= (k >> 5) == 3 ? bitk : 0u;
+      }
+      prime((uint32_t)k + 1u);
     }
-    if (count & 1) step(da, db, qa0, qa1, qb0, qb1);
+
     const unsigned omask[kDecGroup / 32] = {om0, om1, om2, om3};
     if (lane == 0) {
 #pragma unroll
