@@ -448,6 +448,372 @@ int launch_tc(const float* x, const float* gamma, const float* beta, float* y, l
   return TFCB_OK;
 }
 
+
+// =============================================================================================
+// Backward (C = 128): one fused kernel per launch instead of three fp32 passes.
+//
+//   n  = beta + p . gamma                 MMA1   A = p planes (K-major),        B = gamma planes (K-major)
+//   q  = dL/dn (elementwise, from g, x, n)
+//   dp = q . gamma^T                      MMA2   A = q planes (K-major),        B = gamma planes (MN-major view)
+//   dx = g / m + dpool/du * dp            (IGDN: g * m + ...)
+//   dgamma[j, i] += sum_pix p[pix, j] q[pix, i]
+//                                         MMA3   A = p planes (MN-major view),  B = q planes (MN-major view)
+//   dbeta[i] += sum_pix q[pix, i]         warp transpose-reduce of the q registers
+//
+// The MN-major views reuse the very same shared-memory planes: a K-major plane [k / 8][row][8] read with the
+// "transposed" descriptor (instruction-descriptor bits 15 / 16) is the operand with the roles of row and k
+// swapped (core matrix = 8 k-rows of 16 bytes, LBO = 128 B between k groups, SBO = plane row-group stride).
+// TMEM: columns [0, C) n, [C, 2C) dp, [2C, 3C) this CTA's dgamma partial (accumulates over all its tiles).
+// HBM traffic per element: x and dy once (their re-reads in the two epilogues are L2 hits), dx once.
+// =============================================================================================
+constexpr int kBwdThreads = 256;  // two threads per pixel row: thread (r, h) owns 16 of every 32 channels
+
+template <int C>
+struct BwdSmem {
+  static constexpr int kPlaneB = C * C * 2;          // gamma hi / lo
+  static constexpr int kPlaneP = kTileM * C * 2;     // p hi / lo (whole K)
+  static constexpr int kPlaneQ = kTileM * 32 * 2;    // q hi / lo, one 32-channel chunk
+  static constexpr int kOffBh = 0;
+  static constexpr int kOffBl = kOffBh + kPlaneB;
+  static constexpr int kOffPh = kOffBl + kPlaneB;
+  static constexpr int kOffPl = kOffPh + kPlaneP;
+  static constexpr int kOffQ = kOffPl + kPlaneP;     // [2 buffers][hi, lo]
+  static constexpr int kOffBeta = kOffQ + 4 * kPlaneQ;
+  static constexpr int kOffDbeta = kOffBeta + C * 4;
+  static constexpr int kOffBar = kOffDbeta + C * 4;
+  static constexpr int kBytes = kOffBar + 64;
+};
+
+template <bool FAST>
+__device__ __forceinline__ float tc_dl_dn(float g, float x, float n, const TcFlags& f) {
+  const float u = (!FAST && f.rectify) ? fmaxf(x, 0.f) : x;
+  const float r = rcp_approx(n);
+  if (FAST || f.eps_mode == 1) return f.inverse ? g * u : -g * u * r * r;
+  const float rs = rsqrtf(n);
+  return f.inverse ? 0.5f * g * u * rs : -0.5f * g * u * r * rs;
+}
+
+template <bool FAST>
+__device__ __forceinline__ float tc_dx(float g, float x, float n, float dp, const TcFlags& f) {
+  const float u = (!FAST && f.rectify) ? fmaxf(x, 0.f) : x;
+  float direct;
+  if (FAST || f.eps_mode == 1) direct = f.inverse ? g * n : g * rcp_approx(n);
+  else direct = f.inverse ? g * sqrtf(n) : g * rsqrtf(n);
+  float dpool;
+  if (FAST || f.alpha_mode == 1) dpool = (!FAST && f.rectify) ? 1.f : ((u > 0.f) ? 1.f : ((u < 0.f) ? -1.f : 0.f));
+  else dpool = 2.f * u;
+  float d = direct + dpool * dp;
+  if (!FAST && f.rectify && !(x > 0.f)) d = 0.f;
+  return d;
+}
+
+// Sum of v[k] over the 32 lanes for each of 16 values; on return v[0] holds the total of value bwd_channel(lane).
+__device__ __forceinline__ int bwd_channel(int lane) { return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1); }
+__device__ __forceinline__ void transpose_reduce16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int w = 8, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
+    const bool up = (lane & bit) != 0;
+#pragma unroll
+    for (int i = 0; i < w; ++i) {
+      const float send = up ? v[i] : v[i + w];
+      const float keep = up ? v[i + w] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, bit);
+    }
+  }
+  v[0] += __shfl_xor_sync(0xFFFFFFFFu, v[0], 1);
+}
+
+template <int C, bool FAST>
+__global__ void __launch_bounds__(kBwdThreads, 1)
+gdn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, const __nv_bfloat16* __restrict__ planes,
+                  const float* __restrict__ beta, float* __restrict__ dx, float* __restrict__ part_g,
+                  float* __restrict__ part_b, long long n_pix, TcFlags f) {
+  using L = BwdSmem<C>;
+  static_assert(C == 128, "TMEM holds n, dp and the dgamma partial only for C = 128");
+  constexpr int NCH = C / 32;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float* beta_s = reinterpret_cast<float*>(smem + L::kOffBeta);
+  float* dbeta_s = reinterpret_cast<float*>(smem + L::kOffDbeta);
+  uint64_t* mbars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);  // [0] MMA1, [1], [2] q buffers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffBar + 32);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int r = tid & 127, h = tid >> 7, gwarp = (tid >> 5) & 3;
+  constexpr uint32_t kIdesc1 = umma_idesc(kTileM, C);
+  constexpr uint32_t kIdesc2 = umma_idesc(kTileM, C) | (1u << 16);             // B = gamma^T (MN-major view)
+  constexpr uint32_t kIdesc3 = umma_idesc(C, 32) | (1u << 15) | (1u << 16);    // A = p^T, B = q chunk (both views)
+
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(planes);
+    uint4* dst = reinterpret_cast<uint4*>(smem + L::kOffBh);
+    for (int i = tid; i < 2 * L::kPlaneB / 16; i += kBwdThreads) dst[i] = src[i];
+    for (int i = tid; i < C; i += kBwdThreads) {
+      beta_s[i] = beta[i];
+      dbeta_s[i] = 0.f;
+    }
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 3; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbars + i)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_n = *tmem_slot, tmem_dp = tmem_n + C, tmem_dg = tmem_n + 2 * C;
+  const uint32_t lane_sel = (uint32_t)(gwarp * 32) << 16;
+  const uint32_t b_hi = smem_u32(smem + L::kOffBh), b_lo = smem_u32(smem + L::kOffBl);
+  const uint32_t p_hi = smem_u32(smem + L::kOffPh), p_lo = smem_u32(smem + L::kOffPl);
+  uint32_t par0 = 0u, parq[2] = {0u, 0u};
+  float dbeta_acc[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) dbeta_acc[c] = 0.f;
+  bool first_tile = true;
+
+  const long long n_tiles = (n_pix + kTileM - 1) / kTileM;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long p0 = tile * kTileM;
+    const bool live = p0 + r < n_pix;
+    const float* xrow = x + (p0 + r) * C + h * 16;
+    const float* grow = dy + (p0 + r) * C + h * 16;
+    float* orow = dx + (p0 + r) * C + h * 16;
+    // pull the next tile of this CTA into L2 while this one is processed
+    {
+      const long long pn = (tile + gridDim.x) * kTileM;
+      const long long rows = min((long long)kTileM, n_pix - pn);
+      if (rows > 0) {
+        const long long bytes = rows * C * 4;
+        for (long long off = (long long)tid * 128; off < bytes; off += (long long)kBwdThreads * 128) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(x + pn * C) + off));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(dy + pn * C) + off));
+        }
+      }
+    }
+    // ---- P1: p = pool(x) -> hi / lo planes [j / 8][row][8]; MMA1 ----
+    {
+      float4 xv[NCH][4];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          xv[c][i] = live ? __ldg(reinterpret_cast<const float4*>(xrow + c * 32) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float4 a = xv[c][2 * e], b = xv[c][2 * e + 1];
+          float v[8] = {tc_pool<FAST>(a.x, f), tc_pool<FAST>(a.y, f), tc_pool<FAST>(a.z, f), tc_pool<FAST>(a.w, f),
+                        tc_pool<FAST>(b.x, f), tc_pool<FAST>(b.y, f), tc_pool<FAST>(b.z, f), tc_pool<FAST>(b.w, f)};
+          uint4 hi, lo;
+          split8(v, &hi, &lo);
+          const int kg = c * 4 + h * 2 + e;
+          *reinterpret_cast<uint4*>(smem + L::kOffPh + kg * (kTileM * 16) + r * 16) = hi;
+          *reinterpret_cast<uint4*>(smem + L::kOffPl + kg * (kTileM * 16) + r * 16) = lo;
+        }
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int s = 0; s < C / 16; ++s) {
+        const uint64_t dah = umma_desc(p_hi + (uint32_t)(2 * s) * (kTileM * 16), kTileM * 16, 128);
+        const uint64_t dal = umma_desc(p_lo + (uint32_t)(2 * s) * (kTileM * 16), kTileM * 16, 128);
+        const uint64_t dbh = umma_desc(b_hi + (uint32_t)(2 * s) * (C * 16), C * 16, 128);
+        const uint64_t dbl = umma_desc(b_lo + (uint32_t)(2 * s) * (C * 16), C * 16, 128);
+        umma_bf16(tmem_n, dah, dbh, kIdesc1, s ? 1u : 0u);
+        umma_bf16(tmem_n, dal, dbh, kIdesc1, 1u);
+        umma_bf16(tmem_n, dah, dbl, kIdesc1, 1u);
+      }
+      umma_commit(smem_u32(mbars));
+    }
+    // ---- P2: q = dL/dn per 32-channel chunk -> q planes; MMA2 (dp) and MMA3 (dgamma) per chunk ----
+    float4 xq[4], gq[4];
+    auto load_xg = [&](int c) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        xq[i] = live ? __ldg(reinterpret_cast<const float4*>(xrow + c * 32) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        gq[i] = live ? __ldg(reinterpret_cast<const float4*>(grow + c * 32) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    load_xg(0);
+    if (!mbar_wait(smem_u32(mbars), par0)) __trap();
+    par0 ^= 1u;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int b = c & 1;
+      uint32_t acc[16];
+      tmem_load<16>(tmem_n + lane_sel + (uint32_t)(c * 32 + h * 16), acc);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float q[16];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 bv = *reinterpret_cast<const float4*>(beta_s + c * 32 + h * 16 + 4 * i);
+        q[4 * i + 0] = tc_dl_dn<FAST>(gq[i].x, xq[i].x, bv.x + __uint_as_float(acc[4 * i + 0]), f);
+        q[4 * i + 1] = tc_dl_dn<FAST>(gq[i].y, xq[i].y, bv.y + __uint_as_float(acc[4 * i + 1]), f);
+        q[4 * i + 2] = tc_dl_dn<FAST>(gq[i].z, xq[i].z, bv.z + __uint_as_float(acc[4 * i + 2]), f);
+        q[4 * i + 3] = tc_dl_dn<FAST>(gq[i].w, xq[i].w, bv.w + __uint_as_float(acc[4 * i + 3]), f);
+      }
+      if (c + 1 < NCH) load_xg(c + 1);
+      // the q buffer was read by the MMAs of chunk c - 2
+      if (c >= 2) {  // (chunks 2 and 3 of the previous tile were waited for before its dx pass)
+        if (!mbar_wait(smem_u32(mbars + 1 + b), parq[b])) __trap();
+        parq[b] ^= 1u;
+      }
+      uint8_t* qh = smem + L::kOffQ + b * 2 * L::kPlaneQ;
+      uint8_t* ql = qh + L::kPlaneQ;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = q[8 * e + i];
+        uint4 hi, lo;
+        split8(v, &hi, &lo);
+        const int kg = h * 2 + e;
+        *reinterpret_cast<uint4*>(qh + kg * (kTileM * 16) + r * 16) = hi;
+        *reinterpret_cast<uint4*>(ql + kg * (kTileM * 16) + r * 16) = lo;
+      }
+      transpose_reduce16(q, lane);
+      dbeta_acc[c] += q[0];
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t q_hi = smem_u32(qh), q_lo = smem_u32(ql);
+        // MMA2: dp[pix, j] += sum_{i in chunk} q[pix, i] gamma[j, i]   (K = i: 2 steps of 16)
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const uint64_t dah = umma_desc(q_hi + (uint32_t)(2 * s) * (kTileM * 16), kTileM * 16, 128);
+          const uint64_t dal = umma_desc(q_lo + (uint32_t)(2 * s) * (kTileM * 16), kTileM * 16, 128);
+          // gamma plane viewed with n = j, k = i: k rows are 16 B apart, k groups 128 B, n groups C * 16 B
+          const uint32_t koff = (uint32_t)(c * 32 + s * 16) * 16u;
+          const uint64_t dbh = umma_desc(b_hi + koff, 128, C * 16);
+          const uint64_t dbl = umma_desc(b_lo + koff, 128, C * 16);
+          umma_bf16(tmem_dp, dah, dbh, kIdesc2, (c | s) ? 1u : 0u);
+          umma_bf16(tmem_dp, dal, dbh, kIdesc2, 1u);
+          umma_bf16(tmem_dp, dah, dbl, kIdesc2, 1u);
+        }
+        // MMA3: dgamma[j, i in chunk] += sum_pix p[pix, j] q[pix, i]   (K = pix: 8 steps of 16)
+#pragma unroll
+        for (int s = 0; s < kTileM / 16; ++s) {
+          const uint32_t koff = (uint32_t)(s * 16) * 16u;
+          const uint64_t dah = umma_desc(p_hi + koff, 128, kTileM * 16);
+          const uint64_t dal = umma_desc(p_lo + koff, 128, kTileM * 16);
+          const uint64_t dbh = umma_desc(q_hi + koff, 128, kTileM * 16);
+          const uint64_t dbl = umma_desc(q_lo + koff, 128, kTileM * 16);
+          const uint32_t acc_on = (first_tile && s == 0) ? 0u : 1u;
+          umma_bf16(tmem_dg + (uint32_t)(c * 32), dah, dbh, kIdesc3, acc_on);
+          umma_bf16(tmem_dg + (uint32_t)(c * 32), dal, dbh, kIdesc3, 1u);
+          umma_bf16(tmem_dg + (uint32_t)(c * 32), dah, dbl, kIdesc3, 1u);
+        }
+        umma_commit(smem_u32(mbars + 1 + b));
+      }
+    }
+    // ---- P3: dx = g / m + dpool/du * dp ----
+    load_xg(0);
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {  // commits of chunks 2 and 3: all MMAs of this tile are done
+      if (!mbar_wait(smem_u32(mbars + 1 + b), parq[b])) __trap();
+      parq[b] ^= 1u;
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      uint32_t an[16], ad[16];
+      tmem_load<16>(tmem_n + lane_sel + (uint32_t)(c * 32 + h * 16), an);
+      tmem_load<16>(tmem_dp + lane_sel + (uint32_t)(c * 32 + h * 16), ad);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float4 o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 bv = *reinterpret_cast<const float4*>(beta_s + c * 32 + h * 16 + 4 * i);
+        o[i].x = tc_dx<FAST>(gq[i].x, xq[i].x, bv.x + __uint_as_float(an[4 * i + 0]), __uint_as_float(ad[4 * i + 0]), f);
+        o[i].y = tc_dx<FAST>(gq[i].y, xq[i].y, bv.y + __uint_as_float(an[4 * i + 1]), __uint_as_float(ad[4 * i + 1]), f);
+        o[i].z = tc_dx<FAST>(gq[i].z, xq[i].z, bv.z + __uint_as_float(an[4 * i + 2]), __uint_as_float(ad[4 * i + 2]), f);
+        o[i].w = tc_dx<FAST>(gq[i].w, xq[i].w, bv.w + __uint_as_float(an[4 * i + 3]), __uint_as_float(ad[4 * i + 3]), f);
+      }
+      if (c + 1 < NCH) load_xg(c + 1);
+      if (live) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) *(reinterpret_cast<float4*>(orow + c * 32) + i) = o[i];
+      }
+    }
+    // n / dp columns and the p planes are rewritten by the next tile
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    first_tile = false;
+  }
+
+  // ---- this CTA's partial sums ----
+  if (!first_tile) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float* pg = part_g + (long long)blockIdx.x * C * C + (long long)r * C + h * 64;  // lane r = input channel j
+#pragma unroll
+    for (int cb = 0; cb < 4; ++cb) {
+      uint32_t a[16];
+      tmem_load<16>(tmem_dg + lane_sel + (uint32_t)(h * 64 + cb * 16), a);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<float4*>(pg + cb * 16 + 4 * i) = make_float4(__uint_as_float(a[4 * i]), __uint_as_float(a[4 * i + 1]),
+                                                                        __uint_as_float(a[4 * i + 2]), __uint_as_float(a[4 * i + 3]));
+    }
+    if ((lane & 1) == 0) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) atomicAdd(dbeta_s + c * 32 + h * 16 + bwd_channel(lane), dbeta_acc[c]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (tid < C) part_b[(long long)blockIdx.x * C + tid] = dbeta_s[tid];
+  if (first_tile) {  // a CTA without tiles still owns a partial: zeros
+    for (int i = tid; i < C * C; i += kBwdThreads) part_g[(long long)blockIdx.x * C * C + i] = 0.f;
+  }
+  if (tid < 32) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "n"(512));
+  }
+}
+
+template <bool FAST>
+int launch_tc_bwd(const float* x, const float* gamma, const float* beta, const float* dy, float* dx, float* part_g,
+                  float* part_b, int* n_parts, long long n_pix, TcFlags f, cudaStream_t s) {
+  constexpr int C = 128;
+  using L = BwdSmem<C>;
+  __nv_bfloat16* planes = nullptr;
+  TFCB_TRY(dev_alloc((void**)&planes, (size_t)2 * C * C * sizeof(__nv_bfloat16), s));
+  gdn_tc_prep_kernel<<<((C / 8) * C + 255) / 256, 256, 0, s>>>(gamma, C, planes);
+  TFCB_LAUNCHED();
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gdn_tc_bwd_kernel<C, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         L::kBytes);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      dev_free(planes, s);
+      return fail(TFCB_CUDA_ERROR, "cannot reserve %d bytes of shared memory: %s", L::kBytes, cudaGetErrorString(e));
+    }
+    attr_set = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long n_tiles = (n_pix + kTileM - 1) / kTileM;
+  const int grid = (int)std::min<long long>(n_tiles, std::min(sms, 148));
+  gdn_tc_bwd_kernel<C, FAST><<<grid, kBwdThreads, L::kBytes, s>>>(x, dy, planes, beta, dx, part_g, part_b, n_pix, f);
+  TFCB_LAUNCHED();
+  cudaError_t e = cudaGetLastError();
+  dev_free(planes, s);
+  if (e != cudaSuccess) return fail(TFCB_CUDA_ERROR, "GDN tensor-core backward launch failed: %s", cudaGetErrorString(e));
+  *n_parts = grid;
+  return TFCB_OK;
+}
+
 }  // namespace
 
 int gdn_tc_forward(const float* x, const float* gamma, const float* beta, float* y, long long n_pix, int C,
@@ -473,6 +839,33 @@ int gdn_tc_forward(const float* x, const float* gamma, const float* beta, float*
   // C == 192: 147 KB of gamma planes + 2 x 36 KB pipelines = 220 KB
   return fast ? launch_tc<192, 2, 16, true>(x, gamma, beta, y, n_pix, f, s)
               : launch_tc<192, 2, 16, false>(x, gamma, beta, y, n_pix, f, s);
+}
+
+}  // namespace tfcb
+
+namespace tfcb {
+
+// Fused tensor-core backward; fills the per-CTA partial sums (part_g [n_parts][C][C], part_b [n_parts][C]) that
+// the caller reduces.  *handled = false -> the caller runs the fp32 kernels.
+int gdn_tc_backward(const float* x, const float* gamma, const float* beta, const float* dy, float* dx, float* part_g,
+                    float* part_b, int* n_parts, long long n_pix, int C, int flags, float alpha, float eps,
+                    cudaStream_t s, bool* handled) {
+  *handled = false;
+  if (C != 128) return TFCB_OK;
+  if (!(alpha == 1.f || alpha == 2.f) || !(eps == 1.f || eps == 0.5f)) return TFCB_OK;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) return TFCB_OK;
+  if (const char* env = getenv("TFCB_GDN_FP32")) {
+    if (env[0] == '1') return TFCB_OK;
+  }
+  TcFlags f;
+  f.inverse = (flags & TFCB_GDN_INVERSE) ? 1 : 0;
+  f.rectify = (flags & TFCB_GDN_RECTIFY) ? 1 : 0;
+  f.alpha_mode = (alpha == 2.f) ? 2 : 1;
+  f.eps_mode = (eps == 0.5f) ? 2 : 1;
+  *handled = true;
+  const bool fast = (alpha == 1.f) && (eps == 1.f) && !f.rectify;
+  return fast ? launch_tc_bwd<true>(x, gamma, beta, dy, dx, part_g, part_b, n_parts, n_pix, f, s)
+              : launch_tc_bwd<false>(x, gamma, beta, dy, dx, part_g, part_b, n_parts, n_pix, f, s);
 }
 
 }  // namespace tfcb

@@ -80,7 +80,7 @@ def test_forward_variants(F, alpha, epsilon, rectify):
     assert err < 2e-5
 
 
-@pytest.mark.parametrize("C,n_pix", [(128, 3000), (192, 1111), (5, 257)])
+@pytest.mark.parametrize("C,n_pix", [(128, 3000), (128, 128 * 148 * 2 + 77), (192, 1111), (5, 257)])
 @pytest.mark.parametrize("inverse", [False, True])
 def test_backward_vs_fp64_oracle(F, C, n_pix, inverse):
   gamma, beta = _params(C, 14)
