@@ -68,8 +68,8 @@ def test_forward_vs_fp64_oracle(F, C, n_pix, inverse):
 
 @pytest.mark.parametrize("alpha,epsilon,rectify", [(1, 1, True), (2, 0.5, False), (1.5, 0.7, True), (2, 1, False),
                                                    (1, 0.5, False)])
-def test_forward_variants(F, alpha, epsilon, rectify):
-  C = 64
+@pytest.mark.parametrize("C", [64, 128])  # 64: fp32 kernels, 128: tensor-core kernel's general (non-FAST) variant
+def test_forward_variants(F, C, alpha, epsilon, rectify):
   gamma, beta = _params(C, 5)
   x = _x(1000, C, 8)
   for inverse in (False, True):
@@ -96,6 +96,22 @@ def test_backward_vs_fp64_oracle(F, C, n_pix, inverse):
   assert close(dx, wx, 2e-5)
   assert close(dg, wg, 2e-5)
   assert close(db, wb, 2e-5)
+
+
+@pytest.mark.parametrize("C", [64, 128])
+@pytest.mark.parametrize("alpha,epsilon,rectify", [(1, 1, True), (2, 0.5, False), (2, 1, False), (1, 0.5, False),
+                                                   (1.5, 0.7, True)])
+def test_backward_variants(F, C, alpha, epsilon, rectify):
+  gamma, beta = _params(C, 21)
+  x = _x(700, C, 22)
+  dy = torch.randn(700, C, generator=torch.Generator().manual_seed(23))
+  for inverse in (False, True):
+    wx, wg, wb = gdn_oracle.gdn_reference_grads(x, gamma, beta, dy, inverse, rectify, alpha, epsilon)
+    dx, dg, db = F.gdn_backward(x.cuda(), gamma.cuda(), beta.cuda(), dy.cuda(), inverse, rectify, alpha, epsilon)
+    for got, want in ((dx, wx), (dg, wg), (db, wb)):
+      want = torch.nan_to_num(want, nan=0.0, posinf=0.0, neginf=0.0)
+      scale = want.abs().max().item()
+      assert ((got.double().cpu() - want).abs().max().item() / scale) < 3e-5
 
 
 def test_autograd_wrapper(F):
