@@ -466,19 +466,25 @@ int launch_tc(const float* x, const float* gamma, const float* beta, float* y, l
 // TMEM: columns [0, C) n, [C, 2C) dp, [2C, 3C) this CTA's dgamma partial (accumulates over all its tiles).
 // HBM traffic per element: x and dy once (their re-reads in the two epilogues are L2 hits), dx once.
 // =============================================================================================
-constexpr int kBwdThreads = 256;  // two threads per pixel row: thread (r, h) owns 16 of every 32 channels
+constexpr int kBwdThreads = 256;
+constexpr int kKg = kTileM * 16 + 16;  // byte stride between 8-channel groups of an operand plane: one 16-byte row
+                                       // of padding makes the coalesced (row, group) stores bank-conflict free;
+                                       // the descriptors take it as LBO (K-major view) or SBO (MN-major view)
+constexpr int kStLd = 36;              // floats per staging row (32 + 4: conflict-free 128-bit access)
 
 template <int C>
 struct BwdSmem {
-  static constexpr int kPlaneB = C * C * 2;          // gamma hi / lo
-  static constexpr int kPlaneP = kTileM * C * 2;     // p hi / lo (whole K)
-  static constexpr int kPlaneQ = kTileM * 32 * 2;    // q hi / lo, one 32-channel chunk
+  static constexpr int kPlaneB = C * C * 2;            // gamma hi / lo
+  static constexpr int kPlaneP = (C / 8) * kKg;        // p hi / lo (whole K)
+  static constexpr int kPlaneQ = 4 * kKg;              // q hi / lo, one 32-channel chunk
+  static constexpr int kStage = kTileM * kStLd * 4;    // fp32 [128][36]
   static constexpr int kOffBh = 0;
   static constexpr int kOffBl = kOffBh + kPlaneB;
   static constexpr int kOffPh = kOffBl + kPlaneB;
   static constexpr int kOffPl = kOffPh + kPlaneP;
-  static constexpr int kOffQ = kOffPl + kPlaneP;     // [2 buffers][hi, lo]
-  static constexpr int kOffBeta = kOffQ + 4 * kPlaneQ;
+  static constexpr int kOffQ = kOffPl + kPlaneP;       // [2 buffers][hi, lo]
+  static constexpr int kOffStage = kOffQ + 4 * kPlaneQ;  // [2]: n, dp
+  static constexpr int kOffBeta = kOffStage + 2 * kStage;
   static constexpr int kOffDbeta = kOffBeta + C * 4;
   static constexpr int kOffBar = kOffDbeta + C * 4;
   static constexpr int kBytes = kOffBar + 64;
@@ -507,22 +513,16 @@ __device__ __forceinline__ float tc_dx(float g, float x, float n, float dp, cons
   return d;
 }
 
-// Sum of v[k] over the 32 lanes for each of 16 values; on return v[0] holds the total of value bwd_channel(lane).
-__device__ __forceinline__ int bwd_channel(int lane) { return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1); }
-__device__ __forceinline__ void transpose_reduce16(float (&v)[16], int lane) {
+__device__ __forceinline__ void stage_store16(float* dst, const uint32_t (&a)[16]) {
 #pragma unroll
-  for (int w = 8, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
-    const bool up = (lane & bit) != 0;
-#pragma unroll
-    for (int i = 0; i < w; ++i) {
-      const float send = up ? v[i] : v[i + w];
-      const float keep = up ? v[i + w] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, bit);
-    }
-  }
-  v[0] += __shfl_xor_sync(0xFFFFFFFFu, v[0], 1);
+  for (int i = 0; i < 4; ++i)
+    *reinterpret_cast<float4*>(dst + 4 * i) = make_float4(__uint_as_float(a[4 * i]), __uint_as_float(a[4 * i + 1]),
+                                                           __uint_as_float(a[4 * i + 2]), __uint_as_float(a[4 * i + 3]));
 }
 
+// Thread roles: TMEM side, thread (r = tid % 128, h = tid / 128) owns pixel row r (= TMEM lane) and 16 of the 32
+// columns of a chunk; memory side, item (row, kg) = 8 consecutive channels of one pixel, items enumerated row-major
+// so that a warp reads whole 128-byte lines.
 template <int C, bool FAST>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 gdn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, const __nv_bfloat16* __restrict__ planes,
@@ -534,6 +534,8 @@ gdn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, con
   extern __shared__ __align__(1024) uint8_t smem[];
   float* beta_s = reinterpret_cast<float*>(smem + L::kOffBeta);
   float* dbeta_s = reinterpret_cast<float*>(smem + L::kOffDbeta);
+  float* stage_n = reinterpret_cast<float*>(smem + L::kOffStage);
+  float* stage_d = reinterpret_cast<float*>(smem + L::kOffStage + L::kStage);
   uint64_t* mbars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);  // [0] MMA1, [1], [2] q buffers
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffBar + 32);
   const int tid = threadIdx.x, lane = tid & 31;
@@ -568,18 +570,19 @@ gdn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, con
   const uint32_t b_hi = smem_u32(smem + L::kOffBh), b_lo = smem_u32(smem + L::kOffBl);
   const uint32_t p_hi = smem_u32(smem + L::kOffPh), p_lo = smem_u32(smem + L::kOffPl);
   uint32_t par0 = 0u, parq[2] = {0u, 0u};
-  float dbeta_acc[NCH];
+  float dbeta_acc[NCH][8];  // channels c * 32 + (tid % 4) * 8 + e, summed over this thread's rows
 #pragma unroll
-  for (int c = 0; c < NCH; ++c) dbeta_acc[c] = 0.f;
+  for (int c = 0; c < NCH; ++c)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dbeta_acc[c][e] = 0.f;
   bool first_tile = true;
+  // memory-side items of a 32-channel chunk: 2 per thread
+  const int ckg = tid & 3;         // 8-channel group inside the chunk
+  const int crow = tid >> 2;       // rows crow and crow + 64
 
   const long long n_tiles = (n_pix + kTileM - 1) / kTileM;
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long p0 = tile * kTileM;
-    const bool live = p0 + r < n_pix;
-    const float* xrow = x + (p0 + r) * C + h * 16;
-    const float* grow = dy + (p0 + r) * C + h * 16;
-    float* orow = dx + (p0 + r) * C + h * 16;
     // pull the next tile of this CTA into L2 while this one is processed
     {
       const long long pn = (tile + gridDim.x) * kTileM;
@@ -592,27 +595,30 @@ gdn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, con
         }
       }
     }
-    // ---- P1: p = pool(x) -> hi / lo planes [j / 8][row][8]; MMA1 ----
+    // ---- P1: p = pool(x) -> hi / lo planes [j / 8][row][8]; item = (row, kg), 16 groups per row ----
     {
-      float4 xv[NCH][4];
+      constexpr int ITEMS = kTileM * (C / 8) / kBwdThreads;  // 8
+      float4 xv[ITEMS][2];
 #pragma unroll
-      for (int c = 0; c < NCH; ++c)
+      for (int it = 0; it < ITEMS; ++it) {
+        const int id = it * kBwdThreads + tid;
+        const int row = id / (C / 8), kg = id % (C / 8);
+        const bool live = p0 + row < n_pix;
+        const float4* src = reinterpret_cast<const float4*>(x + (p0 + row) * C + kg * 8);
+        xv[it][0] = live ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xv[it][1] = live ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          xv[c][i] = live ? __ldg(reinterpret_cast<const float4*>(xrow + c * 32) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const float4 a = xv[c][2 * e], b = xv[c][2 * e + 1];
-          float v[8] = {tc_pool<FAST>(a.x, f), tc_pool<FAST>(a.y, f), tc_pool<FAST>(a.z, f), tc_pool<FAST>(a.w, f),
-                        tc_pool<FAST>(b.x, f), tc_pool<FAST>(b.y, f), tc_pool<FAST>(b.z, f), tc_pool<FAST>(b.w, f)};
-          uint4 hi, lo;
-          split8(v, &hi, &lo);
-          const int kg = c * 4 + h * 2 + e;
-          *reinterpret_cast<uint4*>(smem + L::kOffPh + kg * (kTileM * 16) + r * 16) = hi;
-          *reinterpret_cast<uint4*>(smem + L::kOffPl + kg * (kTileM * 16) + r * 16) = lo;
-        }
+      for (int it = 0; it < ITEMS; ++it) {
+        const int id = it * kBwdThreads + tid;
+        const int row = id / (C / 8), kg = id % (C / 8);
+        const float4 a = xv[it][0], b = xv[it][1];
+        float v[8] = {tc_pool<FAST>(a.x, f), tc_pool<FAST>(a.y, f), tc_pool<FAST>(a.z, f), tc_pool<FAST>(a.w, f),
+                      tc_pool<FAST>(b.x, f), tc_pool<FAST>(b.y, f), tc_pool<FAST>(b.z, f), tc_pool<FAST>(b.w, f)};
+        uint4 hi, lo;
+        split8(v, &hi, &lo);
+        *reinterpret_cast<uint4*>(smem + L::kOffPh + kg * kKg + row * 16) = hi;
+        *reinterpret_cast<uint4*>(smem + L::kOffPl + kg * kKg + row * 16) = lo;
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -621,8 +627,8 @@ gdn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, con
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
       for (int s = 0; s < C / 16; ++s) {
-        const uint64_t dah = umma_desc(p_hi + (uint32_t)(2 * s) * (kTileM * 16), kTileM * 16, 128);
-        const uint64_t dal = umma_desc(p_lo + (uint32_t)(2 * s) * (kTileM * 16), kTileM * 16, 128);
+        const uint64_t dah = umma_desc(p_hi + (uint32_t)(2 * s) * kKg, kKg, 128);
+        const uint64_t dal = umma_desc(p_lo + (uint32_t)(2 * s) * kKg, kKg, 128);
         const uint64_t dbh = umma_desc(b_hi + (uint32_t)(2 * s) * (C * 16), C * 16, 128);
         const uint64_t dbl = umma_desc(b_lo + (uint32_t)(2 * s) * (C * 16), C * 16, 128);
         umma_bf16(tmem_n, dah, dbh, kIdesc1, s ? 1u : 0u);
@@ -631,15 +637,22 @@ gdn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, con
       }
       umma_commit(smem_u32(mbars));
     }
-    // ---- P2: q = dL/dn per 32-channel chunk -> q planes; MMA2 (dp) and MMA3 (dgamma) per chunk ----
-    float4 xq[4], gq[4];
+    // x and dy of a chunk for this thread's two items (coalesced; L2 hits after the prefetch / P1)
+    float4 xq[2][2], gq[2][2];
     auto load_xg = [&](int c) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        xq[i] = live ? __ldg(reinterpret_cast<const float4*>(xrow + c * 32) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        gq[i] = live ? __ldg(reinterpret_cast<const float4*>(grow + c * 32) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int it = 0; it < 2; ++it) {
+        const int row = crow + 64 * it;
+        const bool live = p0 + row < n_pix;
+        const long long off = (p0 + row) * C + c * 32 + ckg * 8;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        xq[it][0] = live ? __ldg(reinterpret_cast<const float4*>(x + off)) : z;
+        xq[it][1] = live ? __ldg(reinterpret_cast<const float4*>(x + off) + 1) : z;
+        gq[it][0] = live ? __ldg(reinterpret_cast<const float4*>(dy + off)) : z;
+        gq[it][1] = live ? __ldg(reinterpret_cast<const float4*>(dy + off) + 1) : z;
       }
     };
+    // ---- P2: q = dL/dn per 32-channel chunk -> q planes; MMA2 (dp) and MMA3 (dgamma) per chunk ----
     load_xg(0);
     if (!mbar_wait(smem_u32(mbars), par0)) __trap();
     par0 ^= 1u;
@@ -647,50 +660,55 @@ gdn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, con
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int b = c & 1;
-      uint32_t acc[16];
-      tmem_load<16>(tmem_n + lane_sel + (uint32_t)(c * 32 + h * 16), acc);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      float q[16];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 bv = *reinterpret_cast<const float4*>(beta_s + c * 32 + h * 16 + 4 * i);
-        q[4 * i + 0] = tc_dl_dn<FAST>(gq[i].x, xq[i].x, bv.x + __uint_as_float(acc[4 * i + 0]), f);
-        q[4 * i + 1] = tc_dl_dn<FAST>(gq[i].y, xq[i].y, bv.y + __uint_as_float(acc[4 * i + 1]), f);
-        q[4 * i + 2] = tc_dl_dn<FAST>(gq[i].z, xq[i].z, bv.z + __uint_as_float(acc[4 * i + 2]), f);
-        q[4 * i + 3] = tc_dl_dn<FAST>(gq[i].w, xq[i].w, bv.w + __uint_as_float(acc[4 * i + 3]), f);
+      {
+        uint32_t acc[16];
+        tmem_load<16>(tmem_n + lane_sel + (uint32_t)(c * 32 + h * 16), acc);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        stage_store16(stage_n + r * kStLd + h * 16, acc);
       }
-      if (c + 1 < NCH) load_xg(c + 1);
       // the q buffer was read by the MMAs of chunk c - 2
       if (c >= 2) {  // (chunks 2 and 3 of the previous tile were waited for before its dx pass)
         if (!mbar_wait(smem_u32(mbars + 1 + b), parq[b])) __trap();
         parq[b] ^= 1u;
       }
+      __syncthreads();  // n chunk staged
       uint8_t* qh = smem + L::kOffQ + b * 2 * L::kPlaneQ;
       uint8_t* ql = qh + L::kPlaneQ;
+      const float4 bv0 = *reinterpret_cast<const float4*>(beta_s + c * 32 + ckg * 8);
+      const float4 bv1 = *reinterpret_cast<const float4*>(beta_s + c * 32 + ckg * 8 + 4);
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        float v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = q[8 * e + i];
+      for (int it = 0; it < 2; ++it) {
+        const int row = crow + 64 * it;
+        const float4 n0 = *reinterpret_cast<const float4*>(stage_n + row * kStLd + ckg * 8);
+        const float4 n1 = *reinterpret_cast<const float4*>(stage_n + row * kStLd + ckg * 8 + 4);
+        float q[8];
+        q[0] = tc_dl_dn<FAST>(gq[it][0].x, xq[it][0].x, bv0.x + n0.x, f);
+        q[1] = tc_dl_dn<FAST>(gq[it][0].y, xq[it][0].y, bv0.y + n0.y, f);
+        q[2] = tc_dl_dn<FAST>(gq[it][0].z, xq[it][0].z, bv0.z + n0.z, f);
+        q[3] = tc_dl_dn<FAST>(gq[it][0].w, xq[it][0].w, bv0.w + n0.w, f);
+        q[4] = tc_dl_dn<FAST>(gq[it][1].x, xq[it][1].x, bv1.x + n1.x, f);
+        q[5] = tc_dl_dn<FAST>(gq[it][1].y, xq[it][1].y, bv1.y + n1.y, f);
+        q[6] = tc_dl_dn<FAST>(gq[it][1].z, xq[it][1].z, bv1.z + n1.z, f);
+        q[7] = tc_dl_dn<FAST>(gq[it][1].w, xq[it][1].w, bv1.w + n1.w, f);
         uint4 hi, lo;
-        split8(v, &hi, &lo);
-        const int kg = h * 2 + e;
-        *reinterpret_cast<uint4*>(qh + kg * (kTileM * 16) + r * 16) = hi;
-        *reinterpret_cast<uint4*>(ql + kg * (kTileM * 16) + r * 16) = lo;
+        split8(q, &hi, &lo);
+        *reinterpret_cast<uint4*>(qh + ckg * kKg + row * 16) = hi;
+        *reinterpret_cast<uint4*>(ql + ckg * kKg + row * 16) = lo;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dbeta_acc[c][e] += q[e];
       }
-      transpose_reduce16(q, lane);
-      dbeta_acc[c] += q[0];
+      if (c + 1 < NCH) load_xg(c + 1);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncthreads();
+      __syncthreads();  // q planes complete; stage_n free again
       if (tid == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t q_hi = smem_u32(qh), q_lo = smem_u32(ql);
         // MMA2: dp[pix, j] += sum_{i in chunk} q[pix, i] gamma[j, i]   (K = i: 2 steps of 16)
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
-          const uint64_t dah = umma_desc(q_hi + (uint32_t)(2 * s) * (kTileM * 16), kTileM * 16, 128);
-          const uint64_t dal = umma_desc(q_lo + (uint32_t)(2 * s) * (kTileM * 16), kTileM * 16, 128);
+          const uint64_t dah = umma_desc(q_hi + (uint32_t)(2 * s) * kKg, kKg, 128);
+          const uint64_t dal = umma_desc(q_lo + (uint32_t)(2 * s) * kKg, kKg, 128);
           // gamma plane viewed with n = j, k = i: k rows are 16 B apart, k groups 128 B, n groups C * 16 B
           const uint32_t koff = (uint32_t)(c * 32 + s * 16) * 16u;
           const uint64_t dbh = umma_desc(b_hi + koff, 128, C * 16);
@@ -703,10 +721,10 @@ gdn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, con
 #pragma unroll
         for (int s = 0; s < kTileM / 16; ++s) {
           const uint32_t koff = (uint32_t)(s * 16) * 16u;
-          const uint64_t dah = umma_desc(p_hi + koff, 128, kTileM * 16);
-          const uint64_t dal = umma_desc(p_lo + koff, 128, kTileM * 16);
-          const uint64_t dbh = umma_desc(q_hi + koff, 128, kTileM * 16);
-          const uint64_t dbl = umma_desc(q_lo + koff, 128, kTileM * 16);
+          const uint64_t dah = umma_desc(p_hi + koff, 128, kKg);
+          const uint64_t dal = umma_desc(p_lo + koff, 128, kKg);
+          const uint64_t dbh = umma_desc(q_hi + koff, 128, kKg);
+          const uint64_t dbl = umma_desc(q_lo + koff, 128, kKg);
           const uint32_t acc_on = (first_tile && s == 0) ? 0u : 1u;
           umma_bf16(tmem_dg + (uint32_t)(c * 32), dah, dbh, kIdesc3, acc_on);
           umma_bf16(tmem_dg + (uint32_t)(c * 32), dal, dbh, kIdesc3, 1u);
@@ -725,24 +743,41 @@ gdn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, con
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
-      uint32_t an[16], ad[16];
-      tmem_load<16>(tmem_n + lane_sel + (uint32_t)(c * 32 + h * 16), an);
-      tmem_load<16>(tmem_dp + lane_sel + (uint32_t)(c * 32 + h * 16), ad);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      float4 o[4];
+      {
+        uint32_t an[16], ad[16];
+        tmem_load<16>(tmem_n + lane_sel + (uint32_t)(c * 32 + h * 16), an);
+        tmem_load<16>(tmem_dp + lane_sel + (uint32_t)(c * 32 + h * 16), ad);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        stage_store16(stage_n + r * kStLd + h * 16, an);
+        stage_store16(stage_d + r * kStLd + h * 16, ad);
+      }
+      __syncthreads();
+      const float4 bv0 = *reinterpret_cast<const float4*>(beta_s + c * 32 + ckg * 8);
+      const float4 bv1 = *reinterpret_cast<const float4*>(beta_s + c * 32 + ckg * 8 + 4);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 bv = *reinterpret_cast<const float4*>(beta_s + c * 32 + h * 16 + 4 * i);
-        o[i].x = tc_dx<FAST>(gq[i].x, xq[i].x, bv.x + __uint_as_float(an[4 * i + 0]), __uint_as_float(ad[4 * i + 0]), f);
-        o[i].y = tc_dx<FAST>(gq[i].y, xq[i].y, bv.y + __uint_as_float(an[4 * i + 1]), __uint_as_float(ad[4 * i + 1]), f);
-        o[i].z = tc_dx<FAST>(gq[i].z, xq[i].z, bv.z + __uint_as_float(an[4 * i + 2]), __uint_as_float(ad[4 * i + 2]), f);
-        o[i].w = tc_dx<FAST>(gq[i].w, xq[i].w, bv.w + __uint_as_float(an[4 * i + 3]), __uint_as_float(ad[4 * i + 3]), f);
+      for (int it = 0; it < 2; ++it) {
+        const int row = crow + 64 * it;
+        const float4 n0 = *reinterpret_cast<const float4*>(stage_n + row * kStLd + ckg * 8);
+        const float4 n1 = *reinterpret_cast<const float4*>(stage_n + row * kStLd + ckg * 8 + 4);
+        const float4 d0 = *reinterpret_cast<const float4*>(stage_d + row * kStLd + ckg * 8);
+        const float4 d1 = *reinterpret_cast<const float4*>(stage_d + row * kStLd + ckg * 8 + 4);
+        float4 o0, o1;
+        o0.x = tc_dx<FAST>(gq[it][0].x, xq[it][0].x, bv0.x + n0.x, d0.x, f);
+        o0.y = tc_dx<FAST>(gq[it][0].y, xq[it][0].y, bv0.y + n0.y, d0.y, f);
+        o0.z = tc_dx<FAST>(gq[it][0].z, xq[it][0].z, bv0.z + n0.z, d0.z, f);
+        o0.w = tc_dx<FAST>(gq[it][0].w, xq[it][0].w, bv0.w + n0.w, d0.w, f);
+        o1.x = tc_dx<FAST>(gq[it][1].x, xq[it][1].x, bv1.x + n1.x, d1.x, f);
+        o1.y = tc_dx<FAST>(gq[it][1].y, xq[it][1].y, bv1.y + n1.y, d1.y, f);
+        o1.z = tc_dx<FAST>(gq[it][1].z, xq[it][1].z, bv1.z + n1.z, d1.z, f);
+        o1.w = tc_dx<FAST>(gq[it][1].w, xq[it][1].w, bv1.w + n1.w, d1.w, f);
+        if (p0 + row < n_pix) {
+          float4* dst = reinterpret_cast<float4*>(dx + (p0 + row) * C + c * 32 + ckg * 8);
+          dst[0] = o0;
+          dst[1] = o1;
+        }
       }
       if (c + 1 < NCH) load_xg(c + 1);
-      if (live) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) *(reinterpret_cast<float4*>(orow + c * 32) + i) = o[i];
-      }
+      __syncthreads();  // staging free again
     }
     // n / dp columns and the p planes are rewritten by the next tile
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -759,22 +794,23 @@ gdn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, con
       uint32_t a[16];
       tmem_load<16>(tmem_dg + lane_sel + (uint32_t)(h * 64 + cb * 16), a);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        *reinterpret_cast<float4*>(pg + cb * 16 + 4 * i) = make_float4(__uint_as_float(a[4 * i]), __uint_as_float(a[4 * i + 1]),
-                                                                        __uint_as_float(a[4 * i + 2]), __uint_as_float(a[4 * i + 3]));
+      stage_store16(pg + cb * 16, a);
     }
-    if ((lane & 1) == 0) {
+    // dbeta: lanes with the same tid % 4 hold the same channels
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) atomicAdd(dbeta_s + c * 32 + h * 16 + bwd_channel(lane), dbeta_acc[c]);
-    }
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float v = dbeta_acc[c][e];
+        v += __shfl_xor_sync(0xFFFFFFFFu, v, 4);
+        v += __shfl_xor_sync(0xFFFFFFFFu, v, 8);
+        v += __shfl_xor_sync(0xFFFFFFFFu, v, 16);
+        if (lane < 4) atomicAdd(dbeta_s + c * 32 + lane * 8 + e, v);
+      }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (tid < C) part_b[(long long)blockIdx.x * C + tid] = dbeta_s[tid];
-  if (first_tile) {  // a CTA without tiles still owns a partial: zeros
-    for (int i = tid; i < C * C; i += kBwdThreads) part_g[(long long)blockIdx.x * C * C + i] = 0.f;
-  }
   if (tid < 32) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "n"(512));
   }
