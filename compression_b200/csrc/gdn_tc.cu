@@ -637,29 +637,31 @@ gdn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, con
       }
       umma_commit(smem_u32(mbars));
     }
-    // x and dy of a chunk for this thread's two items (coalesced; L2 hits after the prefetch / P1)
-    float4 xq[2][2], gq[2][2];
-    auto load_xg = [&](int c) {
+    // x and dy of a chunk for this thread's two items (coalesced; L2 hits after the prefetch / P1).  Two register
+    // sets: the loads of the next chunk are issued a whole chunk ahead of their use (L2 latency ~1 us).
+    float4 xq[2][2][2], gq[2][2][2];  // [set][item][half]
+    auto load_xg = [&](int set, int c) {
 #pragma unroll
       for (int it = 0; it < 2; ++it) {
         const int row = crow + 64 * it;
         const bool live = p0 + row < n_pix;
         const long long off = (p0 + row) * C + c * 32 + ckg * 8;
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        xq[it][0] = live ? __ldg(reinterpret_cast<const float4*>(x + off)) : z;
-        xq[it][1] = live ? __ldg(reinterpret_cast<const float4*>(x + off) + 1) : z;
-        gq[it][0] = live ? __ldg(reinterpret_cast<const float4*>(dy + off)) : z;
-        gq[it][1] = live ? __ldg(reinterpret_cast<const float4*>(dy + off) + 1) : z;
+        xq[set][it][0] = live ? __ldg(reinterpret_cast<const float4*>(x + off)) : z;
+        xq[set][it][1] = live ? __ldg(reinterpret_cast<const float4*>(x + off) + 1) : z;
+        gq[set][it][0] = live ? __ldg(reinterpret_cast<const float4*>(dy + off)) : z;
+        gq[set][it][1] = live ? __ldg(reinterpret_cast<const float4*>(dy + off) + 1) : z;
       }
     };
     // ---- P2: q = dL/dn per 32-channel chunk -> q planes; MMA2 (dp) and MMA3 (dgamma) per chunk ----
-    load_xg(0);
+    load_xg(0, 0);
     if (!mbar_wait(smem_u32(mbars), par0)) __trap();
     par0 ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int b = c & 1;
+      load_xg(b ^ 1, (c + 1) % NCH);  // next chunk; after the last one: chunk 0 again, for the dx pass
       {
         uint32_t acc[16];
         tmem_load<16>(tmem_n + lane_sel + (uint32_t)(c * 32 + h * 16), acc);
@@ -681,15 +683,16 @@ gdn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, con
         const int row = crow + 64 * it;
         const float4 n0 = *reinterpret_cast<const float4*>(stage_n + row * kStLd + ckg * 8);
         const float4 n1 = *reinterpret_cast<const float4*>(stage_n + row * kStLd + ckg * 8 + 4);
+        const float4 x0 = xq[b][it][0], x1 = xq[b][it][1], g0 = gq[b][it][0], g1 = gq[b][it][1];
         float q[8];
-        q[0] = tc_dl_dn<FAST>(gq[it][0].x, xq[it][0].x, bv0.x + n0.x, f);
-        q[1] = tc_dl_dn<FAST>(gq[it][0].y, xq[it][0].y, bv0.y + n0.y, f);
-        q[2] = tc_dl_dn<FAST>(gq[it][0].z, xq[it][0].z, bv0.z + n0.z, f);
-        q[3] = tc_dl_dn<FAST>(gq[it][0].w, xq[it][0].w, bv0.w + n0.w, f);
-        q[4] = tc_dl_dn<FAST>(gq[it][1].x, xq[it][1].x, bv1.x + n1.x, f);
-        q[5] = tc_dl_dn<FAST>(gq[it][1].y, xq[it][1].y, bv1.y + n1.y, f);
-        q[6] = tc_dl_dn<FAST>(gq[it][1].z, xq[it][1].z, bv1.z + n1.z, f);
-        q[7] = tc_dl_dn<FAST>(gq[it][1].w, xq[it][1].w, bv1.w + n1.w, f);
+        q[0] = tc_dl_dn<FAST>(g0.x, x0.x, bv0.x + n0.x, f);
+        q[1] = tc_dl_dn<FAST>(g0.y, x0.y, bv0.y + n0.y, f);
+        q[2] = tc_dl_dn<FAST>(g0.z, x0.z, bv0.z + n0.z, f);
+        q[3] = tc_dl_dn<FAST>(g0.w, x0.w, bv0.w + n0.w, f);
+        q[4] = tc_dl_dn<FAST>(g1.x, x1.x, bv1.x + n1.x, f);
+        q[5] = tc_dl_dn<FAST>(g1.y, x1.y, bv1.y + n1.y, f);
+        q[6] = tc_dl_dn<FAST>(g1.z, x1.z, bv1.z + n1.z, f);
+        q[7] = tc_dl_dn<FAST>(g1.w, x1.w, bv1.w + n1.w, f);
         uint4 hi, lo;
         split8(q, &hi, &lo);
         *reinterpret_cast<uint4*>(qh + ckg * kKg + row * 16) = hi;
@@ -697,7 +700,6 @@ gdn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, con
 #pragma unroll
         for (int e = 0; e < 8; ++e) dbeta_acc[c][e] += q[e];
       }
-      if (c + 1 < NCH) load_xg(c + 1);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncthreads();  // q planes complete; stage_n free again
@@ -733,8 +735,7 @@ gdn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, con
         umma_commit(smem_u32(mbars + 1 + b));
       }
     }
-    // ---- P3: dx = g / m + dpool/du * dp ----
-    load_xg(0);
+    // ---- P3: dx = g / m + dpool/du * dp  (chunk 0 is already in register set 0) ----
 #pragma unroll
     for (int b = 0; b < 2; ++b) {  // commits of chunks 2 and 3: all MMAs of this tile are done
       if (!mbar_wait(smem_u32(mbars + 1 + b), parq[b])) __trap();
@@ -743,6 +744,8 @@ gdn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, con
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
+      const int b = c & 1;
+      if (c + 1 < NCH) load_xg(b ^ 1, c + 1);
       {
         uint32_t an[16], ad[16];
         tmem_load<16>(tmem_n + lane_sel + (uint32_t)(c * 32 + h * 16), an);
@@ -761,22 +764,22 @@ gdn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, con
         const float4 n1 = *reinterpret_cast<const float4*>(stage_n + row * kStLd + ckg * 8 + 4);
         const float4 d0 = *reinterpret_cast<const float4*>(stage_d + row * kStLd + ckg * 8);
         const float4 d1 = *reinterpret_cast<const float4*>(stage_d + row * kStLd + ckg * 8 + 4);
+        const float4 x0 = xq[b][it][0], x1 = xq[b][it][1], g0 = gq[b][it][0], g1 = gq[b][it][1];
         float4 o0, o1;
-        o0.x = tc_dx<FAST>(gq[it][0].x, xq[it][0].x, bv0.x + n0.x, d0.x, f);
-        o0.y = tc_dx<FAST>(gq[it][0].y, xq[it][0].y, bv0.y + n0.y, d0.y, f);
-        o0.z = tc_dx<FAST>(gq[it][0].z, xq[it][0].z, bv0.z + n0.z, d0.z, f);
-        o0.w = tc_dx<FAST>(gq[it][0].w, xq[it][0].w, bv0.w + n0.w, d0.w, f);
-        o1.x = tc_dx<FAST>(gq[it][1].x, xq[it][1].x, bv1.x + n1.x, d1.x, f);
-        o1.y = tc_dx<FAST>(gq[it][1].y, xq[it][1].y, bv1.y + n1.y, d1.y, f);
-        o1.z = tc_dx<FAST>(gq[it][1].z, xq[it][1].z, bv1.z + n1.z, d1.z, f);
-        o1.w = tc_dx<FAST>(gq[it][1].w, xq[it][1].w, bv1.w + n1.w, d1.w, f);
+        o0.x = tc_dx<FAST>(g0.x, x0.x, bv0.x + n0.x, d0.x, f);
+        o0.y = tc_dx<FAST>(g0.y, x0.y, bv0.y + n0.y, d0.y, f);
+        o0.z = tc_dx<FAST>(g0.z, x0.z, bv0.z + n0.z, d0.z, f);
+        o0.w = tc_dx<FAST>(g0.w, x0.w, bv0.w + n0.w, d0.w, f);
+        o1.x = tc_dx<FAST>(g1.x, x1.x, bv1.x + n1.x, d1.x, f);
+        o1.y = tc_dx<FAST>(g1.y, x1.y, bv1.y + n1.y, d1.y, f);
+        o1.z = tc_dx<FAST>(g1.z, x1.z, bv1.z + n1.z, d1.z, f);
+        o1.w = tc_dx<FAST>(g1.w, x1.w, bv1.w + n1.w, d1.w, f);
         if (p0 + row < n_pix) {
           float4* dst = reinterpret_cast<float4*>(dx + (p0 + row) * C + c * 32 + ckg * 8);
           dst[0] = o0;
           dst[1] = o1;
         }
       }
-      if (c + 1 < NCH) load_xg(c + 1);
       __syncthreads();  // staging free again
     }
     // n / dp columns and the p planes are rewritten by the next tile
