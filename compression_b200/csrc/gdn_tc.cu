@@ -416,6 +416,251 @@ gdn_tc_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__
   }
 }
 
+
+// =============================================================================================
+// Forward, second generation (C = 128): the whole x tile lives in shared memory.
+//
+//   bulk async copies (cp.async.bulk, one 512-byte pixel row each, completion on an mbarrier) bring tile t+1
+//   into a padded [128][132] fp32 buffer while tile t is processed; the same buffer is the epilogue's x source
+//   and, rewritten in place with y, the source of the bulk stores.  Nothing is re-read from L2, no thread ever
+//   waits on a global load, and the 528-byte row stride makes the thread-per-pixel-row accesses (the mapping
+//   tcgen05.ld imposes) bank-conflict free, so no staging transposes and no barriers inside the epilogue.
+//   K is consumed in chunks of 16 channels through two small operand-plane buffers.
+// =============================================================================================
+constexpr int kStLd = 36;  // floats per staging row (32 + 4: conflict-free 128-bit access)
+
+__device__ __forceinline__ void stage_store16(float* dst, const uint32_t (&a)[16]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    *reinterpret_cast<float4*>(dst + 4 * i) = make_float4(__uint_as_float(a[4 * i]), __uint_as_float(a[4 * i + 1]),
+                                                           __uint_as_float(a[4 * i + 2]), __uint_as_float(a[4 * i + 3]));
+}
+
+constexpr int kF2Threads = 256;
+constexpr int kF2XBuf = kTileM * 128 * 4;          // one x / y tile, dense [128][128] fp32 (one bulk copy)
+constexpr int kF2Kg = kTileM * 16 + 32;            // plane group stride: 32 B of padding -> conflict-free stores
+constexpr int kF2Plane = 4 * kF2Kg;                // one hi or lo plane of a 32-channel chunk
+
+struct Fwd2Smem {
+  static constexpr int C = 128;
+  static constexpr int kOffBh = 0;
+  static constexpr int kOffBl = kOffBh + C * C * 2;
+  static constexpr int kOffX = kOffBl + C * C * 2;            // [2] x / y tiles
+  static constexpr int kOffP = kOffX + 2 * kF2XBuf;           // [2 buffers][hi, lo]; the epilogue's staging aliases it
+  static constexpr int kOffBeta = kOffP + 4 * kF2Plane;
+  static constexpr int kOffBar = kOffBeta + C * 4;            // full[2], plane[2]
+  static constexpr int kBytes = kOffBar + 64;
+  static_assert(4 * kF2Plane >= kTileM * kStLd * 4, "staging must fit in the operand-plane area");
+};
+
+template <bool FAST>
+__global__ void __launch_bounds__(kF2Threads, 1)
+gdn_tc_fwd2_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ planes,
+                   const float* __restrict__ beta, float* __restrict__ y, long long n_pix, TcFlags f) {
+  using L = Fwd2Smem;
+  constexpr int C = 128;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float* beta_s = reinterpret_cast<float*>(smem + L::kOffBeta);
+  float* stage = reinterpret_cast<float*>(smem + L::kOffP);          // [128][36] fp32, only during the epilogue
+  uint64_t* mbars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);  // [0,1] full, [2,3] plane
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffBar + 48);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r = tid & 127, h = tid >> 7, gwarp = warp & 3;
+  constexpr uint32_t kIdesc = umma_idesc(kTileM, C);
+
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(planes);
+    uint4* dst = reinterpret_cast<uint4*>(smem + L::kOffBh);
+    for (int i = tid; i < 2 * C * C * 2 / 16; i += kF2Threads) dst[i] = src[i];
+    for (int i = tid; i < C; i += kF2Threads) beta_s[i] = beta[i];
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbars + i)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_n = *tmem_slot;
+  const uint32_t lane_sel = (uint32_t)(gwarp * 32) << 16;
+  const uint32_t b_hi = smem_u32(smem + L::kOffBh), b_lo = smem_u32(smem + L::kOffBl);
+  const uint32_t xs = smem_u32(smem + L::kOffX);
+  uint32_t par_full[2] = {0u, 0u}, par_plane[2] = {0u, 0u};
+
+  const long long n_tiles = (n_pix + kTileM - 1) / kTileM;
+  // thread 0 moves the tiles: a tile is one contiguous block of rows * 512 bytes
+  auto issue_load = [&](long long tile, int b) {
+    const long long p0 = tile * kTileM;
+    const uint32_t bytes = (uint32_t)min((long long)kTileM, n_pix - p0) * 512u;
+    const uint32_t mbar = smem_u32(mbars + b);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     xs + b * kF2XBuf),
+                 "l"(x + p0 * C), "r"(bytes), "r"(mbar)
+                 : "memory");
+  };
+  if (tid == 0 && blockIdx.x < n_tiles) issue_load(blockIdx.x, 0);
+
+  // memory-side items of a 32-channel chunk: (row, kg) = 8 channels of one pixel, two per thread.  Odd rows touch
+  // the two 16-byte halves of their 32 bytes in the opposite order: with the dense 512-byte row stride two
+  // neighbouring rows would otherwise hit the same banks.
+  const int ckg = tid & 3, crow = tid >> 2;
+  const int swap = crow & 1;
+
+  int it = 0;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int b = it & 1;
+    const long long p0 = tile * kTileM;
+    const uint32_t bytes = (uint32_t)min((long long)kTileM, n_pix - p0) * 512u;
+    // (a) next tile into the other buffer, once the store that read it (tile it - 1) is done with it
+    if (tid == 0 && tile + gridDim.x < n_tiles) {
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      issue_load(tile + gridDim.x, b ^ 1);
+    }
+    // (b) this tile has landed
+    if (!mbar_wait(smem_u32(mbars + b), par_full[b])) __trap();
+    par_full[b] ^= 1u;
+    uint8_t* xt = smem + L::kOffX + b * kF2XBuf;
+    // (c) pool + bf16 split, 32 channels at a time
+#pragma unroll
+    for (int c = 0; c < C / 32; ++c) {
+      const int pb = c & 1;
+      if (c >= 2) {
+        if (!mbar_wait(smem_u32(mbars + 2 + pb), par_plane[pb])) __trap();
+        par_plane[pb] ^= 1u;
+      }
+      uint8_t* ph = smem + L::kOffP + pb * 2 * kF2Plane;
+      uint8_t* pl = ph + kF2Plane;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int row = crow + 64 * i;
+        const uint8_t* src = xt + row * 512 + (c * 32 + ckg * 8) * 4;
+        const float4 va = *reinterpret_cast<const float4*>(src + (swap ? 16 : 0));
+        const float4 vb = *reinterpret_cast<const float4*>(src + (swap ? 0 : 16));
+        const float4 v0 = swap ? vb : va, v1 = swap ? va : vb;
+        float v[8] = {tc_pool<FAST>(v0.x, f), tc_pool<FAST>(v0.y, f), tc_pool<FAST>(v0.z, f), tc_pool<FAST>(v0.w, f),
+                      tc_pool<FAST>(v1.x, f), tc_pool<FAST>(v1.y, f), tc_pool<FAST>(v1.z, f), tc_pool<FAST>(v1.w, f)};
+        uint4 hi, lo;
+        split8(v, &hi, &lo);
+        *reinterpret_cast<uint4*>(ph + ckg * kF2Kg + row * 16) = hi;
+        *reinterpret_cast<uint4*>(pl + ckg * kF2Kg + row * 16) = lo;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2) {
+          const uint64_t dah = umma_desc(smem_u32(ph) + (uint32_t)(2 * s2) * kF2Kg, kF2Kg, 128);
+          const uint64_t dal = umma_desc(smem_u32(pl) + (uint32_t)(2 * s2) * kF2Kg, kF2Kg, 128);
+          const uint32_t b_off = (uint32_t)(c * 4 + 2 * s2) * (C * 16);
+          const uint64_t dbh = umma_desc(b_hi + b_off, C * 16, 128);
+          const uint64_t dbl = umma_desc(b_lo + b_off, C * 16, 128);
+          umma_bf16(tmem_n, dah, dbh, kIdesc, (c | s2) ? 1u : 0u);
+          umma_bf16(tmem_n, dal, dbh, kIdesc, 1u);
+          umma_bf16(tmem_n, dah, dbl, kIdesc, 1u);
+        }
+        umma_commit(smem_u32(mbars + 2 + pb));
+      }
+    }
+    // (d) epilogue in place: y = x / (beta + n).  The last two commits cover every MMA of the tile, after which
+    // the operand planes are dead and their memory is the staging buffer for the TMEM -> row-major transpose.
+#pragma unroll
+    for (int pb = 0; pb < 2; ++pb) {
+      if (!mbar_wait(smem_u32(mbars + 2 + pb), par_plane[pb])) __trap();
+      par_plane[pb] ^= 1u;
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+    for (int cc = 0; cc < C / 32; ++cc) {
+      {
+        uint32_t acc[16];
+        tmem_load<16>(tmem_n + lane_sel + (uint32_t)(cc * 32 + h * 16), acc);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        stage_store16(stage + r * kStLd + h * 16, acc);
+      }
+      __syncthreads();
+      const float4 bv0 = *reinterpret_cast<const float4*>(beta_s + cc * 32 + ckg * 8);
+      const float4 bv1 = *reinterpret_cast<const float4*>(beta_s + cc * 32 + ckg * 8 + 4);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int row = crow + 64 * i;
+        uint8_t* src = xt + row * 512 + (cc * 32 + ckg * 8) * 4;
+        float4* pa = reinterpret_cast<float4*>(src + (swap ? 16 : 0));
+        float4* pb2 = reinterpret_cast<float4*>(src + (swap ? 0 : 16));
+        const float4 va = *pa, vb = *pb2;
+        const float4 n0 = *reinterpret_cast<const float4*>(stage + row * kStLd + ckg * 8);
+        const float4 n1 = *reinterpret_cast<const float4*>(stage + row * kStLd + ckg * 8 + 4);
+        const float4 x0 = swap ? vb : va, x1 = swap ? va : vb;
+        float4 o0, o1;
+        o0.x = tc_out<FAST>(x0.x, bv0.x + n0.x, f);
+        o0.y = tc_out<FAST>(x0.y, bv0.y + n0.y, f);
+        o0.z = tc_out<FAST>(x0.z, bv0.z + n0.z, f);
+        o0.w = tc_out<FAST>(x0.w, bv0.w + n0.w, f);
+        o1.x = tc_out<FAST>(x1.x, bv1.x + n1.x, f);
+        o1.y = tc_out<FAST>(x1.y, bv1.y + n1.y, f);
+        o1.z = tc_out<FAST>(x1.z, bv1.z + n1.z, f);
+        o1.w = tc_out<FAST>(x1.w, bv1.w + n1.w, f);
+        *pa = swap ? o1 : o0;
+        *pb2 = swap ? o0 : o1;
+      }
+      if (cc == C / 32 - 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // y tile -> bulk store
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();  // staging free again (and, after the last chunk, for the next tile's operand planes)
+    }
+    // (e) y tile out
+    if (tid == 0) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(y + p0 * C), "r"(xs + b * kF2XBuf),
+                   "r"(bytes)
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (tid < 32) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "n"(128));
+  }
+}
+
+template <bool FAST>
+int launch_tc_fwd2(const float* x, const float* gamma, const float* beta, float* y, long long n_pix, TcFlags f,
+                   cudaStream_t s) {
+  constexpr int C = 128;
+  using L = Fwd2Smem;
+  __nv_bfloat16* planes = nullptr;
+  TFCB_TRY(dev_alloc((void**)&planes, (size_t)2 * C * C * sizeof(__nv_bfloat16), s));
+  gdn_tc_prep_kernel<<<((C / 8) * C + 255) / 256, 256, 0, s>>>(gamma, C, planes);
+  TFCB_LAUNCHED();
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gdn_tc_fwd2_kernel<FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      dev_free(planes, s);
+      return fail(TFCB_CUDA_ERROR, "cannot reserve %d bytes of shared memory: %s", L::kBytes, cudaGetErrorString(e));
+    }
+    attr_set = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long n_tiles = (n_pix + kTileM - 1) / kTileM;
+  const int grid = (int)std::min<long long>(n_tiles, sms);
+  gdn_tc_fwd2_kernel<FAST><<<grid, kF2Threads, L::kBytes, s>>>(x, planes, beta, y, n_pix, f);
+  TFCB_LAUNCHED();
+  cudaError_t e = cudaGetLastError();
+  dev_free(planes, s);
+  if (e != cudaSuccess) return fail(TFCB_CUDA_ERROR, "GDN tensor-core kernel launch failed: %s", cudaGetErrorString(e));
+  return TFCB_OK;
+}
+
 template <int C, int G, int KC, bool FAST>
 int launch_tc(const float* x, const float* gamma, const float* beta, float* y, long long n_pix, TcFlags f,
               cudaStream_t s) {
@@ -470,7 +715,6 @@ constexpr int kBwdThreads = 256;
 constexpr int kKg = kTileM * 16 + 16;  // byte stride between 8-channel groups of an operand plane: one 16-byte row
                                        // of padding makes the coalesced (row, group) stores bank-conflict free;
                                        // the descriptors take it as LBO (K-major view) or SBO (MN-major view)
-constexpr int kStLd = 36;              // floats per staging row (32 + 4: conflict-free 128-bit access)
 
 template <int C>
 struct BwdSmem {
@@ -511,13 +755,6 @@ __device__ __forceinline__ float tc_dx(float g, float x, float n, float dp, cons
   float d = direct + dpool * dp;
   if (!FAST && f.rectify && !(x > 0.f)) d = 0.f;
   return d;
-}
-
-__device__ __forceinline__ void stage_store16(float* dst, const uint32_t (&a)[16]) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-    *reinterpret_cast<float4*>(dst + 4 * i) = make_float4(__uint_as_float(a[4 * i]), __uint_as_float(a[4 * i + 1]),
-                                                           __uint_as_float(a[4 * i + 2]), __uint_as_float(a[4 * i + 3]));
 }
 
 // Thread roles: TMEM side, thread (r = tid % 128, h = tid / 128) owns pixel row r (= TMEM lane) and 16 of the 32
@@ -871,7 +1108,11 @@ int gdn_tc_forward(const float* x, const float* gamma, const float* beta, float*
   f.eps_mode = (eps == 0.5f) ? 2 : 1;
   *handled = true;
   const bool fast = (alpha == 1.f) && (eps == 1.f) && !f.rectify;
-  if (C == 128) {  // 64 KB of gamma planes + 2 x 69 KB pipelines = 202 KB
+  if (C == 128) {
+    const char* v1 = getenv("TFCB_GDN_FWD1");
+    if (!(v1 && v1[0] == '1'))  // default: x tile resident in shared memory, bulk async copies
+      return fast ? launch_tc_fwd2<true>(x, gamma, beta, y, n_pix, f, s) : launch_tc_fwd2<false>(x, gamma, beta, y, n_pix, f, s);
+    // first generation: 64 KB of gamma planes + 2 x 69 KB cp.async pipelines = 202 KB
     return fast ? launch_tc<128, 2, 32, true>(x, gamma, beta, y, n_pix, f, s)
                 : launch_tc<128, 2, 32, false>(x, gamma, beta, y, n_pix, f, s);
   }
