@@ -436,7 +436,8 @@ __device__ __forceinline__ void stage_store16(float* dst, const uint32_t (&a)[16
                                                            __uint_as_float(a[4 * i + 2]), __uint_as_float(a[4 * i + 3]));
 }
 
-constexpr int kF2Threads = 256;
+constexpr int kF2Threads = 288;   // 8 compute warps + 1 copy warp
+constexpr int kF2Compute = 256;
 constexpr int kF2XBuf = kTileM * 128 * 4;          // one x / y tile, dense [128][128] fp32 (one bulk copy)
 constexpr int kF2Kg = kTileM * 16 + 32;            // plane group stride: 32 B of padding -> conflict-free stores
 constexpr int kF2Plane = 4 * kF2Kg;                // one hi or lo plane of a 32-channel chunk
@@ -462,8 +463,8 @@ gdn_tc_fwd2_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict_
   extern __shared__ __align__(1024) uint8_t smem[];
   float* beta_s = reinterpret_cast<float*>(smem + L::kOffBeta);
   float* stage = reinterpret_cast<float*>(smem + L::kOffP);          // [128][36] fp32, only during the epilogue
-  uint64_t* mbars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);  // [0,1] full, [2,3] plane
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffBar + 48);
+  uint64_t* mbars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);  // [0,1] full, [2,3] plane, [4,5] y tile ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffBar + 56);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r = tid & 127, h = tid >> 7, gwarp = warp & 3;
   constexpr uint32_t kIdesc = umma_idesc(kTileM, C);
@@ -475,7 +476,7 @@ gdn_tc_fwd2_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict_
     for (int i = tid; i < C; i += kF2Threads) beta_s[i] = beta[i];
   }
   if (tid == 0) {
-    for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbars + i)));
+    for (int i = 0; i < 6; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbars + i)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < 32) {
@@ -504,7 +505,36 @@ gdn_tc_fwd2_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict_
                  "l"(x + p0 * C), "r"(bytes), "r"(mbar)
                  : "memory");
   };
-  if (tid == 0 && blockIdx.x < n_tiles) issue_load(blockIdx.x, 0);
+  if (warp == kF2Compute / 32) {
+    // ------------------------------ copy warp ------------------------------
+    // Both buffers are filled up front; afterwards, per tile: wait until the compute warps have rewritten the
+    // buffer with y, store it, and as soon as the store has read the buffer refill it with the tile after next.
+    if (lane == 0) {
+      uint32_t par_y[2] = {0u, 0u};
+      if (blockIdx.x < n_tiles) issue_load(blockIdx.x, 0);
+      if (blockIdx.x + (long long)gridDim.x < n_tiles) issue_load(blockIdx.x + gridDim.x, 1);
+      int it = 0;
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int b = it & 1;
+        const long long p0 = tile * kTileM;
+        const uint32_t bytes = (uint32_t)min((long long)kTileM, n_pix - p0) * 512u;
+        if (!mbar_wait(smem_u32(mbars + 4 + b), par_y[b])) __trap();
+        par_y[b] ^= 1u;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(y + p0 * C),
+                     "r"(xs + b * kF2XBuf), "r"(bytes)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        const long long nxt = tile + 2ll * gridDim.x;
+        if (nxt < n_tiles) {
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          issue_load(nxt, b);
+        }
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
+  } else {
+  // ----------------------------- compute warps -----------------------------
 
   // memory-side items of a 32-channel chunk: (row, kg) = 8 channels of one pixel, two per thread.  Odd rows touch
   // the two 16-byte halves of their 32 bytes in the opposite order: with the dense 512-byte row stride two
@@ -512,16 +542,10 @@ gdn_tc_fwd2_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict_
   const int ckg = tid & 3, crow = tid >> 2;
   const int swap = crow & 1;
 
+  auto compute_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(kF2Compute) : "memory"); };
   int it = 0;
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
     const int b = it & 1;
-    const long long p0 = tile * kTileM;
-    const uint32_t bytes = (uint32_t)min((long long)kTileM, n_pix - p0) * 512u;
-    // (a) next tile into the other buffer, once the store that read it (tile it - 1) is done with it
-    if (tid == 0 && tile + gridDim.x < n_tiles) {
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      issue_load(tile + gridDim.x, b ^ 1);
-    }
     // (b) this tile has landed
     if (!mbar_wait(smem_u32(mbars + b), par_full[b])) __trap();
     par_full[b] ^= 1u;
@@ -551,7 +575,7 @@ gdn_tc_fwd2_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict_
         *reinterpret_cast<uint4*>(pl + ckg * kF2Kg + row * 16) = lo;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncthreads();
+      compute_sync();
       if (tid == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
@@ -584,7 +608,7 @@ gdn_tc_fwd2_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict_
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         stage_store16(stage + r * kStLd + h * 16, acc);
       }
-      __syncthreads();
+      compute_sync();
       const float4 bv0 = *reinterpret_cast<const float4*>(beta_s + cc * 32 + ckg * 8);
       const float4 bv1 = *reinterpret_cast<const float4*>(beta_s + cc * 32 + ckg * 8 + 4);
 #pragma unroll
@@ -611,17 +635,12 @@ gdn_tc_fwd2_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict_
       }
       if (cc == C / 32 - 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // y tile -> bulk store
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncthreads();  // staging free again (and, after the last chunk, for the next tile's operand planes)
+      compute_sync();  // staging free again (and, after the last chunk, for the next tile's operand planes)
     }
-    // (e) y tile out
-    if (tid == 0) {
-      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(y + p0 * C), "r"(xs + b * kF2XBuf),
-                   "r"(bytes)
-                   : "memory");
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    }
+    // (e) hand the y tile to the copy warp
+    if (tid == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(mbars + 4 + b)) : "memory");
   }
-  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }  // compute warps
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (tid < 32) {
