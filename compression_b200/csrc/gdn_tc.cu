@@ -436,10 +436,12 @@ __device__ __forceinline__ void stage_store16(float* dst, const uint32_t (&a)[16
                                                            __uint_as_float(a[4 * i + 2]), __uint_as_float(a[4 * i + 3]));
 }
 
-constexpr int kF2Threads = 288;   // 8 compute warps + 1 copy warp
+constexpr int kF2Threads = 320;   // 8 compute warps + 1 copy warp + 1 MMA-issue warp
 constexpr int kF2Compute = 256;
 constexpr int kF2XBuf = kTileM * 128 * 4;          // one x / y tile, dense [128][128] fp32 (one bulk copy)
-constexpr int kF2Kg = kTileM * 16 + 32;            // plane group stride: 32 B of padding -> conflict-free stores
+constexpr int kF2Kg = kTileM * 16 + 160;           // plane group stride: padding = 2 (mod 8) 16-byte units -> conflict-free
+                                                   // stores; sized so that the epilogue's [128][68] staging fits in the planes
+constexpr int kF2StLd = 68;                        // floats per staging row (64 + 4)
 constexpr int kF2Plane = 4 * kF2Kg;                // one hi or lo plane of a 32-channel chunk
 
 struct Fwd2Smem {
@@ -448,10 +450,10 @@ struct Fwd2Smem {
   static constexpr int kOffBl = kOffBh + C * C * 2;
   static constexpr int kOffX = kOffBl + C * C * 2;            // [2] x / y tiles
   static constexpr int kOffP = kOffX + 2 * kF2XBuf;           // [2 buffers][hi, lo]; the epilogue's staging aliases it
-  static constexpr int kOffBeta = kOffP + 4 * kF2Plane;
-  static constexpr int kOffBar = kOffBeta + C * 4;            // full[2], plane[2]
+  static constexpr int kOffBar = kOffP + 4 * kF2Plane;        // full[2], plane[2], y ready[2], TMEM slot
   static constexpr int kBytes = kOffBar + 64;
-  static_assert(4 * kF2Plane >= kTileM * kStLd * 4, "staging must fit in the operand-plane area");
+  static_assert(4 * kF2Plane >= kTileM * kF2StLd * 4, "staging must fit in the operand-plane area");
+  static_assert(kBytes <= 232448, "shared memory budget");
 };
 
 template <bool FAST>
@@ -461,8 +463,7 @@ gdn_tc_fwd2_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict_
   using L = Fwd2Smem;
   constexpr int C = 128;
   extern __shared__ __align__(1024) uint8_t smem[];
-  float* beta_s = reinterpret_cast<float*>(smem + L::kOffBeta);
-  float* stage = reinterpret_cast<float*>(smem + L::kOffP);          // [128][36] fp32, only during the epilogue
+  float* stage = reinterpret_cast<float*>(smem + L::kOffP);          // [128][68] fp32, only during the epilogue
   uint64_t* mbars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);  // [0,1] full, [2,3] plane, [4,5] y tile ready
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffBar + 56);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -473,7 +474,6 @@ gdn_tc_fwd2_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict_
     const uint4* src = reinterpret_cast<const uint4*>(planes);
     uint4* dst = reinterpret_cast<uint4*>(smem + L::kOffBh);
     for (int i = tid; i < 2 * C * C * 2 / 16; i += kF2Threads) dst[i] = src[i];
-    for (int i = tid; i < C; i += kF2Threads) beta_s[i] = beta[i];
   }
   if (tid == 0) {
     for (int i = 0; i < 6; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbars + i)));
@@ -533,6 +533,35 @@ gdn_tc_fwd2_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict_
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     __syncwarp();
+  } else if (warp == kF2Compute / 32 + 1) {
+    // ---------------------------- MMA-issue warp ----------------------------
+    // The compute warps only ARRIVE on the chunk's named barrier once their operand planes are written and
+    // fenced; this warp waits on it, issues the chunk's MMAs and commits to the plane mbarrier.  (Barrier ids
+    // alternate with the plane buffer: a buffer is rewritten only after its commit has been waited for.)
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+#pragma unroll
+      for (int c = 0; c < C / 32; ++c) {
+        const int pb = c & 1;
+        asm volatile("bar.sync %0, %1;" ::"r"(2 + pb), "n"(kF2Compute + 32) : "memory");
+        if (lane == 0) {
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t ph = smem_u32(smem + L::kOffP + pb * 2 * kF2Plane), pl = ph + kF2Plane;
+#pragma unroll
+          for (int s2 = 0; s2 < 2; ++s2) {
+            const uint64_t dah = umma_desc(ph + (uint32_t)(2 * s2) * kF2Kg, kF2Kg, 128);
+            const uint64_t dal = umma_desc(pl + (uint32_t)(2 * s2) * kF2Kg, kF2Kg, 128);
+            const uint32_t b_off = (uint32_t)(c * 4 + 2 * s2) * (C * 16);
+            const uint64_t dbh = umma_desc(b_hi + b_off, C * 16, 128);
+            const uint64_t dbl = umma_desc(b_lo + b_off, C * 16, 128);
+            umma_bf16(tmem_n, dah, dbh, kIdesc, (c | s2) ? 1u : 0u);
+            umma_bf16(tmem_n, dal, dbh, kIdesc, 1u);
+            umma_bf16(tmem_n, dah, dbl, kIdesc, 1u);
+          }
+          umma_commit(smem_u32(mbars + 2 + pb));
+        }
+        __syncwarp();
+      }
+    }
   } else {
   // ----------------------------- compute warps -----------------------------
 
@@ -575,22 +604,8 @@ gdn_tc_fwd2_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict_
         *reinterpret_cast<uint4*>(pl + ckg * kF2Kg + row * 16) = lo;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      compute_sync();
-      if (tid == 0) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-        for (int s2 = 0; s2 < 2; ++s2) {
-          const uint64_t dah = umma_desc(smem_u32(ph) + (uint32_t)(2 * s2) * kF2Kg, kF2Kg, 128);
-          const uint64_t dal = umma_desc(smem_u32(pl) + (uint32_t)(2 * s2) * kF2Kg, kF2Kg, 128);
-          const uint32_t b_off = (uint32_t)(c * 4 + 2 * s2) * (C * 16);
-          const uint64_t dbh = umma_desc(b_hi + b_off, C * 16, 128);
-          const uint64_t dbl = umma_desc(b_lo + b_off, C * 16, 128);
-          umma_bf16(tmem_n, dah, dbh, kIdesc, (c | s2) ? 1u : 0u);
-          umma_bf16(tmem_n, dal, dbh, kIdesc, 1u);
-          umma_bf16(tmem_n, dah, dbl, kIdesc, 1u);
-        }
-        umma_commit(smem_u32(mbars + 2 + pb));
-      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("bar.arrive %0, %1;" ::"r"(2 + pb), "n"(kF2Compute + 32) : "memory");
     }
     // (d) epilogue in place: y = x / (beta + n).  The last two commits cover every MMA of the tile, after which
     // the operand planes are dead and their memory is the staging buffer for the TMEM -> row-major transpose.
@@ -600,40 +615,49 @@ gdn_tc_fwd2_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict_
       par_plane[pb] ^= 1u;
     }
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // 64 output channels at a time: thread (r, h) moves 32 accumulator columns of its row to the staging buffer,
+    // then every thread finishes four (row, 8-channel) items; lanes 4..7 of each 8-lane group touch the two
+    // 16-byte halves in the opposite order (a row's eight items span 256 B = two passes over the banks).
+    const int ekg = tid & 7, erow = tid >> 3, eswap = (ekg >> 2) & 1;
 #pragma unroll
-    for (int cc = 0; cc < C / 32; ++cc) {
+    for (int cc = 0; cc < C / 64; ++cc) {
       {
-        uint32_t acc[16];
-        tmem_load<16>(tmem_n + lane_sel + (uint32_t)(cc * 32 + h * 16), acc);
+        uint32_t acc[32];
+        tmem_load<32>(tmem_n + lane_sel + (uint32_t)(cc * 64 + h * 32), acc);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        stage_store16(stage + r * kStLd + h * 16, acc);
+        float* dst = stage + r * kF2StLd + h * 32;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<float4*>(dst + 4 * i) = make_float4(__uint_as_float(acc[4 * i]), __uint_as_float(acc[4 * i + 1]),
+                                                                 __uint_as_float(acc[4 * i + 2]), __uint_as_float(acc[4 * i + 3]));
       }
       compute_sync();
-      const float4 bv0 = *reinterpret_cast<const float4*>(beta_s + cc * 32 + ckg * 8);
-      const float4 bv1 = *reinterpret_cast<const float4*>(beta_s + cc * 32 + ckg * 8 + 4);
+      const float4 bv0 = __ldg(reinterpret_cast<const float4*>(beta + cc * 64 + ekg * 8));
+      const float4 bv1 = __ldg(reinterpret_cast<const float4*>(beta + cc * 64 + ekg * 8) + 1);
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int row = crow + 64 * i;
-        uint8_t* src = xt + row * 512 + (cc * 32 + ckg * 8) * 4;
-        float4* pa = reinterpret_cast<float4*>(src + (swap ? 16 : 0));
-        float4* pb2 = reinterpret_cast<float4*>(src + (swap ? 0 : 16));
+      for (int i = 0; i < 4; ++i) {
+        const int row = erow + 32 * i;
+        uint8_t* src = xt + row * 512 + (cc * 64 + ekg * 8) * 4;
+        const uint8_t* nsrc = reinterpret_cast<const uint8_t*>(stage + row * kF2StLd + ekg * 8);
+        float4* pa = reinterpret_cast<float4*>(src + (eswap ? 16 : 0));
+        float4* pb2 = reinterpret_cast<float4*>(src + (eswap ? 0 : 16));
         const float4 va = *pa, vb = *pb2;
-        const float4 n0 = *reinterpret_cast<const float4*>(stage + row * kStLd + ckg * 8);
-        const float4 n1 = *reinterpret_cast<const float4*>(stage + row * kStLd + ckg * 8 + 4);
-        const float4 x0 = swap ? vb : va, x1 = swap ? va : vb;
-        float4 o0, o1;
-        o0.x = tc_out<FAST>(x0.x, bv0.x + n0.x, f);
-        o0.y = tc_out<FAST>(x0.y, bv0.y + n0.y, f);
-        o0.z = tc_out<FAST>(x0.z, bv0.z + n0.z, f);
-        o0.w = tc_out<FAST>(x0.w, bv0.w + n0.w, f);
-        o1.x = tc_out<FAST>(x1.x, bv1.x + n1.x, f);
-        o1.y = tc_out<FAST>(x1.y, bv1.y + n1.y, f);
-        o1.z = tc_out<FAST>(x1.z, bv1.z + n1.z, f);
-        o1.w = tc_out<FAST>(x1.w, bv1.w + n1.w, f);
-        *pa = swap ? o1 : o0;
-        *pb2 = swap ? o0 : o1;
+        const float4 na = *reinterpret_cast<const float4*>(nsrc + (eswap ? 16 : 0));
+        const float4 nb = *reinterpret_cast<const float4*>(nsrc + (eswap ? 0 : 16));
+        const float4 ba = eswap ? bv1 : bv0, bb = eswap ? bv0 : bv1;
+        float4 oa, ob;
+        oa.x = tc_out<FAST>(va.x, ba.x + na.x, f);
+        oa.y = tc_out<FAST>(va.y, ba.y + na.y, f);
+        oa.z = tc_out<FAST>(va.z, ba.z + na.z, f);
+        oa.w = tc_out<FAST>(va.w, ba.w + na.w, f);
+        ob.x = tc_out<FAST>(vb.x, bb.x + nb.x, f);
+        ob.y = tc_out<FAST>(vb.y, bb.y + nb.y, f);
+        ob.z = tc_out<FAST>(vb.z, bb.z + nb.z, f);
+        ob.w = tc_out<FAST>(vb.w, bb.w + nb.w, f);
+        *pa = oa;
+        *pb2 = ob;
       }
-      if (cc == C / 32 - 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // y tile -> bulk store
+      if (cc == C / 64 - 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // y tile -> bulk store
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       compute_sync();  // staging free again (and, after the last chunk, for the next tile's operand planes)
     }
@@ -1116,7 +1140,7 @@ int gdn_tc_forward(const float* x, const float* gamma, const float* beta, float*
   *handled = false;
   if (!(C == 128 || C == 192)) return TFCB_OK;
   if (!(alpha == 1.f || alpha == 2.f) || !(eps == 1.f || eps == 0.5f)) return TFCB_OK;
-  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) return TFCB_OK;  // 16-byte rows
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(beta)) & 15) return TFCB_OK;  // 16-byte rows
   if (const char* env = getenv("TFCB_GDN_FP32")) {
     if (env[0] == '1') return TFCB_OK;  // debugging aid: force the CUDA-core kernels
   }
