@@ -754,7 +754,7 @@ int launch_tc(const float* x, const float* gamma, const float* beta, float* y, l
 // TMEM: columns [0, C) n, [C, 2C) dp, [2C, 3C) this CTA's dgamma partial (accumulates over all its tiles).
 // HBM traffic per element: x and dy once (their re-reads in the two epilogues are L2 hits), dx once.
 // =============================================================================================
-constexpr int kBwdThreads = 256;
+constexpr int kBwdThreads = 288;  // 8 compute warps + 1 MMA-issue warp
 constexpr int kKg = kTileM * 16 + 16;  // byte stride between 8-channel groups of an operand plane: one 16-byte row
                                        // of padding makes the coalesced (row, group) stores bank-conflict free;
                                        // the descriptors take it as LBO (K-major view) or SBO (MN-major view)
@@ -800,9 +800,15 @@ __device__ __forceinline__ float tc_dx(float g, float x, float n, float dp, cons
   return d;
 }
 
-// Thread roles: TMEM side, thread (r = tid % 128, h = tid / 128) owns pixel row r (= TMEM lane) and 16 of the 32
-// columns of a chunk; memory side, item (row, kg) = 8 consecutive channels of one pixel, items enumerated row-major
-// so that a warp reads whole 128-byte lines.
+// Warp roles: 8 compute warps + 1 MMA-issue warp.  Compute threads never block on a CTA-wide barrier to hand
+// operands over: they ARRIVE on a named barrier once their planes are written and fenced; the issue warp waits
+// on it, issues the MMAs and commits to an mbarrier.  TMEM side, compute thread (r = tid % 128, h = tid / 128)
+// owns pixel row r (= TMEM lane) and half of the columns being moved; memory side, item (row, kg) = 8
+// consecutive channels of one pixel, items enumerated row-major so that a warp reads whole 128-byte lines.
+constexpr int kBwdCompute = 256;
+constexpr int kBwdStLd2 = 68;    // staging row of the 64-column n passes (P2)
+constexpr int kBwdStLd3 = 132;   // staging row of the full n / dp tiles (P3; aliases the dead operand planes)
+
 template <int C, bool FAST>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 gdn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, const __nv_bfloat16* __restrict__ planes,
@@ -810,17 +816,20 @@ gdn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, con
                   float* __restrict__ part_b, long long n_pix, TcFlags f) {
   using L = BwdSmem<C>;
   static_assert(C == 128, "TMEM holds n, dp and the dgamma partial only for C = 128");
+  static_assert(2 * L::kStage >= kTileM * kBwdStLd2 * 4, "P2 staging");
+  static_assert(2 * L::kPlaneP + 4 * L::kPlaneQ + 2 * L::kStage >= 2 * kTileM * kBwdStLd3 * 4, "P3 staging");
   constexpr int NCH = C / 32;
   extern __shared__ __align__(1024) uint8_t smem[];
   float* beta_s = reinterpret_cast<float*>(smem + L::kOffBeta);
   float* dbeta_s = reinterpret_cast<float*>(smem + L::kOffDbeta);
-  float* stage_n = reinterpret_cast<float*>(smem + L::kOffStage);
-  float* stage_d = reinterpret_cast<float*>(smem + L::kOffStage + L::kStage);
-  uint64_t* mbars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);  // [0] MMA1, [1], [2] q buffers
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffBar + 32);
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int r = tid & 127, h = tid >> 7, gwarp = (tid >> 5) & 3;
-  constexpr uint32_t kIdesc1 = umma_idesc(kTileM, C);
+  float* stage2 = reinterpret_cast<float*>(smem + L::kOffStage);                 // [128][68]
+  float* stage3n = reinterpret_cast<float*>(smem + L::kOffPh);                   // [128][132], planes are dead
+  float* stage3d = stage3n + kTileM * kBwdStLd3;
+  uint64_t* mbars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);  // [0,1] MMA1 halves, [2,3] q buffers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffBar + 40);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r = tid & 127, h = (tid >> 7) & 1, gwarp = warp & 3;
+  constexpr uint32_t kIdesc1 = umma_idesc(kTileM, 64);                         // MMA1, one 64-column half of n
   constexpr uint32_t kIdesc2 = umma_idesc(kTileM, C) | (1u << 16);             // B = gamma^T (MN-major view)
   constexpr uint32_t kIdesc3 = umma_idesc(C, 32) | (1u << 15) | (1u << 16);    // A = p^T, B = q chunk (both views)
 
@@ -834,7 +843,7 @@ gdn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, con
     }
   }
   if (tid == 0) {
-    for (int i = 0; i < 3; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbars + i)));
+    for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbars + i)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < 32) {
@@ -849,39 +858,102 @@ gdn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, con
   const uint32_t lane_sel = (uint32_t)(gwarp * 32) << 16;
   const uint32_t b_hi = smem_u32(smem + L::kOffBh), b_lo = smem_u32(smem + L::kOffBl);
   const uint32_t p_hi = smem_u32(smem + L::kOffPh), p_lo = smem_u32(smem + L::kOffPl);
-  uint32_t par0 = 0u, parq[2] = {0u, 0u};
+  const long long n_tiles = (n_pix + kTileM - 1) / kTileM;
+  bool first_tile = true;
+
+  if (warp == kBwdCompute / 32) {
+    // ------------------------------- MMA-issue warp -------------------------------
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      // next tile of this CTA -> L2 (one bulk prefetch per array: the tile is contiguous)
+      if (lane == 1) {
+        const long long pn = (tile + gridDim.x) * kTileM;
+        const long long rows = min((long long)kTileM, n_pix - pn);
+        if (rows > 0) {
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(x + pn * C), "r"((uint32_t)(rows * C * 4)) : "memory");
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(dy + pn * C), "r"((uint32_t)(rows * C * 4)) : "memory");
+        }
+      }
+      // MMA1: n = p . gamma, the two 64-column halves one after the other so that P2 can start on the first
+      asm volatile("bar.sync 2, %0;" ::"n"(kBwdThreads) : "memory");
+      if (lane == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+          for (int s = 0; s < C / 16; ++s) {
+            const uint64_t dah = umma_desc(p_hi + (uint32_t)(2 * s) * kKg, kKg, 128);
+            const uint64_t dal = umma_desc(p_lo + (uint32_t)(2 * s) * kKg, kKg, 128);
+            const uint32_t boff = (uint32_t)(2 * s) * (C * 16) + (uint32_t)(half * 64) * 16u;
+            const uint64_t dbh = umma_desc(b_hi + boff, C * 16, 128);
+            const uint64_t dbl = umma_desc(b_lo + boff, C * 16, 128);
+            umma_bf16(tmem_n + (uint32_t)(half * 64), dah, dbh, kIdesc1, s ? 1u : 0u);
+            umma_bf16(tmem_n + (uint32_t)(half * 64), dal, dbh, kIdesc1, 1u);
+            umma_bf16(tmem_n + (uint32_t)(half * 64), dah, dbl, kIdesc1, 1u);
+          }
+          umma_commit(smem_u32(mbars + half));
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int b = c & 1;
+        asm volatile("bar.sync %0, %1;" ::"r"(3 + b), "n"(kBwdThreads) : "memory");
+        if (lane == 0) {
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t q_hi = smem_u32(smem + L::kOffQ + b * 2 * L::kPlaneQ), q_lo = q_hi + L::kPlaneQ;
+          // MMA2: dp[pix, j] += sum_{i in chunk} q[pix, i] gamma[j, i]   (K = i: 2 steps of 16)
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            const uint64_t dah = umma_desc(q_hi + (uint32_t)(2 * s) * kKg, kKg, 128);
+            const uint64_t dal = umma_desc(q_lo + (uint32_t)(2 * s) * kKg, kKg, 128);
+            // gamma plane viewed with n = j, k = i: k rows are 16 B apart, k groups 128 B, n groups C * 16 B
+            const uint32_t koff = (uint32_t)(c * 32 + s * 16) * 16u;
+            const uint64_t dbh = umma_desc(b_hi + koff, 128, C * 16);
+            const uint64_t dbl = umma_desc(b_lo + koff, 128, C * 16);
+            umma_bf16(tmem_dp, dah, dbh, kIdesc2, (c | s) ? 1u : 0u);
+            umma_bf16(tmem_dp, dal, dbh, kIdesc2, 1u);
+            umma_bf16(tmem_dp, dah, dbl, kIdesc2, 1u);
+          }
+          // MMA3: dgamma[j, i in chunk] += sum_pix p[pix, j] q[pix, i]   (K = pix: 8 steps of 16)
+#pragma unroll
+          for (int s = 0; s < kTileM / 16; ++s) {
+            const uint32_t koff = (uint32_t)(s * 16) * 16u;
+            const uint64_t dah = umma_desc(p_hi + koff, 128, kKg);
+            const uint64_t dal = umma_desc(p_lo + koff, 128, kKg);
+            const uint64_t dbh = umma_desc(q_hi + koff, 128, kKg);
+            const uint64_t dbl = umma_desc(q_lo + koff, 128, kKg);
+            const uint32_t acc_on = (first_tile && s == 0) ? 0u : 1u;
+            umma_bf16(tmem_dg + (uint32_t)(c * 32), dah, dbh, kIdesc3, acc_on);
+            umma_bf16(tmem_dg + (uint32_t)(c * 32), dal, dbh, kIdesc3, 1u);
+            umma_bf16(tmem_dg + (uint32_t)(c * 32), dah, dbl, kIdesc3, 1u);
+          }
+          umma_commit(smem_u32(mbars + 2 + b));
+        }
+        __syncwarp();
+      }
+      first_tile = false;
+    }
+  } else {
+  // --------------------------------- compute warps ---------------------------------
+  uint32_t parn[2] = {0u, 0u}, parq[2] = {0u, 0u};
   float dbeta_acc[NCH][8];  // channels c * 32 + (tid % 4) * 8 + e, summed over this thread's rows
 #pragma unroll
   for (int c = 0; c < NCH; ++c)
 #pragma unroll
     for (int e = 0; e < 8; ++e) dbeta_acc[c][e] = 0.f;
-  bool first_tile = true;
-  // memory-side items of a 32-channel chunk: 2 per thread
-  const int ckg = tid & 3;         // 8-channel group inside the chunk
+  const int ckg = tid & 3;         // 8-channel group inside a 32-channel chunk
   const int crow = tid >> 2;       // rows crow and crow + 64
+  auto compute_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(kBwdCompute) : "memory"); };
 
-  const long long n_tiles = (n_pix + kTileM - 1) / kTileM;
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long p0 = tile * kTileM;
-    // pull the next tile of this CTA into L2 while this one is processed
-    {
-      const long long pn = (tile + gridDim.x) * kTileM;
-      const long long rows = min((long long)kTileM, n_pix - pn);
-      if (rows > 0) {
-        const long long bytes = rows * C * 4;
-        for (long long off = (long long)tid * 128; off < bytes; off += (long long)kBwdThreads * 128) {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(x + pn * C) + off));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(dy + pn * C) + off));
-        }
-      }
-    }
     // ---- P1: p = pool(x) -> hi / lo planes [j / 8][row][8]; item = (row, kg), 16 groups per row ----
     {
-      constexpr int ITEMS = kTileM * (C / 8) / kBwdThreads;  // 8
+      constexpr int ITEMS = kTileM * (C / 8) / kBwdCompute;  // 8
       float4 xv[ITEMS][2];
 #pragma unroll
       for (int it = 0; it < ITEMS; ++it) {
-        const int id = it * kBwdThreads + tid;
+        const int id = it * kBwdCompute + tid;
         const int row = id / (C / 8), kg = id % (C / 8);
         const bool live = p0 + row < n_pix;
         const float4* src = reinterpret_cast<const float4*>(x + (p0 + row) * C + kg * 8);
@@ -890,7 +962,7 @@ gdn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, con
       }
 #pragma unroll
       for (int it = 0; it < ITEMS; ++it) {
-        const int id = it * kBwdThreads + tid;
+        const int id = it * kBwdCompute + tid;
         const int row = id / (C / 8), kg = id % (C / 8);
         const float4 a = xv[it][0], b = xv[it][1];
         float v[8] = {tc_pool<FAST>(a.x, f), tc_pool<FAST>(a.y, f), tc_pool<FAST>(a.z, f), tc_pool<FAST>(a.w, f),
@@ -902,23 +974,10 @@ gdn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, con
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    if (tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-      for (int s = 0; s < C / 16; ++s) {
-        const uint64_t dah = umma_desc(p_hi + (uint32_t)(2 * s) * kKg, kKg, 128);
-        const uint64_t dal = umma_desc(p_lo + (uint32_t)(2 * s) * kKg, kKg, 128);
-        const uint64_t dbh = umma_desc(b_hi + (uint32_t)(2 * s) * (C * 16), C * 16, 128);
-        const uint64_t dbl = umma_desc(b_lo + (uint32_t)(2 * s) * (C * 16), C * 16, 128);
-        umma_bf16(tmem_n, dah, dbh, kIdesc1, s ? 1u : 0u);
-        umma_bf16(tmem_n, dal, dbh, kIdesc1, 1u);
-        umma_bf16(tmem_n, dah, dbl, kIdesc1, 1u);
-      }
-      umma_commit(smem_u32(mbars));
-    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    asm volatile("bar.arrive 2, %0;" ::"n"(kBwdThreads) : "memory");
     // x and dy of a chunk for this thread's two items (coalesced; L2 hits after the prefetch / P1).  Two register
-    // sets: the loads of the next chunk are issued a whole chunk ahead of their use (L2 latency ~1 us).
+    // sets: the loads of the next chunk are issued a whole chunk ahead of their use.
     float4 xq[2][2][2], gq[2][2][2];  // [set][item][half]
     auto load_xg = [&](int set, int c) {
 #pragma unroll
@@ -933,27 +992,33 @@ gdn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, con
         gq[set][it][1] = live ? __ldg(reinterpret_cast<const float4*>(dy + off) + 1) : z;
       }
     };
-    // ---- P2: q = dL/dn per 32-channel chunk -> q planes; MMA2 (dp) and MMA3 (dgamma) per chunk ----
+    // ---- P2: q = dL/dn -> q planes (32-channel chunks); n is staged 64 columns at a time ----
     load_xg(0, 0);
-    if (!mbar_wait(smem_u32(mbars), par0)) __trap();
-    par0 ^= 1u;
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int b = c & 1;
       load_xg(b ^ 1, (c + 1) % NCH);  // next chunk; after the last one: chunk 0 again, for the dx pass
-      {
-        uint32_t acc[16];
-        tmem_load<16>(tmem_n + lane_sel + (uint32_t)(c * 32 + h * 16), acc);
+      if ((c & 1) == 0) {
+        const int half = c >> 1;
+        if (c) compute_sync();  // everyone is done reading the previous 64 staged columns
+        if (!mbar_wait(smem_u32(mbars + half), parn[half])) __trap();
+        parn[half] ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t acc[32];
+        tmem_load<32>(tmem_n + lane_sel + (uint32_t)(half * 64 + h * 32), acc);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        stage_store16(stage_n + r * kStLd + h * 16, acc);
+        float* dst = stage2 + r * kBwdStLd2 + h * 32;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<float4*>(dst + 4 * i) = make_float4(__uint_as_float(acc[4 * i]), __uint_as_float(acc[4 * i + 1]),
+                                                                 __uint_as_float(acc[4 * i + 2]), __uint_as_float(acc[4 * i + 3]));
+        compute_sync();
       }
-      // the q buffer was read by the MMAs of chunk c - 2
-      if (c >= 2) {  // (chunks 2 and 3 of the previous tile were waited for before its dx pass)
-        if (!mbar_wait(smem_u32(mbars + 1 + b), parq[b])) __trap();
+      // the q buffer was read by the MMAs of chunk c - 2 (chunks 2, 3 of the previous tile: waited for before its dx pass)
+      if (c >= 2) {
+        if (!mbar_wait(smem_u32(mbars + 2 + b), parq[b])) __trap();
         parq[b] ^= 1u;
       }
-      __syncthreads();  // n chunk staged
       uint8_t* qh = smem + L::kOffQ + b * 2 * L::kPlaneQ;
       uint8_t* ql = qh + L::kPlaneQ;
       const float4 bv0 = *reinterpret_cast<const float4*>(beta_s + c * 32 + ckg * 8);
@@ -961,8 +1026,9 @@ gdn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, con
 #pragma unroll
       for (int it = 0; it < 2; ++it) {
         const int row = crow + 64 * it;
-        const float4 n0 = *reinterpret_cast<const float4*>(stage_n + row * kStLd + ckg * 8);
-        const float4 n1 = *reinterpret_cast<const float4*>(stage_n + row * kStLd + ckg * 8 + 4);
+        const float* ns = stage2 + row * kBwdStLd2 + (c & 1) * 32 + ckg * 8;
+        const float4 n0 = *reinterpret_cast<const float4*>(ns);
+        const float4 n1 = *reinterpret_cast<const float4*>(ns + 4);
         const float4 x0 = xq[b][it][0], x1 = xq[b][it][1], g0 = gq[b][it][0], g1 = gq[b][it][1];
         float q[8];
         q[0] = tc_dl_dn<FAST>(g0.x, x0.x, bv0.x + n0.x, f);
@@ -982,68 +1048,42 @@ gdn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, con
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncthreads();  // q planes complete; stage_n free again
-      if (tid == 0) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t q_hi = smem_u32(qh), q_lo = smem_u32(ql);
-        // MMA2: dp[pix, j] += sum_{i in chunk} q[pix, i] gamma[j, i]   (K = i: 2 steps of 16)
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          const uint64_t dah = umma_desc(q_hi + (uint32_t)(2 * s) * kKg, kKg, 128);
-          const uint64_t dal = umma_desc(q_lo + (uint32_t)(2 * s) * kKg, kKg, 128);
-          // gamma plane viewed with n = j, k = i: k rows are 16 B apart, k groups 128 B, n groups C * 16 B
-          const uint32_t koff = (uint32_t)(c * 32 + s * 16) * 16u;
-          const uint64_t dbh = umma_desc(b_hi + koff, 128, C * 16);
-          const uint64_t dbl = umma_desc(b_lo + koff, 128, C * 16);
-          umma_bf16(tmem_dp, dah, dbh, kIdesc2, (c | s) ? 1u : 0u);
-          umma_bf16(tmem_dp, dal, dbh, kIdesc2, 1u);
-          umma_bf16(tmem_dp, dah, dbl, kIdesc2, 1u);
-        }
-        // MMA3: dgamma[j, i in chunk] += sum_pix p[pix, j] q[pix, i]   (K = pix: 8 steps of 16)
-#pragma unroll
-        for (int s = 0; s < kTileM / 16; ++s) {
-          const uint32_t koff = (uint32_t)(s * 16) * 16u;
-          const uint64_t dah = umma_desc(p_hi + koff, 128, kKg);
-          const uint64_t dal = umma_desc(p_lo + koff, 128, kKg);
-          const uint64_t dbh = umma_desc(q_hi + koff, 128, kKg);
-          const uint64_t dbl = umma_desc(q_lo + koff, 128, kKg);
-          const uint32_t acc_on = (first_tile && s == 0) ? 0u : 1u;
-          umma_bf16(tmem_dg + (uint32_t)(c * 32), dah, dbh, kIdesc3, acc_on);
-          umma_bf16(tmem_dg + (uint32_t)(c * 32), dal, dbh, kIdesc3, 1u);
-          umma_bf16(tmem_dg + (uint32_t)(c * 32), dah, dbl, kIdesc3, 1u);
-        }
-        umma_commit(smem_u32(mbars + 1 + b));
-      }
+      asm volatile("bar.arrive %0, %1;" ::"r"(3 + b), "n"(kBwdThreads) : "memory");
     }
     // ---- P3: dx = g / m + dpool/du * dp  (chunk 0 is already in register set 0) ----
 #pragma unroll
-    for (int b = 0; b < 2; ++b) {  // commits of chunks 2 and 3: all MMAs of this tile are done
-      if (!mbar_wait(smem_u32(mbars + 1 + b), parq[b])) __trap();
+    for (int b = 0; b < 2; ++b) {  // commits of chunks 2 and 3: all MMAs of this tile are done, the planes are dead
+      if (!mbar_wait(smem_u32(mbars + 2 + b), parq[b])) __trap();
       parq[b] ^= 1u;
     }
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // whole n and dp tiles -> staging (over the dead operand planes), thread (r, h) moves 64 columns of each
+#pragma unroll
+    for (int part = 0; part < 4; ++part) {
+      const uint32_t col = (uint32_t)(h * 64 + (part & 1) * 32);
+      uint32_t acc[32];
+      tmem_load<32>(((part >> 1) ? tmem_dp : tmem_n) + lane_sel + col, acc);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float* dst = ((part >> 1) ? stage3d : stage3n) + r * kBwdStLd3 + col;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<float4*>(dst + 4 * i) = make_float4(__uint_as_float(acc[4 * i]), __uint_as_float(acc[4 * i + 1]),
+                                                               __uint_as_float(acc[4 * i + 2]), __uint_as_float(acc[4 * i + 3]));
+    }
+    compute_sync();
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int b = c & 1;
       if (c + 1 < NCH) load_xg(b ^ 1, c + 1);
-      {
-        uint32_t an[16], ad[16];
-        tmem_load<16>(tmem_n + lane_sel + (uint32_t)(c * 32 + h * 16), an);
-        tmem_load<16>(tmem_dp + lane_sel + (uint32_t)(c * 32 + h * 16), ad);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        stage_store16(stage_n + r * kStLd + h * 16, an);
-        stage_store16(stage_d + r * kStLd + h * 16, ad);
-      }
-      __syncthreads();
       const float4 bv0 = *reinterpret_cast<const float4*>(beta_s + c * 32 + ckg * 8);
       const float4 bv1 = *reinterpret_cast<const float4*>(beta_s + c * 32 + ckg * 8 + 4);
 #pragma unroll
       for (int it = 0; it < 2; ++it) {
         const int row = crow + 64 * it;
-        const float4 n0 = *reinterpret_cast<const float4*>(stage_n + row * kStLd + ckg * 8);
-        const float4 n1 = *reinterpret_cast<const float4*>(stage_n + row * kStLd + ckg * 8 + 4);
-        const float4 d0 = *reinterpret_cast<const float4*>(stage_d + row * kStLd + ckg * 8);
-        const float4 d1 = *reinterpret_cast<const float4*>(stage_d + row * kStLd + ckg * 8 + 4);
+        const float* ns = stage3n + row * kBwdStLd3 + c * 32 + ckg * 8;
+        const float* ds = stage3d + row * kBwdStLd3 + c * 32 + ckg * 8;
+        const float4 n0 = *reinterpret_cast<const float4*>(ns), n1 = *reinterpret_cast<const float4*>(ns + 4);
+        const float4 d0 = *reinterpret_cast<const float4*>(ds), d1 = *reinterpret_cast<const float4*>(ds + 4);
         const float4 x0 = xq[b][it][0], x1 = xq[b][it][1], g0 = gq[b][it][0], g1 = gq[b][it][1];
         float4 o0, o1;
         o0.x = tc_dx<FAST>(g0.x, x0.x, bv0.x + n0.x, d0.x, f);
@@ -1060,11 +1100,10 @@ gdn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, con
           dst[1] = o1;
         }
       }
-      __syncthreads();  // staging free again
     }
-    // n / dp columns and the p planes are rewritten by the next tile
+    // the staging (= operand planes) and the n / dp columns are rewritten by the next tile
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    compute_sync();
     first_tile = false;
   }
 
@@ -1091,6 +1130,7 @@ gdn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, con
         if (lane < 4) atomicAdd(dbeta_s + c * 32 + lane * 8 + e, v);
       }
   }
+  }  // compute warps
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (tid < C) part_b[(long long)blockIdx.x * C + tid] = dbeta_s[tid];
