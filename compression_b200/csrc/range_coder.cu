@@ -23,6 +23,10 @@
 #include <cstring>
 #include <vector>
 
+#include <cstring>
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 
 namespace tfcb {
@@ -1616,10 +1620,118 @@ int device_sm_count() {
   return n;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Device-table cache.  A model creates a handle per compress()/decompress() call with the same `lookup`
+// every time (continuous_batched.py:381, :408): parsing and uploading it again (plus the stream
+// synchronisation that keeps the host staging alive) would sit on the host's critical path of every step.
+// Entries are keyed by content (hash, then full compare), pinned while a handle uses them, and evicted
+// least-recently-used beyond kMaxEntries.  Uploads are complete (stream-synchronised) before an entry becomes
+// visible, so any stream may use it.
+// ---------------------------------------------------------------------------------------------
+struct LookupCache {
+  struct Entry {
+    uint64_t hash = 0;
+    int64_t cols = 0;
+    bool for_decoder = false;
+    int device = 0;
+    int pins = 0;
+    uint64_t last_use = 0;
+    std::vector<int32_t> host;
+    DeviceLookup lut;      // shallow copy of a cache entry's tables
+  void* lut_token = nullptr;
+  };
+  static constexpr size_t kMaxEntries = 16;
+  std::mutex mu;
+  std::vector<Entry*> entries;
+  uint64_t clock = 0;
+
+  static uint64_t hash_of(const int32_t* p, int64_t n) {
+    uint64_t hsh = 1469598103934665603ull;
+    for (int64_t i = 0; i < n; ++i) hsh = (hsh ^ (uint32_t)p[i]) * 1099511628211ull;
+    return hsh;
+  }
+
+  int acquire(const int32_t* host, int64_t len, int64_t cols, bool for_decoder, cudaStream_t s, DeviceLookup* out,
+              void** token) {
+    *token = nullptr;
+    if (len < 0 || (len > 0 && !host)) return fail(TFCB_INVALID_ARGUMENT, "bad lookup table");
+    int device = 0;
+    cudaGetDevice(&device);
+    const uint64_t hsh = hash_of(host, len);
+    std::lock_guard<std::mutex> lock(mu);
+    for (Entry* e : entries) {
+      if (e->hash == hsh && e->cols == cols && e->for_decoder == for_decoder && e->device == device &&
+          (int64_t)e->host.size() == len && (len == 0 || std::memcmp(e->host.data(), host, len * sizeof(int32_t)) == 0)) {
+        e->pins++;
+        e->last_use = ++clock;
+        *out = e->lut;
+        *token = e;
+        return TFCB_OK;
+      }
+    }
+    Entry* e = new Entry;
+    int rc = e->lut.upload(host, len, cols, s, for_decoder);  // synchronises s: the tables are resident on return
+    if (rc != TFCB_OK) {
+      e->lut.release(s);
+      delete e;
+      return rc;
+    }
+    e->hash = hsh;
+    e->cols = cols;
+    e->for_decoder = for_decoder;
+    e->device = device;
+    e->pins = 1;
+    e->last_use = ++clock;
+    e->host.assign(host, host + len);
+    entries.push_back(e);
+    while (entries.size() > kMaxEntries) {
+      size_t victim = entries.size();
+      for (size_t i = 0; i < entries.size(); ++i)
+        if (entries[i]->pins == 0 && (victim == entries.size() || entries[i]->last_use < entries[victim]->last_use)) victim = i;
+      if (victim == entries.size()) break;  // everything is in use
+      entries[victim]->lut.release(s);
+      delete entries[victim];
+      entries.erase(entries.begin() + victim);
+    }
+    *out = e->lut;
+    *token = e;
+    return TFCB_OK;
+  }
+
+  void release(void* token) {
+    if (!token) return;
+    std::lock_guard<std::mutex> lock(mu);
+    static_cast<Entry*>(token)->pins--;
+  }
+};
+
+LookupCache& lookup_cache() {
+  static LookupCache* c = new LookupCache;  // leaked on purpose: no destructor order problems at exit
+  return *c;
+}
+
+// Small pinned scratch per host thread for the device -> host words read at finalize.
+void* pinned_scratch() {
+  thread_local void* p = nullptr;
+  if (!p) {
+    if (cudaHostAlloc(&p, 256, cudaHostAllocDefault) != cudaSuccess) {
+      (void)cudaGetLastError();
+      p = nullptr;
+    }
+  }
+  return p;
+}
+
+int decode_error(const DevError& e, const char* what);
+
 int fetch_error(DevError* d_err, cudaStream_t s, const char* what) {
   DevError e;
   TFCB_CUDA_TRY(cudaMemcpyAsync(&e, d_err, sizeof e, cudaMemcpyDeviceToHost, s));
   TFCB_CUDA_TRY(cudaStreamSynchronize(s));
+  return decode_error(e, what);
+}
+
+int decode_error(const DevError& e, const char* what) {
   switch (e.code) {
     case kErrNone:
       return TFCB_OK;
@@ -1652,7 +1764,8 @@ int fetch_error(DevError* d_err, cudaStream_t s, const char* what) {
 using namespace tfcb;
 
 struct tfcb_encoder {
-  DeviceLookup lut;
+  DeviceLookup lut;      // shallow copy of a cache entry's tables
+  void* lut_token = nullptr;
   long long n_streams = 0;
   EncState* state = nullptr;
   uint16_t* words = nullptr;
@@ -1752,7 +1865,7 @@ int tfcb_encoder_create(const int32_t* lookup_host, int64_t lookup_len, int64_t 
   tfcb_encoder* h = new tfcb_encoder;
   h->home = s;
   h->n_streams = n_streams;
-  int rc = h->lut.upload(lookup_host, lookup_len, lookup_cols, s);
+  int rc = lookup_cache().acquire(lookup_host, lookup_len, lookup_cols, /*for_decoder=*/false, s, &h->lut, &h->lut_token);
   if (rc == TFCB_OK) rc = dev_alloc((void**)&h->state, std::max<int64_t>(n_streams, 1) * sizeof(EncState), s);
   if (rc == TFCB_OK) rc = dev_alloc((void**)&h->err, sizeof(DevError), s);
   if (rc != TFCB_OK) {
@@ -1805,7 +1918,6 @@ int tfcb_encode_finalize(tfcb_encoder* h, void* stream, int64_t* total_bytes_hos
   if (!h) return fail(TFCB_INVALID_ARGUMENT, "'handle' is not an encoder");
   if (h->finalized) return fail(TFCB_INVALID_ARGUMENT, "encoder handle was already finalized");
   cudaStream_t s = as_stream(stream);
-  TFCB_TRY(fetch_error(h->err, s, "encode"));
   const long long S = h->n_streams;
   TFCB_TRY(dev_alloc((void**)&h->lens, std::max<long long>(S, 1) * sizeof(long long), s));
   TFCB_TRY(dev_alloc((void**)&h->offsets, (S + 1) * sizeof(long long), s));
@@ -1817,9 +1929,21 @@ int tfcb_encode_finalize(tfcb_encoder* h, void* stream, int64_t* total_bytes_hos
   exclusive_scan_kernel<<<1, 1024, 0, s>>>(h->lens, S, h->offsets);
   TFCB_LAUNCHED();
   TFCB_CUDA_TRY(cudaGetLastError());
+  // one host round trip for both the deferred argument errors and the total size
   long long total = 0;
-  TFCB_CUDA_TRY(cudaMemcpyAsync(&total, h->offsets + S, sizeof total, cudaMemcpyDeviceToHost, s));
-  TFCB_CUDA_TRY(cudaStreamSynchronize(s));
+  DevError err;
+  if (char* scratch = static_cast<char*>(pinned_scratch())) {
+    TFCB_CUDA_TRY(cudaMemcpyAsync(scratch, h->offsets + S, sizeof total, cudaMemcpyDeviceToHost, s));
+    TFCB_CUDA_TRY(cudaMemcpyAsync(scratch + 64, h->err, sizeof err, cudaMemcpyDeviceToHost, s));
+    TFCB_CUDA_TRY(cudaStreamSynchronize(s));
+    std::memcpy(&total, scratch, sizeof total);
+    std::memcpy(&err, scratch + 64, sizeof err);
+  } else {
+    TFCB_CUDA_TRY(cudaMemcpyAsync(&total, h->offsets + S, sizeof total, cudaMemcpyDeviceToHost, s));
+    TFCB_CUDA_TRY(cudaMemcpyAsync(&err, h->err, sizeof err, cudaMemcpyDeviceToHost, s));
+    TFCB_CUDA_TRY(cudaStreamSynchronize(s));
+  }
+  TFCB_TRY(decode_error(err, "encode"));
   h->total = total;
   TFCB_TRY(dev_alloc((void**)&h->out, (size_t)std::max<long long>(total, 1), s));
   if (S > 0) {
@@ -1860,7 +1984,7 @@ int tfcb_encoder_copy_output(tfcb_encoder* h, uint8_t* bytes_host, int64_t* offs
 void tfcb_encoder_destroy(tfcb_encoder* h) {
   if (!h) return;
   cudaStream_t s = h->home;
-  h->lut.release(s);
+  lookup_cache().release(h->lut_token);
   dev_free(h->state, s);
   dev_free(h->words, s);
   dev_free(h->cbits, s);
@@ -1874,7 +1998,8 @@ void tfcb_encoder_destroy(tfcb_encoder* h) {
 }  // extern "C"
 
 struct tfcb_decoder {
-  DeviceLookup lut;
+  DeviceLookup lut;      // shallow copy of a cache entry's tables
+  void* lut_token = nullptr;
   long long n_streams = 0;
   const uint8_t* bytes = nullptr;
   const long long* offsets = nullptr;
@@ -1945,7 +2070,7 @@ int tfcb_decoder_create(const uint8_t* bytes_dev, const int64_t* offsets_dev, in
   h->n_streams = n_streams;
   h->bytes = bytes_dev;
   h->offsets = reinterpret_cast<const long long*>(offsets_dev);
-  int rc = h->lut.upload(lookup_host, lookup_len, lookup_cols, s, /*for_decoder=*/true);
+  int rc = lookup_cache().acquire(lookup_host, lookup_len, lookup_cols, /*for_decoder=*/true, s, &h->lut, &h->lut_token);
   if (rc == TFCB_OK) rc = dev_alloc((void**)&h->state, n_streams * sizeof(DecState), s);
   if (rc == TFCB_OK) rc = dev_alloc((void**)&h->err, sizeof(DevError), s);
   if (rc == TFCB_OK) rc = dev_alloc((void**)&h->ok, n_streams, s);
@@ -2003,7 +2128,7 @@ int tfcb_decode_finalize(tfcb_decoder* h, uint8_t* ok_host, void* stream) {
 void tfcb_decoder_destroy(tfcb_decoder* h) {
   if (!h) return;
   cudaStream_t s = h->home;
-  h->lut.release(s);
+  lookup_cache().release(h->lut_token);
   dev_free(h->state, s);
   dev_free(h->err, s);
   dev_free(h->ok, s);
