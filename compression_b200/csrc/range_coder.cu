@@ -921,82 +921,6 @@ __device__ __forceinline__ int dec_symbol(DecChain& c, ByteWindow& w, const int3
   return i - 1;
 }
 
-// DecodeLinearly({0,1,2}, 1), range_coder_kernels.cc:450,461-469.
-__device__ __forceinline__ uint32_t dec_bit(DecChain& c, ByteWindow& w, int lane) {
-  const uint32_t v = c.value - c.base;
-  const uint32_t half = scale_cum(c.span, 1, 1);
-  const uint32_t whole = scale_cum(c.span, 2, 1);  // size, truncated
-  // bit = 0 iff v < half  (half = floor(size/2) <= 2^31 never truncates)
-  const uint32_t bit = (v < half) ? 0u : 1u;
-  dec_update(c, w, bit ? half : 0u, bit ? whole : half, lane);
-  return bit;
-}
-
-// Candidate positions of one search round over cdf indices [lo_i, hi_i] (invariant:
-// scale(cdf[lo_i]) <= v < scale(cdf[hi_i])).  Every lane owns two candidates m = lane, lane + 32.
-//   len <= 63 : final round, candidate m -> index lo_i + m (valid while <= hi_i)
-//   else      : coarse round, stride s = ceil(len / 64), candidate m -> min(lo_i + (m+1) s, hi_i)
-struct Round {
-  int stride;  // 0 = final round
-  int idx0, idx1;
-  bool v0, v1;
-};
-
-__device__ __forceinline__ Round plan_round(int lo_i, int hi_i, int lane) {
-  Round r;
-  const int len = hi_i - lo_i;
-  if (len <= 63) {
-    r.stride = 0;
-    r.idx0 = lo_i + lane;
-    r.idx1 = lo_i + lane + 32;
-    r.v0 = r.idx0 <= hi_i;
-    r.v1 = r.idx1 <= hi_i;
-    if (!r.v0) r.idx0 = hi_i;
-    if (!r.v1) r.idx1 = hi_i;
-  } else {
-    r.stride = (len + 63) >> 6;
-    r.idx0 = min(lo_i + (lane + 1) * r.stride, hi_i);
-    r.idx1 = min(lo_i + (lane + 33) * r.stride, hi_i);
-    r.v0 = r.v1 = true;
-  }
-  return r;
-}
-
-// Decodes one symbol given the (possibly prefetched) candidates of the first round.
-// Equivalent to RangeDecoder::DecodeInternal<BinarySearch> (range_coder.h:224-271): smallest i >= 1
-// with scale(cdf[i]) > value - base.  span == 2^32-1 (where scale(2^p) wraps) takes the slow path.
-__device__ __forceinline__ int dec_symbol_fast(DecChain& c, ByteWindow& w, const int32_t* cdf, int ncdf,
-                                               uint32_t p, Round r, uint32_t c0, uint32_t c1, int lane) {
-  if (c.span == 0xFFFFFFFFu) return dec_symbol(c, w, cdf, ncdf, p, lane);
-  const uint32_t v = c.value - c.base;
-  int lo_i = 0, hi_i = ncdf - 1;
-  for (;;) {
-    const uint32_t t0 = scale_cum(c.span, c0, p);
-    const uint32_t t1 = scale_cum(c.span, c1, p);
-    const bool le0 = r.v0 && t0 <= v;
-    const bool le1 = r.v1 && t1 <= v;
-    const int below = __popc(__ballot_sync(kFull, le0)) + __popc(__ballot_sync(kFull, le1));
-    if (r.stride == 0) {
-      const uint32_t amax = max(le0 ? t0 : 0u, le1 ? t1 : 0u);
-      const uint32_t bmin = min((r.v0 && !le0) ? t0 : 0xFFFFFFFFu, (r.v1 && !le1) ? t1 : 0xFFFFFFFFu);
-      const uint32_t a = __reduce_max_sync(kFull, amax);
-      const uint32_t b = __reduce_min_sync(kFull, bmin);
-      dec_update(c, w, a, b, lane);
-      // `below` counts the indices lo_i .. with scale <= v; lo_i itself always qualifies
-      int i = lo_i + max(below, 1);
-      i = min(i, ncdf - 1);
-      return i - 1;
-    }
-    const int f = min(below, 63);
-    const int nlo = (f == 0) ? lo_i : min(lo_i + f * r.stride, hi_i);
-    const int nhi = min(lo_i + (f + 1) * r.stride, hi_i);
-    lo_i = min(nlo, nhi - 1);
-    hi_i = nhi;
-    r = plan_round(lo_i, hi_i, lane);
-    c0 = (uint32_t)cdf[r.idx0];
-    c1 = (uint32_t)cdf[r.idx1];
-  }
-}
 
 // ---------------------------------------------------------------------------------------------
 // Decoder v2: three warps per stream (prepare / chain / resolve), pre-scaled search keys

@@ -56,7 +56,8 @@ def test_closed_forms(F, C):
   assert torch.allclose(y, xa / xa.sum(-1, keepdim=True), rtol=1e-5, atol=1e-6)
 
 
-@pytest.mark.parametrize("C,n_pix", [(128, 4099), (192, 2500), (64, 333), (7, 129)])
+@pytest.mark.parametrize("C,n_pix", [(128, 4099), (128, 1), (128, 129), (128, 128 * 148 * 3 + 5), (192, 2500),
+                                     (192, 128 * 148 * 2 + 9), (64, 333), (7, 129)])
 @pytest.mark.parametrize("inverse", [False, True])
 def test_forward_vs_fp64_oracle(F, C, n_pix, inverse):
   gamma, beta = _params(C, 4)
@@ -80,7 +81,7 @@ def test_forward_variants(F, C, alpha, epsilon, rectify):
     assert err < 2e-5
 
 
-@pytest.mark.parametrize("C,n_pix", [(128, 3000), (128, 128 * 148 * 2 + 77), (192, 1111), (5, 257)])
+@pytest.mark.parametrize("C,n_pix", [(128, 3000), (128, 1), (128, 129), (128, 128 * 148 * 2 + 77), (192, 1111), (5, 257)])
 @pytest.mark.parametrize("inverse", [False, True])
 def test_backward_vs_fp64_oracle(F, C, n_pix, inverse):
   gamma, beta = _params(C, 14)
