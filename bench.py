@@ -75,11 +75,40 @@ class ClockSampler:
   Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-  def __init__(self, index):
-    self.index, self.rows, self._stop = index, [], threading.Event()
+  def __init__(self, index, uuid=None):
+    self.index, self.uuid, self.rows, self._stop = index, uuid, [], threading.Event()
     self._t = threading.Thread(target=self._run, daemon=True)
 
+  def _run_nvml(self):
+    """In-process NVML sampling (no nvidia-smi process per sample: those perturb the timed region)."""
+    import pynvml
+    pynvml.nvmlInit()
+    h = None
+    if self.uuid:
+      for u in (self.uuid, "GPU-" + self.uuid):
+        try:
+          h = pynvml.nvmlDeviceGetHandleByUUID(u if isinstance(u, bytes) else u.encode())
+          break
+        except Exception:  # pylint:disable=broad-except
+          h = None
+    if h is None:
+      h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+    mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+    get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+    bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+    while not self._stop.is_set():
+      sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+      r = int(get_reasons(h))
+      self.rows.append([str(sm), str(mx)] + [("Active" if r & bits[n] else "Not Active")
+                                              for n in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")])
+      self._stop.wait(0.05)
+
   def _run(self):
+    try:
+      self._run_nvml()
+      return
+    except Exception:  # pylint:disable=broad-except
+      pass
     while not self._stop.is_set():
       try:
         out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
@@ -87,7 +116,7 @@ class ClockSampler:
         self.rows.append([c.strip() for c in out.strip().split(",")])
       except Exception:  # pylint:disable=broad-except
         pass
-      self._stop.wait(0.1)
+      self._stop.wait(0.5)
 
   def __enter__(self):
     self._t.start()
@@ -234,13 +263,18 @@ def main():
   # ---- the timed region: exactly K steps, CUDA events, max over ranks ----
   launches0 = _lib.launch_count()
   ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-  with ClockSampler(local) as clocks:
-    barrier()
-    ev0.record()
-    for i in range(args.steps):
-      strings = step(i)
-    ev1.record()
-    barrier()
+  # clocks are sampled by rank 0 only (its own GPU, in-process NVML): one sampler per rank disturbed the others
+  clocks = ClockSampler(local, str(torch.cuda.get_device_properties(dev).uuid)) if rank == 0 else None
+  if clocks:
+    clocks.__enter__()
+  barrier()
+  ev0.record()
+  for i in range(args.steps):
+    strings = step(i)
+  ev1.record()
+  barrier()
+  if clocks:
+    clocks.__exit__()
   elapsed_ms = ev0.elapsed_time(ev1)
   launches = _lib.launch_count() - launches0
   t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
@@ -399,6 +433,37 @@ def main():
         gbs = 12.0 * npix * 128 / (ms * 1e-3) / 1e9
         gdn[name].update({"bwd_ms": ms, "bwd_GBps": gbs, "bwd_frac_of_hbm_peak": gbs / peak})
       del x
+    # --- configs[3]: GDN microbench, 192 channels, 64x64 tiles (batch 4096 if memory allows, else 1024)
+    try:
+      free_b, _ = torch.cuda.mem_get_info(dev)
+      batch4 = 4096 if free_b > 90e9 else 1024
+      npix = batch4 * 64 * 64
+      gamma192 = (0.1 * torch.eye(192) + (0.02 * torch.randn(192, 192)).abs()).to(dev)
+      beta192 = (1 + 0.5 * torch.rand(192)).to(dev)
+      x = torch.randn(npix, 192, device=dev)
+      functional.gdn_forward(x, gamma192, beta192)
+      a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      a.record()
+      for _ in range(3):
+        functional.gdn_forward(x, gamma192, beta192)
+      b.record()
+      torch.cuda.synchronize()
+      ms = a.elapsed_time(b) / 3
+      gbs = 8.0 * npix * 192 / (ms * 1e-3) / 1e9
+      entry = {"fwd_ms": ms, "fwd_GBps": gbs, "fwd_frac_of_hbm_peak": gbs / peak, "fwd_kernel": "tcgen05 (gdn_tc_fwd_kernel<192,2,16>)"}
+      dy = torch.randn_like(x)
+      functional.gdn_backward(x, gamma192, beta192, dy)
+      a.record()
+      functional.gdn_backward(x, gamma192, beta192, dy)
+      b.record()
+      torch.cuda.synchronize()
+      ms = a.elapsed_time(b)
+      gbs = 12.0 * npix * 192 / (ms * 1e-3) / 1e9
+      entry.update({"bwd_ms": ms, "bwd_GBps": gbs, "bwd_frac_of_hbm_peak": gbs / peak, "bwd_kernel": "fp32 CUDA cores (no tensor-core path for C=192 yet)"})
+      gdn[f"cfg4 [{batch4},64,64,192]"] = entry
+      del x, dy
+    except Exception as e:  # pylint:disable=broad-except
+      gdn["cfg4 [4096,64,64,192]"] = {"error": repr(e)}
     result["gdn"] = gdn
     # --- CPU baseline: the reference's own range coder on this box's host cores (bounded: one batch)
     try:
