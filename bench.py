@@ -404,6 +404,47 @@ def main():
     ok = bool(torch.equal(out, model.quantize(ys[0])))
     result["decode"] = {"value": sym_per_step / (dec_ms * 1e-3) / 1e6, "unit": "Msymbols/s", "ms_per_step": dec_ms,
                         "roundtrip_equals_quantize": ok}
+    # --- configs[2]: bmshj2018 hyperprior, batch 128 of 256x256 images: y[128,16,16,192] coded with the indexed
+    #     NoisyNormal model (64 scales, per-element index + mean), z[128,4,4,192] with the batched model
+    try:
+      B3, C3 = 128, 192
+      num_scales, smin, smax = 64, .11, 256.
+      off3, fac3 = np.log(smin), (np.log(smax) - np.log(smin)) / (num_scales - 1.)
+      scale_fn = lambda i: torch.exp(off3 + fac3 * i)
+      em_y = tfc.LocationScaleIndexedEntropyModel(tfc.NoisyNormal, num_scales, scale_fn, coding_rank=3, compression=True)
+      g3 = torch.Generator(device=dev).manual_seed(7)
+      idx3 = torch.rand(B3, 16, 16, C3, device=dev, generator=g3) * 40.0
+      sig3 = scale_fn(torch.clamp(idx3, 0, num_scales - 1).to(torch.int32).float())
+      loc3 = torch.randn(B3, 16, 16, C3, device=dev, generator=g3)
+      y3 = loc3 + sig3 * torch.randn(B3, 16, 16, C3, device=dev, generator=g3)
+      zs = torch.exp(torch.linspace(np.log(0.5), np.log(6.0), C3))
+      em_z = tfc.ContinuousBatchedEntropyModel(tfc.NoisyLaplace(loc=torch.zeros_like(zs), scale=zs), coding_rank=3,
+                                               compression=True).to(dev)
+      z3 = (torch.randn(B3, 4, 4, C3, device=dev, generator=g3) * zs.to(dev))
+      def enc3():
+        return em_z.compress(z3), em_y.compress(y3, idx3, loc=loc3)
+      sz, sy = enc3()
+      def dec3():
+        return em_z.decompress(sz, (4, 4)), em_y.decompress(sy, idx3, loc=loc3)
+      res3 = {}
+      for name, fn in (("encode", enc3), ("decode", dec3)):
+        fn(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+          out3 = fn()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 10
+        nsym = y3.numel() + z3.numel()
+        res3[name] = {"ms_per_step": ms, "value": nsym / (ms * 1e-3) / 1e6, "unit": "Msymbols/s"}
+      zhat, yhat = out3
+      res3["roundtrip_equals_quantize"] = bool(torch.equal(yhat, em_y.quantize(y3, loc3)) and torch.equal(zhat, em_z.quantize(z3)))
+      res3["bits_per_symbol_y"] = 8.0 * sy.nbytes() / y3.numel()
+      res3["workload"] = "bmshj2018 two-level: y[128,16,16,192] indexed NoisyNormal (64 scales, loc) + z[128,4,4,192] batched NoisyLaplace; 128 streams each"
+      result["cfg3_bmshj2018"] = res3
+    except Exception as e:  # pylint:disable=broad-except
+      result["cfg3_bmshj2018"] = {"error": repr(e)}
     # --- GDN at the two analysis-transform shapes of cfg2 (forward) and backward at the first
     gdn = {}
     gamma = (0.1 * torch.eye(128) + (0.02 * torch.randn(128, 128)).abs()).to(dev)
@@ -440,7 +481,7 @@ def main():
       npix = batch4 * 64 * 64
       gamma192 = (0.1 * torch.eye(192) + (0.02 * torch.randn(192, 192)).abs()).to(dev)
       beta192 = (1 + 0.5 * torch.rand(192)).to(dev)
-      x = torch.randn(npix, 192, device=dev)
+      x = torch.randn(npix, 192, device=dev) * (0.05 + 3.95 * torch.rand(192, device=dev))  # SURVEY 8(d) cfg4 recipe
       functional.gdn_forward(x, gamma192, beta192)
       a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
       a.record()
