@@ -500,7 +500,7 @@ def main():
       torch.cuda.synchronize()
       ms = a.elapsed_time(b)
       gbs = 12.0 * npix * 192 / (ms * 1e-3) / 1e9
-      entry.update({"bwd_ms": ms, "bwd_GBps": gbs, "bwd_frac_of_hbm_peak": gbs / peak, "bwd_kernel": "fp32 CUDA cores (no tensor-core path for C=192 yet)"})
+      entry.update({"bwd_ms": ms, "bwd_GBps": gbs, "bwd_frac_of_hbm_peak": gbs / peak, "bwd_kernel": "tcgen05, two kernels (gdn_tc_bwd_dx_kernel<192> + gdn_tc_bwd_dgamma_kernel<192>)"})
       gdn[f"cfg4 [{batch4},64,64,192]"] = entry
       del x, dy
     except Exception as e:  # pylint:disable=broad-except

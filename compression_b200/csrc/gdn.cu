@@ -426,9 +426,9 @@ constexpr int kDgammaGrid = 148;
 
 int gdn_tc_forward(const float* x, const float* gamma, const float* beta, float* y, long long n_pix, int C,
                    int flags, float alpha, float eps, cudaStream_t s, bool* handled);
-int gdn_tc_backward(const float* x, const float* gamma, const float* beta, const float* dy, float* dx, float* part_g,
-                    float* part_b, int* n_parts, long long n_pix, int C, int flags, float alpha, float eps,
-                    cudaStream_t s, bool* handled);
+int gdn_tc_backward(const float* x, const float* gamma, const float* beta, const float* dy, float* dx, float* q_ws,
+                    float* part_g, float* part_b, int* n_parts, long long n_pix, int C, int flags, float alpha,
+                    float eps, cudaStream_t s, bool* handled);
 
 }  // namespace tfcb
 
@@ -500,8 +500,8 @@ int tfcb_gdn_backward(const float* x_dev, const float* gamma_dev, const float* b
   float* part_b = part_g + (size_t)kDgammaGrid * C * C;
   bool handled = false;
   int n_parts = 0;
-  TFCB_TRY(gdn_tc_backward(x_dev, gamma_dev, beta_dev, dy_dev, dx_dev, part_g, part_b, &n_parts, n_pix, C, flags, alpha,
-                           epsilon, s, &handled));
+  TFCB_TRY(gdn_tc_backward(x_dev, gamma_dev, beta_dev, dy_dev, dx_dev, q, part_g, part_b, &n_parts, n_pix, C, flags,
+                           alpha, epsilon, s, &handled));
   if (handled) {
     const long long ng = (long long)C * C;
     reduce_partials_kernel<<<(unsigned)((ng + 255) / 256), 256, 0, s>>>(part_g, n_parts, ng, dgamma_dev);

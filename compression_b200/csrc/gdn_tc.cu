@@ -1139,6 +1139,507 @@ gdn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, con
   }
 }
 
+// =============================================================================================
+// Backward for C = 192: two kernels.  n, dp and a dgamma accumulator would need 3 x 192 TMEM columns and the
+// gamma planes plus a full-K p plane 243 KB of shared memory, so the dgamma contraction moves to its own
+// kernel and q = dL/dn travels through global memory (fp32, the caller's workspace):
+//   K1  gdn_tc_bwd_dx_kernel     : n = beta + p.gamma (p converted 16 channels at a time) -> q (stored) ->
+//                                  dp = q.gamma^T -> dx.   TMEM: n | dp (2 x 192 columns).
+//   K2  gdn_tc_bwd_dgamma_kernel : dgamma += p^T q over all tiles of the CTA, dbeta = column sums of q.  No gamma:
+//                                  the full-K p and q planes fill the shared memory.  M = 192 does not exist, so
+//                                  rows j in [0,128) and [64,192) are two overlapping M = 128 blocks.
+// HBM traffic: K1 x, dy in; dx, q out.  K2 x, q in.  (6 passes against the fused kernel's 3.)
+// =============================================================================================
+template <int C>
+struct Bwd2Smem {
+  static constexpr int kPlaneB = C * C * 2;          // gamma hi / lo
+  static constexpr int kPlaneP = 2 * kKg;            // p hi or lo, one 16-channel chunk
+  static constexpr int kPlaneQ = 4 * kKg;            // q hi or lo, one 32-channel chunk
+  static constexpr int kStage = kTileM * kStLd * 4;  // fp32 [128][36]
+  static constexpr int kOffBh = 0;
+  static constexpr int kOffBl = kOffBh + kPlaneB;
+  static constexpr int kOffP = kOffBl + kPlaneB;     // [2 buffers][hi, lo]
+  static constexpr int kOffQ = kOffP + 4 * kPlaneP;  // [2 buffers][hi, lo]; the dx pass stages dp here
+  static constexpr int kOffStage = kOffQ + 4 * kPlaneQ;
+  static constexpr int kOffBeta = kOffStage + kStage;
+  static constexpr int kOffBar = kOffBeta + C * 4;
+  static constexpr int kBytes = kOffBar + 64;
+  static_assert(4 * kPlaneQ >= kStage, "dp staging aliases the q planes");
+  static_assert(kBytes <= 232448, "shared memory budget");
+};
+
+template <int C, bool FAST>
+__global__ void __launch_bounds__(kBwdThreads, 1)
+gdn_tc_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ dy, const __nv_bfloat16* __restrict__ planes,
+                     const float* __restrict__ beta, float* __restrict__ dx, float* __restrict__ q_out, long long n_pix,
+                     TcFlags f) {
+  using L = Bwd2Smem<C>;
+  constexpr int NCH = C / 32;   // q / dx chunks
+  constexpr int NK = C / 16;    // p chunks (one MMA K step each)
+  static_assert(2 * C <= 512 && NK % 2 == 0 && NCH % 2 == 0, "layout");
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float* beta_s = reinterpret_cast<float*>(smem + L::kOffBeta);
+  float* stage_n = reinterpret_cast<float*>(smem + L::kOffStage);
+  float* stage_d = reinterpret_cast<float*>(smem + L::kOffQ);
+  uint64_t* mbars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);  // [0,1] p buffers, [2,3] q buffers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffBar + 40);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r = tid & 127, h = (tid >> 7) & 1, gwarp = warp & 3;
+  constexpr uint32_t kIdesc1 = umma_idesc(kTileM, C);
+  constexpr uint32_t kIdesc2 = umma_idesc(kTileM, C) | (1u << 16);  // B = gamma^T (MN-major view)
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(planes);
+    uint4* dst = reinterpret_cast<uint4*>(smem + L::kOffBh);
+    for (int i = tid; i < 2 * L::kPlaneB / 16; i += kBwdThreads) dst[i] = src[i];
+    for (int i = tid; i < C; i += kBwdThreads) beta_s[i] = beta[i];
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbars + i)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_n = *tmem_slot, tmem_dp = tmem_n + C;
+  const uint32_t lane_sel = (uint32_t)(gwarp * 32) << 16;
+  const uint32_t b_hi = smem_u32(smem + L::kOffBh), b_lo = smem_u32(smem + L::kOffBl);
+  const long long n_tiles = (n_pix + kTileM - 1) / kTileM;
+
+  if (warp == kBwdCompute / 32) {
+    // ------------------------------- MMA-issue warp -------------------------------
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      if (lane == 1) {
+        const long long pn = (tile + gridDim.x) * kTileM;
+        const long long rows = min((long long)kTileM, n_pix - pn);
+        if (rows > 0) {
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(x + pn * C), "r"((uint32_t)(rows * C * 4)) : "memory");
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(dy + pn * C), "r"((uint32_t)(rows * C * 4)) : "memory");
+        }
+      }
+#pragma unroll 1
+      for (int c = 0; c < NK; ++c) {  // MMA1: one K step per 16-channel p chunk
+        const int pb = c & 1;
+        asm volatile("bar.sync %0, %1;" ::"r"(2 + pb), "n"(kBwdThreads) : "memory");
+        if (lane == 0) {
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t ph = smem_u32(smem + L::kOffP + pb * 2 * L::kPlaneP), pl = ph + L::kPlaneP;
+          const uint64_t dah = umma_desc(ph, kKg, 128), dal = umma_desc(pl, kKg, 128);
+          const uint64_t dbh = umma_desc(b_hi + (uint32_t)(2 * c) * (C * 16), C * 16, 128);
+          const uint64_t dbl = umma_desc(b_lo + (uint32_t)(2 * c) * (C * 16), C * 16, 128);
+          umma_bf16(tmem_n, dah, dbh, kIdesc1, c ? 1u : 0u);
+          umma_bf16(tmem_n, dal, dbh, kIdesc1, 1u);
+          umma_bf16(tmem_n, dah, dbl, kIdesc1, 1u);
+          umma_commit(smem_u32(mbars + pb));
+        }
+        __syncwarp();
+      }
+#pragma unroll 1
+      for (int c = 0; c < NCH; ++c) {  // MMA2: dp += q chunk . gamma^T
+        const int b = c & 1;
+        asm volatile("bar.sync %0, %1;" ::"r"(4 + b), "n"(kBwdThreads) : "memory");
+        if (lane == 0) {
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t q_hi = smem_u32(smem + L::kOffQ + b * 2 * L::kPlaneQ), q_lo = q_hi + L::kPlaneQ;
+#pragma unroll
+          for (int s2 = 0; s2 < 2; ++s2) {
+            const uint64_t dah = umma_desc(q_hi + (uint32_t)(2 * s2) * kKg, kKg, 128);
+            const uint64_t dal = umma_desc(q_lo + (uint32_t)(2 * s2) * kKg, kKg, 128);
+            const uint32_t koff = (uint32_t)(c * 32 + s2 * 16) * 16u;
+            const uint64_t dbh = umma_desc(b_hi + koff, 128, C * 16);
+            const uint64_t dbl = umma_desc(b_lo + koff, 128, C * 16);
+            umma_bf16(tmem_dp, dah, dbh, kIdesc2, (c | s2) ? 1u : 0u);
+            umma_bf16(tmem_dp, dal, dbh, kIdesc2, 1u);
+            umma_bf16(tmem_dp, dah, dbl, kIdesc2, 1u);
+          }
+          umma_commit(smem_u32(mbars + 2 + b));
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+  // --------------------------------- compute warps ---------------------------------
+  uint32_t parp[2] = {0u, 0u}, parq[2] = {0u, 0u};
+  const int ckg = tid & 3, crow = tid >> 2;   // items of a 32-channel chunk: rows crow, crow + 64
+  const int pkg = tid & 1, prow = tid >> 1;   // item of a 16-channel p chunk
+  auto compute_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(kBwdCompute) : "memory"); };
+
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long p0 = tile * kTileM;
+    // ---- P1: p chunks -> planes -> MMA1, the loads of six chunks in flight at a time ----
+    {
+      const bool live = p0 + prow < n_pix;
+      const float* xr = x + (p0 + prow) * C + pkg * 8;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float4 xv[NK / 2][2];
+#pragma unroll
+        for (int k = 0; k < NK / 2; ++k) {
+          const float4* src = reinterpret_cast<const float4*>(xr + (half * (NK / 2) + k) * 16);
+          xv[k][0] = live ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+          xv[k][1] = live ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int k = 0; k < NK / 2; ++k) {
+          const int c = half * (NK / 2) + k, pb = c & 1;
+          if (c >= 2) {
+            if (!mbar_wait(smem_u32(mbars + pb), parp[pb])) __trap();
+            parp[pb] ^= 1u;
+          }
+          const float4 a = xv[k][0], b = xv[k][1];
+          float v[8] = {tc_pool<FAST>(a.x, f), tc_pool<FAST>(a.y, f), tc_pool<FAST>(a.z, f), tc_pool<FAST>(a.w, f),
+                        tc_pool<FAST>(b.x, f), tc_pool<FAST>(b.y, f), tc_pool<FAST>(b.z, f), tc_pool<FAST>(b.w, f)};
+          uint4 hi, lo;
+          split8(v, &hi, &lo);
+          uint8_t* ph = smem + L::kOffP + pb * 2 * L::kPlaneP;
+          *reinterpret_cast<uint4*>(ph + pkg * kKg + prow * 16) = hi;
+          *reinterpret_cast<uint4*>(ph + L::kPlaneP + pkg * kKg + prow * 16) = lo;
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          asm volatile("bar.arrive %0, %1;" ::"r"(2 + pb), "n"(kBwdThreads) : "memory");
+        }
+      }
+    }
+    float4 xq[2][2][2], gq[2][2][2];  // [set][item][half]
+    auto load_xg = [&](int set, int c) {
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int row = crow + 64 * it;
+        const bool live = p0 + row < n_pix;
+        const long long off = (p0 + row) * C + c * 32 + ckg * 8;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        xq[set][it][0] = live ? __ldg(reinterpret_cast<const float4*>(x + off)) : z;
+        xq[set][it][1] = live ? __ldg(reinterpret_cast<const float4*>(x + off) + 1) : z;
+        gq[set][it][0] = live ? __ldg(reinterpret_cast<const float4*>(dy + off)) : z;
+        gq[set][it][1] = live ? __ldg(reinterpret_cast<const float4*>(dy + off) + 1) : z;
+      }
+    };
+    load_xg(0, 0);
+    // the last two p commits cover every MMA1 step: n is complete
+#pragma unroll
+    for (int pb = 0; pb < 2; ++pb) {
+      if (!mbar_wait(smem_u32(mbars + pb), parp[pb])) __trap();
+      parp[pb] ^= 1u;
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // ---- P2: q = dL/dn per 32-channel chunk -> q planes + global q; MMA2 ----
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int b = c & 1;
+      load_xg(b ^ 1, (c + 1) % NCH);
+      {
+        uint32_t acc[16];
+        tmem_load<16>(tmem_n + lane_sel + (uint32_t)(c * 32 + h * 16), acc);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        stage_store16(stage_n + r * kStLd + h * 16, acc);
+      }
+      if (c >= 2) {
+        if (!mbar_wait(smem_u32(mbars + 2 + b), parq[b])) __trap();
+        parq[b] ^= 1u;
+      }
+      compute_sync();
+      uint8_t* qh = smem + L::kOffQ + b * 2 * L::kPlaneQ;
+      uint8_t* ql = qh + L::kPlaneQ;
+      const float4 bv0 = *reinterpret_cast<const float4*>(beta_s + c * 32 + ckg * 8);
+      const float4 bv1 = *reinterpret_cast<const float4*>(beta_s + c * 32 + ckg * 8 + 4);
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int row = crow + 64 * it;
+        const float4 n0 = *reinterpret_cast<const float4*>(stage_n + row * kStLd + ckg * 8);
+        const float4 n1 = *reinterpret_cast<const float4*>(stage_n + row * kStLd + ckg * 8 + 4);
+        const float4 x0 = xq[b][it][0], x1 = xq[b][it][1], g0 = gq[b][it][0], g1 = gq[b][it][1];
+        float q[8];
+        q[0] = tc_dl_dn<FAST>(g0.x, x0.x, bv0.x + n0.x, f);
+        q[1] = tc_dl_dn<FAST>(g0.y, x0.y, bv0.y + n0.y, f);
+        q[2] = tc_dl_dn<FAST>(g0.z, x0.z, bv0.z + n0.z, f);
+        q[3] = tc_dl_dn<FAST>(g0.w, x0.w, bv0.w + n0.w, f);
+        q[4] = tc_dl_dn<FAST>(g1.x, x1.x, bv1.x + n1.x, f);
+        q[5] = tc_dl_dn<FAST>(g1.y, x1.y, bv1.y + n1.y, f);
+        q[6] = tc_dl_dn<FAST>(g1.z, x1.z, bv1.z + n1.z, f);
+        q[7] = tc_dl_dn<FAST>(g1.w, x1.w, bv1.w + n1.w, f);
+        uint4 hi, lo;
+        split8(q, &hi, &lo);
+        *reinterpret_cast<uint4*>(qh + ckg * kKg + row * 16) = hi;
+        *reinterpret_cast<uint4*>(ql + ckg * kKg + row * 16) = lo;
+        if (p0 + row < n_pix) {
+          float4* dst = reinterpret_cast<float4*>(q_out + (p0 + row) * C + c * 32 + ckg * 8);
+          dst[0] = make_float4(q[0], q[1], q[2], q[3]);
+          dst[1] = make_float4(q[4], q[5], q[6], q[7]);
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("bar.arrive %0, %1;" ::"r"(4 + b), "n"(kBwdThreads) : "memory");
+      compute_sync();  // staging free again
+    }
+    // ---- P3: dx = g / m + dpool/du * dp ----
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      if (!mbar_wait(smem_u32(mbars + 2 + b), parq[b])) __trap();
+      parq[b] ^= 1u;
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int b = c & 1;
+      if (c + 1 < NCH) load_xg(b ^ 1, c + 1);
+      {
+        uint32_t an[16], ad[16];
+        tmem_load<16>(tmem_n + lane_sel + (uint32_t)(c * 32 + h * 16), an);
+        tmem_load<16>(tmem_dp + lane_sel + (uint32_t)(c * 32 + h * 16), ad);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        stage_store16(stage_n + r * kStLd + h * 16, an);
+        stage_store16(stage_d + r * kStLd + h * 16, ad);
+      }
+      compute_sync();
+      const float4 bv0 = *reinterpret_cast<const float4*>(beta_s + c * 32 + ckg * 8);
+      const float4 bv1 = *reinterpret_cast<const float4*>(beta_s + c * 32 + ckg * 8 + 4);
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int row = crow + 64 * it;
+        const float4 n0 = *reinterpret_cast<const float4*>(stage_n + row * kStLd + ckg * 8);
+        const float4 n1 = *reinterpret_cast<const float4*>(stage_n + row * kStLd + ckg * 8 + 4);
+        const float4 d0 = *reinterpret_cast<const float4*>(stage_d + row * kStLd + ckg * 8);
+        const float4 d1 = *reinterpret_cast<const float4*>(stage_d + row * kStLd + ckg * 8 + 4);
+        const float4 x0 = xq[b][it][0], x1 = xq[b][it][1], g0 = gq[b][it][0], g1 = gq[b][it][1];
+        float4 o0, o1;
+        o0.x = tc_dx<FAST>(g0.x, x0.x, bv0.x + n0.x, d0.x, f);
+        o0.y = tc_dx<FAST>(g0.y, x0.y, bv0.y + n0.y, d0.y, f);
+        o0.z = tc_dx<FAST>(g0.z, x0.z, bv0.z + n0.z, d0.z, f);
+        o0.w = tc_dx<FAST>(g0.w, x0.w, bv0.w + n0.w, d0.w, f);
+        o1.x = tc_dx<FAST>(g1.x, x1.x, bv1.x + n1.x, d1.x, f);
+        o1.y = tc_dx<FAST>(g1.y, x1.y, bv1.y + n1.y, d1.y, f);
+        o1.z = tc_dx<FAST>(g1.z, x1.z, bv1.z + n1.z, d1.z, f);
+        o1.w = tc_dx<FAST>(g1.w, x1.w, bv1.w + n1.w, d1.w, f);
+        if (p0 + row < n_pix) {
+          float4* dst = reinterpret_cast<float4*>(dx + (p0 + row) * C + c * 32 + ckg * 8);
+          dst[0] = o0;
+          dst[1] = o1;
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      compute_sync();
+    }
+  }
+  }  // compute warps
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (tid < 32) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "n"(512));
+  }
+}
+
+template <int C>
+struct Bwd3Smem {
+  static constexpr int kPlane = (C / 8) * kKg;       // one full-K plane
+  static constexpr int kOffPh = 0;
+  static constexpr int kOffPl = kOffPh + kPlane;
+  static constexpr int kOffQh = kOffPl + kPlane;
+  static constexpr int kOffQl = kOffQh + kPlane;
+  static constexpr int kOffDbeta = kOffQl + kPlane;
+  static constexpr int kOffBar = kOffDbeta + C * 4;
+  static constexpr int kBytes = kOffBar + 64;
+  static_assert(kBytes <= 232448, "shared memory budget");
+};
+
+template <int C, bool FAST>
+__global__ void __launch_bounds__(kBwdThreads, 1)
+gdn_tc_bwd_dgamma_kernel(const float* __restrict__ x, const float* __restrict__ q, float* __restrict__ part_g,
+                         float* __restrict__ part_b, long long n_pix, TcFlags f) {
+  using L = Bwd3Smem<C>;
+  constexpr int KG = C / 8;                                     // 8-channel groups per row
+  constexpr int ITEMS = kTileM * KG / kBwdCompute;              // (row, kg) items per thread and array: 12
+  constexpr int PERIOD = 3;                                     // kg of a thread's items repeats with this period
+  static_assert(C == 192 && (kTileM * KG) % kBwdCompute == 0 && ITEMS % 4 == 0, "item mapping");
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float* dbeta_s = reinterpret_cast<float*>(smem + L::kOffDbeta);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffBar + 16);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r = tid & 127, h = (tid >> 7) & 1, gwarp = warp & 3;
+  constexpr uint32_t kIdesc = umma_idesc(kTileM, C) | (1u << 15) | (1u << 16);  // A = p^T, B = q, both MN-major views
+  for (int i = tid; i < C; i += kBwdThreads) dbeta_s[i] = 0.f;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_a = *tmem_slot, tmem_b = tmem_a + C;  // rows j in [0,128) | rows j in [64,192)
+  const uint32_t lane_sel = (uint32_t)(gwarp * 32) << 16;
+  const long long n_tiles = (n_pix + kTileM - 1) / kTileM;
+  bool first_tile = true;
+
+  if (warp == kBwdCompute / 32) {
+    const uint32_t p_hi = smem_u32(smem + L::kOffPh), p_lo = smem_u32(smem + L::kOffPl);
+    const uint32_t q_hi = smem_u32(smem + L::kOffQh), q_lo = smem_u32(smem + L::kOffQl);
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      if (lane == 1) {
+        const long long pn = (tile + gridDim.x) * kTileM;
+        const long long rows = min((long long)kTileM, n_pix - pn);
+        if (rows > 0) {
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(x + pn * C), "r"((uint32_t)(rows * C * 4)) : "memory");
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(q + pn * C), "r"((uint32_t)(rows * C * 4)) : "memory");
+        }
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(kBwdThreads) : "memory");
+      if (lane == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+        for (int blk = 0; blk < 2; ++blk) {
+          const uint32_t moff = (uint32_t)(blk * 8) * kKg;  // second block starts at channel 64 = m group 8
+          const uint32_t td = blk ? tmem_b : tmem_a;
+#pragma unroll
+          for (int s = 0; s < kTileM / 16; ++s) {
+            const uint32_t koff = (uint32_t)(s * 16) * 16u;
+            const uint64_t dah = umma_desc(p_hi + moff + koff, 128, kKg);
+            const uint64_t dal = umma_desc(p_lo + moff + koff, 128, kKg);
+            const uint64_t dbh = umma_desc(q_hi + koff, 128, kKg);
+            const uint64_t dbl = umma_desc(q_lo + koff, 128, kKg);
+            umma_bf16(td, dah, dbh, kIdesc, (first_tile && s == 0) ? 0u : 1u);
+            umma_bf16(td, dal, dbh, kIdesc, 1u);
+            umma_bf16(td, dah, dbl, kIdesc, 1u);
+          }
+        }
+        umma_commit(smem_u32(mbar));
+      }
+      __syncwarp();
+      first_tile = false;
+    }
+  } else {
+  uint32_t par = 0u;
+  float dbeta_acc[PERIOD][8];
+#pragma unroll
+  for (int a = 0; a < PERIOD; ++a)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dbeta_acc[a][e] = 0.f;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long p0 = tile * kTileM;
+    bool waited = first_tile;
+#pragma unroll
+    for (int pass = 0; pass < ITEMS / 4; ++pass) {
+      float4 xv[4][2], qv[4][2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int id = (pass * 4 + i) * kBwdCompute + tid;
+        const int row = id / KG, kg = id % KG;
+        const bool live = p0 + row < n_pix;
+        const long long off = (p0 + row) * C + kg * 8;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        xv[i][0] = live ? __ldg(reinterpret_cast<const float4*>(x + off)) : z;
+        xv[i][1] = live ? __ldg(reinterpret_cast<const float4*>(x + off) + 1) : z;
+        qv[i][0] = live ? __ldg(reinterpret_cast<const float4*>(q + off)) : z;
+        qv[i][1] = live ? __ldg(reinterpret_cast<const float4*>(q + off) + 1) : z;
+      }
+      if (!waited) {  // the planes are being read by the previous tile's MMAs
+        if (!mbar_wait(smem_u32(mbar), par)) __trap();
+        par ^= 1u;
+        waited = true;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = pass * 4 + i;
+        const int id = j * kBwdCompute + tid;
+        const int row = id / KG, kg = id % KG;
+        const float4 a = xv[i][0], b = xv[i][1];
+        float v[8] = {tc_pool<FAST>(a.x, f), tc_pool<FAST>(a.y, f), tc_pool<FAST>(a.z, f), tc_pool<FAST>(a.w, f),
+                      tc_pool<FAST>(b.x, f), tc_pool<FAST>(b.y, f), tc_pool<FAST>(b.z, f), tc_pool<FAST>(b.w, f)};
+        uint4 hi, lo;
+        split8(v, &hi, &lo);
+        *reinterpret_cast<uint4*>(smem + L::kOffPh + kg * kKg + row * 16) = hi;
+        *reinterpret_cast<uint4*>(smem + L::kOffPl + kg * kKg + row * 16) = lo;
+        float w[8] = {qv[i][0].x, qv[i][0].y, qv[i][0].z, qv[i][0].w, qv[i][1].x, qv[i][1].y, qv[i][1].z, qv[i][1].w};
+        split8(w, &hi, &lo);
+        *reinterpret_cast<uint4*>(smem + L::kOffQh + kg * kKg + row * 16) = hi;
+        *reinterpret_cast<uint4*>(smem + L::kOffQl + kg * kKg + row * 16) = lo;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dbeta_acc[j % PERIOD][e] += w[e];
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    asm volatile("bar.arrive 2, %0;" ::"n"(kBwdThreads) : "memory");
+    first_tile = false;
+  }
+  if (!first_tile) {
+    if (!mbar_wait(smem_u32(mbar), par)) __trap();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // block a: lane r = channel j = r; block b: lane r = channel 64 + r (only its rows >= 128 are new)
+#pragma unroll 1
+    for (int blk = 0; blk < 2; ++blk) {
+      const int j = blk ? 64 + r : r;
+      float* pg = part_g + (long long)blockIdx.x * C * C + (long long)j * C + h * (C / 2);
+#pragma unroll
+      for (int cb = 0; cb < C / 32; ++cb) {
+        uint32_t a[16];
+        tmem_load<16>((blk ? tmem_b : tmem_a) + lane_sel + (uint32_t)(h * (C / 2) + cb * 16), a);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (!blk || r >= 64) stage_store16(pg + cb * 16, a);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < PERIOD; ++a) {
+      const int kg = (a * kBwdCompute + tid) % KG;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) atomicAdd(dbeta_s + kg * 8 + e, dbeta_acc[a][e]);
+    }
+  }
+  }  // compute warps
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  for (int i = tid; i < C; i += kBwdThreads) part_b[(long long)blockIdx.x * C + i] = dbeta_s[i];
+  if (tid < 32) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "n"(512));
+  }
+}
+
+template <bool FAST>
+int launch_tc_bwd192(const float* x, const float* gamma, const float* beta, const float* dy, float* dx, float* q_ws,
+                     float* part_g, float* part_b, int* n_parts, long long n_pix, TcFlags f, cudaStream_t s) {
+  constexpr int C = 192;
+  __nv_bfloat16* planes = nullptr;
+  TFCB_TRY(dev_alloc((void**)&planes, (size_t)2 * C * C * sizeof(__nv_bfloat16), s));
+  gdn_tc_prep_kernel<<<((C / 8) * C + 255) / 256, 256, 0, s>>>(gamma, C, planes);
+  TFCB_LAUNCHED();
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gdn_tc_bwd_dx_kernel<C, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Bwd2Smem<C>::kBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gdn_tc_bwd_dgamma_kernel<C, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               Bwd3Smem<C>::kBytes);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      dev_free(planes, s);
+      return fail(TFCB_CUDA_ERROR, "cannot reserve shared memory for the C=192 backward: %s", cudaGetErrorString(e));
+    }
+    attr_set = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long n_tiles = (n_pix + kTileM - 1) / kTileM;
+  const int grid = (int)std::min<long long>(n_tiles, std::min(sms, 148));
+  gdn_tc_bwd_dx_kernel<C, FAST><<<grid, kBwdThreads, Bwd2Smem<C>::kBytes, s>>>(x, dy, planes, beta, dx, q_ws, n_pix, f);
+  TFCB_LAUNCHED();
+  gdn_tc_bwd_dgamma_kernel<C, FAST><<<grid, kBwdThreads, Bwd3Smem<C>::kBytes, s>>>(x, q_ws, part_g, part_b, n_pix, f);
+  TFCB_LAUNCHED();
+  cudaError_t e = cudaGetLastError();
+  dev_free(planes, s);
+  if (e != cudaSuccess) return fail(TFCB_CUDA_ERROR, "GDN tensor-core backward (C=192) launch failed: %s", cudaGetErrorString(e));
+  *n_parts = grid;
+  return TFCB_OK;
+}
+
 template <bool FAST>
 int launch_tc_bwd(const float* x, const float* gamma, const float* beta, const float* dy, float* dx, float* part_g,
                   float* part_b, int* n_parts, long long n_pix, TcFlags f, cudaStream_t s) {
@@ -1210,11 +1711,12 @@ namespace tfcb {
 
 // Fused tensor-core backward; fills the per-CTA partial sums (part_g [n_parts][C][C], part_b [n_parts][C]) that
 // the caller reduces.  *handled = false -> the caller runs the fp32 kernels.
-int gdn_tc_backward(const float* x, const float* gamma, const float* beta, const float* dy, float* dx, float* part_g,
-                    float* part_b, int* n_parts, long long n_pix, int C, int flags, float alpha, float eps,
-                    cudaStream_t s, bool* handled) {
+int gdn_tc_backward(const float* x, const float* gamma, const float* beta, const float* dy, float* dx, float* q_ws,
+                    float* part_g, float* part_b, int* n_parts, long long n_pix, int C, int flags, float alpha,
+                    float eps, cudaStream_t s, bool* handled) {
   *handled = false;
-  if (C != 128) return TFCB_OK;
+  if (C != 128 && C != 192) return TFCB_OK;
+  if (C == 192 && (reinterpret_cast<uintptr_t>(q_ws) & 15)) return TFCB_OK;
   if (!(alpha == 1.f || alpha == 2.f) || !(eps == 1.f || eps == 0.5f)) return TFCB_OK;
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) return TFCB_OK;
   if (const char* env = getenv("TFCB_GDN_FP32")) {
@@ -1227,6 +1729,9 @@ int gdn_tc_backward(const float* x, const float* gamma, const float* beta, const
   f.eps_mode = (eps == 0.5f) ? 2 : 1;
   *handled = true;
   const bool fast = (alpha == 1.f) && (eps == 1.f) && !f.rectify;
+  if (C == 192)
+    return fast ? launch_tc_bwd192<true>(x, gamma, beta, dy, dx, q_ws, part_g, part_b, n_parts, n_pix, f, s)
+                : launch_tc_bwd192<false>(x, gamma, beta, dy, dx, q_ws, part_g, part_b, n_parts, n_pix, f, s);
   return fast ? launch_tc_bwd<true>(x, gamma, beta, dy, dx, part_g, part_b, n_parts, n_pix, f, s)
               : launch_tc_bwd<false>(x, gamma, beta, dy, dx, part_g, part_b, n_parts, n_pix, f, s);
 }

@@ -81,7 +81,8 @@ def test_forward_variants(F, C, alpha, epsilon, rectify):
     assert err < 2e-5
 
 
-@pytest.mark.parametrize("C,n_pix", [(128, 3000), (128, 1), (128, 129), (128, 128 * 148 * 2 + 77), (192, 1111), (5, 257)])
+@pytest.mark.parametrize("C,n_pix", [(128, 3000), (128, 1), (128, 129), (128, 128 * 148 * 2 + 77), (192, 1111), (192, 1),
+                                     (192, 128 * 148 * 2 + 300), (5, 257)])
 @pytest.mark.parametrize("inverse", [False, True])
 def test_backward_vs_fp64_oracle(F, C, n_pix, inverse):
   gamma, beta = _params(C, 14)
@@ -99,7 +100,7 @@ def test_backward_vs_fp64_oracle(F, C, n_pix, inverse):
   assert close(db, wb, 2e-5)
 
 
-@pytest.mark.parametrize("C", [64, 128])
+@pytest.mark.parametrize("C", [64, 128, 192])
 @pytest.mark.parametrize("alpha,epsilon,rectify", [(1, 1, True), (2, 0.5, False), (2, 1, False), (1, 0.5, False),
                                                    (1.5, 0.7, True)])
 def test_backward_variants(F, C, alpha, epsilon, rectify):
