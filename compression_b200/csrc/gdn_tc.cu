@@ -738,6 +738,246 @@ int launch_tc(const float* x, const float* gamma, const float* beta, float* y, l
 
 
 // =============================================================================================
+// Forward, C = 192 (third kernel shape): gamma's planes take 144 KB, so the x tile cannot live in shared
+// memory.  8 compute warps + 1 MMA-issue warp; x is converted straight from registers (coalesced loads, three
+// 32-channel chunks in flight), the issue warp runs the MMAs as the chunks arrive, and the epilogue transposes
+// n through a [128][68] staging buffer (over the dead operand planes) 64 columns at a time while x comes back
+// from L2 one chunk ahead.
+// =============================================================================================
+constexpr int kF3Threads = 288, kF3Compute = 256;
+constexpr int kF3Kg = kTileM * 16 + 160;        // see kF2Kg
+constexpr int kF3Plane = 4 * kF3Kg;             // hi or lo plane of a 32-channel chunk
+
+template <int C>
+struct Fwd3Smem {
+  static constexpr int kPlaneB = C * C * 2;
+  static constexpr int kOffBh = 0;
+  static constexpr int kOffBl = kOffBh + kPlaneB;
+  static constexpr int kOffP = kOffBl + kPlaneB;            // [2 buffers][hi, lo]; staging aliases it
+  static constexpr int kOffBar = kOffP + 4 * kF3Plane;
+  static constexpr int kBytes = kOffBar + 64;
+  static_assert(4 * kF3Plane >= kTileM * kF2StLd * 4, "staging must fit in the operand-plane area");
+  static_assert(kBytes <= 232448, "shared memory budget");
+};
+
+template <int C, bool FAST>
+__global__ void __launch_bounds__(kF3Threads, 1)
+gdn_tc_fwd3_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ planes,
+                   const float* __restrict__ beta, float* __restrict__ y, long long n_pix, TcFlags f) {
+  using L = Fwd3Smem<C>;
+  constexpr int NCH = C / 32;  // 6 conversion chunks
+  constexpr int NEP = C / 64;  // 3 epilogue chunks
+  static_assert(C % 64 == 0 && NCH % 2 == 0, "chunking");
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float* stage = reinterpret_cast<float*>(smem + L::kOffP);
+  uint64_t* mbars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);  // [0,1] plane buffers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffBar + 24);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r = tid & 127, h = (tid >> 7) & 1, gwarp = warp & 3;
+  constexpr uint32_t kIdesc = umma_idesc(kTileM, C);
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(planes);
+    uint4* dst = reinterpret_cast<uint4*>(smem + L::kOffBh);
+    for (int i = tid; i < 2 * L::kPlaneB / 16; i += kF3Threads) dst[i] = src[i];
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbars + i)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_n = *tmem_slot;
+  const uint32_t lane_sel = (uint32_t)(gwarp * 32) << 16;
+  const uint32_t b_hi = smem_u32(smem + L::kOffBh), b_lo = smem_u32(smem + L::kOffBl);
+  const long long n_tiles = (n_pix + kTileM - 1) / kTileM;
+
+  if (warp == kF3Compute / 32) {
+    // ------------------------------- MMA-issue warp -------------------------------
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      if (lane == 1) {
+        const long long pn = (tile + gridDim.x) * kTileM;
+        const long long rows = min((long long)kTileM, n_pix - pn);
+        if (rows > 0)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(x + pn * C), "r"((uint32_t)(rows * C * 4)) : "memory");
+      }
+#pragma unroll 1
+      for (int c = 0; c < NCH; ++c) {
+        const int pb = c & 1;
+        asm volatile("bar.sync %0, %1;" ::"r"(2 + pb), "n"(kF3Threads) : "memory");
+        if (lane == 0) {
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t ph = smem_u32(smem + L::kOffP + pb * 2 * kF3Plane), pl = ph + kF3Plane;
+#pragma unroll
+          for (int s2 = 0; s2 < 2; ++s2) {
+            const uint64_t dah = umma_desc(ph + (uint32_t)(2 * s2) * kF3Kg, kF3Kg, 128);
+            const uint64_t dal = umma_desc(pl + (uint32_t)(2 * s2) * kF3Kg, kF3Kg, 128);
+            const uint32_t b_off = (uint32_t)(c * 4 + 2 * s2) * (C * 16);
+            const uint64_t dbh = umma_desc(b_hi + b_off, C * 16, 128);
+            const uint64_t dbl = umma_desc(b_lo + b_off, C * 16, 128);
+            umma_bf16(tmem_n, dah, dbh, kIdesc, (c | s2) ? 1u : 0u);
+            umma_bf16(tmem_n, dal, dbh, kIdesc, 1u);
+            umma_bf16(tmem_n, dah, dbl, kIdesc, 1u);
+          }
+          umma_commit(smem_u32(mbars + pb));
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+  // --------------------------------- compute warps ---------------------------------
+  uint32_t parp[2] = {0u, 0u};
+  const int ckg = tid & 3, crow = tid >> 2;    // conversion items of a 32-channel chunk: rows crow, crow + 64
+  const int ekg = tid & 7, erow = tid >> 3;    // epilogue items of a 64-channel chunk: rows erow + 32 i
+  auto compute_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(kF3Compute) : "memory"); };
+
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long p0 = tile * kTileM;
+    // ---- pool + split, 32 channels at a time, the loads of three chunks in flight ----
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float4 xv[NCH / 2][2][2];
+#pragma unroll
+      for (int k = 0; k < NCH / 2; ++k)
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          const int row = crow + 64 * it;
+          const bool live = p0 + row < n_pix;
+          const float4* src = reinterpret_cast<const float4*>(x + (p0 + row) * C + (half * (NCH / 2) + k) * 32 + ckg * 8);
+          xv[k][it][0] = live ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+          xv[k][it][1] = live ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+      for (int k = 0; k < NCH / 2; ++k) {
+        const int c = half * (NCH / 2) + k, pb = c & 1;
+        if (c >= 2) {
+          if (!mbar_wait(smem_u32(mbars + pb), parp[pb])) __trap();
+          parp[pb] ^= 1u;
+        }
+        uint8_t* ph = smem + L::kOffP + pb * 2 * kF3Plane;
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          const int row = crow + 64 * it;
+          const float4 a = xv[k][it][0], b = xv[k][it][1];
+          float v[8] = {tc_pool<FAST>(a.x, f), tc_pool<FAST>(a.y, f), tc_pool<FAST>(a.z, f), tc_pool<FAST>(a.w, f),
+                        tc_pool<FAST>(b.x, f), tc_pool<FAST>(b.y, f), tc_pool<FAST>(b.z, f), tc_pool<FAST>(b.w, f)};
+          uint4 hi, lo;
+          split8(v, &hi, &lo);
+          *reinterpret_cast<uint4*>(ph + ckg * kF3Kg + row * 16) = hi;
+          *reinterpret_cast<uint4*>(ph + kF3Plane + ckg * kF3Kg + row * 16) = lo;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("bar.arrive %0, %1;" ::"r"(2 + pb), "n"(kF3Threads) : "memory");
+      }
+    }
+    // ---- epilogue: y = x / (beta + n), 64 channels at a time; x of the next chunk is in flight ----
+    float4 xe[2][4][2];
+    auto load_xe = [&](int set, int cc) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = erow + 32 * i;
+        const bool live = p0 + row < n_pix;
+        const float4* src = reinterpret_cast<const float4*>(x + (p0 + row) * C + cc * 64 + ekg * 8);
+        xe[set][i][0] = live ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xe[set][i][1] = live ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    load_xe(0, 0);
+#pragma unroll
+    for (int pb = 0; pb < 2; ++pb) {  // the last two commits cover every MMA of the tile; the planes are dead
+      if (!mbar_wait(smem_u32(mbars + pb), parp[pb])) __trap();
+      parp[pb] ^= 1u;
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+    for (int cc = 0; cc < NEP; ++cc) {
+      const int set = cc & 1;
+      if (cc + 1 < NEP) load_xe(set ^ 1, cc + 1);
+      {
+        uint32_t acc[32];
+        tmem_load<32>(tmem_n + lane_sel + (uint32_t)(cc * 64 + h * 32), acc);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float* dst = stage + r * kF2StLd + h * 32;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<float4*>(dst + 4 * i) = make_float4(__uint_as_float(acc[4 * i]), __uint_as_float(acc[4 * i + 1]),
+                                                                 __uint_as_float(acc[4 * i + 2]), __uint_as_float(acc[4 * i + 3]));
+      }
+      compute_sync();
+      const float4 bv0 = __ldg(reinterpret_cast<const float4*>(beta + cc * 64 + ekg * 8));
+      const float4 bv1 = __ldg(reinterpret_cast<const float4*>(beta + cc * 64 + ekg * 8) + 1);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = erow + 32 * i;
+        const float* ns = stage + row * kF2StLd + ekg * 8;
+        const float4 n0 = *reinterpret_cast<const float4*>(ns), n1 = *reinterpret_cast<const float4*>(ns + 4);
+        const float4 x0 = xe[set][i][0], x1 = xe[set][i][1];
+        float4 o0, o1;
+        o0.x = tc_out<FAST>(x0.x, bv0.x + n0.x, f);
+        o0.y = tc_out<FAST>(x0.y, bv0.y + n0.y, f);
+        o0.z = tc_out<FAST>(x0.z, bv0.z + n0.z, f);
+        o0.w = tc_out<FAST>(x0.w, bv0.w + n0.w, f);
+        o1.x = tc_out<FAST>(x1.x, bv1.x + n1.x, f);
+        o1.y = tc_out<FAST>(x1.y, bv1.y + n1.y, f);
+        o1.z = tc_out<FAST>(x1.z, bv1.z + n1.z, f);
+        o1.w = tc_out<FAST>(x1.w, bv1.w + n1.w, f);
+        if (p0 + row < n_pix) {
+          float4* dst = reinterpret_cast<float4*>(y + (p0 + row) * C + cc * 64 + ekg * 8);
+          dst[0] = o0;
+          dst[1] = o1;
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      compute_sync();  // staging free again (and, after the last chunk, for the next tile's operand planes)
+    }
+  }
+  }  // compute warps
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (tid < 32) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "n"(256));
+  }
+}
+
+template <bool FAST>
+int launch_tc_fwd3(const float* x, const float* gamma, const float* beta, float* y, long long n_pix, TcFlags f,
+                   cudaStream_t s) {
+  constexpr int C = 192;
+  using L = Fwd3Smem<C>;
+  __nv_bfloat16* planes = nullptr;
+  TFCB_TRY(dev_alloc((void**)&planes, (size_t)2 * C * C * sizeof(__nv_bfloat16), s));
+  gdn_tc_prep_kernel<<<((C / 8) * C + 255) / 256, 256, 0, s>>>(gamma, C, planes);
+  TFCB_LAUNCHED();
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gdn_tc_fwd3_kernel<C, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      dev_free(planes, s);
+      return fail(TFCB_CUDA_ERROR, "cannot reserve %d bytes of shared memory: %s", L::kBytes, cudaGetErrorString(e));
+    }
+    attr_set = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long n_tiles = (n_pix + kTileM - 1) / kTileM;
+  const int grid = (int)std::min<long long>(n_tiles, sms);
+  gdn_tc_fwd3_kernel<C, FAST><<<grid, kF3Threads, L::kBytes, s>>>(x, planes, beta, y, n_pix, f);
+  TFCB_LAUNCHED();
+  cudaError_t e = cudaGetLastError();
+  dev_free(planes, s);
+  if (e != cudaSuccess) return fail(TFCB_CUDA_ERROR, "GDN tensor-core kernel launch failed: %s", cudaGetErrorString(e));
+  return TFCB_OK;
+}
+
+// =============================================================================================
 // Backward (C = 128): one fused kernel per launch instead of three fp32 passes.
 //
 //   n  = beta + p . gamma                 MMA1   A = p planes (K-major),        B = gamma planes (K-major)
@@ -1700,7 +1940,12 @@ int gdn_tc_forward(const float* x, const float* gamma, const float* beta, float*
     return fast ? launch_tc<128, 2, 32, true>(x, gamma, beta, y, n_pix, f, s)
                 : launch_tc<128, 2, 32, false>(x, gamma, beta, y, n_pix, f, s);
   }
-  // C == 192: 147 KB of gamma planes + 2 x 36 KB pipelines = 220 KB
+  {
+    const char* v1 = getenv("TFCB_GDN_FWD1");
+    if (!(v1 && v1[0] == '1'))  // default for C == 192: register-fed conversion + MMA-issue warp
+      return fast ? launch_tc_fwd3<true>(x, gamma, beta, y, n_pix, f, s) : launch_tc_fwd3<false>(x, gamma, beta, y, n_pix, f, s);
+  }
+  // first generation, C == 192: 147 KB of gamma planes + 2 x 36 KB cp.async pipelines = 220 KB
   return fast ? launch_tc<192, 2, 16, true>(x, gamma, beta, y, n_pix, f, s)
               : launch_tc<192, 2, 16, false>(x, gamma, beta, y, n_pix, f, s);
 }
