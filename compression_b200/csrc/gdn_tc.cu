@@ -836,46 +836,58 @@ gdn_tc_fwd3_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict_
   const int ekg = tid & 7, erow = tid >> 3;    // epilogue items of a 64-channel chunk: rows erow + 32 i
   auto compute_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(kF3Compute) : "memory"); };
 
+  // x of half a tile (three 32-channel chunks) in registers; the first half of the NEXT tile is requested before
+  // the epilogue of the current one, so its latency is hidden behind the epilogue.
+  auto load_half = [&](long long tile, int half, float4 (&xv)[NCH / 2][2][2]) {
+    const long long p0 = tile * kTileM;
+#pragma unroll
+    for (int k = 0; k < NCH / 2; ++k)
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int row = crow + 64 * it;
+        const bool live = tile < n_tiles && p0 + row < n_pix;
+        const float4* src = reinterpret_cast<const float4*>(x + (p0 + row) * C + (half * (NCH / 2) + k) * 32 + ckg * 8);
+        xv[k][it][0] = live ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xv[k][it][1] = live ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+  };
+  auto convert_half = [&](int half, const float4 (&xv)[NCH / 2][2][2]) {
+#pragma unroll
+    for (int k = 0; k < NCH / 2; ++k) {
+      const int c = half * (NCH / 2) + k, pb = c & 1;
+      if (c >= 2) {
+        if (!mbar_wait(smem_u32(mbars + pb), parp[pb])) __trap();
+        parp[pb] ^= 1u;
+      }
+      uint8_t* ph = smem + L::kOffP + pb * 2 * kF3Plane;
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int row = crow + 64 * it;
+        const float4 a = xv[k][it][0], b = xv[k][it][1];
+        float v[8] = {tc_pool<FAST>(a.x, f), tc_pool<FAST>(a.y, f), tc_pool<FAST>(a.z, f), tc_pool<FAST>(a.w, f),
+                      tc_pool<FAST>(b.x, f), tc_pool<FAST>(b.y, f), tc_pool<FAST>(b.z, f), tc_pool<FAST>(b.w, f)};
+        uint4 hi, lo;
+        split8(v, &hi, &lo);
+        *reinterpret_cast<uint4*>(ph + ckg * kF3Kg + row * 16) = hi;
+        *reinterpret_cast<uint4*>(ph + kF3Plane + ckg * kF3Kg + row * 16) = lo;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("bar.arrive %0, %1;" ::"r"(2 + pb), "n"(kF3Threads) : "memory");
+    }
+  };
+  float4 xa[NCH / 2][2][2];
+  load_half(blockIdx.x, 0, xa);
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long p0 = tile * kTileM;
-    // ---- pool + split, 32 channels at a time, the loads of three chunks in flight ----
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      float4 xv[NCH / 2][2][2];
-#pragma unroll
-      for (int k = 0; k < NCH / 2; ++k)
-#pragma unroll
-        for (int it = 0; it < 2; ++it) {
-          const int row = crow + 64 * it;
-          const bool live = p0 + row < n_pix;
-          const float4* src = reinterpret_cast<const float4*>(x + (p0 + row) * C + (half * (NCH / 2) + k) * 32 + ckg * 8);
-          xv[k][it][0] = live ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
-          xv[k][it][1] = live ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-      for (int k = 0; k < NCH / 2; ++k) {
-        const int c = half * (NCH / 2) + k, pb = c & 1;
-        if (c >= 2) {
-          if (!mbar_wait(smem_u32(mbars + pb), parp[pb])) __trap();
-          parp[pb] ^= 1u;
-        }
-        uint8_t* ph = smem + L::kOffP + pb * 2 * kF3Plane;
-#pragma unroll
-        for (int it = 0; it < 2; ++it) {
-          const int row = crow + 64 * it;
-          const float4 a = xv[k][it][0], b = xv[k][it][1];
-          float v[8] = {tc_pool<FAST>(a.x, f), tc_pool<FAST>(a.y, f), tc_pool<FAST>(a.z, f), tc_pool<FAST>(a.w, f),
-                        tc_pool<FAST>(b.x, f), tc_pool<FAST>(b.y, f), tc_pool<FAST>(b.z, f), tc_pool<FAST>(b.w, f)};
-          uint4 hi, lo;
-          split8(v, &hi, &lo);
-          *reinterpret_cast<uint4*>(ph + ckg * kF3Kg + row * 16) = hi;
-          *reinterpret_cast<uint4*>(ph + kF3Plane + ckg * kF3Kg + row * 16) = lo;
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        asm volatile("bar.arrive %0, %1;" ::"r"(2 + pb), "n"(kF3Threads) : "memory");
-      }
+    // ---- pool + split, 32 channels at a time ----
+    {
+      float4 xb[NCH / 2][2][2];
+      load_half(tile, 1, xb);
+      convert_half(0, xa);
+      convert_half(1, xb);
     }
+    load_half(tile + gridDim.x, 0, xa);
     // ---- epilogue: y = x / (beta + n), 64 channels at a time; x of the next chunk is in flight ----
     float4 xe[2][4][2];
     auto load_xe = [&](int set, int cc) {
