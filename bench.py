@@ -491,7 +491,7 @@ def main():
       torch.cuda.synchronize()
       ms = a.elapsed_time(b) / 3
       gbs = 8.0 * npix * 192 / (ms * 1e-3) / 1e9
-      entry = {"fwd_ms": ms, "fwd_GBps": gbs, "fwd_frac_of_hbm_peak": gbs / peak, "fwd_kernel": "tcgen05 (gdn_tc_fwd_kernel<192,2,16>)"}
+      entry = {"fwd_ms": ms, "fwd_GBps": gbs, "fwd_frac_of_hbm_peak": gbs / peak, "fwd_kernel": "tcgen05 (gdn_tc_fwd3_kernel<192>)"}
       dy = torch.randn_like(x)
       functional.gdn_backward(x, gamma192, beta192, dy)
       a.record()
