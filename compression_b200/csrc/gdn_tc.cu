@@ -681,7 +681,7 @@ int launch_tc_fwd2(const float* x, const float* gamma, const float* beta, float*
   TFCB_TRY(dev_alloc((void**)&planes, (size_t)2 * C * C * sizeof(__nv_bfloat16), s));
   gdn_tc_prep_kernel<<<((C / 8) * C + 255) / 256, 256, 0, s>>>(gamma, C, planes);
   TFCB_LAUNCHED();
-  static bool attr_set = false;
+  bool attr_set = false;  // the attribute is per device: set it on every launch (microseconds)
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gdn_tc_fwd2_kernel<FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes);
     if (e != cudaSuccess) {
@@ -712,7 +712,7 @@ int launch_tc(const float* x, const float* gamma, const float* beta, float* y, l
   TFCB_TRY(dev_alloc((void**)&planes, (size_t)2 * C * C * sizeof(__nv_bfloat16), s));
   gdn_tc_prep_kernel<<<((C / 8) * C + 255) / 256, 256, 0, s>>>(gamma, C, planes);
   TFCB_LAUNCHED();
-  static bool attr_set = false;
+  bool attr_set = false;  // the attribute is per device: set it on every launch (microseconds)
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gdn_tc_fwd_kernel<C, G, KC, FAST>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes);
@@ -966,7 +966,7 @@ int launch_tc_fwd3(const float* x, const float* gamma, const float* beta, float*
   TFCB_TRY(dev_alloc((void**)&planes, (size_t)2 * C * C * sizeof(__nv_bfloat16), s));
   gdn_tc_prep_kernel<<<((C / 8) * C + 255) / 256, 256, 0, s>>>(gamma, C, planes);
   TFCB_LAUNCHED();
-  static bool attr_set = false;
+  bool attr_set = false;  // the attribute is per device: set it on every launch (microseconds)
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gdn_tc_fwd3_kernel<C, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes);
     if (e != cudaSuccess) {
@@ -1862,7 +1862,7 @@ int launch_tc_bwd192(const float* x, const float* gamma, const float* beta, cons
   TFCB_TRY(dev_alloc((void**)&planes, (size_t)2 * C * C * sizeof(__nv_bfloat16), s));
   gdn_tc_prep_kernel<<<((C / 8) * C + 255) / 256, 256, 0, s>>>(gamma, C, planes);
   TFCB_LAUNCHED();
-  static bool attr_set = false;
+  bool attr_set = false;  // the attribute is per device: set it on every launch (microseconds)
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gdn_tc_bwd_dx_kernel<C, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Bwd2Smem<C>::kBytes);
@@ -1901,7 +1901,7 @@ int launch_tc_bwd(const float* x, const float* gamma, const float* beta, const f
   TFCB_TRY(dev_alloc((void**)&planes, (size_t)2 * C * C * sizeof(__nv_bfloat16), s));
   gdn_tc_prep_kernel<<<((C / 8) * C + 255) / 256, 256, 0, s>>>(gamma, C, planes);
   TFCB_LAUNCHED();
-  static bool attr_set = false;
+  bool attr_set = false;  // the attribute is per device: set it on every launch (microseconds)
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gdn_tc_bwd_kernel<C, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          L::kBytes);

@@ -1618,6 +1618,7 @@ struct LookupCache {
       for (size_t i = 0; i < entries.size(); ++i)
         if (entries[i]->pins == 0 && (victim == entries.size() || entries[i]->last_use < entries[victim]->last_use)) victim = i;
       if (victim == entries.size()) break;  // everything is in use
+      cudaDeviceSynchronize();  // rare (> kMaxEntries distinct tables): no kernel of any stream may still read it
       entries[victim]->lut.release(s);
       delete entries[victim];
       entries.erase(entries.begin() + victim);
