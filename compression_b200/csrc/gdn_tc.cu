@@ -941,8 +941,8 @@ gdn_tc_fwd3_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict_
         o1.w = tc_out<FAST>(x1.w, bv1.w + n1.w, f);
         if (p0 + row < n_pix) {
           float4* dst = reinterpret_cast<float4*>(y + (p0 + row) * C + cc * 64 + ekg * 8);
-          dst[0] = o0;
-          dst[1] = o1;
+          __stcs(dst, o0);  // streaming stores: keep x / dy (re-read from L2) resident instead of the outputs
+          __stcs(dst + 1, o1);
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -1348,8 +1348,8 @@ gdn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, con
         o1.w = tc_dx<FAST>(g1.w, x1.w, bv1.w + n1.w, d1.w, f);
         if (p0 + row < n_pix) {
           float4* dst = reinterpret_cast<float4*>(dx + (p0 + row) * C + c * 32 + ckg * 8);
-          dst[0] = o0;
-          dst[1] = o1;
+          __stcs(dst, o0);  // streaming stores: keep x / dy (re-read from L2) resident instead of the outputs
+          __stcs(dst + 1, o1);
         }
       }
     }
@@ -1619,8 +1619,8 @@ gdn_tc_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ dy, 
         *reinterpret_cast<uint4*>(ql + ckg * kKg + row * 16) = lo;
         if (p0 + row < n_pix) {
           float4* dst = reinterpret_cast<float4*>(q_out + (p0 + row) * C + c * 32 + ckg * 8);
-          dst[0] = make_float4(q[0], q[1], q[2], q[3]);
-          dst[1] = make_float4(q[4], q[5], q[6], q[7]);
+          __stcs(dst, make_float4(q[0], q[1], q[2], q[3]));
+          __stcs(dst + 1, make_float4(q[4], q[5], q[6], q[7]));
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -1669,8 +1669,8 @@ gdn_tc_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ dy, 
         o1.w = tc_dx<FAST>(g1.w, x1.w, bv1.w + n1.w, d1.w, f);
         if (p0 + row < n_pix) {
           float4* dst = reinterpret_cast<float4*>(dx + (p0 + row) * C + c * 32 + ckg * 8);
-          dst[0] = o0;
-          dst[1] = o1;
+          __stcs(dst, o0);  // streaming stores: keep x / dy (re-read from L2) resident instead of the outputs
+          __stcs(dst + 1, o1);
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
