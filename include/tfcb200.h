@@ -172,6 +172,9 @@ int tfcb_build_lookup(const float* pmf_dev, int64_t rows, int64_t max_len, const
  *   y_i = u_i / n_i^eps  (GDN)   or   u_i * n_i^eps  (IGDN)
  * x, y: float32 [n_pix, C] row-major;  gamma float32 [C, C] (row j, column i);  beta float32 [C].
  * alpha in {1, 2} and eps in {1, 0.5} take the reference's fast paths; other values use powf.
+ * C in {128, 192} with those alpha / eps and 16-byte aligned pointers run on the tensor cores (bf16 split with
+ * fp32 accumulation: <= 1e-5 relative forward, <= 2e-5 of the largest gradient backward); every other shape
+ * runs the fp32 kernels.  TFCB_GDN_FP32=1 in the environment forces the fp32 kernels.
  * The reference has no native GDN code (TF graph of abs / conv1x1 / bias_add / div); the backward
  * pass replaces TF autodiff of that graph.
  * ---------------------------------------------------------------------------------------------- */
