@@ -382,7 +382,7 @@ def main():
       with open(prof) as f:
         traffic = json.load(f).get("dram_bytes_per_launch")
     result["roofline"] = {
-        "kernel": "encode_kernel (fused quantise + range encode, one warp per stream)", "bound": "hbm",
+        "kernel": "encode_kernel (fused quantise + range encode; one CTA per stream: gather, chain and drain warps)", "bound": "hbm",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
         "peak_source": peak_src, "kernel_ms": enc_ms, "algorithmic_bytes": alg_bytes,
         "kernel_msym_s": sym_per_step / (enc_ms * 1e-3) / 1e6,

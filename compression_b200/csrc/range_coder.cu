@@ -928,11 +928,12 @@ __device__ __forceinline__ int dec_symbol(DecChain& c, ByteWindow& w, const int3
 
 
 // ---------------------------------------------------------------------------------------------
-// Decoder v2: three warps per stream (prepare / chain / resolve), pre-scaled search keys
+// Decoder: three warps per stream (prepare / chain / resolve), pre-scaled search keys
 // ---------------------------------------------------------------------------------------------
 // The decoder has the encoder's recurrence plus a search per symbol.  As in the encoder everything that
 // is not the recurrence leaves the latency-critical warp:
-//   prepare warp : per symbol the row's search window (64 pre-scaled keys around the row's median);
+//   prepare warp : per symbol the row's search window (64 pre-scaled keys around the row's median), and the
+//                  stream's next 16-bit words in a shared-memory ring well ahead of the chain;
 //   chain warp   : every lane evaluates two keys B'(c) = T(c) - 1 = hi32(span*c' + addend) (one IMAD.HI
 //                  each), two warp reductions give the bracketing pair (a, b1) and the new interval; the
 //                  SYMBOL INDEX is not needed to continue -- only {value - base, span} are recorded;
