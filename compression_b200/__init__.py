@@ -10,7 +10,7 @@ from compression_b200._lib import InvalidArgumentError
 
 def __getattr__(name):  # lazy: importing the package must not require torch / the built library
   import importlib
-  modules = ("gen_ops", "functional", "math_ops", "distributions", "entropy_models", "gdn")
+  modules = ("gen_ops", "functional", "math_ops", "distributions", "entropy_models", "gdn", "packed_tensors")
   if name in modules:
     return importlib.import_module("compression_b200." + name)
   exported = {
@@ -20,7 +20,7 @@ def __getattr__(name):  # lazy: importing the package must not require torch / t
       "NoisyDeepFactorized": "distributions", "DeepFactorized": "distributions", "NoisyNormal": "distributions",
       "NoisyLaplace": "distributions", "NoisyLogistic": "distributions",
       "round_st": "math_ops", "lower_bound": "math_ops", "upper_bound": "math_ops",
-      "perturb_and_apply": "math_ops",
+      "perturb_and_apply": "math_ops", "PackedTensors": "packed_tensors",
   }
   if name in exported:
     return getattr(importlib.import_module("compression_b200." + exported[name]), name)
