@@ -1,0 +1,91 @@
+"""CPU: the entropy models' host logic that needs no range coder (compression=False): construction contract,
+quantisation, straight-through gradients, the differentiable bit cost, index normalisation.  Cases from
+py/entropy_models/continuous_batched_test.py:27-101 and continuous_indexed_test.py:96-137."""
+import numpy as np
+import pytest
+import scipy.stats
+import torch
+
+import compression_b200 as tfc
+
+
+def test_batched_model_contract_without_compression():
+  noisy = tfc.NoisyNormal(loc=torch.tensor(0.), scale=torch.tensor(1.))
+  em = tfc.ContinuousBatchedEntropyModel(noisy, 1)
+  assert em.prior is noisy and em.coding_rank == 1 and em.tail_mass == 2**-8
+  assert em.bottleneck_dtype == torch.float32 and em.compression is False
+  x = torch.randn(100)
+  with pytest.raises(RuntimeError):   # continuous_batched_test.py:93-101
+    em.compress(x)
+  with pytest.raises(RuntimeError):
+    em.decompress([b""], [100])
+  with pytest.raises(ValueError):     # :65-72 coding_rank must cover the prior's batch dimensions
+    tfc.ContinuousBatchedEntropyModel(tfc.NoisyLaplace(loc=torch.zeros(1, 1), scale=torch.ones(1, 1)), 1)
+
+
+def test_batched_quantizes_to_integers_modulo_offset_with_straight_through_gradients():
+  torch.manual_seed(0)
+  noisy = tfc.NoisyNormal(loc=torch.tensor(.25), scale=torch.tensor(10.))
+  em = tfc.ContinuousBatchedEntropyModel(noisy, 1)
+  x = (torch.randn(100) * 10 + .25).requires_grad_(True)
+  q = em.quantize(x)
+  np.testing.assert_allclose(((q.detach() - .25) % 1).numpy(), 0.0, atol=1e-5)   # :74-80
+  assert float((q.detach() - x.detach()).abs().max()) <= 0.5 + 1e-6
+  q.sum().backward()
+  assert x.grad.tolist() == [1.0] * 100                                            # :82-91
+
+
+def test_batched_bit_cost_matches_the_noisy_prior():
+  torch.manual_seed(1)
+  loc, scale = torch.tensor([.5, -1.0]), torch.tensor([2.0, 0.7])
+  em = tfc.ContinuousBatchedEntropyModel(tfc.NoisyNormal(loc=loc, scale=scale), coding_rank=2)
+  x = torch.randn(3, 50, 2) * scale + loc
+  x_hat, bits = em(x, training=False)
+  assert bits.shape == (3,) and torch.equal(x_hat, em.quantize(x))
+  ref = scipy.stats.norm(loc=loc.numpy().astype(np.float64), scale=scale.numpy().astype(np.float64))
+  xq = x_hat.numpy().astype(np.float64)
+  want = -np.log2(ref.cdf(xq + .5) - ref.cdf(xq - .5)).sum(axis=(1, 2))
+  np.testing.assert_allclose(bits.numpy(), want, rtol=2e-4)
+  # training: additive uniform noise in [-1/2, 1/2], bits finite and differentiable w.r.t. the input
+  xin = x.clone().requires_grad_(True)
+  x_noisy, bits_t = em(xin, training=True)
+  assert float((x_noisy.detach() - x).abs().max()) <= 0.5 and bool(torch.isfinite(bits_t).all())
+  bits_t.sum().backward()
+  assert xin.grad is not None and bool(torch.isfinite(xin.grad).all())
+
+
+def _indexed(**kw):
+  return tfc.ContinuousIndexedEntropyModel(
+      tfc.NoisyNormal, index_ranges=(10, 10),
+      parameter_fns=dict(loc=lambda i: i[..., 0] - 5.0, scale=lambda i: torch.exp(i[..., 1] / 3.0 - 2)),
+      coding_rank=1, channel_axis=-1, **kw)
+
+
+def test_indexes_are_clipped_and_flattened():
+  em = _indexed()
+  idx = torch.tensor([[[-1.0, 3.2], [4.9, 12.0]]])
+  norm = em._normalize_indexes(idx)                     # continuous_indexed_test.py:96-103
+  assert norm.tolist() == [[[0.0, pytest.approx(3.2)], [pytest.approx(4.9), 9.0]]]
+  assert em._flatten_indexes(norm).tolist() == [[3, 49]]   # row = i0 * 10 + i1, truncated towards zero
+  with pytest.raises(RuntimeError):                      # :130-137
+    em.compress(torch.zeros(1, 2), idx)
+
+
+def test_indexed_quantizes_to_integers_and_bits_follow_the_indexed_prior():
+  torch.manual_seed(2)
+  em = _indexed()
+  idx = torch.stack([torch.randint(0, 10, (4, 30)).float(), torch.randint(0, 10, (4, 30)).float()], dim=-1)
+  x = torch.randn(4, 30) * 3
+  x_hat, bits = em(x, idx, training=False)
+  assert torch.equal(x_hat, torch.round(x)) and bits.shape == (4,)   # :113-118 (no offset in indexed models)
+  loc = (idx[..., 0] - 5.0).numpy().astype(np.float64)
+  scale = np.exp(idx[..., 1].numpy().astype(np.float64) / 3.0 - 2)
+  xq = x_hat.numpy().astype(np.float64)
+  p = np.where(xq > loc, scipy.stats.norm.sf(xq - .5, loc, scale) - scipy.stats.norm.sf(xq + .5, loc, scale),
+               scipy.stats.norm.cdf(xq + .5, loc, scale) - scipy.stats.norm.cdf(xq - .5, loc, scale))
+  # the model floors the likelihood (likelihood bound) so that a symbol far in a narrow prior's tail costs a
+  # finite number of bits: compare where the closed form is representable
+  ok = p > 1e-8
+  got = em(torch.where(torch.from_numpy(ok), x, torch.from_numpy(loc).float()), idx, training=False)[1]
+  want = -np.log2(np.where(ok, p, scipy.stats.norm.cdf(.5, 0, scale) - scipy.stats.norm.cdf(-.5, 0, scale))).sum(axis=1)
+  np.testing.assert_allclose(got.numpy(), want, rtol=2e-3)
