@@ -1,21 +1,26 @@
 """bench.py -- headline benchmark of the B200-native tensorflow/compression hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--no-extras]
     (N > 1: launched by `python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...`)
 
 Workload (BASELINE.json configs[1], "cfg2"): bls2017 compress path at batch 256, 256x256x3 images,
 num_filters=128  ->  latents y [256,16,16,128] fp32 (256 code streams x 32768 symbols, 128 channel
 tables, precision 12, overflow/Elias-gamma escape enabled).  One STEP = one pass of the entropy-bottleneck
 hot path over one batch: quantise (y - offset -> rint -> - cdf_offset), range-encode every stream,
-finalize and pack the strings (ContinuousBatchedEntropyModel.compress).  The GDN layers of the analysis
-transform ([256,64,64,128] and [256,32,32,128]) and the decode path are measured in the same run and
-reported in the `gdn` / `decode` objects of the JSON line.
+finalize and pack the strings (ContinuousBatchedEntropyModel.compress).  The decode path, the GDN layers,
+cfg3 (bmshj2018 two-level) and the image -> strings model path are measured in the same run and reported in
+the `decode` / `gdn` / `cfg3_bmshj2018` / `model_path` objects of the JSON line (extras, rank 0, N = 1).
 
-`value`   = symbols / s with y resident in HBM (whole job, all ranks).
+`value`   = symbols / s with y resident in HBM (whole job, all ranks), EXACTLY K steps, CUDA events.
 `e2e`     = the same metric through the public API with HOST buffers: pinned-host y -> H2D -> compress ->
-            D2H of the packed strings + offsets, every step.
+            D2H of the packed strings + offsets, every step; the K-step region is repeated 7 times and the
+            median is reported (min / max beside it).
 `--impl reference` = the reference's own CPU range coder (oracle/_ref: cc/lib/range_coder.cc compiled in
-            place, driven by the restated op loops with all host threads), same symbols and tables.
+            place, driven by the restated op loops on a persistent pool of all host threads), same symbols
+            and tables (tests/golden/cfg2_tables.npz, written by tools/make_cfg_fixtures.py from the product's
+            table builder); this arm never imports compression_b200.
+Parity: outside the timed region every rank checks its first batch against the oracle, byte for byte, and
+cross-decodes it (`parity_checked`).
 
 Weak scaling: every rank codes its own 256-stream batch; rank 0 builds the tables and broadcasts them
 (NCCL); there is no data-path collective.
@@ -34,6 +39,12 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 CFG = dict(batch=256, hw=16, channels=128, precision=12, tail_mass=2**-8, n_rot=6)
+METRIC = "range-code throughput (bls2017 compress path, cfg2)"
+WORKLOAD = ("cfg2: bls2017 compress, y[256,16,16,128] fp32 per GPU, 256 streams x 32768 symbols, "
+            "128 NoisyLaplace channel tables, precision 12, overflow on; step = quantise + range-encode + "
+            "finalize/pack")
+FIXTURE = os.path.join(ROOT, "tests", "golden", "cfg2_tables.npz")
+E2E_REPEATS = 7
 
 
 def _peaks():
@@ -45,10 +56,13 @@ def _peaks():
   return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def synth_latents(rank, n_rot, device=None):
-  """y[b,h,w,c] ~ Laplace(0, s_c), s_c log-spaced 0.3..8 over channels."""
+# ------------------------------------------------------------------------------------------------
+# Workloads; shared with tests/test_baseline_configs_gpu.py
+# ------------------------------------------------------------------------------------------------
+def synth_latents(rank, n_rot, batch=None):
+  """cfg2: y[b,h,w,c] ~ Laplace(0, s_c), s_c log-spaced 0.3..8 over channels (seed 2)."""
   import torch
-  C, B, HW = CFG["channels"], CFG["batch"], CFG["hw"]
+  C, B, HW = CFG["channels"], batch or CFG["batch"], CFG["hw"]
   g = torch.Generator().manual_seed(2 + 1000 * rank)
   scales = torch.exp(torch.linspace(np.log(0.3), np.log(8.0), C))
   out = []
@@ -59,19 +73,146 @@ def synth_latents(rank, n_rot, device=None):
   return scales, out
 
 
-def build_model(scales, device):
-  """ContinuousBatchedEntropyModel over per-channel NoisyLaplace priors (exercises the device table
-  builder, tfcb_build_lookup)."""
+def build_model(scales, device, prior="laplace"):
+  """cfg2 entropy model: ContinuousBatchedEntropyModel over per-channel NoisyLaplace priors (bench) or the
+  models' own NoisyDeepFactorized(batch_shape=(128,)) (models/bls2017.py:103); both exercise the device table
+  builder, tfcb_build_lookup."""
   import torch
   import compression_b200 as tfc
-  prior = tfc.NoisyLaplace(loc=torch.zeros_like(scales), scale=scales)
-  return tfc.ContinuousBatchedEntropyModel(prior, coding_rank=3, compression=True,
-                                           tail_mass=CFG["tail_mass"],
+  if prior == "laplace":
+    p = tfc.NoisyLaplace(loc=torch.zeros_like(scales), scale=scales)
+  else:
+    torch.manual_seed(11)
+    p = tfc.NoisyDeepFactorized(batch_shape=(len(scales),))
+  return tfc.ContinuousBatchedEntropyModel(p, coding_rank=3, compression=True, tail_mass=CFG["tail_mass"],
                                            range_coder_precision=CFG["precision"]).to(device)
 
 
+def cfg3_workload(dev, batch=128):
+  """cfg3 (bmshj2018, batch 128 of 256x256): y[128,16,16,192] coded by LocationScaleIndexedEntropyModel over
+  64 NoisyNormal tables sigma = exp(log .11 + i (log 256 - log .11)/63), indexes uniform in [0, 64) as floats
+  (seed 5), y ~ loc + N(0, sigma_idx); z[128,4,4,192] ~ N(0, s_c) coded by the batched model (NoisyLaplace)."""
+  import torch
+  import compression_b200 as tfc
+  C3, num_scales, smin, smax = 192, 64, .11, 256.
+  off3, fac3 = np.log(smin), (np.log(smax) - np.log(smin)) / (num_scales - 1.)
+  scale_fn = lambda i: torch.exp(off3 + fac3 * i)
+  em_y = tfc.LocationScaleIndexedEntropyModel(tfc.NoisyNormal, num_scales, scale_fn, coding_rank=3, compression=True)
+  g = torch.Generator().manual_seed(5)
+  idx = torch.rand(batch, 16, 16, C3, generator=g) * num_scales
+  sig = scale_fn(torch.clamp(idx, 0, num_scales - 1).to(torch.int32).float())
+  loc = torch.randn(batch, 16, 16, C3, generator=g)
+  y = loc + sig * torch.randn(batch, 16, 16, C3, generator=g)
+  zs = torch.exp(torch.linspace(np.log(0.5), np.log(6.0), C3))
+  em_z = tfc.ContinuousBatchedEntropyModel(tfc.NoisyLaplace(loc=torch.zeros_like(zs), scale=zs), coding_rank=3,
+                                           compression=True).to(dev)
+  z = torch.randn(batch, 4, 4, C3, generator=g) * zs
+  return dict(em_y=em_y, em_z=em_z, y=y.to(dev), idx=idx.to(dev), loc=loc.to(dev), z=z.to(dev),
+              workload="bmshj2018 two-level: y[128,16,16,192] indexed NoisyNormal (64 scales up to sigma=256, "
+                       "loc) + z[128,4,4,192] batched NoisyLaplace; 128 streams each")
+
+
+def cfg1_workload(per_channel):
+  """cfg1 exactly as SURVEY.md 8(d): one image of 32 768 int16 symbols, legacy op shapes data[1,16,16,128] with
+  cdf[1,1,1,1,65] or cdf[1,1,1,128,65]; 64-bin discretised Laplace/Gaussian PMFs integerised at precision 14 by the
+  oracle's PerShard; symbols drawn from the PMF (torch.manual_seed(0))."""
+  import torch
+  import oracle
+  torch.manual_seed(0)
+  rows = 128 if per_channel else 1
+  k = np.arange(64) - 31.5
+  pmfs = []
+  for r in range(rows):
+    s = 2.0 + 10.0 * r / max(rows - 1, 1)
+    w = np.exp(-np.abs(k) / s) if r % 2 == 0 else np.exp(-0.5 * (k / s)**2)
+    pmfs.append((w / w.sum()).astype(np.float32))
+  pmf = np.stack(pmfs)
+  cdf = oracle.port().pmf_to_cdf(pmf, 14)                       # [rows, 65]
+  p = torch.from_numpy(np.diff(cdf, axis=-1).astype(np.float64))
+  data = torch.multinomial(p / p.sum(-1, keepdim=True), 256 * (128 // rows), replacement=True)  # [rows, n]
+  data = data.t().reshape(1, 16, 16, 128).to(torch.int16).numpy() if per_channel else \
+      data.reshape(1, 16, 16, 128).to(torch.int16).numpy()
+  cshape = (1, 1, 1, 128, 65) if per_channel else (1, 1, 1, 1, 65)
+  return data, cdf.reshape(cshape).astype(np.int32), 14
+
+
+def symbols_of(cdf_offset, qoff, y):
+  """Host int32 symbols exactly as ContinuousBatchedEntropyModel.compress derives them
+  (continuous_batched.py:375-380)."""
+  import torch
+  b = y if qoff is None else y - torch.as_tensor(qoff)
+  sym = torch.round(b).to(torch.int32) - torch.as_tensor(cdf_offset, dtype=torch.int32)
+  return sym.reshape(y.shape[0], -1).numpy()
+
+
+def load_fixture():
+  """cfg2 tables written once from the product's table builder (tools/make_cfg_fixtures.py)."""
+  if not os.path.exists(FIXTURE):
+    return None
+  z = np.load(FIXTURE)
+  return dict(lookup=z["lookup"], cdf_offset=z["cdf_offset"],
+              qoff=(z["quantization_offset"] if z["has_qoff"] else None))
+
+
+def stand_in_tables(scales):
+  """Only when the fixture is missing: Laplace tables of the same widths from tests/util.py."""
+  sys.path.insert(0, os.path.join(ROOT, "tests"))
+  import util
+  cdfs = [util.laplace_cdf(2 * int(6 * s + 3) + 1, CFG["precision"], float(s)) for s in scales]
+  lookup = util.make_lookup_1d(cdfs, [CFG["precision"]] * len(cdfs), [True] * len(cdfs))
+  off = -np.asarray([(len(c) - 1) // 2 for c in cdfs], np.int32)
+  return dict(lookup=lookup, cdf_offset=off, qoff=None)
+
+
+# ------------------------------------------------------------------------------------------------
+# Host placement, clocks
+# ------------------------------------------------------------------------------------------------
+def pin_to_gpu_numa_node(dev_index):
+  """Pins the process (and the threads it spawns later) to the CPUs of the GPU's NUMA node: the H2D/D2H copies
+  and the launch thread then do not cross the socket interconnect.  Best effort; returns what was done."""
+  try:
+    import torch
+    p = torch.cuda.get_device_properties(dev_index)
+    bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+    with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+      node = int(f.read())
+    if node < 0:
+      return {"node": node, "pinned": False}
+    with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+      cpus = set()
+      for part in f.read().strip().split(","):
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    cpus &= os.sched_getaffinity(0)
+    if not cpus:
+      return {"node": node, "pinned": False}
+    os.sched_setaffinity(0, cpus)
+    return {"node": node, "pinned": True, "cpus": len(cpus)}
+  except Exception as e:  # pylint:disable=broad-except
+    return {"pinned": False, "why": repr(e)[:80]}
+
+
+def physical_cores():
+  try:
+    seen = set()
+    phys = core = None
+    with open("/proc/cpuinfo") as f:
+      for line in f:
+        if line.startswith("physical id"):
+          phys = line.split(":")[1].strip()
+        elif line.startswith("core id"):
+          core = line.split(":")[1].strip()
+        elif not line.strip():
+          if phys is not None and core is not None:
+            seen.add((phys, core))
+          phys = core = None
+    return len(seen) or (os.cpu_count() or 1)
+  except Exception:  # pylint:disable=broad-except
+    return os.cpu_count() or 1
+
+
 class ClockSampler:
-  """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+  """Samples SM clocks / throttle reasons while the timed region runs (in-process NVML, else nvidia-smi)."""
   Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -80,7 +221,6 @@ class ClockSampler:
     self._t = threading.Thread(target=self._run, daemon=True)
 
   def _run_nvml(self):
-    """In-process NVML sampling (no nvidia-smi process per sample: those perturb the timed region)."""
     import pynvml
     pynvml.nvmlInit()
     h = None
@@ -135,73 +275,154 @@ class ClockSampler:
             "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_reference(value, lookup, threads, repeats=3):
-  """Times the reference CPU range coder (EntropyEncodeChannel + Finalize) on int32 symbols."""
+# ------------------------------------------------------------------------------------------------
+# CPU legs (the only places that execute oracle/)
+# ------------------------------------------------------------------------------------------------
+def cpu_coder_times(value, lookup, threads, repeats=5, decode=True):
+  """Median Msymbols/s of the reference CPU coder (EntropyEncodeChannel + Finalize, and CreateRangeDecoder +
+  EntropyDecodeChannel + Finalize) over `repeats` runs after one warm-up; the worker pool persists."""
   import oracle
   O = oracle.best()
   S, N = value.shape
-  best = None
-  for _ in range(repeats):
+  enc_t, dec_t, strings = [], [], None
+  for i in range(repeats + 1):
     enc = O.encoder(lookup, S)
     t0 = time.perf_counter()
     enc.encode(value, None, threads)
-    enc.finalize()
+    strings = enc.finalize()
     dt = time.perf_counter() - t0
     enc.close()
-    best = dt if best is None else min(best, dt)
-  return S * N / best / 1e6, O.kind
+    if i:
+      enc_t.append(dt)
+  if decode:
+    for i in range(repeats + 1):
+      t0 = time.perf_counter()
+      dec = O.decoder(strings, lookup)
+      out = dec.decode(N, None, threads)
+      dec.finalize()
+      dt = time.perf_counter() - t0
+      dec.close()
+      if i:
+        dec_t.append(dt)
+    assert np.array_equal(out, value)
+  f = lambda ts: {"median": S * N / float(np.median(ts)) / 1e6, "min": S * N / max(ts) / 1e6,
+                  "max": S * N / min(ts) / 1e6} if ts else None
+  return f(enc_t), f(dec_t), O.kind
 
 
-def symbols_of(model, y):
-  """Host int32 symbols exactly as ContinuousBatchedEntropyModel.compress derives them."""
+def cpu_gdn_baseline(C=192, n_pix=262144, repeats=3):
+  """PyTorch-CPU fp32 GDN (abs -> matmul -> + beta -> div) on all host threads; GB/s on the
+  same algorithmic-bytes scale as the GPU numbers (8 B/element)."""
   import torch
-  q = model.quantization_offset
-  b = y if q is None else y - q.cpu()
-  sym = torch.round(b).to(torch.int32) - model.cdf_offset.cpu()
-  return sym.reshape(y.shape[0], -1).numpy()
+  g = torch.Generator().manual_seed(4)
+  gamma = 0.1 * torch.eye(C) + (0.02 * torch.randn(C, C, generator=g)).abs()
+  beta = 1 + 0.5 * torch.rand(C, generator=g)
+  x = torch.randn(n_pix, C, generator=g)
+  ts = []
+  for i in range(repeats + 1):
+    t0 = time.perf_counter()
+    y = x / (x.abs() @ gamma + beta)
+    dt = time.perf_counter() - t0
+    if i:
+      ts.append(dt)
+  del y
+  gbs = 8.0 * n_pix * C / float(np.median(ts)) / 1e9
+  return {"fwd_GBps": gbs, "threads": torch.get_num_threads(), "sample": f"[{n_pix},{C}] fp32, median of {repeats}"}
+
+
+def warm_oracle_pool():
+  """Creates the oracle's persistent workers now (unpinned, one per host thread), with a trivial job."""
+  import oracle
+  cores = os.cpu_count() or 1
+  lookup = np.asarray([4, 0, 8, 16], np.int32)
+  oracle.best().encode(lookup, np.zeros((cores, 1), np.int32), None, cores)
 
 
 def run_reference(args):
-  """--impl reference: rank 0 only; every step codes the full cfg2 batch on the host cores."""
+  """--impl reference: rank 0 only; every step codes the full cfg2 batch on the host cores.  Never imports
+  compression_b200: tables come from the committed fixture."""
   rank = int(os.environ.get("RANK", "0"))
   if rank != 0:
     return
-  import torch
   import oracle
   scales, ys = synth_latents(0, 1)
   cores = os.cpu_count() or 1
-  # tables: build on the GPU when there is one (same tables as the main arm), else a Laplace stand-in
-  if torch.cuda.is_available():
-    model = build_model(scales, "cuda")
-    lookup = model.cdf.cpu().numpy()
-    value = symbols_of(model, ys[0])
-  else:
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import util
-    cdfs = [util.laplace_cdf(2 * int(6 * s + 3) + 1, CFG["precision"], float(s)) for s in scales]
-    lookup = util.make_lookup_1d(cdfs, [CFG["precision"]] * len(cdfs), [True] * len(cdfs))
-    off = np.asarray([(len(c) - 1) // 2 for c in cdfs], np.int32)
-    value = (torch.round(ys[0]).to(torch.int32).reshape(CFG["batch"], -1).numpy() +
-             np.tile(off, CFG["hw"] * CFG["hw"])).astype(np.int32)
+  tab = load_fixture()
+  tables = "tests/golden/cfg2_tables.npz (product table builder)"
+  if tab is None:
+    tab, tables = stand_in_tables(scales), "stand-in Laplace tables (fixture missing)"
+  value = symbols_of(tab["cdf_offset"], tab["qoff"], ys[0])
+  lookup = tab["lookup"]
   O = oracle.best()
   S, N = value.shape
-  for _ in range(args.warmup):
-    e = O.encoder(lookup, S); e.encode(value, None, cores); e.finalize(); e.close()
-  t0 = time.perf_counter()
-  for _ in range(args.steps):
-    e = O.encoder(lookup, S); e.encode(value, None, cores); e.finalize(); e.close()
-  dt = time.perf_counter() - t0
+
+  def one():
+    e = O.encoder(lookup, S)
+    e.encode(value, None, cores)
+    e.finalize()
+    e.close()
+
+  for _ in range(max(args.warmup, 1)):
+    one()
+  # the K-step region, repeated: the line's value is the median region
+  regions = []
+  for _ in range(E2E_REPEATS):
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+      one()
+    regions.append(time.perf_counter() - t0)
+  dt = float(np.median(regions))
   val = S * N * args.steps / dt / 1e6
-  sample = f"full cfg2 batch ({S} streams x {N} int32 symbols) per step; EntropyEncodeChannel+Finalize only"
+  spread = {"min": S * N * args.steps / max(regions) / 1e6, "max": S * N * args.steps / min(regions) / 1e6,
+            "repeats": len(regions)}
+  sample = (f"full cfg2 batch ({S} streams x {N} int32 symbols) per step; EntropyEncodeChannel+Finalize only; "
+            f"persistent pool of {cores} threads; median of {len(regions)} regions of {args.steps} steps")
   print(json.dumps({
-      "impl": "reference", "metric": "range-code throughput (bls2017 compress path, cfg2)", "value": val,
-      "unit": "Msymbols/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+      "impl": "reference", "metric": METRIC, "value": val,
+      "unit": "Msymbols/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1),
       "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
       "dtype": "u32", "data": "synthetic",
-      "config": {"workload": "cfg2: bls2017 compress, y[256,16,16,128], 256 streams x 32768 symbols, 128 tables"},
+      "config": {"workload": WORKLOAD, "tables": tables},
+      "spread": spread,
       "cpu_baseline": {"value": val, "unit": "Msymbols/s", "cores": cores, "kind": O.kind, "sample": sample},
       "e2e": {"value": val, "unit": "Msymbols/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
   }))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def _time_ms(fn, reps, warm=1):
+  import torch
+  for _ in range(warm):
+    fn()
+  a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  torch.cuda.synchronize()
+  a.record()
+  for _ in range(reps):
+    out = fn()
+  b.record()
+  torch.cuda.synchronize()
+  return a.elapsed_time(b) / reps, out
+
+
+def parity_check(model, y_host, strings, threads):
+  """One batch against the oracle: same bytes, oracle decodes ours, we decode the oracle's."""
+  import torch
+  import oracle
+  O = oracle.best()
+  lookup = model._lookup_host()
+  q = model.quantization_offset
+  value = symbols_of(model.cdf_offset.cpu().numpy(), None if q is None else q.cpu(), y_host)
+  want = O.encode(lookup, value, None, threads)
+  got = strings.tolist()
+  same = got == want
+  back, ok = O.decode(lookup, got, value.shape[1], None, threads)
+  cross1 = bool(np.array_equal(back, value) and ok.all())
+  dec = model.decompress(want, (CFG["hw"], CFG["hw"]))
+  cross2 = bool(torch.equal(dec.cpu(), model.quantize(y_host)))
+  return bool(same and cross1 and cross2), {"bytes_equal": bool(same), "oracle_decodes_gpu": cross1,
+                                           "gpu_decodes_oracle": cross2, "oracle": O.kind}
 
 
 def main():
@@ -210,7 +431,7 @@ def main():
   ap.add_argument("--steps", type=int, default=200)
   ap.add_argument("--warmup", type=int, default=5)
   ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-  ap.add_argument("--no-extras", action="store_true", help="skip the decode / GDN / CPU-baseline side measurements")
+  ap.add_argument("--no-extras", action="store_true", help="skip the decode / GDN / cfg3 / model-path / CPU side measurements")
   args = ap.parse_args()
   if args.impl == "reference":
     return run_reference(args)
@@ -218,7 +439,7 @@ def main():
   import torch
   import torch.distributed as dist
   import compression_b200 as tfc
-  from compression_b200 import _lib, functional, gen_ops
+  from compression_b200 import _lib, functional, gen_ops, sharding
 
   rank = int(os.environ.get("RANK", "0"))
   world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -226,6 +447,8 @@ def main():
   assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
   torch.cuda.set_device(local)
   dev = torch.device("cuda", local)
+  warm_oracle_pool()                      # before pinning: the checker's workers keep the whole machine
+  numa = pin_to_gpu_numa_node(local)
   if world > 1:
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     dist.init_process_group("nccl", device_id=dev)
@@ -233,7 +456,6 @@ def main():
   n_rot = CFG["n_rot"]
   scales, ys_host = synth_latents(rank, n_rot)
   # rank 0 builds the tables; everyone else receives them (the only collective on the path)
-  from compression_b200 import sharding
   if rank == 0:
     model = build_model(scales, dev)
   else:
@@ -255,33 +477,50 @@ def main():
     if world > 1:
       dist.barrier()
 
+  def allmax(ms):
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
   for i in range(max(args.warmup, 3)):
     strings = step(i)
   barrier()
   bits_per_symbol = 8.0 * strings.nbytes() / sym_per_step
 
+  # ---- parity, outside the timed region: every rank, its own first batch, byte for byte against the oracle ----
+  threads = max(1, (os.cpu_count() or 1) // world)
+  ok, parity = parity_check(model, ys_host[0], model.compress(ys[0]), threads)
+  flag = torch.tensor([1 if ok else 0], device=dev)
+  if world > 1:
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+  parity["all_ranks"] = bool(flag.item())
+  fixture = load_fixture()
+  tables_match = None if fixture is None else bool(np.array_equal(fixture["lookup"], model._lookup_host()))
+
   # ---- the timed region: exactly K steps, CUDA events, max over ranks ----
+  def timed_region(k):
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(k):
+      step(i)
+    ev1.record()
+    barrier()
+    return allmax(ev0.elapsed_time(ev1))
+
   launches0 = _lib.launch_count()
-  ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   # clocks are sampled by rank 0 only (its own GPU, in-process NVML): one sampler per rank disturbed the others
   clocks = ClockSampler(local, str(torch.cuda.get_device_properties(dev).uuid)) if rank == 0 else None
   if clocks:
     clocks.__enter__()
-  barrier()
-  ev0.record()
-  for i in range(args.steps):
-    strings = step(i)
-  ev1.record()
-  barrier()
+  elapsed_ms = timed_region(args.steps)
   if clocks:
     clocks.__exit__()
-  elapsed_ms = ev0.elapsed_time(ev1)
   launches = _lib.launch_count() - launches0
-  t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
-  if world > 1:
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-  elapsed_ms = float(t.item())
   value = world * sym_per_step * args.steps / (elapsed_ms * 1e-3) / 1e6
+  more = [timed_region(args.steps) for _ in range(4)]   # informational spread of the same region
+  vals = sorted(world * sym_per_step * args.steps / (m * 1e-3) / 1e6 for m in [elapsed_ms] + more)
 
   # ---- e2e: pinned host y -> H2D -> compress -> D2H(bytes, offsets), same K steps ----
   # Two staging buffers and a copy stream: the H2D copy of batch i+1 runs while batch i is encoded (compress()
@@ -322,210 +561,199 @@ def main():
     return nb
 
   e2e_run(3)
-  barrier()
-  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-  e0.record()
-  nb = e2e_run(args.steps)
-  e1.record()
-  barrier()
-  e2e_ms = e0.elapsed_time(e1)
-  t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-  if world > 1:
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-  e2e_value = world * sym_per_step * args.steps / (float(t.item()) * 1e-3) / 1e6
+  e2e_ms = []
+  for _ in range(E2E_REPEATS):
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    nb = e2e_run(args.steps)
+    e1.record()
+    barrier()
+    e2e_ms.append(allmax(e0.elapsed_time(e1)))
+  to_val = lambda ms: world * sym_per_step * args.steps / (ms * 1e-3) / 1e6
+  e2e_value = to_val(float(np.median(e2e_ms)))
 
   result = {
-      "metric": "range-code throughput (bls2017 compress path, cfg2)",
+      "metric": METRIC,
       "value": value, "unit": "Msymbols/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
       "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
       "dtype": "u32", "data": "synthetic",
       "config": {
-          "workload": "cfg2: bls2017 compress, y[256,16,16,128] fp32 per GPU, 256 streams x 32768 symbols, "
-                      "128 NoisyLaplace channel tables, precision 12, overflow on; step = fused quantise + "
-                      "range-encode + finalize/pack",
+          "workload": WORKLOAD,
           "bits_per_symbol": round(bits_per_symbol, 4), "streams_per_gpu": S, "symbols_per_stream": N,
           "l2": f"inputs rotate over {n_rot} distinct batches ({n_rot * 33.5:.0f} MB > 126 MB L2)",
           "parallelism": f"batch-shard x{world}, tables broadcast from rank 0",
+          "tables_match_fixture": tables_match,
       },
+      "value_repeats": {"median": float(np.median(vals)), "min": vals[0], "max": vals[-1], "regions": len(vals)},
       "e2e": {"value": e2e_value, "unit": "Msymbols/s", "h2d_bytes_per_step": int(world * ys[0].numel() * 4),
               "d2h_bytes_per_step": int(world * (nb + 8 * (S + 1))),
-              "note": "bytes summed over all ranks; H2D of batch i+1 overlaps the encode of batch i (2 staging buffers)"},
+              "min": to_val(max(e2e_ms)), "max": to_val(min(e2e_ms)), "repeats": len(e2e_ms),
+              "note": "median of the repeated K-step region; bytes summed over all ranks; H2D of batch i+1 overlaps "
+                      "the encode of batch i (2 staging buffers)"},
       "gpu_launches": int(launches),
+      "parity_checked": parity["all_ranks"], "parity": parity,
+      "numa": numa,
   }
 
   if rank == 0:
     result["clocks"] = clocks.summary()
 
   if rank == 0 and not args.no_extras:
-    peak, peak_src = _peaks()
-    # --- dominant kernel of the step: the encode kernel, timed alone with events on the launch stream
-    coff = model.cdf_offset.reshape(-1)
-    qoff = model.quantization_offset
-    lookup = model._lookup_host()
-    times = []
-    for i in range(6):
-      h = gen_ops.create_range_encoder([S], lookup)
-      torch.cuda.synchronize()
-      a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-      a.record()
-      functional.encode_channel_f32(h, ys[i % n_rot], qoff, coff)
-      b.record()
-      torch.cuda.synchronize()
-      times.append(a.elapsed_time(b))
-      h.close()
-    enc_ms = float(np.median(times[1:]))
-    alg_bytes = sym_per_step * 4 + strings.nbytes()
-    achieved = alg_bytes / (enc_ms * 1e-3) / 1e9
-    traffic = None
-    prof = os.path.join(ROOT, "profiles", "encode_kernel_traffic.json")
-    if os.path.exists(prof):
-      with open(prof) as f:
-        traffic = json.load(f).get("dram_bytes_per_launch")
-    result["roofline"] = {
-        "kernel": "encode_kernel (fused quantise + range encode; one CTA per stream: gather, chain and drain warps)", "bound": "hbm",
-        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-        "peak_source": peak_src, "kernel_ms": enc_ms, "algorithmic_bytes": alg_bytes,
-        "kernel_msym_s": sym_per_step / (enc_ms * 1e-3) / 1e6,
-        "note": "latency-bound serial recurrence per stream (256 warps on 148 SMs); HBM fraction is small by construction",
-    }
-    # --- decode path (create + fused decode/dequantise + finalize), same strings
-    strings = model.compress(ys[0])
-    for _ in range(2):
-      out = model.decompress(strings, (CFG["hw"], CFG["hw"]))
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = max(3, min(args.steps, 10))
-    a.record()
-    for _ in range(reps):
-      out = model.decompress(strings, (CFG["hw"], CFG["hw"]))
-    b.record()
-    torch.cuda.synchronize()
-    dec_ms = a.elapsed_time(b) / reps
-    ok = bool(torch.equal(out, model.quantize(ys[0])))
-    result["decode"] = {"value": sym_per_step / (dec_ms * 1e-3) / 1e6, "unit": "Msymbols/s", "ms_per_step": dec_ms,
-                        "roundtrip_equals_quantize": ok}
-    # --- configs[2]: bmshj2018 hyperprior, batch 128 of 256x256 images: y[128,16,16,192] coded with the indexed
-    #     NoisyNormal model (64 scales, per-element index + mean), z[128,4,4,192] with the batched model
     try:
-      B3, C3 = 128, 192
-      num_scales, smin, smax = 64, .11, 256.
-      off3, fac3 = np.log(smin), (np.log(smax) - np.log(smin)) / (num_scales - 1.)
-      scale_fn = lambda i: torch.exp(off3 + fac3 * i)
-      em_y = tfc.LocationScaleIndexedEntropyModel(tfc.NoisyNormal, num_scales, scale_fn, coding_rank=3, compression=True)
-      g3 = torch.Generator(device=dev).manual_seed(7)
-      idx3 = torch.rand(B3, 16, 16, C3, device=dev, generator=g3) * 40.0
-      sig3 = scale_fn(torch.clamp(idx3, 0, num_scales - 1).to(torch.int32).float())
-      loc3 = torch.randn(B3, 16, 16, C3, device=dev, generator=g3)
-      y3 = loc3 + sig3 * torch.randn(B3, 16, 16, C3, device=dev, generator=g3)
-      zs = torch.exp(torch.linspace(np.log(0.5), np.log(6.0), C3))
-      em_z = tfc.ContinuousBatchedEntropyModel(tfc.NoisyLaplace(loc=torch.zeros_like(zs), scale=zs), coding_rank=3,
-                                               compression=True).to(dev)
-      z3 = (torch.randn(B3, 4, 4, C3, device=dev, generator=g3) * zs.to(dev))
-      def enc3():
-        return em_z.compress(z3), em_y.compress(y3, idx3, loc=loc3)
-      sz, sy = enc3()
-      def dec3():
-        return em_z.decompress(sz, (4, 4)), em_y.decompress(sy, idx3, loc=loc3)
-      res3 = {}
-      for name, fn in (("encode", enc3), ("decode", dec3)):
-        fn(); torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(10):
-          out3 = fn()
-        b.record()
-        torch.cuda.synchronize()
-        ms = a.elapsed_time(b) / 10
-        nsym = y3.numel() + z3.numel()
-        res3[name] = {"ms_per_step": ms, "value": nsym / (ms * 1e-3) / 1e6, "unit": "Msymbols/s"}
-      zhat, yhat = out3
-      res3["roundtrip_equals_quantize"] = bool(torch.equal(yhat, em_y.quantize(y3, loc3)) and torch.equal(zhat, em_z.quantize(z3)))
-      res3["bits_per_symbol_y"] = 8.0 * sy.nbytes() / y3.numel()
-      res3["workload"] = "bmshj2018 two-level: y[128,16,16,192] indexed NoisyNormal (64 scales, loc) + z[128,4,4,192] batched NoisyLaplace; 128 streams each"
-      result["cfg3_bmshj2018"] = res3
+      extras(result, model, ys, ys_host, strings, dev, args, sym_per_step, S, N)
     except Exception as e:  # pylint:disable=broad-except
-      result["cfg3_bmshj2018"] = {"error": repr(e)}
-    # --- GDN at the two analysis-transform shapes of cfg2 (forward) and backward at the first
-    gdn = {}
-    gamma = (0.1 * torch.eye(128) + (0.02 * torch.randn(128, 128)).abs()).to(dev)
-    beta = (1 + 0.5 * torch.rand(128)).to(dev)
-    for name, npix in (("gdn_0 [256,64,64,128]", 256 * 64 * 64), ("gdn_1 [256,32,32,128]", 256 * 32 * 32)):
-      x = torch.randn(npix, 128, device=dev)
-      for _ in range(2):
-        functional.gdn_forward(x, gamma, beta)
-      a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-      a.record()
-      for _ in range(5):
-        functional.gdn_forward(x, gamma, beta)
-      b.record()
-      torch.cuda.synchronize()
-      ms = a.elapsed_time(b) / 5
-      gbs = 8.0 * npix * 128 / (ms * 1e-3) / 1e9
-      gdn[name] = {"fwd_ms": ms, "fwd_GBps": gbs, "fwd_frac_of_hbm_peak": gbs / peak}
-      if npix == 256 * 64 * 64:
-        dy = torch.randn_like(x)
-        functional.gdn_backward(x, gamma, beta, dy)
-        a.record()
-        for _ in range(3):
-          functional.gdn_backward(x, gamma, beta, dy)
-        b.record()
-        torch.cuda.synchronize()
-        ms = a.elapsed_time(b) / 3
-        gbs = 12.0 * npix * 128 / (ms * 1e-3) / 1e9
-        gdn[name].update({"bwd_ms": ms, "bwd_GBps": gbs, "bwd_frac_of_hbm_peak": gbs / peak})
-      del x
-    # --- configs[3]: GDN microbench, 192 channels, 64x64 tiles (batch 4096 if memory allows, else 1024)
-    try:
-      free_b, _ = torch.cuda.mem_get_info(dev)
-      batch4 = 4096 if free_b > 90e9 else 1024
-      npix = batch4 * 64 * 64
-      gamma192 = (0.1 * torch.eye(192) + (0.02 * torch.randn(192, 192)).abs()).to(dev)
-      beta192 = (1 + 0.5 * torch.rand(192)).to(dev)
-      x = torch.randn(npix, 192, device=dev) * (0.05 + 3.95 * torch.rand(192, device=dev))  # SURVEY 8(d) cfg4 recipe
-      functional.gdn_forward(x, gamma192, beta192)
-      a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-      a.record()
-      for _ in range(3):
-        functional.gdn_forward(x, gamma192, beta192)
-      b.record()
-      torch.cuda.synchronize()
-      ms = a.elapsed_time(b) / 3
-      gbs = 8.0 * npix * 192 / (ms * 1e-3) / 1e9
-      entry = {"fwd_ms": ms, "fwd_GBps": gbs, "fwd_frac_of_hbm_peak": gbs / peak, "fwd_kernel": "tcgen05 (gdn_tc_fwd3_kernel<192>)"}
-      dy = torch.randn_like(x)
-      functional.gdn_backward(x, gamma192, beta192, dy)
-      a.record()
-      functional.gdn_backward(x, gamma192, beta192, dy)
-      b.record()
-      torch.cuda.synchronize()
-      ms = a.elapsed_time(b)
-      gbs = 12.0 * npix * 192 / (ms * 1e-3) / 1e9
-      entry.update({"bwd_ms": ms, "bwd_GBps": gbs, "bwd_frac_of_hbm_peak": gbs / peak, "bwd_kernel": "tcgen05, two kernels (gdn_tc_bwd_dx_kernel<192> + gdn_tc_bwd_dgamma_kernel<192>)"})
-      gdn[f"cfg4 [{batch4},64,64,192]"] = entry
-      del x, dy
-    except Exception as e:  # pylint:disable=broad-except
-      gdn["cfg4 [4096,64,64,192]"] = {"error": repr(e)}
-    result["gdn"] = gdn
-    # --- CPU baseline: the reference's own range coder on this box's host cores (bounded: one batch)
-    try:
-      value_host = symbols_of(model, ys_host[0])
-      cores = os.cpu_count() or 1
-      all_cores, kind = cpu_reference(value_host, lookup, cores)
-      one_core, _ = cpu_reference(value_host[:16], lookup, 1, repeats=2)
-      result["cpu_baseline"] = {
-          "value": all_cores, "unit": "Msymbols/s", "cores": cores, "kind": kind,
-          "sample": f"one full cfg2 batch ({S} streams x {N} int32 symbols), EntropyEncodeChannel+Finalize, "
-                    f"best of 3, streams sharded over {cores} threads",
-          "single_core_value": one_core, "single_core_sample": "16 streams x 32768 symbols, 1 thread",
-      }
-    except Exception as e:  # pylint:disable=broad-except
-      result["cpu_baseline"] = {"error": repr(e)}
+      result["extras_error"] = repr(e)
 
   if rank == 0:
     print(json.dumps(result))
   if world > 1:
     dist.barrier()
     dist.destroy_process_group()
+
+
+def extras(result, model, ys, ys_host, strings, dev, args, sym_per_step, S, N):
+  """Side measurements of the same run (rank 0): dominant-kernel roofline, decode, cfg3, GDN, model path, CPU."""
+  import torch
+  import compression_b200 as tfc
+  from compression_b200 import functional, gen_ops
+  n_rot = CFG["n_rot"]
+  peak, peak_src = _peaks()
+  # --- dominant kernel of the step: the encode kernel, timed alone with events on the launch stream
+  coff = model.cdf_offset.reshape(-1)
+  qoff = model.quantization_offset
+  lookup = model._lookup_host()
+  times = []
+  for i in range(8):
+    h = gen_ops.create_range_encoder([S], lookup)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    functional.encode_channel_f32(h, ys[i % n_rot], qoff, coff)
+    b.record()
+    torch.cuda.synchronize()
+    times.append(a.elapsed_time(b))
+    h.close()
+  enc_ms = float(np.median(times[2:]))
+  alg_bytes = sym_per_step * 4 + strings.nbytes()
+  achieved = alg_bytes / (enc_ms * 1e-3) / 1e9
+  traffic, traffic_note = None, "no ncu capture of this build of the kernel"
+  prof = os.path.join(ROOT, "profiles", "encode_kernel_traffic.json")
+  if os.path.exists(prof):
+    import hashlib
+    with open(prof) as f:
+      tj = json.load(f)
+    src = os.path.join(ROOT, "compression_b200", "csrc", "range_coder.cu")
+    cur = hashlib.sha256(open(src, "rb").read()).hexdigest()[:16] if os.path.exists(src) else None
+    if tj.get("source_sha256_16") == cur:
+      traffic, traffic_note = tj.get("dram_bytes_per_launch"), tj.get("note", "ncu --set full capture of this build")
+    else:
+      traffic_note = "profiles/encode_kernel_traffic.json was captured on another build of range_coder.cu: not reported"
+  sm_clock = (result.get("clocks") or {}).get("sm_mhz") or 1965
+  result["roofline"] = {
+      "kernel": "encode_kernel (fused quantise + range encode; gather / chain / drain warps per stream)", "bound": "hbm",
+      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+      "traffic_note": traffic_note,
+      "peak_source": peak_src, "kernel_ms": enc_ms, "algorithmic_bytes": alg_bytes,
+      "kernel_msym_s": sym_per_step / (enc_ms * 1e-3) / 1e6,
+      "chain_cycles_per_symbol": enc_ms * 1e-3 * sm_clock * 1e6 / N,
+      "note": "latency-bound serial recurrence per stream (256 streams on 148 SMs); the HBM fraction is small by "
+              "construction, chain_cycles_per_symbol is the figure that bounds it",
+  }
+  # --- decode path (create + fused decode/dequantise + finalize), same strings
+  strings = model.compress(ys[0])
+  dec_ms, out = _time_ms(lambda: model.decompress(strings, (CFG["hw"], CFG["hw"])), max(3, min(args.steps, 10)), warm=2)
+  result["decode"] = {"value": sym_per_step / (dec_ms * 1e-3) / 1e6, "unit": "Msymbols/s", "ms_per_step": dec_ms,
+                      "roundtrip_equals_quantize": bool(torch.equal(out, model.quantize(ys[0])))}
+  # --- configs[2]: bmshj2018 hyperprior, both levels, encode and decode
+  try:
+    w = cfg3_workload(dev)
+    em_y, em_z, y3, idx3, loc3, z3 = (w[k] for k in ("em_y", "em_z", "y", "idx", "loc", "z"))
+    enc3 = lambda: (em_z.compress(z3), em_y.compress(y3, idx3, loc=loc3))
+    sz, sy = enc3()
+    dec3 = lambda: (em_z.decompress(sz, (4, 4)), em_y.decompress(sy, idx3, loc=loc3))
+    res3 = {}
+    nsym = y3.numel() + z3.numel()
+    for name, fn in (("encode", enc3), ("decode", dec3)):
+      ms, out3 = _time_ms(fn, 10)
+      res3[name] = {"ms_per_step": ms, "value": nsym / (ms * 1e-3) / 1e6, "unit": "Msymbols/s"}
+    zhat, yhat = out3
+    res3["roundtrip_equals_quantize"] = bool(torch.equal(yhat, em_y.quantize(y3, loc3)) and torch.equal(zhat, em_z.quantize(z3)))
+    res3["bits_per_symbol_y"] = 8.0 * sy.nbytes() / y3.numel()
+    res3["workload"] = w["workload"]
+    result["cfg3_bmshj2018"] = res3
+    del w, y3, idx3, loc3, z3
+  except Exception as e:  # pylint:disable=broad-except
+    result["cfg3_bmshj2018"] = {"error": repr(e)}
+  # --- GDN at the two analysis-transform shapes of cfg2 (forward) and backward at the first
+  gdn = {}
+  gamma = (0.1 * torch.eye(128) + (0.02 * torch.randn(128, 128)).abs()).to(dev)
+  beta = (1 + 0.5 * torch.rand(128)).to(dev)
+  for name, npix in (("gdn_0 [256,64,64,128]", 256 * 64 * 64), ("gdn_1 [256,32,32,128]", 256 * 32 * 32)):
+    x = torch.randn(npix, 128, device=dev)
+    ms, _ = _time_ms(lambda: functional.gdn_forward(x, gamma, beta), 5, warm=2)
+    gbs = 8.0 * npix * 128 / (ms * 1e-3) / 1e9
+    gdn[name] = {"fwd_ms": ms, "fwd_GBps": gbs, "fwd_frac_of_hbm_peak": gbs / peak}
+    if npix == 256 * 64 * 64:
+      dy = torch.randn_like(x)
+      ms, _ = _time_ms(lambda: functional.gdn_backward(x, gamma, beta, dy), 3)
+      gbs = 12.0 * npix * 128 / (ms * 1e-3) / 1e9
+      gdn[name].update({"bwd_ms": ms, "bwd_GBps": gbs, "bwd_frac_of_hbm_peak": gbs / peak})
+      del dy
+    del x
+  # --- configs[3]: GDN microbench, 192 channels, 64x64 tiles (batch 4096 if memory allows, else 1024)
+  try:
+    free_b, _ = torch.cuda.mem_get_info(dev)
+    batch4 = 4096 if free_b > 90e9 else 1024
+    npix = batch4 * 64 * 64
+    gamma192 = (0.1 * torch.eye(192) + (0.02 * torch.randn(192, 192)).abs()).to(dev)
+    beta192 = (1 + 0.5 * torch.rand(192)).to(dev)
+    x = torch.randn(npix, 192, device=dev) * (0.05 + 3.95 * torch.rand(192, device=dev))  # SURVEY 8(d) cfg4 recipe
+    ms, _ = _time_ms(lambda: functional.gdn_forward(x, gamma192, beta192), 3)
+    gbs = 8.0 * npix * 192 / (ms * 1e-3) / 1e9
+    entry = {"fwd_ms": ms, "fwd_GBps": gbs, "fwd_frac_of_hbm_peak": gbs / peak}
+    dy = torch.randn_like(x)
+    ms, _ = _time_ms(lambda: functional.gdn_backward(x, gamma192, beta192, dy), 2)
+    gbs = 12.0 * npix * 192 / (ms * 1e-3) / 1e9
+    entry.update({"bwd_ms": ms, "bwd_GBps": gbs, "bwd_frac_of_hbm_peak": gbs / peak})
+    gdn[f"cfg4 [{batch4},64,64,192]"] = entry
+    del x, dy
+  except Exception as e:  # pylint:disable=broad-except
+    gdn["cfg4 [4096,64,64,192]"] = {"error": repr(e)}
+  result["gdn"] = gdn
+  torch.cuda.empty_cache()
+  # --- the model path as configs[1]/[2] name it: images -> analysis transform (conv glue + GDN) -> strings
+  try:
+    from compression_b200 import models
+    result["model_path"] = models.bench_model_paths(dev)
+  except Exception as e:  # pylint:disable=broad-except
+    result["model_path"] = {"error": repr(e)}
+  # --- CPU baselines on this box's host cores (bounded: one cfg2 batch; persistent worker pool)
+  try:
+    q = model.quantization_offset
+    value_host = symbols_of(model.cdf_offset.cpu().numpy(), None if q is None else q.cpu(), ys_host[0])
+    cores, phys = os.cpu_count() or 1, physical_cores()
+    os.sched_setaffinity(0, range(cores)) if hasattr(os, "sched_setaffinity") else None  # un-pin: all host cores
+    enc_all, dec_all, kind = cpu_coder_times(value_host, lookup, cores)
+    enc_phys, dec_phys, _ = cpu_coder_times(value_host, lookup, phys)
+    enc_one, dec_one, _ = cpu_coder_times(value_host[:16], lookup, 1, repeats=3)
+    result["cpu_baseline"] = {
+        "value": enc_all["median"], "unit": "Msymbols/s", "cores": cores, "kind": kind,
+        "sample": f"one full cfg2 batch ({S} streams x {N} int32 symbols), EntropyEncodeChannel+Finalize, median of 5 "
+                  f"after warm-up, streams on a persistent pool of {cores} threads",
+        "encode": {"threads_all": enc_all, "threads_physical": enc_phys, "threads_1": enc_one},
+        "decode": {"threads_all": dec_all, "threads_physical": dec_phys, "threads_1": dec_one},
+        "physical_cores": phys, "single_core_value": enc_one["median"],
+        "single_core_sample": "16 streams x 32768 symbols, 1 thread",
+        "gdn_torch_cpu": cpu_gdn_baseline(),
+    }
+    result["speedup_vs_cpu"] = {
+        "encode_vs_1_thread": result["value"] / enc_one["median"], "encode_vs_all_threads": result["value"] / enc_all["median"],
+        "decode_vs_1_thread": result["decode"]["value"] / dec_one["median"],
+        "decode_vs_all_threads": result["decode"]["value"] / dec_all["median"],
+    }
+  except Exception as e:  # pylint:disable=broad-except
+    result["cpu_baseline"] = {"error": repr(e)}
 
 
 if __name__ == "__main__":

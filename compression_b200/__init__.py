@@ -10,7 +10,8 @@ from compression_b200._lib import InvalidArgumentError
 
 def __getattr__(name):  # lazy: importing the package must not require torch / the built library
   import importlib
-  modules = ("gen_ops", "functional", "math_ops", "distributions", "entropy_models", "gdn", "packed_tensors")
+  modules = ("gen_ops", "functional", "math_ops", "distributions", "entropy_models", "gdn", "packed_tensors",
+             "signal_conv", "models", "sharding")
   if name in modules:
     return importlib.import_module("compression_b200." + name)
   exported = {
@@ -21,6 +22,8 @@ def __getattr__(name):  # lazy: importing the package must not require torch / t
       "NoisyLaplace": "distributions", "NoisyLogistic": "distributions",
       "round_st": "math_ops", "lower_bound": "math_ops", "upper_bound": "math_ops",
       "perturb_and_apply": "math_ops", "PackedTensors": "packed_tensors",
+      "SignalConv2D": "signal_conv", "RDFTParameter": "signal_conv", "same_padding_for_kernel": "signal_conv",
+      "BLS2017Model": "models", "BMSHJ2018Model": "models",
   }
   if name in exported:
     return getattr(importlib.import_module("compression_b200." + exported[name]), name)

@@ -141,38 +141,6 @@ __global__ void gdn_tc_prep_kernel(const float* __restrict__ gamma, int C, __nv_
   reinterpret_cast<uint4*>(planes + (size_t)C * C)[idx] = lo;
 }
 
-// G independent 128-thread groups per CTA (each runs the tile pipeline on its own tiles with its own staging,
-// operand planes, TMEM columns and mbarriers); they share gamma's planes.  Several groups per CTA give the
-// latency overlap that several CTAs per SM would, which the 64-147 KB of gamma planes rules out: every group
-// spends most of a tile's time waiting (barriers, MMA completion, L2), so 4 groups keep the SM issuing.
-//
-// Inside a group the K chunks (KC channels) of all its tiles form one software pipeline with double-buffered
-// staging and operand planes:
-//   step i :  cp.async(chunk i+1)  |  wait chunk i  |  (planes[b] free <- MMAs of chunk i-2 done)  |
-//             convert chunk i -> planes[b]  |  issue MMAs(chunk i), commit -> mbar[b]
-//   last chunk of a tile: wait mbar[b], epilogue through staging[b] (staging[b^1] is receiving chunk i+1).
-constexpr int kGroupThreads = 128;  // = kTileM: one thread per pixel row / TMEM lane
-
-template <int C, int G, int KC>
-struct TcSmem {
-  static constexpr int kStageLd = KC + 4;                   // floats; conflict-free 128-bit row access
-  static constexpr int kPlaneB = C * C * 2;                 // one gamma plane
-  static constexpr int kPlaneA = kTileM * KC * 2;           // one operand-chunk plane
-  static constexpr int kStage = kTileM * kStageLd * 4;      // fp32 staging
-  static constexpr int kBuf = 2 * kPlaneA + kStage;         // one pipeline buffer: hi plane, lo plane, staging
-  static constexpr int kGroup = 2 * kBuf;                   // double buffered
-  static constexpr int kOffBh = 0;
-  static constexpr int kOffBl = kOffBh + kPlaneB;
-  static constexpr int kOffGroups = kOffBl + kPlaneB;
-  static constexpr int kOffBeta = kOffGroups + G * kGroup;
-  static constexpr int kOffBar = kOffBeta + C * 4;
-  static constexpr int kBytes = kOffBar + 128;
-};
-
-__device__ __forceinline__ void group_sync(int g) {
-  asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(kGroupThreads) : "memory");
-}
-
 template <int N>
 __device__ __forceinline__ void tmem_load(uint32_t taddr, uint32_t (&r)[N]);
 
@@ -198,224 +166,6 @@ __device__ __forceinline__ void tmem_load<16>(uint32_t taddr, uint32_t (&r)[16])
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
-
-template <int C, int G, int KC, bool FAST>
-__global__ void __launch_bounds__(kGroupThreads * G, 1)
-gdn_tc_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ planes,
-                  const float* __restrict__ beta, float* __restrict__ y, long long n_pix, TcFlags f) {
-  using L = TcSmem<C, G, KC>;
-  constexpr int kThreads = kGroupThreads * G;
-  constexpr int NCH = C / KC;                          // K chunks per tile
-  constexpr int F4R = KC / 4;                          // float4 per staging row
-  constexpr int LDS_PER_T = (kTileM * F4R) / kGroupThreads;  // float4 per thread for one [128 x KC] block
-  constexpr int kStageLd = L::kStageLd;
-  extern __shared__ __align__(1024) uint8_t smem[];
-  float* beta_s = reinterpret_cast<float*>(smem + L::kOffBeta);
-  uint64_t* mbars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);  // [G][2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffBar + 96);
-  const int tid = threadIdx.x;
-  const int g = tid / kGroupThreads, gtid = tid % kGroupThreads, gwarp = gtid >> 5;
-  constexpr int kTmemCols = (G * C <= 128) ? 128 : ((G * C <= 256) ? 256 : 512);
-  static_assert(G * C <= 512, "accumulators do not fit TMEM");
-  constexpr uint32_t kIdesc = umma_idesc(kTileM, C);
-
-  // ---- one-time setup: gamma planes -> smem, beta, mbarriers, TMEM ----
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(planes);
-    uint4* dst = reinterpret_cast<uint4*>(smem + L::kOffBh);
-    for (int i = tid; i < 2 * L::kPlaneB / 16; i += kThreads) dst[i] = src[i];
-    for (int i = tid; i < C; i += kThreads) beta_s[i] = beta[i];
-  }
-  if (tid == 0) {
-    for (int i = 0; i < 2 * G; ++i)
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbars + i)));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (tid < 32) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(kTmemCols));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-  }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // plane stores -> visible to the tensor core
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot + (uint32_t)(g * C);  // this group's accumulator columns
-  uint8_t* gbuf = smem + L::kOffGroups + g * L::kGroup;
-  const uint32_t b_hi = smem_u32(smem + L::kOffBh), b_lo = smem_u32(smem + L::kOffBl);
-  uint32_t par[2] = {0u, 0u};      // phase parity of mbar[0], mbar[1]
-  uint32_t pending[2] = {0u, 0u};  // a commit on mbar[b] has not been waited for yet
-
-  const long long n_tiles = (n_pix + kTileM - 1) / kTileM;
-  const long long t_step = (long long)gridDim.x * G;
-  const long long t_first = (long long)blockIdx.x * G + g;
-  const long long my_tiles = (t_first < n_tiles) ? (n_tiles - t_first + t_step - 1) / t_step : 0;
-  const long long n_steps = my_tiles * NCH;
-
-  auto issue_load = [&](long long tile, int kc, int b) {
-    const long long p0 = tile * kTileM;
-    float* stage = reinterpret_cast<float*>(gbuf + b * L::kBuf + 2 * L::kPlaneA);
-#pragma unroll
-    for (int it = 0; it < LDS_PER_T; ++it) {
-      const int idx = it * kGroupThreads + gtid;
-      const int row = idx / F4R, c4 = idx % F4R;
-      float* dst = stage + row * kStageLd + c4 * 4;
-      if (p0 + row < n_pix) {
-        const float* src = x + (p0 + row) * C + kc * KC + c4 * 4;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-      } else {
-        *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-
-  long long tile = t_first;
-  int kc = 0;
-  if (n_steps > 0) issue_load(tile, 0, 0);
-  for (long long step = 0; step < n_steps; ++step) {
-    const int b = (int)(step & 1);
-    const long long p0 = tile * kTileM;
-    uint8_t* ah_p = gbuf + b * L::kBuf;
-    uint8_t* al_p = ah_p + L::kPlaneA;
-    float* stage = reinterpret_cast<float*>(ah_p + 2 * L::kPlaneA);
-    const uint32_t mbar_addr = smem_u32(mbars + 2 * g + b);
-    const bool last_chunk = (kc == NCH - 1);
-    const long long next_tile = last_chunk ? tile + t_step : tile;
-    const int next_kc = last_chunk ? 0 : kc + 1;
-
-    // (0) next chunk's load goes out first; at the start of a tile also pull the group's next tile into L2
-    if (step + 1 < n_steps) {
-      issue_load(next_tile, next_kc, b ^ 1);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");  // chunk `step` has landed, `step + 1` is in flight
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-    if (kc == 0) {
-      const long long pn = (tile + t_step) * kTileM;
-      const long long rows = min((long long)kTileM, n_pix - pn);
-      if (rows > 0) {
-        const char* base = reinterpret_cast<const char*>(x + pn * C);
-        const long long bytes = rows * C * 4;
-        for (long long off = (long long)gtid * 128; off < bytes; off += (long long)kGroupThreads * 128)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
-      }
-    }
-    // (1) the operand planes of this buffer were read by the MMAs of chunk step-2: wait for them
-    if (pending[b]) {
-      if (!mbar_wait(mbar_addr, par[b])) __trap();  // a descriptor bug must fail loudly, never hang the GPU
-      par[b] ^= 1u;
-      pending[b] = 0u;
-    }
-    group_sync(g);  // every thread's cp.async of this chunk is visible
-    // (2) pool + bf16 split -> operand planes ([kchunk][row][8] bf16); thread = pixel row
-    {
-      const float* src = stage + gtid * kStageLd;
-#pragma unroll
-      for (int q = 0; q < KC / 8; ++q) {
-        const float4 v0 = *reinterpret_cast<const float4*>(src + q * 8);
-        const float4 v1 = *reinterpret_cast<const float4*>(src + q * 8 + 4);
-        float v[8] = {tc_pool<FAST>(v0.x, f), tc_pool<FAST>(v0.y, f), tc_pool<FAST>(v0.z, f), tc_pool<FAST>(v0.w, f),
-                      tc_pool<FAST>(v1.x, f), tc_pool<FAST>(v1.y, f), tc_pool<FAST>(v1.z, f), tc_pool<FAST>(v1.w, f)};
-        uint4 hi, lo;
-        split8(v, &hi, &lo);
-        *reinterpret_cast<uint4*>(ah_p + q * (kTileM * 16) + gtid * 16) = hi;
-        *reinterpret_cast<uint4*>(al_p + q * (kTileM * 16) + gtid * 16) = lo;
-      }
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    group_sync(g);
-    // (3) one thread issues the MMAs of this chunk: KC/16 K-steps x (hi*hi + lo*hi + hi*lo)
-    if (gtid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a_hi = smem_u32(ah_p), a_lo = smem_u32(al_p);
-#pragma unroll
-      for (int s = 0; s < KC / 16; ++s) {
-        const uint32_t a_off = (uint32_t)(2 * s) * (kTileM * 16);
-        const uint32_t b_off = (uint32_t)(kc * (KC / 8) + 2 * s) * (C * 16);
-        const uint64_t dah = umma_desc(a_hi + a_off, kTileM * 16, 128);
-        const uint64_t dal = umma_desc(a_lo + a_off, kTileM * 16, 128);
-        const uint64_t dbh = umma_desc(b_hi + b_off, C * 16, 128);
-        const uint64_t dbl = umma_desc(b_lo + b_off, C * 16, 128);
-        umma_bf16(tmem_base, dah, dbh, kIdesc, (kc | s) ? 1u : 0u);
-        umma_bf16(tmem_base, dal, dbh, kIdesc, 1u);
-        umma_bf16(tmem_base, dah, dbl, kIdesc, 1u);
-      }
-      umma_commit(mbar_addr);  // arrives when every MMA issued so far has completed
-    }
-    pending[b] = 1u;
-    if (!last_chunk) {
-      kc = next_kc;
-      continue;
-    }
-
-    // ================= end of tile: epilogue, KC output channels at a time =================
-    // x of the first column block: coalesced re-read (L2 hits), issued before waiting for the tensor core
-    float4 xv[LDS_PER_T];
-    auto load_x = [&](int cc) {
-#pragma unroll
-      for (int it = 0; it < LDS_PER_T; ++it) {
-        const int idx = it * kGroupThreads + gtid;
-        const int row = idx / F4R, c4 = idx % F4R;
-        xv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p0 + row < n_pix) xv[it] = __ldg(reinterpret_cast<const float4*>(x + (p0 + row) * C + cc * KC + c4 * 4));
-      }
-    };
-    load_x(0);
-    if (!mbar_wait(mbar_addr, par[b])) __trap();
-    par[b] ^= 1u;
-    pending[b] = 0u;
-    if (pending[b ^ 1]) {  // chunk step-1's commit completed earlier (in order): consume its phase
-      if (!mbar_wait(smem_u32(mbars + 2 * g + (b ^ 1)), par[b ^ 1])) __trap();
-      par[b ^ 1] ^= 1u;
-      pending[b ^ 1] = 0u;
-    }
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    for (int cc = 0; cc < C / KC; ++cc) {
-      {
-        const uint32_t taddr = tmem_base + ((uint32_t)(gwarp * 32) << 16) + (uint32_t)(cc * KC);
-        uint32_t r[KC];
-        tmem_load<KC>(taddr, r);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        float* dst = stage + gtid * kStageLd;
-#pragma unroll
-        for (int i = 0; i < KC / 4; ++i)
-          *reinterpret_cast<float4*>(dst + 4 * i) =
-              make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
-                          __uint_as_float(r[4 * i + 3]));
-      }
-      group_sync(g);
-#pragma unroll
-      for (int it = 0; it < LDS_PER_T; ++it) {
-        const int idx = it * kGroupThreads + gtid;
-        const int row = idx / F4R, c4 = idx % F4R;
-        if (p0 + row < n_pix) {
-          const float4 nv = *reinterpret_cast<const float4*>(stage + row * kStageLd + c4 * 4);
-          const float4 bv = *reinterpret_cast<const float4*>(beta_s + cc * KC + c4 * 4);
-          float4 o;
-          o.x = tc_out<FAST>(xv[it].x, bv.x + nv.x, f);
-          o.y = tc_out<FAST>(xv[it].y, bv.y + nv.y, f);
-          o.z = tc_out<FAST>(xv[it].z, bv.z + nv.z, f);
-          o.w = tc_out<FAST>(xv[it].w, bv.w + nv.w, f);
-          *reinterpret_cast<float4*>(y + (p0 + row) * C + cc * KC + c4 * 4) = o;
-        }
-      }
-      if (cc + 1 < C / KC) load_x(cc + 1);  // next block's x: in flight across the barrier and the TMEM load
-      group_sync(g);
-    }
-    // TMEM is overwritten by the next tile's first MMA: order the tcgen05.ld's before it
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    group_sync(g);
-    tile = next_tile;
-    kc = 0;
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (tid < 32) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "r"(kTmemCols));
-  }
-}
-
 
 // =============================================================================================
 // Forward, second generation (C = 128): the whole x tile lives in shared memory.
@@ -700,38 +450,6 @@ int launch_tc_fwd2(const float* x, const float* gamma, const float* beta, float*
   TFCB_LAUNCHED();
   cudaError_t e = cudaGetLastError();
   dev_free(planes, s);
-  if (e != cudaSuccess) return fail(TFCB_CUDA_ERROR, "GDN tensor-core kernel launch failed: %s", cudaGetErrorString(e));
-  return TFCB_OK;
-}
-
-template <int C, int G, int KC, bool FAST>
-int launch_tc(const float* x, const float* gamma, const float* beta, float* y, long long n_pix, TcFlags f,
-              cudaStream_t s) {
-  using L = TcSmem<C, G, KC>;
-  __nv_bfloat16* planes = nullptr;
-  TFCB_TRY(dev_alloc((void**)&planes, (size_t)2 * C * C * sizeof(__nv_bfloat16), s));
-  gdn_tc_prep_kernel<<<((C / 8) * C + 255) / 256, 256, 0, s>>>(gamma, C, planes);
-  TFCB_LAUNCHED();
-  bool attr_set = false;  // the attribute is per device: set it on every launch (microseconds)
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gdn_tc_fwd_kernel<C, G, KC, FAST>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes);
-    if (e != cudaSuccess) {
-      (void)cudaGetLastError();
-      dev_free(planes, s);
-      return fail(TFCB_CUDA_ERROR, "cannot reserve %d bytes of shared memory: %s", L::kBytes, cudaGetErrorString(e));
-    }
-    attr_set = true;
-  }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const long long n_tiles = (n_pix + kTileM - 1) / kTileM;
-  const int grid = (int)std::min<long long>((n_tiles + G - 1) / G, sms);
-  gdn_tc_fwd_kernel<C, G, KC, FAST><<<grid, kGroupThreads * G, L::kBytes, s>>>(x, planes, beta, y, n_pix, f);
-  TFCB_LAUNCHED();
-  cudaError_t e = cudaGetLastError();
-  dev_free(planes, s);  // stream ordered: released after the kernel
   if (e != cudaSuccess) return fail(TFCB_CUDA_ERROR, "GDN tensor-core kernel launch failed: %s", cudaGetErrorString(e));
   return TFCB_OK;
 }
@@ -1944,22 +1662,10 @@ int gdn_tc_forward(const float* x, const float* gamma, const float* beta, float*
   f.eps_mode = (eps == 0.5f) ? 2 : 1;
   *handled = true;
   const bool fast = (alpha == 1.f) && (eps == 1.f) && !f.rectify;
-  if (C == 128) {
-    const char* v1 = getenv("TFCB_GDN_FWD1");
-    if (!(v1 && v1[0] == '1'))  // default: x tile resident in shared memory, bulk async copies
-      return fast ? launch_tc_fwd2<true>(x, gamma, beta, y, n_pix, f, s) : launch_tc_fwd2<false>(x, gamma, beta, y, n_pix, f, s);
-    // first generation: 64 KB of gamma planes + 2 x 69 KB cp.async pipelines = 202 KB
-    return fast ? launch_tc<128, 2, 32, true>(x, gamma, beta, y, n_pix, f, s)
-                : launch_tc<128, 2, 32, false>(x, gamma, beta, y, n_pix, f, s);
-  }
-  {
-    const char* v1 = getenv("TFCB_GDN_FWD1");
-    if (!(v1 && v1[0] == '1'))  // default for C == 192: register-fed conversion + MMA-issue warp
-      return fast ? launch_tc_fwd3<true>(x, gamma, beta, y, n_pix, f, s) : launch_tc_fwd3<false>(x, gamma, beta, y, n_pix, f, s);
-  }
-  // first generation, C == 192: 147 KB of gamma planes + 2 x 36 KB cp.async pipelines = 220 KB
-  return fast ? launch_tc<192, 2, 16, true>(x, gamma, beta, y, n_pix, f, s)
-              : launch_tc<192, 2, 16, false>(x, gamma, beta, y, n_pix, f, s);
+  if (C == 128)  // x tile resident in shared memory, bulk async copies
+    return fast ? launch_tc_fwd2<true>(x, gamma, beta, y, n_pix, f, s) : launch_tc_fwd2<false>(x, gamma, beta, y, n_pix, f, s);
+  // C == 192: register-fed conversion + MMA-issue warp
+  return fast ? launch_tc_fwd3<true>(x, gamma, beta, y, n_pix, f, s) : launch_tc_fwd3<false>(x, gamma, beta, y, n_pix, f, s);
 }
 
 }  // namespace tfcb

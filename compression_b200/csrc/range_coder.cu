@@ -1319,7 +1319,7 @@ __global__ void __launch_bounds__(96) decode_kernel(const DecParams P) {
       bool finished = miss;
       if (ovf && sym == n - 1) {  // OverflowDecode, range_coder_kernels.cc:449-471
         int nb = 0;
-        while (c.bit() == 0 && nb < 64) ++nb;
+        while (c.bit() == 0 && nb < 32) ++nb;  // valid int32 gamma codes have <= 31 zeros; bounds what a corrupt stream can consume (kRingAhead)
         uint32_t val = (nb < 32) ? (1u << nb) : 0u;
         int t = nb;
         while (--t >= 0) {
@@ -1850,8 +1850,9 @@ int tfcb_encode_finalize(tfcb_encoder* h, void* stream, int64_t* total_bytes_hos
   if (h->finalized) return fail(TFCB_INVALID_ARGUMENT, "encoder handle was already finalized");
   cudaStream_t s = as_stream(stream);
   const long long S = h->n_streams;
-  TFCB_TRY(dev_alloc((void**)&h->lens, std::max<long long>(S, 1) * sizeof(long long), s));
-  TFCB_TRY(dev_alloc((void**)&h->offsets, (S + 1) * sizeof(long long), s));
+  // (a finalize retried after a deferred argument error reuses the buffers of the first attempt)
+  if (!h->lens) TFCB_TRY(dev_alloc((void**)&h->lens, std::max<long long>(S, 1) * sizeof(long long), s));
+  if (!h->offsets) TFCB_TRY(dev_alloc((void**)&h->offsets, (S + 1) * sizeof(long long), s));
   if (h->cap == 0) TFCB_TRY(ensure_capacity(h, 0, s));
   if (S > 0) {
     enc_lengths_kernel<<<(unsigned)((S + 127) / 128), 128, 0, s>>>(h->state, h->words, h->cap, S, h->lens);

@@ -168,21 +168,28 @@ class DeepFactorized(nn.Module):
   def survival_function(self, x):
     return torch.sigmoid(-self._logits_cumulative(x))
 
+  def _live(self, x):
+    """The point the density is differentiated at: x itself when it is already part of a graph (so the density
+    stays differentiable in x, deep_factorized.py:195-230), else a fresh leaf."""
+    x = self._broadcast(x)
+    return x if (torch.is_grad_enabled() and x.requires_grad) else x.detach().requires_grad_(True)
+
   def prob(self, x):
-    x = self._broadcast(x).detach().requires_grad_(True)
+    keep = torch.is_grad_enabled()
+    x = self._live(x)
     with torch.enable_grad():
       c = self.cdf(x)
-      p, = torch.autograd.grad(c.sum(), x, create_graph=torch.is_grad_enabled())
+      p, = torch.autograd.grad(c.sum(), x, create_graph=keep)
     return p
 
   def log_prob(self, x):
-    x = self._broadcast(x)
-    xr = x.detach().requires_grad_(True)
+    keep = torch.is_grad_enabled()
+    x = self._live(x)
     with torch.enable_grad():
-      logits = self._logits_cumulative(xr)
-      dlogits, = torch.autograd.grad(logits.sum(), xr, create_graph=torch.is_grad_enabled())
-    lg = self._logits_cumulative(x)
-    return torch.nn.functional.logsigmoid(lg) + torch.nn.functional.logsigmoid(-lg) + torch.log(dlogits)
+      logits = self._logits_cumulative(x)
+      dlogits, = torch.autograd.grad(logits.sum(), x, create_graph=keep)
+      out = torch.nn.functional.logsigmoid(logits) + torch.nn.functional.logsigmoid(-logits) + torch.log(dlogits)
+    return out if keep else out.detach()
 
   def quantile(self, q):
     raise NotImplementedError

@@ -36,7 +36,7 @@ class ContinuousEntropyModelBase(nn.Module):
   def __init__(self, coding_rank=None, compression=False, stateless=False, expected_grads=False,
                tail_mass=2**-8, bottleneck_dtype=None, laplace_tail_mass=0):
     super().__init__()
-    object.__setattr__(self, "_prior", None)  # never a registered submodule: tables, not priors, are state
+    self._prior = None  # set by the subclasses; an nn.Module prior registers as a submodule (see _set_prior)
     self._coding_rank = int(coding_rank)
     self._compression = bool(compression)
     self._stateless = bool(stateless)
@@ -64,7 +64,18 @@ class ContinuousEntropyModelBase(nn.Module):
 
   @prior.deleter
   def prior(self):
-    object.__setattr__(self, "_prior", None)
+    self._prior = None
+
+  def _set_prior(self, prior, register=True):
+    """A prior the caller hands in is part of the model exactly as in the reference, where assigning it on the
+    tf.Module makes its variables trainable_variables / checkpoint state (continuous_batched.py:205): an
+    nn.Module prior becomes a registered submodule (parameters(), state_dict(), .to()).  Priors the model
+    derives itself from `indexes` (continuous_indexed.py:226-232) hold no variables and stay plain attributes."""
+    if register or not isinstance(prior, nn.Module):
+      self._prior = prior
+    else:
+      self._modules.pop("_prior", None)
+      object.__setattr__(self, "_prior", prior)
 
   @property
   def cdf(self):
@@ -123,6 +134,12 @@ class ContinuousEntropyModelBase(nn.Module):
         setattr(self, name, state_dict[key].clone())
     self._cdf_host = None
     super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+    if self._prior is None:
+      # a model rebuilt from its config holds tables, not a prior (continuous_base.py:336-360): prior weights
+      # saved next to the tables are ignored instead of being reported as unexpected keys
+      unexpected = args[3] if len(args) > 3 else kwargs.get("unexpected_keys")
+      if unexpected is not None:
+        unexpected[:] = [k for k in unexpected if not k.startswith(prefix + "_prior.")]
 
   @torch.no_grad()
   def _build_tables(self, prior, precision, offset=None):
@@ -211,7 +228,7 @@ class ContinuousBatchedEntropyModel(ContinuousEntropyModelBase):
     super().__init__(coding_rank=coding_rank, compression=compression, stateless=stateless,
                      expected_grads=expected_grads, tail_mass=tail_mass, bottleneck_dtype=bottleneck_dtype,
                      laplace_tail_mass=laplace_tail_mass)
-    object.__setattr__(self, "_prior", prior)
+    self._set_prior(prior)
     self._offset_heuristic = bool(offset_heuristic)
     self._prior_shape = tuple(int(s) for s in (prior_shape if prior is None else prior.batch_shape))
     if self.coding_rank < len(self.prior_shape):
@@ -389,7 +406,7 @@ class ContinuousIndexedEntropyModel(ContinuousEntropyModelBase):
       else:
         grids = torch.meshgrid(*[torch.arange(r, dtype=torch.int32) for r in self.index_ranges], indexing="ij")
         indexes = torch.stack(grids, dim=self.channel_axis)
-      object.__setattr__(self, "_prior", self._make_prior(indexes))
+      self._set_prior(self._make_prior(indexes), register=False)
       cdf, cdf_offset = self._build_tables(self.prior, range_coder_precision)
       self._init_compression(cdf, cdf_offset, None)
 

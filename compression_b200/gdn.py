@@ -155,9 +155,25 @@ class GDN(nn.Module):
     return y.movedim(-1, 1) if self.data_format == "channels_first" else y
 
   def _torch_graph(self, x, dev):
+    """gdn.py:377-415 literally: the fixed-exponent special cases are kept even when the OTHER exponent is
+    trainable (|x| for alpha == 1 without rectify, square for alpha == 2, sqrt for epsilon == .5)."""
     u = torch.relu(x) if self.rectify else x
-    n = (u**self._param("alpha", device=dev)) @ self._param("gamma", device=dev) + self._param("beta", device=dev)
-    n = n**self._param("epsilon", device=dev)
+    alpha, epsilon = self.alpha_parameter, self.epsilon_parameter
+    if not callable(alpha) and alpha == 1 and self.rectify:
+      pool = u
+    elif not callable(alpha) and alpha == 1:
+      pool = u.abs()
+    elif not callable(alpha) and alpha == 2:
+      pool = u.square()
+    else:
+      pool = u**self._param("alpha", device=dev)
+    n = pool @ self._param("gamma", device=dev) + self._param("beta", device=dev)
+    if not callable(epsilon) and epsilon == 1:
+      pass
+    elif not callable(epsilon) and epsilon == .5:
+      n = n.sqrt()
+    else:
+      n = n**self._param("epsilon", device=dev)
     return u * n if self.inverse else u / n
 
   def compute_output_shape(self, input_shape):

@@ -1,0 +1,347 @@
+"""The two models the hot path serves, driven end to end: `BLS2017Model` (models/bls2017.py:55-190) and
+`BMSHJ2018Model` (models/bmshj2018.py:53-264) -- analysis / synthesis (and hyper) transforms built from
+`SignalConv2D` glue + the CUDA `GDN`, the entropy models on the CUDA range coder, `compress` / `decompress`
+with the reference's signatures and the `.tfci` container (`PackedTensors`) around them.
+
+The convolutions are cuDNN through torch (glue, no kernel claim); GDN/IGDN, quantisation, table build and range
+coding are this repo's kernels.  There is no TF here, so weights are the layers' own initialisers (or a
+state_dict); what is reproduced is the data path: shapes, cropping, casts, the order of the coded tensors and the
+bytes of the container.
+
+Batches: the reference's `compress` takes ONE image `[H, W, 3]` uint8 (it adds the batch dimension itself);
+`compress_batch` / `decompress_batch` take `[B, H, W, 3]` and code B streams in one launch -- what
+BASELINE.json configs[1]/[2] ("batch=256 / 128") time.
+"""
+import math
+
+import numpy as np
+import torch
+from torch import nn
+
+from compression_b200 import distributions as D
+from compression_b200 import entropy_models as E
+from compression_b200.gdn import GDN
+from compression_b200.packed_tensors import PackedTensors
+from compression_b200.signal_conv import SignalConv2D
+
+__all__ = ["BLS2017Model", "BMSHJ2018Model", "AnalysisTransform", "SynthesisTransform", "HyperAnalysisTransform",
+           "HyperSynthesisTransform", "bench_model_paths"]
+
+
+class _Scale(nn.Module):
+  """tf.keras.layers.Lambda(lambda x: x / 255.) and its inverse."""
+
+  def __init__(self, factor):
+    super().__init__()
+    self.factor = factor
+
+  def forward(self, x):
+    return x * self.factor
+
+
+def _conv(filters, k, name, down=1, up=1, corr=True, use_bias=True, activation=None, **kw):
+  return SignalConv2D(filters, (k, k), name=name, corr=corr, strides_down=down, strides_up=up, padding="same_zeros",
+                      use_bias=use_bias, activation=activation, **kw)
+
+
+class AnalysisTransform(nn.Sequential):
+  """bls2017.py:55-72 (three layers, 9x9/4 then 5x5/2 twice) or bmshj2018.py:53-74 (`hyperprior=True`: four 5x5/2)."""
+
+  def __init__(self, num_filters, hyperprior=False):
+    if hyperprior:
+      layers = [_conv(num_filters, 5, f"layer_{i}", down=2, activation=GDN(name=f"gdn_{i}")) for i in range(3)]
+      layers.append(_conv(num_filters, 5, "layer_3", down=2))
+    else:
+      layers = [_conv(num_filters, 9, "layer_0", down=4, activation=GDN(name="gdn_0")),
+                _conv(num_filters, 5, "layer_1", down=2, activation=GDN(name="gdn_1")),
+                _conv(num_filters, 5, "layer_2", down=2, use_bias=False)]
+    super().__init__(_Scale(1 / 255.), *layers)
+
+
+class SynthesisTransform(nn.Sequential):
+  """bls2017.py:75-92 / bmshj2018.py:77-98."""
+
+  def __init__(self, num_filters, hyperprior=False):
+    if hyperprior:
+      layers = [_conv(num_filters, 5, f"layer_{i}", up=2, corr=False, activation=GDN(name=f"igdn_{i}", inverse=True))
+                for i in range(3)]
+      layers.append(_conv(3, 5, "layer_3", up=2, corr=False))
+    else:
+      layers = [_conv(num_filters, 5, "layer_0", up=2, corr=False, activation=GDN(name="igdn_0", inverse=True)),
+                _conv(num_filters, 5, "layer_1", up=2, corr=False, activation=GDN(name="igdn_1", inverse=True)),
+                _conv(3, 9, "layer_2", up=4, corr=False)]
+    super().__init__(*layers, _Scale(255.))
+
+
+class HyperAnalysisTransform(nn.Sequential):
+  """bmshj2018.py:101-118."""
+
+  def __init__(self, num_filters):
+    super().__init__(_conv(num_filters, 3, "layer_0", activation=torch.relu),
+                     _conv(num_filters, 5, "layer_1", down=2, activation=torch.relu),
+                     _conv(num_filters, 5, "layer_2", down=2, use_bias=False))
+
+
+class HyperSynthesisTransform(nn.Sequential):
+  """bmshj2018.py:121-138 (plain-variable kernels)."""
+
+  def __init__(self, num_filters):
+    super().__init__(_conv(num_filters, 5, "layer_0", up=2, corr=False, kernel_parameter="variable", activation=torch.relu),
+                     _conv(num_filters, 5, "layer_1", up=2, corr=False, kernel_parameter="variable", activation=torch.relu),
+                     _conv(num_filters, 3, "layer_2", corr=False, kernel_parameter="variable"))
+
+
+def _to_uint8(x_hat):
+  """tf.saturate_cast(tf.round(x_hat), tf.uint8)."""
+  return torch.clamp(torch.round(x_hat), 0, 255).to(torch.uint8)
+
+
+def _as_batch(x):
+  x = torch.as_tensor(x)
+  if x.dim() != 4 or x.shape[-1] != 3:
+    raise ValueError(f"expected images [B, H, W, 3], received shape {tuple(x.shape)}")
+  return x
+
+
+class _Model(nn.Module):
+
+  def _device(self):
+    return next(self.parameters()).device
+
+  def build(self, device="cuda", patch=(64, 64)):
+    """Keras `self.build((None, None, None, 3))`: creates every variable (the layers build lazily on a first pass)."""
+    self.to(device)
+    with torch.no_grad():
+      self(torch.zeros((1,) + tuple(patch) + (3,), device=device), training=False)
+    return self
+
+  def rate_distortion(self, x, bits):
+    num_pixels = float(np.prod(x.shape[:-1]))
+    bpp = bits / num_pixels
+    mse = torch.mean((x - self._last_x_hat)**2)
+    return bpp + self.lmbda * mse, bpp, mse
+
+
+class BLS2017Model(_Model):
+  """models/bls2017.py:95-190."""
+
+  def __init__(self, lmbda=0.01, num_filters=128):
+    super().__init__()
+    self.lmbda = lmbda
+    self.num_filters = int(num_filters)
+    self.analysis_transform = AnalysisTransform(num_filters)
+    self.synthesis_transform = SynthesisTransform(num_filters)
+    self.prior = D.NoisyDeepFactorized(batch_shape=(num_filters,))
+    self.entropy_model = None
+
+  def forward(self, x, training=True):
+    """bls2017.py:106-124 -> (loss, bpp, mse)."""
+    entropy_model = E.ContinuousBatchedEntropyModel(self.prior, coding_rank=3, compression=False)
+    x = x.to(torch.float32)
+    y = self.analysis_transform(x)
+    y_hat, bits = entropy_model(y, training=training)
+    self._last_x_hat = self.synthesis_transform(y_hat)
+    return self.rate_distortion(x, bits.sum())
+
+  def fix_tables(self):
+    """bls2017.py:156-161 (end of `fit`): fixes the range-coding tables from the trained prior."""
+    self.entropy_model = E.ContinuousBatchedEntropyModel(self.prior, coding_rank=3, compression=True).to(self._device())
+    return self
+
+  # -- one image, the reference's signatures (bls2017.py:163-190) --
+  def compress(self, x):
+    """x: uint8 [H, W, 3] -> (string [1], x_shape [2], y_shape [2])."""
+    x = torch.as_tensor(x)
+    if x.dim() != 3 or x.shape[-1] != 3:
+      raise ValueError(f"expected one image [H, W, 3], received shape {tuple(x.shape)}")
+    strings, x_shape, y_shape = self.compress_batch(x[None])
+    return strings, x_shape, y_shape
+
+  def decompress(self, string, x_shape, y_shape):
+    """-> uint8 [H, W, 3]."""
+    return self.decompress_batch(string, x_shape, y_shape)[0]
+
+  # -- batches --
+  @torch.no_grad()
+  def compress_batch(self, x):
+    x = _as_batch(x).to(device=self._device(), dtype=torch.float32)
+    y = self.analysis_transform(x)
+    x_shape = torch.tensor(x.shape[1:-1], dtype=torch.int32)
+    y_shape = torch.tensor(y.shape[1:-1], dtype=torch.int32)
+    return self.entropy_model.compress(y), x_shape, y_shape
+
+  @torch.no_grad()
+  def decompress_batch(self, strings, x_shape, y_shape):
+    y_hat = self.entropy_model.decompress(strings, tuple(int(v) for v in y_shape))
+    x_hat = self.synthesis_transform(y_hat)
+    x_hat = x_hat[:, :int(x_shape[0]), :int(x_shape[1]), :]
+    return _to_uint8(x_hat)
+
+  # -- .tfci container (bls2017.py:262-282 `compress`, :308-321 `decompress`) --
+  def compress_to_tfci(self, x):
+    packed = PackedTensors()
+    packed.pack(self.compress(x))
+    return packed.string
+
+  def decompress_from_tfci(self, data):
+    string, x_shape, y_shape = PackedTensors(data).unpack([bytes, torch.int32, torch.int32])
+    return self.decompress(string, x_shape, y_shape)
+
+
+class BMSHJ2018Model(_Model):
+  """models/bmshj2018.py:141-264 (scale hyperprior)."""
+
+  def __init__(self, lmbda=0.01, num_filters=192, num_scales=64, scale_min=.11, scale_max=256.):
+    super().__init__()
+    self.lmbda = lmbda
+    self.num_scales = int(num_scales)
+    offset = math.log(scale_min)
+    factor = (math.log(scale_max) - math.log(scale_min)) / (num_scales - 1.)
+    self.scale_fn = lambda i: torch.exp(offset + factor * i)
+    self.analysis_transform = AnalysisTransform(num_filters, hyperprior=True)
+    self.synthesis_transform = SynthesisTransform(num_filters, hyperprior=True)
+    self.hyper_analysis_transform = HyperAnalysisTransform(num_filters)
+    self.hyper_synthesis_transform = HyperSynthesisTransform(num_filters)
+    self.hyperprior = D.NoisyDeepFactorized(batch_shape=(num_filters,))
+    self.entropy_model = None
+    self.side_entropy_model = None
+
+  def forward(self, x, training=True):
+    """bmshj2018.py:159-184."""
+    entropy_model = E.LocationScaleIndexedEntropyModel(D.NoisyNormal, self.num_scales, self.scale_fn, coding_rank=3,
+                                                       compression=False)
+    side_entropy_model = E.ContinuousBatchedEntropyModel(self.hyperprior, coding_rank=3, compression=False)
+    x = x.to(torch.float32)
+    y = self.analysis_transform(x)
+    z = self.hyper_analysis_transform(y.abs())
+    z_hat, side_bits = side_entropy_model(z, training=training)
+    indexes = self.hyper_synthesis_transform(z_hat)
+    indexes = indexes[:, :y.shape[1], :y.shape[2], :]
+    y_hat, bits = entropy_model(y, indexes, training=training)
+    self._last_x_hat = self.synthesis_transform(y_hat)[:, :x.shape[1], :x.shape[2], :]
+    return self.rate_distortion(x, bits.sum() + side_bits.sum())
+
+  def fix_tables(self):
+    """bmshj2018.py:216-223."""
+    self.entropy_model = E.LocationScaleIndexedEntropyModel(D.NoisyNormal, self.num_scales, self.scale_fn,
+                                                            coding_rank=3, compression=True)
+    self.side_entropy_model = E.ContinuousBatchedEntropyModel(self.hyperprior, coding_rank=3, compression=True)
+    self.entropy_model.to(self._device())
+    self.side_entropy_model.to(self._device())
+    return self
+
+  def compress(self, x):
+    """bmshj2018.py:225-245: uint8 [H, W, 3] -> (string, side_string, x_shape, y_shape, z_shape)."""
+    x = torch.as_tensor(x)
+    if x.dim() != 3 or x.shape[-1] != 3:
+      raise ValueError(f"expected one image [H, W, 3], received shape {tuple(x.shape)}")
+    return self.compress_batch(x[None])
+
+  def decompress(self, string, side_string, x_shape, y_shape, z_shape):
+    """bmshj2018.py:247-264."""
+    return self.decompress_batch(string, side_string, x_shape, y_shape, z_shape)[0]
+
+  @torch.no_grad()
+  def compress_batch(self, x):
+    x = _as_batch(x).to(device=self._device(), dtype=torch.float32)
+    y = self.analysis_transform(x)
+    z = self.hyper_analysis_transform(y.abs())
+    x_shape = torch.tensor(x.shape[1:-1], dtype=torch.int32)
+    y_shape = torch.tensor(y.shape[1:-1], dtype=torch.int32)
+    z_shape = torch.tensor(z.shape[1:-1], dtype=torch.int32)
+    z_hat = self.side_entropy_model.quantize(z)
+    indexes = self.hyper_synthesis_transform(z_hat)
+    indexes = indexes[:, :y.shape[1], :y.shape[2], :]
+    side_string = self.side_entropy_model.compress(z)
+    string = self.entropy_model.compress(y, indexes)
+    return string, side_string, x_shape, y_shape, z_shape
+
+  @torch.no_grad()
+  def decompress_batch(self, string, side_string, x_shape, y_shape, z_shape):
+    z_hat = self.side_entropy_model.decompress(side_string, tuple(int(v) for v in z_shape))
+    indexes = self.hyper_synthesis_transform(z_hat)
+    indexes = indexes[:, :int(y_shape[0]), :int(y_shape[1]), :]
+    y_hat = self.entropy_model.decompress(string, indexes)
+    x_hat = self.synthesis_transform(y_hat)
+    x_hat = x_hat[:, :int(x_shape[0]), :int(x_shape[1]), :]
+    return _to_uint8(x_hat)
+
+  def compress_to_tfci(self, x):
+    packed = PackedTensors()
+    packed.pack(self.compress(x))
+    return packed.string
+
+  def decompress_from_tfci(self, data):
+    dtypes = [bytes, bytes, torch.int32, torch.int32, torch.int32]
+    return self.decompress(*PackedTensors(data).unpack(dtypes))
+
+
+# ------------------------------------------------------------------------------------------------
+# bench extra: BASELINE.json configs[1] / [2] as the configs name them (images -> strings, strings -> images)
+# ------------------------------------------------------------------------------------------------
+def _stage_ms(fn, reps=3):
+  fn()
+  a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  torch.cuda.synchronize()
+  a.record()
+  for _ in range(reps):
+    out = fn()
+  b.record()
+  torch.cuda.synchronize()
+  return a.elapsed_time(b) / reps, out
+
+
+def bench_model_paths(dev, batch2=256, batch3=128, hw=256):
+  """Times image batch -> strings and strings -> image batch for both models with a per-stage breakdown.  The conv
+  stages are cuDNN glue and are reported only so that the coder / GDN share of the path is visible."""
+  out = {}
+  g = torch.Generator().manual_seed(1)
+  for name, model, batch in (("cfg2_bls2017", BLS2017Model(num_filters=128), batch2),
+                             ("cfg3_bmshj2018", BMSHJ2018Model(num_filters=192), batch3)):
+    torch.manual_seed(3)
+    model.build(dev).fix_tables()
+    x = torch.randint(0, 256, (batch, hw, hw, 3), generator=g, dtype=torch.uint8).to(dev)
+    enc_ms, packed = _stage_ms(lambda: model.compress_batch(x))
+    dec_ms, x_hat = _stage_ms(lambda: model.decompress_batch(*packed))
+    xf = x.float()
+    ana_ms, y = _stage_ms(lambda: model.analysis_transform(xf))
+    if name == "cfg2_bls2017":
+      code_ms, strings = _stage_ms(lambda: model.entropy_model.compress(y))
+      n_sym = y.numel()
+      nbytes = strings.nbytes()
+      decode_ms, y_hat = _stage_ms(lambda: model.entropy_model.decompress(strings, tuple(y.shape[1:-1])))
+    else:
+      z = model.hyper_analysis_transform(y.abs())
+      idx = model.hyper_synthesis_transform(model.side_entropy_model.quantize(z))[:, :y.shape[1], :y.shape[2], :]
+      code_ms, (s_y, s_z) = _stage_ms(lambda: (model.entropy_model.compress(y, idx), model.side_entropy_model.compress(z)))
+      n_sym = y.numel() + z.numel()
+      nbytes = s_y.nbytes() + s_z.nbytes()
+      decode_ms, y_hat = _stage_ms(lambda: (model.side_entropy_model.decompress(s_z, tuple(z.shape[1:-1])),
+                                            model.entropy_model.decompress(s_y, idx))[1])
+    syn_ms, _ = _stage_ms(lambda: model.synthesis_transform(y_hat))
+    gdn_ms = 0.0
+    h = xf * (1 / 255.)
+    for layer in list(model.analysis_transform)[1:]:
+      act, layer.activation = layer.activation, None
+      pre = layer(h)
+      layer.activation = act
+      if isinstance(act, GDN):
+        ms, h = _stage_ms(lambda: act(pre))
+        gdn_ms += ms
+      else:
+        h = pre if act is None else act(pre)
+    out[name] = {
+        "images": f"[{batch},{hw},{hw},3] uint8 (synthetic, seed 1), random-init weights",
+        "compress_ms": enc_ms, "decompress_ms": dec_ms,
+        "images_per_s_compress": batch / (enc_ms * 1e-3), "images_per_s_decompress": batch / (dec_ms * 1e-3),
+        "stages_ms": {"analysis_transform (cuDNN convs + GDN kernels)": ana_ms, "of which GDN kernels": gdn_ms,
+                      "entropy models compress (quantise + range encode + pack)": code_ms,
+                      "entropy models decompress": decode_ms,
+                      "synthesis_transform (cuDNN transposed convs + IGDN kernels)": syn_ms},
+        "symbols": int(n_sym), "bits_per_pixel": 8.0 * nbytes / (batch * hw * hw),
+        "coder_msym_s": n_sym / (code_ms * 1e-3) / 1e6,
+        "reconstruction_shape": list(x_hat.shape), "round_trip_is_uint8": bool(x_hat.dtype == torch.uint8),
+    }
+    del model, x, xf, y, y_hat, x_hat, packed
+    torch.cuda.empty_cache()
+  return out

@@ -16,13 +16,16 @@
 //
 // Every arithmetic step of the coder itself is executed by the reference's
 // tensorflow_compression::RangeEncoder / RangeDecoder objects.  Streams are sharded
-// over std::thread workers to emulate the reference's ParallelFor over streams
+// over a PERSISTENT pool of std::thread workers (created once, reused by every call) to
+// emulate the reference's ParallelFor over streams on TF's intra-op pool
 // (range_coder_kernels.cc:212-218).
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
 // legs may load the library built from this file.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -148,18 +151,86 @@ int32_t OverflowDecode(tfc::RangeDecoder& dec, const Row& row) {
   return sign ? -value : value + max_value - 1;
 }
 
+// Persistent worker pool: the reference runs its per-stream loop on TensorFlow's intra-op pool through
+// ParallelFor (range_coder_kernels.cc:212-218) -- threads that already exist when the op is called.  The
+// workers here are created once, on the first multi-threaded call, and sleep between calls; a call hands
+// out contiguous blocks of streams through an atomic cursor (the analogue of ParallelFor's cost-based
+// sharding: enough blocks per thread to balance streams of unequal length).
+class StreamPool {
+ public:
+  static StreamPool& Get() {
+    static StreamPool* pool = new StreamPool;  // never destroyed: workers outlive every caller
+    return *pool;
+  }
+
+  void Run(int64_t n, int threads, const std::function<void(int64_t, int64_t)>& fn) {
+    if (threads <= 1 || n <= 1) {
+      fn(0, n);
+      return;
+    }
+    std::lock_guard<std::mutex> serial(run_mu_);  // one parallel region at a time
+    const int want = static_cast<int>(std::min<int64_t>(threads, n)) - 1;  // the caller works too
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      while (static_cast<int>(workers_.size()) < want) {
+        const int id = static_cast<int>(workers_.size());
+        workers_.emplace_back([this, id] { Worker(id); });
+      }
+      fn_ = &fn;
+      n_ = n;
+      block_ = std::max<int64_t>(1, n / (4 * (want + 1)));
+      next_.store(0, std::memory_order_relaxed);
+      active_ = want;
+      pending_ = want;
+      ++epoch_;
+    }
+    wake_.notify_all();
+    Drain();
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [this] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+
+  int size() {
+    std::lock_guard<std::mutex> lk(mu_);
+    return static_cast<int>(workers_.size());
+  }
+
+ private:
+  void Drain() {
+    for (;;) {
+      const int64_t lo = next_.fetch_add(block_, std::memory_order_relaxed);
+      if (lo >= n_) return;
+      (*fn_)(lo, std::min(n_, lo + block_));
+    }
+  }
+  void Worker(int id) {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        wake_.wait(lk, [&] { return epoch_ != seen; });
+        seen = epoch_;
+        if (id >= active_) continue;  // this region uses fewer threads than the pool holds
+      }
+      Drain();
+      std::lock_guard<std::mutex> lk(mu_);
+      if (--pending_ == 0) done_.notify_one();
+    }
+  }
+
+  std::mutex run_mu_, mu_;
+  std::condition_variable wake_, done_;
+  std::vector<std::thread> workers_;
+  const std::function<void(int64_t, int64_t)>* fn_ = nullptr;
+  int64_t n_ = 0, block_ = 1;
+  std::atomic<int64_t> next_{0};
+  int active_ = 0, pending_ = 0;
+  uint64_t epoch_ = 0;
+};
+
 void ParallelOverStreams(int64_t n, int threads, const std::function<void(int64_t, int64_t)>& fn) {
-  if (threads <= 1 || n <= 1) {
-    fn(0, n);
-    return;
-  }
-  const int64_t t = std::min<int64_t>(threads, n);
-  std::vector<std::thread> pool;
-  for (int64_t k = 0; k < t; ++k) {
-    const int64_t lo = n * k / t, hi = n * (k + 1) / t;
-    pool.emplace_back([=, &fn] { fn(lo, hi); });
-  }
-  for (auto& th : pool) th.join();
+  StreamPool::Get().Run(n, threads, fn);
 }
 
 struct Encoder {
@@ -597,5 +668,7 @@ int tfcref_pmf_to_cdf(const float* pmf, int64_t rows, int64_t n, int precision, 
 }
 
 int tfcref_hardware_threads() { return static_cast<int>(std::thread::hardware_concurrency()); }
+// Workers currently parked in the persistent pool (0 until the first multi-threaded call).
+int tfcref_pool_threads() { return StreamPool::Get().size(); }
 
 }  // extern "C"

@@ -89,3 +89,46 @@ def test_indexed_quantizes_to_integers_and_bits_follow_the_indexed_prior():
   got = em(torch.where(torch.from_numpy(ok), x, torch.from_numpy(loc).float()), idx, training=False)[1]
   want = -np.log2(np.where(ok, p, scipy.stats.norm.cdf(.5, 0, scale) - scipy.stats.norm.cdf(-.5, 0, scale))).sum(axis=1)
   np.testing.assert_allclose(got.numpy(), want, rtol=2e-3)
+
+
+def test_prior_handed_to_the_model_is_registered_like_a_tf_module_attribute():
+  """continuous_batched.py:205 (`self._prior = prior` on a tf.Module): the prior's variables are the model's
+  trainable variables and checkpoint state."""
+  prior = tfc.NoisyDeepFactorized(batch_shape=(4,))
+  em = tfc.ContinuousBatchedEntropyModel(prior, coding_rank=1)
+  names = {n for n, _ in em.named_parameters()}
+  assert len(names) == len(list(prior.parameters())) > 0
+  assert all(n.startswith("_prior.") for n in names)
+  assert set(em.state_dict()) >= {"_prior." + k for k in prior.state_dict()}
+  eb = tfc.EntropyBottleneck(num_channels=4, compression=False)
+  assert len(list(eb.parameters())) == 8         # 3 matrices + 3 biases + 2 factors for (3, 3) filters
+  # an optimiser built from model.parameters() moves the prior
+  x = torch.randn(16, 4)
+  opt = torch.optim.SGD(em.parameters(), lr=0.1)
+  before = [p.detach().clone() for p in prior.parameters()]
+  _, bits = em(x, training=True)
+  bits.sum().backward()
+  opt.step()
+  assert any(not torch.equal(a, b) for a, b in zip(before, prior.parameters()))
+  del em.prior
+  assert list(em.parameters()) == []
+  with pytest.raises(RuntimeError):
+    em.prior  # pylint:disable=pointless-statement
+
+
+def test_deep_factorized_density_is_differentiable_in_its_input():
+  """deep_factorized.py:195-230: prob/log_prob are functions of x (finite-difference check, factors != 0)."""
+  torch.manual_seed(3)
+  d = tfc.DeepFactorized(batch_shape=(3,), dtype=torch.float64)
+  with torch.no_grad():
+    for f in d.factors:
+      f.copy_(torch.randn_like(f))
+  x = torch.randn(5, 3, dtype=torch.float64).requires_grad_(True)
+  for fn in (d.prob, d.log_prob):
+    g, = torch.autograd.grad(fn(x).sum(), x)
+    h = 1e-5
+    fd = (fn((x + h).detach()) - fn((x - h).detach())) / (2 * h)
+    np.testing.assert_allclose(g.numpy(), fd.detach().numpy(), rtol=1e-5, atol=1e-8)
+  # and under no_grad they still evaluate
+  with torch.no_grad():
+    assert d.prob(x).shape == (5, 3) and not d.log_prob(x).requires_grad

@@ -125,3 +125,32 @@ def test_autograd_wrapper(F):
   y = F.gdn(x, g, b)
   y.square().sum().backward()
   assert x.grad is not None and g.grad.shape == (C, C) and b.grad.shape == (C,)
+
+
+def _err_report(got, want):
+  """(max |err| / max |want|,  max elementwise relative error over entries with |want| >= 1e-2 max |want|)."""
+  got, want = got.double().cpu(), want.double()
+  scale = want.abs().max().item()
+  err = (got - want).abs()
+  big = want.abs() >= 1e-2 * scale
+  return err.max().item() / scale, (err[big] / want.abs()[big]).max().item()
+
+
+@pytest.mark.parametrize("C,n_pix", [(128, 2 * 1024 * 1024 + 77), (192, 2 * 1024 * 1024 + 300)])
+def test_backward_at_two_million_pixels_vs_fp64_oracle(F, C, n_pix):
+  """dgamma / dbeta reduce over every pixel (148 per-CTA partials x thousands of tiles): the accumulation error
+  must not grow past the contract at training-sized inputs.  Measured errors are printed (pytest -s / the log)."""
+  gamma, beta = _params(C, 31)
+  x = _x(n_pix, C, 32)
+  dy = torch.randn(n_pix, C, generator=torch.Generator().manual_seed(33))
+  wx, wg, wb = gdn_oracle.gdn_reference_grads(x, gamma, beta, dy)
+  dx, dg, db = F.gdn_backward(x.cuda(), gamma.cuda(), beta.cuda(), dy.cuda())
+  rep = {name: _err_report(g, w) for name, g, w in (("dx", dx, wx), ("dgamma", dg, wg), ("dbeta", db, wb))}
+  print(f"GDN backward C={C} n_pix={n_pix}: (max err / max |want|, max elementwise rel. err where |want| >= 1% of max) =", rep)
+  for name, (of_max, rel) in rep.items():
+    assert of_max < 1e-5, (name, of_max)
+    assert rel < 2e-5, (name, rel)
+  # forward at the same size, elementwise
+  want = gdn_oracle.gdn_reference(x, gamma, beta)
+  got = F.gdn_forward(x.cuda(), gamma.cuda(), beta.cuda())
+  assert _relerr(got, want) < RTOL

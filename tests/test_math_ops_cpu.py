@@ -6,6 +6,7 @@ import scipy.stats
 import torch
 
 from compression_b200 import math_ops
+import compression_b200 as tfc
 from compression_b200.gdn import GDNParameter
 
 
@@ -91,3 +92,39 @@ def test_gdn_parameter_gradients_propagate():
   assert p.variable.grad is not None and bool((p.variable.grad != 0).all())
   with pytest.raises(ValueError):
     GDNParameter(None)
+
+
+@pytest.mark.parametrize("kw", [dict(epsilon_parameter=None), dict(alpha_parameter=None),
+                                dict(alpha_parameter=None, epsilon_parameter=None, rectify=True),
+                                dict(alpha_parameter=2, epsilon_parameter=None),
+                                dict(alpha_parameter=None, epsilon_parameter=.5, inverse=True)])
+def test_gdn_trainable_exponent_graph_keeps_the_fixed_special_cases(kw):
+  """layers/gdn.py:377-415: |x| for a FIXED alpha == 1 (no rectify), square for a fixed 2, sqrt for a fixed
+  epsilon == .5 -- also when the other exponent is a trainable GDNParameter; a trainable alpha is a plain
+  `inputs ** alpha` on the signed input, as in the reference."""
+  torch.manual_seed(0)
+  C = 6
+  layer = tfc.GDN(**kw)
+  x = torch.randn(9, C)
+  layer.build(x.shape)
+  y = layer._torch_graph(x, x.device)   # the branch GDN.forward takes for callable exponents (device-free)
+  xd, gamma, beta = x.double(), layer.gamma.detach().double(), layer.beta.detach().double()
+  u = torch.relu(xd) if layer.rectify else xd
+  a, e = layer.alpha_parameter, layer.epsilon_parameter
+  if callable(a):
+    pool = u**float(layer.alpha.detach())
+  else:
+    pool = {1: u if layer.rectify else u.abs(), 2: u * u}[a]
+  n = pool @ gamma + beta
+  if callable(e):
+    n = n**float(layer.epsilon.detach())
+  elif e == .5:
+    n = n.sqrt()
+  want = u * n if layer.inverse else u / n
+  assert torch.isfinite(y).all()
+  np.testing.assert_allclose(y.detach().double().numpy(), want.numpy(), rtol=1e-5, atol=1e-6)
+  if not callable(a):   # the fixed-alpha cases are exactly the oracle's graph
+    from oracle import gdn_oracle
+    eps = float(layer.epsilon.detach()) if callable(e) else e
+    ref = gdn_oracle.gdn_reference(x, gamma, beta, layer.inverse, layer.rectify, a, eps)
+    np.testing.assert_allclose(y.detach().double().numpy(), ref.numpy(), rtol=1e-5, atol=1e-6)
