@@ -8,7 +8,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtfcb200.so")
+LIB_PATH = os.environ.get("TFCB_LIB_PATH") or os.path.join(_HERE, "libtfcb200.so")  # (override: kernel experiments)
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "tfcb200.h")
 
 OK, INVALID_ARGUMENT, CUDA_ERROR, OUT_OF_MEMORY = 0, 1, 2, 3

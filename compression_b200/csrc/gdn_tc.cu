@@ -186,6 +186,23 @@ __device__ __forceinline__ void stage_store16(float* dst, const uint32_t (&a)[16
                                                            __uint_as_float(a[4 * i + 2]), __uint_as_float(a[4 * i + 3]));
 }
 
+// dgamma accumulates in TMEM across a CTA's tiles.  The tensor core adds every MMA into the fp32 accumulator with
+// TRUNCATION, so a long-running accumulator shrinks by ~2^-25 per accumulation step: measured 6e-6 of max |dgamma|
+// after one tile per CTA, 6.4e-5 after 110 (2 M pixels), linear in the tile count.  The accumulator is therefore
+// flushed into the CTA's fp32 partial in global memory (round-to-nearest adds, L2 resident) every kDgFlush tiles
+// and restarted; the drift stays below 3e-6 at any pixel count.
+constexpr int kDgFlush = 4;
+
+__device__ __forceinline__ void accum_store16(float* dst, const uint32_t (&a)[16], bool accumulate) {
+  float4 o[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) o[i] = accumulate ? *reinterpret_cast<const float4*>(dst + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    *reinterpret_cast<float4*>(dst + 4 * i) = make_float4(o[i].x + __uint_as_float(a[4 * i]), o[i].y + __uint_as_float(a[4 * i + 1]),
+                                                           o[i].z + __uint_as_float(a[4 * i + 2]), o[i].w + __uint_as_float(a[4 * i + 3]));
+}
+
 constexpr int kF2Threads = 320;   // 8 compute warps + 1 copy warp + 1 MMA-issue warp
 constexpr int kF2Compute = 256;
 constexpr int kF2XBuf = kTileM * 128 * 4;          // one x / y tile, dense [128][128] fp32 (one bulk copy)
@@ -829,11 +846,11 @@ gdn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, con
   const uint32_t b_hi = smem_u32(smem + L::kOffBh), b_lo = smem_u32(smem + L::kOffBl);
   const uint32_t p_hi = smem_u32(smem + L::kOffPh), p_lo = smem_u32(smem + L::kOffPl);
   const long long n_tiles = (n_pix + kTileM - 1) / kTileM;
-  bool first_tile = true;
+  int t_idx = 0;  // this CTA's tile counter (both roles count alike)
 
   if (warp == kBwdCompute / 32) {
     // ------------------------------- MMA-issue warp -------------------------------
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t_idx) {
       // next tile of this CTA -> L2 (one bulk prefetch per array: the tile is contiguous)
       if (lane == 1) {
         const long long pn = (tile + gridDim.x) * kTileM;
@@ -892,7 +909,7 @@ gdn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, con
             const uint64_t dal = umma_desc(p_lo + koff, 128, kKg);
             const uint64_t dbh = umma_desc(q_hi + koff, 128, kKg);
             const uint64_t dbl = umma_desc(q_lo + koff, 128, kKg);
-            const uint32_t acc_on = (first_tile && s == 0) ? 0u : 1u;
+            const uint32_t acc_on = ((t_idx % kDgFlush) == 0 && s == 0) ? 0u : 1u;  // restarted after every flush
             umma_bf16(tmem_dg + (uint32_t)(c * 32), dah, dbh, kIdesc3, acc_on);
             umma_bf16(tmem_dg + (uint32_t)(c * 32), dal, dbh, kIdesc3, 1u);
             umma_bf16(tmem_dg + (uint32_t)(c * 32), dah, dbl, kIdesc3, 1u);
@@ -901,7 +918,6 @@ gdn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, con
         }
         __syncwarp();
       }
-      first_tile = false;
     }
   } else {
   // --------------------------------- compute warps ---------------------------------
@@ -914,8 +930,21 @@ gdn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, con
   const int ckg = tid & 3;         // 8-channel group inside a 32-channel chunk
   const int crow = tid >> 2;       // rows crow and crow + 64
   auto compute_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(kBwdCompute) : "memory"); };
+  bool flushed = false;  // the global partial holds earlier flushes
+  // adds the TMEM dgamma accumulator (lane r = input channel j, this thread's 64 columns) into the CTA's partial
+  auto flush_dgamma = [&]() {
+    float* pg = part_g + (long long)blockIdx.x * C * C + (long long)r * C + h * 64;
+#pragma unroll
+    for (int cb = 0; cb < 4; ++cb) {
+      uint32_t a[16];
+      tmem_load<16>(tmem_dg + lane_sel + (uint32_t)(h * 64 + cb * 16), a);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      accum_store16(pg + cb * 16, a, flushed);
+    }
+    flushed = true;
+  };
 
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t_idx) {
     const long long p0 = tile * kTileM;
     // ---- P1: p = pool(x) -> hi / lo planes [j / 8][row][8]; item = (row, kg), 16 groups per row ----
     {
@@ -1071,23 +1100,17 @@ gdn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, con
         }
       }
     }
+    // every MMA of this tile has completed (the two waits above): flush the dgamma accumulator when due
+    if ((t_idx % kDgFlush) == kDgFlush - 1) flush_dgamma();
     // the staging (= operand planes) and the n / dp columns are rewritten by the next tile
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     compute_sync();
-    first_tile = false;
   }
 
   // ---- this CTA's partial sums ----
-  if (!first_tile) {
+  if (t_idx > 0) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    float* pg = part_g + (long long)blockIdx.x * C * C + (long long)r * C + h * 64;  // lane r = input channel j
-#pragma unroll
-    for (int cb = 0; cb < 4; ++cb) {
-      uint32_t a[16];
-      tmem_load<16>(tmem_dg + lane_sel + (uint32_t)(h * 64 + cb * 16), a);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      stage_store16(pg + cb * 16, a);
-    }
+    if ((t_idx % kDgFlush) != 0) flush_dgamma();  // tiles since the last flush
     // dbeta: lanes with the same tid % 4 hold the same channels
 #pragma unroll
     for (int c = 0; c < NCH; ++c)
@@ -1447,12 +1470,12 @@ gdn_tc_bwd_dgamma_kernel(const float* __restrict__ x, const float* __restrict__ 
   const uint32_t tmem_a = *tmem_slot, tmem_b = tmem_a + C;  // rows j in [0,128) | rows j in [64,192)
   const uint32_t lane_sel = (uint32_t)(gwarp * 32) << 16;
   const long long n_tiles = (n_pix + kTileM - 1) / kTileM;
-  bool first_tile = true;
+  int t_idx = 0;  // this CTA's tile counter (both roles count alike)
 
   if (warp == kBwdCompute / 32) {
     const uint32_t p_hi = smem_u32(smem + L::kOffPh), p_lo = smem_u32(smem + L::kOffPl);
     const uint32_t q_hi = smem_u32(smem + L::kOffQh), q_lo = smem_u32(smem + L::kOffQl);
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t_idx) {
       if (lane == 1) {
         const long long pn = (tile + gridDim.x) * kTileM;
         const long long rows = min((long long)kTileM, n_pix - pn);
@@ -1475,7 +1498,7 @@ gdn_tc_bwd_dgamma_kernel(const float* __restrict__ x, const float* __restrict__ 
             const uint64_t dal = umma_desc(p_lo + moff + koff, 128, kKg);
             const uint64_t dbh = umma_desc(q_hi + koff, 128, kKg);
             const uint64_t dbl = umma_desc(q_lo + koff, 128, kKg);
-            umma_bf16(td, dah, dbh, kIdesc, (first_tile && s == 0) ? 0u : 1u);
+            umma_bf16(td, dah, dbh, kIdesc, ((t_idx % kDgFlush) == 0 && s == 0) ? 0u : 1u);  // restarted after a flush
             umma_bf16(td, dal, dbh, kIdesc, 1u);
             umma_bf16(td, dah, dbl, kIdesc, 1u);
           }
@@ -1483,18 +1506,36 @@ gdn_tc_bwd_dgamma_kernel(const float* __restrict__ x, const float* __restrict__ 
         umma_commit(smem_u32(mbar));
       }
       __syncwarp();
-      first_tile = false;
     }
   } else {
   uint32_t par = 0u;
+  bool flushed = false;  // the global partial holds earlier flushes
+  // block a: lane r = channel j = r; block b: lane r = channel 64 + r (only its rows >= 128 are new)
+  auto flush_dgamma = [&]() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+    for (int blk = 0; blk < 2; ++blk) {
+      const int j = blk ? 64 + r : r;
+      float* pg = part_g + (long long)blockIdx.x * C * C + (long long)j * C + h * (C / 2);
+#pragma unroll
+      for (int cb = 0; cb < C / 32; ++cb) {
+        uint32_t a[16];
+        tmem_load<16>((blk ? tmem_b : tmem_a) + lane_sel + (uint32_t)(h * (C / 2) + cb * 16), a);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (!blk || r >= 64) accum_store16(pg + cb * 16, a, flushed);
+      }
+    }
+    flushed = true;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  };
   float dbeta_acc[PERIOD][8];
 #pragma unroll
   for (int a = 0; a < PERIOD; ++a)
 #pragma unroll
     for (int e = 0; e < 8; ++e) dbeta_acc[a][e] = 0.f;
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t_idx) {
     const long long p0 = tile * kTileM;
-    bool waited = first_tile;
+    bool waited = t_idx == 0;
 #pragma unroll
     for (int pass = 0; pass < ITEMS / 4; ++pass) {
       float4 xv[4][2], qv[4][2];
@@ -1514,6 +1555,7 @@ gdn_tc_bwd_dgamma_kernel(const float* __restrict__ x, const float* __restrict__ 
         if (!mbar_wait(smem_u32(mbar), par)) __trap();
         par ^= 1u;
         waited = true;
+        if ((t_idx % kDgFlush) == 0) flush_dgamma();  // t_idx tiles are in the accumulator and complete
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -1538,24 +1580,11 @@ gdn_tc_bwd_dgamma_kernel(const float* __restrict__ x, const float* __restrict__ 
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     asm volatile("bar.arrive 2, %0;" ::"n"(kBwdThreads) : "memory");
-    first_tile = false;
   }
-  if (!first_tile) {
+  if (t_idx > 0) {
     if (!mbar_wait(smem_u32(mbar), par)) __trap();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // block a: lane r = channel j = r; block b: lane r = channel 64 + r (only its rows >= 128 are new)
-#pragma unroll 1
-    for (int blk = 0; blk < 2; ++blk) {
-      const int j = blk ? 64 + r : r;
-      float* pg = part_g + (long long)blockIdx.x * C * C + (long long)j * C + h * (C / 2);
-#pragma unroll
-      for (int cb = 0; cb < C / 32; ++cb) {
-        uint32_t a[16];
-        tmem_load<16>((blk ? tmem_b : tmem_a) + lane_sel + (uint32_t)(h * (C / 2) + cb * 16), a);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (!blk || r >= 64) stage_store16(pg + cb * 16, a);
-      }
-    }
+    // the tiles since the last flush (a flush is due at the top of a NEXT tile, so a full period may be pending)
+    flush_dgamma();
 #pragma unroll
     for (int a = 0; a < PERIOD; ++a) {
       const int kg = (a * kBwdCompute + tid) % KG;

@@ -184,64 +184,65 @@ struct DeviceLookup {
 // (`cbits`, bit w = "a carry left the 32-bit window while word w was its top half", i.e. +1 into
 // word w-1; bit `cnt` is the pending carry of the not yet emitted top word).
 struct EncState {
-  uint32_t base;  // low end of the interval (32-bit window, wraps)
-  uint32_t span;  // size - 1
-  uint32_t cnt;   // 16-bit words appended so far
-  uint32_t pad;
+  uint32_t base;  // low end of the interval (32-bit window, wraps), renormalised
+  uint32_t span;  // size - 1, renormalised (what RangeEncoder::Finalize looks at)
+  uint32_t cnt;   // 16-bit words appended so far (a stream holds < 2^31 words = 4 GB)
+  uint32_t raw;   // size - 1 BEFORE the renormalisation that followed the last symbol (what the chain resumes from)
 };
 
-// Pre-scaled operands of one Encode(lower, upper, p): {lower', 0, upper', addend_hi}.
-//   lower' = lower << (32 - p);  a  = hi32(span * lower' + {lower', 0})          = floor(size*lower/2^p)
-//   upper' = upper << (32 - p);  b1 = hi32(span * upper' + {upper', 0xFFFFFFFF}) = floor(size*upper/2^p) - 1
-//   upper == 2^p (does not fit 32 bits): upper' = 0xFFFFFFFF, addend_hi = 0      -> b1 = span = size - 1
-// (exact for every span in [2^16 - 1, 2^32 - 1]; checked exhaustively against the reference formula.)
+// THE RECURRENCE.  The reference keeps (base, size - 1) and, after every Encode, multiplies both by 2^16 when
+// size - 1 < 2^16 (range_coder.cc:69-84).  Only the interval SIZE feeds back into the next symbol, and the
+// renormalisation is a select between two multiplies on that dependent chain.  Here the chain carries the
+// UN-renormalised span `s` of the last symbol and never materialises the shifted one:
+//
+//   r    = s < 2^16                                 (the renormalisation the reference did after the last symbol)
+//   Q(c) = s * ch + ch,   ch = c << (16 - p)        (64-bit: (s + 1) * c * 2^(16-p); c = 2^p fits: ch = 2^16)
+//   floor(size * c / 2^p) = r ? Q : Q >> 16         (size = (s + 1) << 16r; exact; low 32 bits)
+//   L = that for `lower`, U = that for `upper`;   s' = U - L - 1   (mod 2^32: a full-range symbol at size 2^32 wraps
+//                                                                   to the right value)
+// i.e. per symbol the dependent chain is  IADD3 -> IMAD.WIDE -> SHF (funnel by 0 or 16) -> IADD3, with the predicate
+// of the shift amount evaluated beside the multiply -- no select between two multiplies.  {L, s'} per Encode is
+// all the chain produces; the interval's low end, the carries, the emitted words and the word count are PREFIX
+// computations over those entries and are done by the drain warp, 32 entries at a time (EncDrain).
+// (Formula checked against the reference's on random triples: precisions 1..16, full-range, single-count and
+// top-hugging symbols, from the initial state; the GPU tests compare whole streams with the compiled reference.)
+
+// Pre-scaled operands of one Encode(lower, upper, p): {lower << (16-p), 0, upper << (16-p), 0}.  The zeros are
+// the high halves of the two multiply-adds' 64-bit addends: one 128-bit shared-memory load puts each bound's
+// addend in a register pair of its own.
 __device__ __forceinline__ uint4 enc_operands(uint32_t lower, uint32_t upper, uint32_t p) {
-  const uint32_t sh = 32u - p;
-  const bool full = upper == (1u << p);
-  return make_uint4(lower << sh, 0u, full ? 0xFFFFFFFFu : (upper << sh), full ? 0u : 0xFFFFFFFFu);
+  const uint32_t sh = 16u - p;
+  return make_uint4(lower << sh, 0u, upper << sh, 0u);
 }
 
-// A single warp per stream is LATENCY bound by the serial recurrence (measured: IMAD.HI ~10 cycles,
-// ISETP->SEL ~7; ~37 cycles per symbol for the 4-instruction dependent chain), so everything that is
-// not the recurrence is moved off that warp:
-//   chain warp   : span / base / word-count recurrence; leaves one {base after the add, word count}
-//                  entry per Encode() in shared memory (EncChain);
-//   drain warp   : reconstructs carries, 16-bit words and carry bits from 32 entries at a time, all
-//                  lanes in parallel (EncDrain);
-//   gather warp  : symbol loads, quantisation, table lookups, operand pre-scaling (encode_kernel).
-struct ChunkInfo {
-  uint32_t n;         // entries in this chunk (<= 32)
-  uint32_t cnt_end;   // word count after the last entry
-  uint32_t last;      // nonzero: no further chunk follows
-  uint32_t pad;
-};
-
 struct EncChain {
-  uint32_t base, span, cnt;
-  uint2* ent;  // current entry buffer (shared, 32 entries)
+  uint32_t s;  // un-renormalised span after the last symbol
 
-  // One Encode(lower, upper, precision) of range_coder.cc:37-264; `slot` is where its entry goes.
-  // Operands come pre-scaled (see enc_operands): with c' = c << (32 - p) the reference's
-  // floor(size * c / 2^p) is the HIGH word of  span * c' + c'  -- one IMAD.HI, no shift -- and the
-  // upper bound's "- 1" (and the c == 2^p corner) is folded into the 64-bit addend.
-  __device__ __forceinline__ void step(uint4 o, int slot) { step(make_uint2(o.x, o.y), make_uint2(o.z, o.w), slot); }
-  __device__ __forceinline__ void step(uint2 ol, uint2 oh, int slot) {
-    const unsigned long long ta = (unsigned long long)span * ol.x + (((unsigned long long)ol.y << 32) | ol.x);
-    const unsigned long long tb = (unsigned long long)span * oh.x + (((unsigned long long)oh.y << 32) | oh.x);
-    const uint32_t a = (uint32_t)(ta >> 32);   // floor(size * lower / 2^p)
-    const uint32_t b1 = (uint32_t)(tb >> 32);  // floor(size * upper / 2^p) - 1
-    const uint32_t nb = base + a;
-    const uint32_t s = b1 - a;
-    ent[slot] = make_uint2(nb, cnt);
-    const bool renorm = s < 65536u;
-    span = renorm ? ((s << 16) | 0xFFFFu) : s;
-    base = renorm ? (nb << 16) : nb;
-    cnt += renorm ? 1u : 0u;
+  // One Encode(lower, upper, precision) of range_coder.cc:37-264 -> the entry {L, s'}.
+  __device__ __forceinline__ uint2 step(uint2 ol, uint2 oh) {
+    const unsigned long long ql = (unsigned long long)s * ol.x + (((unsigned long long)ol.y << 32) | ol.x);
+    const unsigned long long qu = (unsigned long long)s * oh.x + (((unsigned long long)oh.y << 32) | oh.x);
+    const uint32_t shift = (s < 65536u) ? 0u : 16u;
+    const uint32_t L = __funnelshift_r((uint32_t)ql, (uint32_t)(ql >> 32), shift);
+    const uint32_t U = __funnelshift_r((uint32_t)qu, (uint32_t)(qu >> 32), shift);
+    s = U - L - 1u;
+    return make_uint2(L, s);
   }
+  __device__ __forceinline__ uint2 step(uint4 o) { return step(make_uint2(o.x, o.y), make_uint2(o.z, o.w)); }
 };
 
+// x << s for s in [0, 32] (s == 32 gives 0): one funnel shift.
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t x, uint32_t s) { return __funnelshift_lc(0u, x, s); }
+
+// Rebuilds everything the chain left out from its entries {L_k, s'_k}, 32 entries per pass, all lanes in parallel.
+// Entry k renormalises iff s'_k < 2^16.  The low end obeys  base_{k+1} = (base_k + L_k) << sh_k  (sh_k = 16 or 0,
+// mod 2^32), a composition of maps  x -> (x << S) + A  which is closed under composition
+// ((x << S1) + A1) << S2) + A2 = (x << (S1 + S2)) + (A1 << S2) + A2,  so a warp-wide scan over (A, S) gives every
+// lane the base its entry was added to; the carry out of the 32-bit window is then `base_k + L_k` overflowing, the
+// emitted word is the top half of that sum, and the word index is a prefix popcount of the renormalisation flags.
 struct EncDrain {
-  uint32_t dbase;   // base before the first entry of the next chunk
+  uint32_t dbase;   // base before the first entry of the next pass
+  uint32_t cnt;     // words emitted so far
   uint32_t cb_cur;  // carry bits of word group (cnt >> 5) accumulated so far
   uint16_t* words;
   uint32_t* cbits;
@@ -251,6 +252,7 @@ struct EncDrain {
 
   __device__ __forceinline__ void begin(const EncState& st, uint16_t* w, uint32_t* cb, uint32_t cap_, int lane_) {
     dbase = st.base;
+    cnt = st.cnt;
     words = w;
     cbits = cb;
     cap = cap_;
@@ -259,46 +261,75 @@ struct EncDrain {
     cb_cur = (st.cnt == 0) ? 0u : cb[st.cnt >> 5];
   }
 
-  // Resolves entries [0, n) of `ent` (32 per pass): emits the word of every renormalising entry and ORs
-  // the carry bits into the per-32-words carry masks.
-  __device__ __forceinline__ void drain(const uint2* ent, int n, uint32_t cnt_end) {
-    for (int e0 = 0; e0 < n; e0 += 32) {
-      const int m = min(32, n - e0);
-      const uint2* en = ent + e0;
-      const bool act = lane < m;
-      const uint2 me = en[act ? lane : 0];
-      const uint2 pv = en[(act && lane > 0) ? lane - 1 : 0];
-      const uint32_t pass_end = (e0 + 32 < n) ? en[32].y : cnt_end;  // word count after this pass
-      const uint32_t cnt_next = (lane + 1 < m) ? en[lane + 1].y : pass_end;
-      const uint32_t before = (lane == 0) ? dbase : ((me.y != pv.y) ? (pv.x << 16) : pv.x);
-      const bool carry = act && (me.x < before);
-      const bool ren = act && cnt_next != me.y;
+  // Entries [0, n) of `ent`, n <= kPasses * 32.  The scans of the passes do not depend on each other (only the
+  // final application of `dbase` does), so they are issued together and their shuffle latencies overlap.
+  template <int kPasses>
+  __device__ __forceinline__ void drain(const uint2* ent, int n) {
+    uint32_t Lk[kPasses], Ak[kPasses], Sk[kPasses], rmask[kPasses];
+#pragma unroll
+    for (int p = 0; p < kPasses; ++p) {
+      const int k = p * 32 + lane;
+      const bool act = k < n;
+      const uint2 me = ent[act ? k : 0];
+      const bool rr = act && me.y < 65536u;
+      rmask[p] = __ballot_sync(kFull, rr);
+      Lk[p] = act ? me.x : 0u;
+      uint32_t S = rr ? 16u : 0u;
+      uint32_t A = Lk[p] << S;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {  // inclusive scan of the maps: lane l ends with f_l o ... o f_0
+        const uint32_t Ap = __shfl_up_sync(kFull, A, d);
+        const uint32_t Sp = __shfl_up_sync(kFull, S, d);
+        if (lane >= d) {
+          A = shl_clamp(Ap, S) + A;
+          S = min(Sp + S, 32u);
+        }
+      }
+      Ak[p] = A;
+      Sk[p] = S;
+    }
+#pragma unroll
+    for (int p = 0; p < kPasses; ++p) {
+      if (p * 32 >= n) break;
+      // exclusive prefix = the map of the entries before this lane's
+      uint32_t Ax = __shfl_up_sync(kFull, Ak[p], 1);
+      uint32_t Sx = __shfl_up_sync(kFull, Sk[p], 1);
+      if (lane == 0) {
+        Ax = 0u;
+        Sx = 0u;
+      }
+      const uint32_t before = shl_clamp(dbase, Sx) + Ax;  // base this entry's L was added to
+      const uint32_t nb = before + Lk[p];
+      const bool carry = nb < before;                     // (inactive lanes: L = 0, never)
+      const bool ren = (rmask[p] >> lane) & 1u;
+      const uint32_t my_cnt = cnt + __popc(rmask[p] & ((1u << lane) - 1u));  // word count before this entry
       if (ren) {
-        if (me.y < cap) words[me.y] = (uint16_t)(me.x >> 16);
+        if (my_cnt < cap) words[my_cnt] = (uint16_t)(nb >> 16);
         else overflowed = true;
       }
-      const uint32_t g0 = en[0].y >> 5;
-      const uint32_t bit = 1u << (me.y & 31u);
-      const uint32_t m0 = __reduce_or_sync(kFull, (carry && (me.y >> 5) == g0) ? bit : 0u);
-      const uint32_t m1 = __reduce_or_sync(kFull, (carry && (me.y >> 5) != g0) ? bit : 0u);
+      const uint32_t g0 = cnt >> 5;
+      const uint32_t bit = 1u << (my_cnt & 31u);
+      const uint32_t m0 = __reduce_or_sync(kFull, (carry && (my_cnt >> 5) == g0) ? bit : 0u);
+      const uint32_t m1 = __reduce_or_sync(kFull, (carry && (my_cnt >> 5) != g0) ? bit : 0u);
+      const uint32_t pass_end = cnt + __popc(rmask[p]);
       cb_cur |= m0;
       if ((pass_end >> 5) != g0) {
         if (lane == 0 && g0 < (cap >> 5)) cbits[g0] = cb_cur;
         cb_cur = m1;
       }
-      // base after the last entry of this pass = the next pass's "before"
-      const uint2 lastent = en[m - 1];
-      dbase = (pass_end != lastent.y) ? (lastent.x << 16) : lastent.x;
+      cnt = pass_end;
+      // base after the last entry of this pass
+      dbase = shl_clamp(dbase, __shfl_sync(kFull, Sk[p], 31)) + __shfl_sync(kFull, Ak[p], 31);
     }
   }
 
-  __device__ __forceinline__ void end(uint32_t cnt_end, DevError* err, long long stream) {
-    if ((cnt_end >> 5) < (cap >> 5)) {
-      if (lane == 0) cbits[cnt_end >> 5] = cb_cur;
+  __device__ __forceinline__ void end(DevError* err, long long stream) {
+    if ((cnt >> 5) < (cap >> 5)) {
+      if (lane == 0) cbits[cnt >> 5] = cb_cur;
     } else {
       overflowed = true;
     }
-    if (__any_sync(kFull, overflowed)) report(err, kErrCapacity, stream, cnt_end, cnt_end, cap);
+    if (__any_sync(kFull, overflowed)) report(err, kErrCapacity, stream, cnt, cnt, cap);
   }
 };
 
@@ -310,6 +341,7 @@ struct EncParams {
   int n_rows;
   int uniform_prec;        // > 0: every row has this precision
   int n_sms;
+  int rot;                 // warp-role rotation of the CTAs of the second wave (see encode_kernel)
   const void* value;       // int32 or float [S, n]
   const int32_t* index;    // [S, n] or null
   const float* qoff;       // channel+f32: [n_rows] or null; index+f32: loc [S, n] or null
@@ -323,12 +355,12 @@ struct EncParams {
   DevError* err;
 };
 
-// The gather of one group of 32 symbols is split in two stages so that no global-memory latency is
+// The gather of one pass of 32 symbols is split in two stages so that no global-memory latency is
 // ever exposed to the (in-order) warp:
-//   stage A, two groups ahead : the symbol itself (y / value, index, loc) and, in channel mode, the row
-//                               descriptor and the per-row offsets -- all independent loads;
-//   stage B, one group ahead  : quantise, range-check, escape mapping, then the two table loads;
-//   (current group)           : the table values are written to shared memory for the serial chain.
+//   stage A, three passes ahead : the symbol itself (y / value, index, loc) and, in channel mode, the row
+//                                 descriptor and the per-row offsets -- all independent loads;
+//   stage B, current pass       : quantise, range-check, escape mapping, then the two table loads and the
+//                                 operand records written to shared memory for the serial chain.
 struct Fetched {
   float y;
   int v;
@@ -379,7 +411,7 @@ __device__ __forceinline__ Fetched enc_fetch(const EncParams& P, long long s, lo
 template <int MODE>
 __device__ __forceinline__ Gathered enc_gather(const EncParams& P, long long s, long long j, Fetched f) {
   Gathered g;
-  g.ops = make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);
+  g.ops = make_uint4(0u, 0u, 0u, 0u);
   g.prec = 0;
   g.gamma = 0;
   g.sign = 0;
@@ -426,91 +458,111 @@ __device__ __forceinline__ void bar_arrive(int id, int count) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
-struct GroupMeta {
-  unsigned esc_mask;   // lanes whose symbol escapes
-  unsigned sign_mask;  // sign bits of the escapes
-  unsigned bad;        // an argument error was recorded: stop
-  unsigned pad;
+// Shared state of one code stream's CTA.  The unit of every hand-off is a BLOCK of up to kBlock operand records
+// (gather -> chain) and the same number of entries (chain -> drain), double buffered; one barrier round trip per
+// block and direction.  The gather warp writes the record stream the chain consumes blindly: an escaping symbol
+// is followed by the records of its Elias-gamma bits (OverflowEncode, range_coder_kernels.cc:306-321), so the
+// chain warp has no special cases at all.
+#ifndef TFCB_ENC_BLOCK
+#define TFCB_ENC_BLOCK 256
+#endif
+constexpr int kBlock = TFCB_ENC_BLOCK;
+
+struct BlockInfo {
+  uint32_t n;     // records / entries in this block (kBlock except for the last one)
+  uint32_t last;  // nonzero: no further block follows
 };
 
-// Shared state of one code stream's CTA (three warps on three SM sub-partitions).  A hand-off unit is a
-// GROUP of kGroup symbols (kGroup / 32 gather passes); one barrier round trip per group and direction.
-constexpr int kGroup = 128;
-constexpr int kSub = kGroup / 32;
-
 struct EncShared {
-  uint4 ops[2][kGroup + 2];  // gather -> chain: pre-scaled operands, double buffered per group (+2: prefetch overrun)
-  uint32_t gamma[2][kGroup];
-  GroupMeta meta[2][kSub];
-  uint2 ent[2][kGroup + 1];  // chain -> drain: entries, double buffered per chunk (+1: drain reads en[32])
-  ChunkInfo chunk[2];
+  uint4 ops[2][kBlock + 2];   // (+2: the chain's operand prefetch may run two records past the block)
+  uint2 ent[2][kBlock];
+  BlockInfo ops_info[2];
+  BlockInfo ent_info[2];
 };
 
 enum : int { kBarOpsFull = 1, kBarOpsEmpty = 3, kBarEntFull = 5, kBarEntEmpty = 7 };
 
-// Chain-warp helper: publishes the current entry buffer as a chunk and switches to the other one.
-struct ChunkWriter {
+// Gather-warp helper: appends records to the block stream, handing full blocks to the chain warp.
+struct RecordWriter {
   EncShared* sh;
-  long long chunks;
-  int n;  // entries in the current buffer
+  long long blocks;  // blocks published so far
+  int fill;          // records in the current block
 
-  __device__ __forceinline__ void begin(EncShared* sh_, EncChain& c) {
+  __device__ __forceinline__ void begin(EncShared* sh_) {
     sh = sh_;
-    chunks = 0;
-    n = 0;
-    c.ent = sh->ent[0];
+    blocks = 0;
+    fill = 0;
   }
-  __device__ __forceinline__ void publish(EncChain& c, bool last) {
-    const int b = (int)(chunks & 1);
+  __device__ __forceinline__ uint4* cur() { return sh->ops[blocks & 1]; }
+  __device__ __forceinline__ void publish(bool last) {
+    const int b = (int)(blocks & 1);
     if ((threadIdx.x & 31) == 0) {
-      ChunkInfo ci;
-      ci.n = (uint32_t)n;
-      ci.cnt_end = c.cnt;
-      ci.last = last ? 1u : 0u;
-      ci.pad = 0;
-      sh->chunk[b] = ci;
+      BlockInfo bi;
+      bi.n = (uint32_t)fill;
+      bi.last = last ? 1u : 0u;
+      sh->ops_info[b] = bi;
     }
-    bar_arrive(kBarEntFull + b, 64);  // arrive orders the preceding shared-memory writes
-    ++chunks;
-    n = 0;
-    if (!last) {
-      const int nb = (int)(chunks & 1);
-      if (chunks >= 2) bar_sync(kBarEntEmpty + nb, 64);  // the drain warp is done with that buffer
-      c.ent = sh->ent[nb];
-    }
+    bar_arrive(kBarOpsFull + b, 64);  // arrive orders the preceding shared-memory writes
+    ++blocks;
+    fill = 0;
+    if (!last && blocks >= 2) bar_sync(kBarOpsEmpty + (int)(blocks & 1), 64);  // the chain is done with that buffer
   }
-  // slow path: append one step, hand over when the buffer is full
-  __device__ __forceinline__ void step(EncChain& c, uint4 o) {
-    c.step(o, n);
-    if (++n == kGroup) publish(c, false);
-  }
-  // Escape tail of OverflowEncode (range_coder_kernels.cc:306-321): Elias-gamma code of g, then the
-  // sign, every bit coded with the uniform binary CDF {0,1,2} at precision 1.
-  __device__ __forceinline__ void gamma(EncChain& c, uint32_t g, uint32_t sign) {
-    const int nb = 32 - __clz(g);  // g >= 1
-    for (int i = 1; i < nb; ++i) step(c, enc_operands(0, 1, 1));
-    for (int i = nb - 1; i >= 0; --i) {
-      const uint32_t bit = (g >> i) & 1u;
-      step(c, enc_operands(bit, bit + 1, 1));
+  // Appends this pass's records: lane's own record `first` at pass-local position `pre`, followed by `extra` more
+  // produced by `rec(i)`; `total` = all lanes' records.  Blocks are filled exactly; a pass may straddle blocks.
+  template <typename F>
+  __device__ __forceinline__ void append(uint4 first, int pre, int extra, int total, bool has, F rec) {
+    int done = 0;
+    while (done < total) {
+      const int room = kBlock - fill;
+      const int take = min(room, total - done);
+      uint4* dst = cur() + fill - done;  // record with pass-local position i goes to dst[i]
+      if (has) {
+        if (pre >= done && pre < done + take) dst[pre] = first;
+        for (int i = 0; i < extra; ++i) {
+          const int at = pre + 1 + i;
+          if (at >= done && at < done + take) dst[at] = rec(i);
+        }
+      }
+      fill += take;
+      done += take;
+      if (fill == kBlock) publish(false);
     }
-    step(c, enc_operands(sign, sign + 1, 1));
   }
 };
 
+// Record i of the escape tail of OverflowEncode (range_coder_kernels.cc:306-321): nb - 1 zero bits, the nb bits
+// of g (MSB first), then the sign, each coded with the uniform binary CDF {0, 1, 2} at precision 1.
+__device__ __forceinline__ uint4 gamma_record(uint32_t g, uint32_t sign, int nb, int i) {
+  uint32_t bit;
+  if (i < nb - 1) bit = 0u;
+  else if (i < 2 * nb - 1) bit = (g >> (2 * nb - 2 - i)) & 1u;
+  else bit = sign;
+  return enc_operands(bit, bit + 1u, 1u);
+}
+
 template <int MODE>
-__global__ void __launch_bounds__(128) encode_kernel(const EncParams P) {
+__global__ void __launch_bounds__(192) encode_kernel(const EncParams P) {
   __shared__ __align__(16) EncShared sh;
   const long long s = blockIdx.x;
   const int lane = threadIdx.x & 31;
-  // role: 0 chain, 1 gather, 2 drain, 3 idle.  The fourth warp exits at once: with four warps per CTA the two
-  // CTAs that share an SM map role for role onto the same sub-partitions (chain with chain, gather with gather),
-  // instead of the second CTA's gather warp landing on the first CTA's chain warp.  Measured: fused-quantise
-  // mode 1.15 -> 1.07 ms at cfg2; mirroring the roles of the second CTA instead was slower (1.19 ms).
+  // Roles: 0 chain, 1 gather, 2 drain, 3 idle (exits at once).  Only the per-stream latency of the chain warp
+  // matters (there are more schedulers than streams), so the layout's job is to keep a chain warp alone on its
+  // sub-partition (warp slot mod 4) when two CTAs share an SM:
+  //   six warps per CTA (P.rot < 0): warp 0 chain, 1 gather, 5 drain, 2..4 idle -- the first CTA of an SM takes slots
+  //     0..5 (chain on sub-partition 0, gather + drain on 1), the second slots 6..11 (chain on 2, gather + drain on 3);
+  //   four warps per CTA (P.rot = 0..3): roles rotated by P.rot in the CTAs launched after the first wave.
+  // Measured: profiles/r2_encode_notes.md.
   const int warp = threadIdx.x >> 5;
-  if (warp == 3) return;
-  const long long n_groups = (P.n + kGroup - 1) / kGroup;
+  int role;
+  if (P.rot < 0) {
+    role = warp == 0 ? 0 : (warp == 1 ? 1 : (warp == 5 ? 2 : 3));
+  } else {
+    const int rot = (blockIdx.x >= (unsigned)P.n_sms) ? P.rot : 0;
+    role = (warp - rot) & 3;
+  }
+  if (role == 3) return;
 
-  if (warp == 1) {
+  if (role == 1) {
     // ------------------------------- gather warp -------------------------------
     uint32_t row_a = 0, chan_step = 0;
     if (!(MODE & kModeIndex)) {
@@ -530,125 +582,111 @@ __global__ void __launch_bounds__(128) encode_kernel(const EncParams P) {
     advance_row();
     Fetched f2 = enc_fetch<MODE>(P, s, 64 + lane, row_a);
     advance_row();
-    long long pass = 0;
-    for (long long g = 0; g < n_groups; ++g) {
-      const int b = (int)(g & 1);
-      if (g >= 2) bar_sync(kBarOpsEmpty + b, 64);  // the chain warp is done with this buffer
-      unsigned any_bad = 0;
-#pragma unroll
-      for (int sub = 0; sub < kSub; ++sub, ++pass) {
-        const Fetched fcur = f0;
-        f0 = f1;
-        f1 = f2;
-        f2 = enc_fetch<MODE>(P, s, (pass + 3) * 32 + lane, row_a);
-        advance_row();
-        const long long j0 = pass * 32;
-        const Gathered cur = enc_gather<MODE>(P, s, j0 + lane, fcur);
-        const int count = (int)max(0ll, min(32ll, P.n - j0));
-        const unsigned esc_mask = __ballot_sync(kFull, cur.gamma != 0);
-        const unsigned sign_mask = __ballot_sync(kFull, cur.sign != 0);
-        const unsigned bad_mask = __ballot_sync(kFull, cur.prec == 0 && lane < count);
-        sh.ops[b][sub * 32 + lane] = cur.ops;
-        sh.gamma[b][sub * 32 + lane] = cur.gamma;
-        if (lane == 0) {
-          GroupMeta m;
-          m.esc_mask = esc_mask;
-          m.sign_mask = sign_mask;
-          m.bad = bad_mask;
-          m.pad = 0;
-          sh.meta[b][sub] = m;
-        }
-        any_bad |= bad_mask;
+    RecordWriter w;
+    w.begin(&sh);
+    const long long n_pass = (P.n + 31) / 32;
+    bool stop = false;
+    for (long long pass = 0; pass < n_pass && !stop; ++pass) {
+      const Fetched fcur = f0;
+      f0 = f1;
+      f1 = f2;
+      f2 = enc_fetch<MODE>(P, s, (pass + 3) * 32 + lane, row_a);
+      advance_row();
+      const long long j0 = pass * 32;
+      const Gathered cur = enc_gather<MODE>(P, s, j0 + lane, fcur);
+      const int count = (int)min(32ll, P.n - j0);
+      const bool has = lane < count;
+      const unsigned esc_mask = __ballot_sync(kFull, cur.gamma != 0);
+      const unsigned bad_mask = __ballot_sync(kFull, cur.prec == 0 && has);
+      if (bad_mask) {  // argument error already recorded: code nothing more of this stream
+        stop = true;
+        break;
       }
-      bar_arrive(kBarOpsFull + b, 64);
-      if (any_bad) break;
+      if (esc_mask == 0) {
+        if (w.fill + count <= kBlock) {  // the common case: one store per lane
+          if (has) w.cur()[w.fill + lane] = cur.ops;
+          w.fill += count;
+          if (w.fill == kBlock) w.publish(false);
+        } else {
+          w.append(cur.ops, lane, 0, count, has, [&](int) { return cur.ops; });
+        }
+      } else {
+        const int nb = cur.gamma ? 32 - __clz(cur.gamma) : 0;
+        const int mine = has ? 1 + 2 * nb : 0;
+        int incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int t = __shfl_up_sync(kFull, incl, d);
+          if (lane >= d) incl += t;
+        }
+        const int total = __shfl_sync(kFull, incl, 31);
+        w.append(cur.ops, incl - mine, 2 * nb, total, has,
+                 [&](int i) { return gamma_record(cur.gamma, cur.sign, nb, i); });
+      }
     }
+    w.publish(true);  // (possibly empty) final block: lets the other two warps finish
     return;
   }
 
-  if (warp == 2) {
+  if (role == 2) {
     // ------------------------------- drain warp -------------------------------
     EncDrain d;
     d.begin(P.state[s], P.words + s * P.cap, P.cbits + s * (P.cap >> 5), (uint32_t)P.cap, lane);
     for (long long k = 0;; ++k) {
       const int b = (int)(k & 1);
       bar_sync(kBarEntFull + b, 64);
-      const ChunkInfo ci = sh.chunk[b];
-      d.drain(sh.ent[b], (int)ci.n, ci.cnt_end);
-      if (ci.last) {
-        d.end(ci.cnt_end, P.err, s);
-        break;
-      }
+      const BlockInfo bi = sh.ent_info[b];
+      d.drain<kBlock / 32>(sh.ent[b], (int)bi.n);
+      if (bi.last) break;
       bar_arrive(kBarEntEmpty + b, 64);
+    }
+    d.end(P.err, s);
+    if (lane == 0) {
+      P.state[s].base = d.dbase;
+      P.state[s].cnt = d.cnt;
     }
     return;
   }
 
   // --------------------------------- chain warp ---------------------------------
   EncChain c;
-  {
-    const EncState st = P.state[s];
-    c.base = st.base;
-    c.span = st.span;
-    c.cnt = st.cnt;
-  }
-  ChunkWriter w;
-  w.begin(&sh, c);
-  bool stop = false;
-  for (long long g = 0; g < n_groups && !stop; ++g) {
-    const int b = (int)(g & 1);
+  c.s = P.state[s].raw;
+  for (long long k = 0;; ++k) {
+    const int b = (int)(k & 1);
     bar_sync(kBarOpsFull + b, 64);
-    for (int sub = 0; sub < kSub; ++sub) {
-      const GroupMeta meta = sh.meta[b][sub];
-      if (meta.bad) {  // argument error already recorded; stop this stream
-        stop = true;
-        break;
-      }
-      const int count = (int)max(0ll, min(32ll, P.n - (g * kGroup + sub * 32)));
-      const uint4* ops = sh.ops[b] + sub * 32;
-      if (count == 32 && meta.esc_mask == 0 && w.n + 32 <= kGroup) {
-        // static slots; operands are fetched two symbols ahead so that the shared-memory latency stays
-        // off the chain
-        uint2* const ent_save = c.ent;
-        c.ent = ent_save + w.n;
-        // two 64-bit loads per symbol (not one 128-bit one): each multiply-add gets its addend in a
-        // register pair of its own, which keeps ptxas from inserting pair-copy MOVs on the chain warp
-        const uint2* q = reinterpret_cast<const uint2*>(ops);
-        uint2 l0 = q[0], h0 = q[1];
+    const BlockInfo bi = sh.ops_info[b];
+    if (k >= 2) bar_sync(kBarEntEmpty + b, 64);  // the drain warp is done with this entry buffer
+    // operands are fetched two records ahead so that the shared-memory latency stays off the chain; two 64-bit
+    // loads per record: each multiply-add gets its addend in a register pair of its own
+    const uint2* q = reinterpret_cast<const uint2*>(sh.ops[b]);
+    uint2* e = sh.ent[b];
+    const int n = (int)bi.n;
+    int kk = 0;
+    uint2 l0 = q[0], h0 = q[1], l1 = q[2], h1 = q[3];
 #pragma unroll 1
-        for (int kk = 0; kk < 32; kk += 8) {
-          const uint2* p = q + 2 * kk;
-          uint2* const e = c.ent;
+    for (; kk + 8 <= n; kk += 8) {
+      const uint2* p = q + 2 * kk;
+      uint2* const eo = e + kk;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {  // immediates only; the prefetch may run 1 entry past the group (padded)
-            const uint2 ol = l0, oh = h0;
-            l0 = p[2 * j + 2];
-            h0 = p[2 * j + 3];
-            c.step(ol, oh, j);
-          }
-          c.ent = e + 8;
-        }
-        c.ent = ent_save;
-        w.n += 32;
-        if (w.n == kGroup) w.publish(c, false);
-      } else {
-        for (int k = 0; k < count; ++k) {
-          w.step(c, ops[k]);
-          if ((meta.esc_mask >> k) & 1u) w.gamma(c, sh.gamma[b][sub * 32 + k], (meta.sign_mask >> k) & 1u);
-        }
+      for (int j = 0; j < 8; j += 2) {  // immediates only
+        const uint2 a0 = l0, b0 = h0, a1 = l1, b1 = h1;
+        l0 = p[2 * j + 4];
+        h0 = p[2 * j + 5];
+        l1 = p[2 * j + 6];
+        h1 = p[2 * j + 7];
+        eo[j] = c.step(a0, b0);
+        eo[j + 1] = c.step(a1, b1);
       }
     }
-    if (w.n > 0) w.publish(c, false);  // one chunk per group in the common case
-    if (g + 2 < n_groups) bar_arrive(kBarOpsEmpty + b, 64);
+    for (; kk < n; ++kk) e[kk] = c.step(sh.ops[b][kk]);
+    if (lane == 0) sh.ent_info[b] = bi;
+    bar_arrive(kBarEntFull + b, 64);  // arrive orders the preceding shared-memory writes
+    if (bi.last) break;
+    bar_arrive(kBarOpsEmpty + b, 64);
   }
-  w.publish(c, true);  // (possibly empty) final chunk: lets the drain warp finish
   if (lane == 0) {
-    EncState st;
-    st.base = c.base;
-    st.span = c.span;
-    st.cnt = c.cnt;
-    st.pad = 0;
-    P.state[s] = st;
+    P.state[s].span = (c.s < 65536u) ? ((c.s << 16) | 0xFFFFu) : c.s;
+    P.state[s].raw = c.s;
   }
 }
 
@@ -662,7 +700,7 @@ __global__ void enc_init_state_kernel(EncState* st, long long n) {
     s.base = 0;
     s.span = 0xFFFFFFFFu;
     s.cnt = 0;
-    s.pad = 0;
+    s.raw = 0xFFFFFFFFu;
     st[i] = s;
   }
 }
@@ -1461,12 +1499,9 @@ __global__ void __launch_bounds__(32) legacy_encode_kernel(const int16_t* data, 
   st0.base = 0;
   st0.span = 0xFFFFFFFFu;
   st0.cnt = 0;
-  st0.pad = 0;
+  st0.raw = 0xFFFFFFFFu;
   EncChain c;
-  c.base = st0.base;
-  c.span = st0.span;
-  c.cnt = 0;
-  c.ent = s_ent;
+  c.s = st0.raw;
   EncDrain d;
   d.begin(st0, words, cbits, (uint32_t)cap, lane);
   for (long long g0 = 0; g0 < n; g0 += 32) {
@@ -1490,20 +1525,25 @@ __global__ void __launch_bounds__(32) legacy_encode_kernel(const int16_t* data, 
       }
     }
     if (__ballot_sync(kFull, bad)) break;
-    for (int k = 0; k < count; ++k) {
+    uint2 mine = make_uint2(0u, 0u);
+    for (int k = 0; k < count; ++k) {  // every lane runs the same recurrence; lane k keeps entry k
       const uint32_t lo = __shfl_sync(kFull, lower, k);
       const uint32_t hi = __shfl_sync(kFull, upper, k);
-      c.step(enc_operands(lo, hi, (uint32_t)precision), k);
+      const uint2 e = c.step(enc_operands(lo, hi, (uint32_t)precision));
+      if (lane == k) mine = e;
     }
-    d.drain(s_ent, count, c.cnt);
+    s_ent[lane] = mine;
+    __syncwarp();
+    d.drain<1>(s_ent, count);
+    __syncwarp();
   }
-  d.end(c.cnt, err, 0);
+  d.end(err, 0);
   if (lane == 0) {
     EncState st;
-    st.base = c.base;
-    st.span = c.span;
-    st.cnt = c.cnt;
-    st.pad = 0;
+    st.base = d.dbase;
+    st.span = (c.s < 65536u) ? ((c.s << 16) | 0xFFFFu) : c.s;
+    st.cnt = d.cnt;
+    st.raw = c.s;
     state[0] = st;
   }
 }
@@ -1746,6 +1786,16 @@ int ensure_capacity(tfcb_encoder* h, long long extra_words, cudaStream_t s) {
   return TFCB_OK;
 }
 
+// Warp-role rotation of the second-wave CTAs (0..3); TFCB_ENC_ROT overrides the default for experiments.
+int enc_role_rotation() {
+  static int rot = [] {
+    const char* e = getenv("TFCB_ENC_ROT");
+    if (e && e[0] >= '0' && e[0] <= '3') return e[0] - '0';
+    return -1;  // default: the six-warp layout (11.7 vs 11.2 Gsym/s at cfg2, profiles/r2_encode_notes.md)
+  }();
+  return rot;
+}
+
 template <int MODE>
 int launch_encode(tfcb_encoder* h, const void* value, const int32_t* index, const float* qoff,
                   const int32_t* coff, long long n, cudaStream_t s) {
@@ -1765,6 +1815,7 @@ int launch_encode(tfcb_encoder* h, const void* value, const int32_t* index, cons
   P.n_rows = h->lut.n_rows;
   P.uniform_prec = h->lut.uniform_prec;
   P.n_sms = device_sm_count();
+  P.rot = enc_role_rotation();
   P.value = value;
   P.index = index;
   P.qoff = qoff;
@@ -1777,7 +1828,7 @@ int launch_encode(tfcb_encoder* h, const void* value, const int32_t* index, cons
   P.cap = h->cap;
   P.err = h->err;
   if (h->n_streams > 0x7FFFFFFFll) return fail(TFCB_INVALID_ARGUMENT, "too many streams");
-  encode_kernel<MODE><<<(unsigned)h->n_streams, 128, 0, s>>>(P);
+  encode_kernel<MODE><<<(unsigned)h->n_streams, P.rot < 0 ? 192 : 128, 0, s>>>(P);
   TFCB_LAUNCHED();
   TFCB_CUDA_TRY(cudaGetLastError());
   return TFCB_OK;
