@@ -17,6 +17,7 @@
 // coalesced pass  y = x / (beta + n)  with x re-read from L2.
 //
 // Everything outside {C in {128, 192}, alpha in {1, 2}, eps in {1, 0.5}} falls back to the fp32 kernels in gdn.cu.
+#include <cuda.h>  // CUtensorMap (types only; cuTensorMapEncodeTiled is fetched through the runtime)
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -155,6 +156,13 @@ __device__ __forceinline__ void tmem_load<32>(uint32_t taddr, uint32_t (&r)[32])
         "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
+}
+
+template <>
+__device__ __forceinline__ void tmem_load<8>(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
 }
 
 template <>
@@ -473,252 +481,371 @@ int launch_tc_fwd2(const float* x, const float* gamma, const float* beta, float*
 
 
 // =============================================================================================
-// Forward, C = 192 (third kernel shape): gamma's planes take 144 KB, so the x tile cannot live in shared
-// memory.  8 compute warps + 1 MMA-issue warp; x is converted straight from registers (coalesced loads, three
-// 32-channel chunks in flight), the issue warp runs the MMAs as the chunks arrive, and the epilogue transposes
-// n through a [128][68] staging buffer (over the dead operand planes) 64 columns at a time while x comes back
-// from L2 one chunk ahead.
+// Forward, C = 192, fourth kernel shape: everything that touches HBM is asynchronous, and the epilogue of one
+// tile runs between the conversion chunks of the next.
+//
+// gamma's hi + lo planes (144 KB) leave no room for x, and feeding the conversion and the epilogue from registers
+// (the round-1 kernel, 52 % of the HBM roofline) leaves every compute thread waiting on its own loads and stores
+// (clock64 trace of a ring-fed variant with register stores: 5.2 k of 15.9 k cycles per tile in the epilogue's store
+// back-pressure, 3 k waiting for boxes of a three-slot ring, 1.7 k waiting for the tensor pipe).  So:
+//   * only gamma's HI plane is resident (72 KB); the LO plane is needed by one of the three products only and is
+//     streamed from L2 per 32-channel K chunk (12 KB bulk copies, double buffered) by a "gamma" warp;
+//   * x arrives as [128 rows x 32 channels] 2-D TMA boxes (128-byte swizzle) in two three-slot rings, twice per
+//     tile: boxes C0..C5 feed the pool + bf16 split, boxes E0..E5 (L2 hits) feed the epilogue; the whole next tile is
+//     prefetched into L2 with one bulk prefetch;
+//   * the epilogue needs no transpose: thread (r, h) takes 16 accumulator columns of ITS pixel row from TMEM,
+//     reads the same 64 bytes of x from its row of the E box (the swizzle makes the row-per-lane access conflict
+//     free), overwrites them with y = x / (beta + n), and a "store" warp sends the box out with a 2-D TMA store;
+//   * two accumulators in TMEM: while the tensor pipe works on tile t + 1 (it is the slower side of the conversion
+//     phase), the compute warps finish box c - 1 of tile t after converting chunk c of tile t + 1.
+// No compute thread ever waits on a global load or store, and there is no CTA-wide barrier in the steady state.
+// Rows past n_pix: zero-filled on load, clipped on store.
 // =============================================================================================
-constexpr int kF3Threads = 288, kF3Compute = 256;
-constexpr int kF3Kg = kTileM * 16 + 160;        // see kF2Kg
-constexpr int kF3Plane = 4 * kF3Kg;             // hi or lo plane of a 32-channel chunk
+// L2 eviction-priority descriptors for bulk / tensor copies (the values createpolicy.fractional.L2::evict_* produces
+// for fraction 1.0; same constants as CUTLASS's TMA::CacheHintSm90)
+constexpr unsigned long long kEvictFirst = 0x12F0000000000000ull, kEvictLast = 0x14F0000000000000ull;
+
+constexpr int kF4Compute = 512;                  // 16 compute warps: four per scheduler, the work is latency bound
+constexpr int kF4Threads = kF4Compute + 160;     // + MMA-issue, C-copy, E-copy, gamma and store warps
+constexpr int kF4Sync = kF4Compute + 32;         // compute + issue warps (the named barriers of the plane hand-off)
+constexpr int kF4Box = kTileM * 32 * 4;          // one x box: [128][32] fp32, 128-byte rows, 128B-swizzled
+constexpr int kF4Kg = kTileM * 16 + 32;          // plane group stride: padding = 2 (mod 8) 16-byte units (see kF2Kg)
+constexpr int kF4Plane = 4 * kF4Kg;              // hi or lo plane of a 32-channel chunk
 
 template <int C>
-struct Fwd3Smem {
-  static constexpr int kPlaneB = C * C * 2;
+struct Fwd4Smem {
+  static constexpr int kPlaneB = C * C * 2;                 // gamma hi (resident)
+  static constexpr int kGlo = 4 * C * 16;                   // one 32-channel K chunk of gamma lo
   static constexpr int kOffBh = 0;
-  static constexpr int kOffBl = kOffBh + kPlaneB;
-  static constexpr int kOffP = kOffBl + kPlaneB;            // [2 buffers][hi, lo]; staging aliases it
-  static constexpr int kOffBar = kOffP + 4 * kF3Plane;
-  static constexpr int kBytes = kOffBar + 64;
-  static_assert(4 * kF3Plane >= kTileM * kF2StLd * 4, "staging must fit in the operand-plane area");
+  static constexpr int kOffRing = kOffBh + kPlaneB;         // [3] C boxes, [3] E boxes (1024-byte aligned: swizzle atom)
+  static constexpr int kOffGlo = kOffRing + 6 * kF4Box;     // [2] gamma lo chunks
+  static constexpr int kOffP = kOffGlo + 2 * kGlo;          // [2 buffers][hi, lo] operand planes
+  static constexpr int kOffBeta = kOffP + 4 * kF4Plane;
+  static constexpr int kOffBar = kOffBeta + C * 4;
+  // mbarriers: plane[2], gfull[2], cfull[3], cempty[3], efull[3], eempty[3], yready[3]; then the TMEM slot
+  static constexpr int kBarPlane = 0, kBarGfull = 2, kBarCfull = 4, kBarCempty = 7, kBarEfull = 10, kBarEempty = 13,
+                       kBarY = 16, kNumBars = 19;
+  static constexpr int kBytes = kOffBar + kNumBars * 8 + 16;
+  static_assert(kOffRing % 1024 == 0 && kOffGlo % 128 == 0 && kOffP % 128 == 0, "alignment");
   static_assert(kBytes <= 232448, "shared memory budget");
 };
 
 template <int C, bool FAST>
-__global__ void __launch_bounds__(kF3Threads, 1)
-gdn_tc_fwd3_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ planes,
-                   const float* __restrict__ beta, float* __restrict__ y, long long n_pix, TcFlags f) {
-  using L = Fwd3Smem<C>;
-  constexpr int NCH = C / 32;  // 6 conversion chunks
-  constexpr int NEP = C / 64;  // 3 epilogue chunks
-  static_assert(C % 64 == 0 && NCH % 2 == 0, "chunking");
+__global__ void __launch_bounds__(kF4Threads, 1)
+gdn_tc_fwd4_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUtensorMap y_map,
+                   const float* __restrict__ x, const __nv_bfloat16* __restrict__ planes,
+                   const float* __restrict__ beta, long long n_pix, TcFlags f) {
+  using L = Fwd4Smem<C>;
+  constexpr int NCH = C / 32;  // 6 boxes per pass over a tile
   extern __shared__ __align__(1024) uint8_t smem[];
-  float* stage = reinterpret_cast<float*>(smem + L::kOffP);
-  uint64_t* mbars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);  // [0,1] plane buffers
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffBar + 24);
+  float* beta_s = reinterpret_cast<float*>(smem + L::kOffBeta);
+  uint64_t* mbars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffBar + L::kNumBars * 8);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int r = tid & 127, h = (tid >> 7) & 1, gwarp = warp & 3;
+  const int r = tid & 127, h = (tid >> 7) & 3, gwarp = warp & 3;  // compute thread (r, h): pixel row r, column quarter h
   constexpr uint32_t kIdesc = umma_idesc(kTileM, C);
+  auto bar = [&](int i) { return smem_u32(mbars + i); };
   {
-    const uint4* src = reinterpret_cast<const uint4*>(planes);
+    const uint4* src = reinterpret_cast<const uint4*>(planes);  // hi plane first
     uint4* dst = reinterpret_cast<uint4*>(smem + L::kOffBh);
-    for (int i = tid; i < 2 * L::kPlaneB / 16; i += kF3Threads) dst[i] = src[i];
+    for (int i = tid; i < L::kPlaneB / 16; i += kF4Threads) dst[i] = src[i];
+    for (int i = tid; i < C; i += kF4Threads) beta_s[i] = beta[i];
   }
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbars + i)));
+    for (int i = 0; i < L::kNumBars; ++i) {
+      const int count = (i >= L::kBarY) ? kF4Compute / 32 : 1;  // y ready: one arrival per compute warp
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar(i)), "r"(count));
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < 32) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_n = *tmem_slot;
+  const uint32_t tmem_base = *tmem_slot;            // accumulator of tile t: columns (t & 1) * 256 ..
   const uint32_t lane_sel = (uint32_t)(gwarp * 32) << 16;
-  const uint32_t b_hi = smem_u32(smem + L::kOffBh), b_lo = smem_u32(smem + L::kOffBl);
+  const uint32_t b_hi = smem_u32(smem + L::kOffBh);
   const long long n_tiles = (n_pix + kTileM - 1) / kTileM;
 
-  if (warp == kF3Compute / 32) {
-    // ------------------------------- MMA-issue warp -------------------------------
+  // A box ring of three slots: request n uses slot n % 3 in its (n / 3)-th round.
+  auto load_boxes = [&](int ring, bool prefetch_l2) {  // ring 0: C boxes, 1: E boxes
+    const int full0 = ring ? L::kBarEfull : L::kBarCfull, empty0 = ring ? L::kBarEempty : L::kBarCempty;
+    uint32_t n = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      if (lane == 1) {
+      const int row0 = (int)(tile * kTileM);
+      if (prefetch_l2) {  // the next tile of this CTA -> L2 (one contiguous block): its boxes become L2 hits
         const long long pn = (tile + gridDim.x) * kTileM;
         const long long rows = min((long long)kTileM, n_pix - pn);
         if (rows > 0)
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(x + pn * C), "r"((uint32_t)(rows * C * 4)) : "memory");
+          asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(x + pn * C),
+                       "r"((uint32_t)(rows * C * 4)), "l"(kEvictLast)
+                       : "memory");
       }
 #pragma unroll 1
-      for (int c = 0; c < NCH; ++c) {
+      for (int k = 0; k < NCH; ++k, ++n) {
+        const uint32_t slot = n % 3u, round = n / 3u;
+        if (round > 0) {
+          if (!mbar_wait(bar(empty0 + slot), (round - 1u) & 1u)) __trap();
+        }
+        const uint32_t full = bar(full0 + slot);
+        const uint32_t dst = smem_u32(smem + L::kOffRing + (ring * 3 + slot) * kF4Box);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "n"(kF4Box) : "memory");
+        // x is read twice (C box, then E box about a tile later): the first read asks L2 to keep the lines, the
+        // second releases them (ncu before the hints: 1.54x the algorithmic DRAM reads at 16.7 M pixels)
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(dst),
+            "l"(&x_map), "r"(k * 32), "r"(row0), "r"(full), "l"(ring ? kEvictFirst : kEvictLast)
+            : "memory");
+      }
+    }
+  };
+
+  constexpr int W0 = kF4Compute / 32;  // first auxiliary warp
+  if (warp == W0 + 1 || warp == W0 + 2) {
+    // ---------------------------------- copy warps: C boxes / E boxes ----------------------------------
+    if (lane == 0) load_boxes(warp - (W0 + 1), warp == W0 + 1);
+    __syncwarp();
+  } else if (warp == W0 + 3) {
+    // ---------------------------------- gamma warp: lo-plane chunks ----------------------------------
+    if (lane == 0) {
+      const uint8_t* lo_plane = reinterpret_cast<const uint8_t*>(planes) + L::kPlaneB;
+      uint32_t n = 0;  // chunks requested so far; chunk n uses buffer n & 1
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c, ++n) {
+          const uint32_t buf = n & 1u;
+          if (n >= 2) {  // the MMAs of chunk n - 2 (same buffer, same plane mbarrier) have completed
+            if (!mbar_wait(bar(L::kBarPlane + buf), ((n >> 1) - 1u) & 1u)) __trap();
+          }
+          const uint32_t gfull = bar(L::kBarGfull + buf);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gfull), "n"(L::kGlo) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                           smem_u32(smem + L::kOffGlo + buf * L::kGlo)),
+                       "l"(lo_plane + (size_t)c * L::kGlo), "n"(L::kGlo), "r"(gfull)
+                       : "memory");
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == W0 + 4) {
+    // ---------------------------------- store warp: y boxes ----------------------------------
+    if (lane == 0) {
+      uint32_t n = 0;
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int row0 = (int)(tile * kTileM);
+#pragma unroll 1
+        for (int k = 0; k < NCH; ++k, ++n) {
+          const uint32_t slot = n % 3u, round = n / 3u;
+          if (!mbar_wait(bar(L::kBarY + slot), round & 1u)) __trap();
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;" ::"l"(&y_map),
+                       "r"(k * 32), "r"(row0), "r"(smem_u32(smem + L::kOffRing + (3 + slot) * kF4Box)), "l"(kEvictFirst)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the box has been read: the slot is free
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar(L::kBarEempty + slot)) : "memory");
+        }
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
+  } else if (warp == W0) {
+    // ------------------------------- MMA-issue warp -------------------------------
+    uint32_t parg[2] = {0u, 0u};
+    uint32_t n = 0;  // chunk counter = C box counter
+    int t = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+      const uint32_t tmem_n = tmem_base + (uint32_t)(t & 1) * 256u;
+#pragma unroll 1
+      for (int c = 0; c < NCH; ++c, ++n) {
         const int pb = c & 1;
-        asm volatile("bar.sync %0, %1;" ::"r"(2 + pb), "n"(kF3Threads) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"r"(2 + pb), "n"(kF4Sync) : "memory");  // planes of chunk c are written
         if (lane == 0) {
+          // every compute thread is done with this C box: hand its slot back to the copy warp
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar(L::kBarCempty + n % 3u)) : "memory");
+          if (!mbar_wait(bar(L::kBarGfull + pb), parg[pb])) __trap();
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t ph = smem_u32(smem + L::kOffP + pb * 2 * kF3Plane), pl = ph + kF3Plane;
+          const uint32_t ph = smem_u32(smem + L::kOffP + pb * 2 * kF4Plane), pl = ph + kF4Plane;
+          const uint32_t g_lo = smem_u32(smem + L::kOffGlo + pb * L::kGlo);
 #pragma unroll
           for (int s2 = 0; s2 < 2; ++s2) {
-            const uint64_t dah = umma_desc(ph + (uint32_t)(2 * s2) * kF3Kg, kF3Kg, 128);
-            const uint64_t dal = umma_desc(pl + (uint32_t)(2 * s2) * kF3Kg, kF3Kg, 128);
-            const uint32_t b_off = (uint32_t)(c * 4 + 2 * s2) * (C * 16);
-            const uint64_t dbh = umma_desc(b_hi + b_off, C * 16, 128);
-            const uint64_t dbl = umma_desc(b_lo + b_off, C * 16, 128);
+            const uint64_t dah = umma_desc(ph + (uint32_t)(2 * s2) * kF4Kg, kF4Kg, 128);
+            const uint64_t dal = umma_desc(pl + (uint32_t)(2 * s2) * kF4Kg, kF4Kg, 128);
+            const uint64_t dbh = umma_desc(b_hi + (uint32_t)(c * 4 + 2 * s2) * (C * 16), C * 16, 128);
+            const uint64_t dbl = umma_desc(g_lo + (uint32_t)(2 * s2) * (C * 16), C * 16, 128);
             umma_bf16(tmem_n, dah, dbh, kIdesc, (c | s2) ? 1u : 0u);
             umma_bf16(tmem_n, dal, dbh, kIdesc, 1u);
             umma_bf16(tmem_n, dah, dbl, kIdesc, 1u);
           }
-          umma_commit(smem_u32(mbars + pb));
+          umma_commit(bar(L::kBarPlane + pb));
         }
+        parg[pb] ^= 1u;
         __syncwarp();
       }
     }
   } else {
   // --------------------------------- compute warps ---------------------------------
   uint32_t parp[2] = {0u, 0u};
-  const int ckg = tid & 3, crow = tid >> 2;    // conversion items of a 32-channel chunk: rows crow, crow + 64
-  const int ekg = tid & 7, erow = tid >> 3;    // epilogue items of a 64-channel chunk: rows erow + 32 i
-  auto compute_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(kF3Compute) : "memory"); };
+  uint32_t nc = 0, ne = 0;                     // C boxes converted / E boxes finished so far
+  const int ckg = tid & 3, crow = tid >> 2;    // conversion item of a box: row crow, 8 channels
+  // 128-byte swizzle: the 16-byte chunk j of box row `row` sits at chunk j ^ (row & 7)
+  auto chunk_at = [](uint8_t* box, int row, int j) { return reinterpret_cast<float4*>(box + row * 128 + ((j ^ (row & 7)) << 4)); };
 
-  // x of half a tile (three 32-channel chunks) in registers; the first half of the NEXT tile is requested before
-  // the epilogue of the current one, so its latency is hidden behind the epilogue.
-  auto load_half = [&](long long tile, int half, float4 (&xv)[NCH / 2][2][2]) {
-    const long long p0 = tile * kTileM;
-#pragma unroll
-    for (int k = 0; k < NCH / 2; ++k)
-#pragma unroll
-      for (int it = 0; it < 2; ++it) {
-        const int row = crow + 64 * it;
-        const bool live = tile < n_tiles && p0 + row < n_pix;
-        const float4* src = reinterpret_cast<const float4*>(x + (p0 + row) * C + (half * (NCH / 2) + k) * 32 + ckg * 8);
-        xv[k][it][0] = live ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
-        xv[k][it][1] = live ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-  };
-  auto convert_half = [&](int half, const float4 (&xv)[NCH / 2][2][2]) {
-#pragma unroll
-    for (int k = 0; k < NCH / 2; ++k) {
-      const int c = half * (NCH / 2) + k, pb = c & 1;
-      if (c >= 2) {
-        if (!mbar_wait(smem_u32(mbars + pb), parp[pb])) __trap();
-        parp[pb] ^= 1u;
-      }
-      uint8_t* ph = smem + L::kOffP + pb * 2 * kF3Plane;
-#pragma unroll
-      for (int it = 0; it < 2; ++it) {
-        const int row = crow + 64 * it;
-        const float4 a = xv[k][it][0], b = xv[k][it][1];
-        float v[8] = {tc_pool<FAST>(a.x, f), tc_pool<FAST>(a.y, f), tc_pool<FAST>(a.z, f), tc_pool<FAST>(a.w, f),
-                      tc_pool<FAST>(b.x, f), tc_pool<FAST>(b.y, f), tc_pool<FAST>(b.z, f), tc_pool<FAST>(b.w, f)};
-        uint4 hi, lo;
-        split8(v, &hi, &lo);
-        *reinterpret_cast<uint4*>(ph + ckg * kF3Kg + row * 16) = hi;
-        *reinterpret_cast<uint4*>(ph + kF3Plane + ckg * kF3Kg + row * 16) = lo;
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      asm volatile("bar.arrive %0, %1;" ::"r"(2 + pb), "n"(kF3Threads) : "memory");
-    }
-  };
-  float4 xa[NCH / 2][2][2];
-  load_half(blockIdx.x, 0, xa);
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long long p0 = tile * kTileM;
-    // ---- pool + split, 32 channels at a time ----
-    {
-      float4 xb[NCH / 2][2][2];
-      load_half(tile, 1, xb);
-      convert_half(0, xa);
-      convert_half(1, xb);
-    }
-    load_half(tile + gridDim.x, 0, xa);
-    // ---- epilogue: y = x / (beta + n), 64 channels at a time; x of the next chunk is in flight ----
-    float4 xe[2][4][2];
-    auto load_xe = [&](int set, int cc) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int row = erow + 32 * i;
-        const bool live = p0 + row < n_pix;
-        const float4* src = reinterpret_cast<const float4*>(x + (p0 + row) * C + cc * 64 + ekg * 8);
-        xe[set][i][0] = live ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
-        xe[set][i][1] = live ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    };
-    load_xe(0, 0);
-#pragma unroll
-    for (int pb = 0; pb < 2; ++pb) {  // the last two commits cover every MMA of the tile; the planes are dead
-      if (!mbar_wait(smem_u32(mbars + pb), parp[pb])) __trap();
+  auto convert = [&](int c, bool wait_planes) {
+    const int pb = c & 1;
+    const uint32_t slot = nc % 3u, round = nc / 3u;
+    uint8_t* box = smem + L::kOffRing + slot * kF4Box;
+    if (!mbar_wait(bar(L::kBarCfull + slot), round & 1u)) __trap();
+    const float4 a = *chunk_at(box, crow, 2 * ckg), b = *chunk_at(box, crow, 2 * ckg + 1);
+    if (wait_planes) {  // the plane buffer is still being read by the MMAs of the chunk two before this one
+      if (!mbar_wait(bar(L::kBarPlane + pb), parp[pb])) __trap();
       parp[pb] ^= 1u;
     }
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-    for (int cc = 0; cc < NEP; ++cc) {
-      const int set = cc & 1;
-      if (cc + 1 < NEP) load_xe(set ^ 1, cc + 1);
-      {
-        uint32_t acc[32];
-        tmem_load<32>(tmem_n + lane_sel + (uint32_t)(cc * 64 + h * 32), acc);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        float* dst = stage + r * kF2StLd + h * 32;
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          *reinterpret_cast<float4*>(dst + 4 * i) = make_float4(__uint_as_float(acc[4 * i]), __uint_as_float(acc[4 * i + 1]),
-                                                                 __uint_as_float(acc[4 * i + 2]), __uint_as_float(acc[4 * i + 3]));
-      }
-      compute_sync();
-      const float4 bv0 = __ldg(reinterpret_cast<const float4*>(beta + cc * 64 + ekg * 8));
-      const float4 bv1 = __ldg(reinterpret_cast<const float4*>(beta + cc * 64 + ekg * 8) + 1);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int row = erow + 32 * i;
-        const float* ns = stage + row * kF2StLd + ekg * 8;
-        const float4 n0 = *reinterpret_cast<const float4*>(ns), n1 = *reinterpret_cast<const float4*>(ns + 4);
-        const float4 x0 = xe[set][i][0], x1 = xe[set][i][1];
-        float4 o0, o1;
-        o0.x = tc_out<FAST>(x0.x, bv0.x + n0.x, f);
-        o0.y = tc_out<FAST>(x0.y, bv0.y + n0.y, f);
-        o0.z = tc_out<FAST>(x0.z, bv0.z + n0.z, f);
-        o0.w = tc_out<FAST>(x0.w, bv0.w + n0.w, f);
-        o1.x = tc_out<FAST>(x1.x, bv1.x + n1.x, f);
-        o1.y = tc_out<FAST>(x1.y, bv1.y + n1.y, f);
-        o1.z = tc_out<FAST>(x1.z, bv1.z + n1.z, f);
-        o1.w = tc_out<FAST>(x1.w, bv1.w + n1.w, f);
-        if (p0 + row < n_pix) {
-          float4* dst = reinterpret_cast<float4*>(y + (p0 + row) * C + cc * 64 + ekg * 8);
-          __stcs(dst, o0);  // streaming stores: keep x / dy (re-read from L2) resident instead of the outputs
-          __stcs(dst + 1, o1);
-        }
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      compute_sync();  // staging free again (and, after the last chunk, for the next tile's operand planes)
+    uint8_t* ph = smem + L::kOffP + pb * 2 * kF4Plane;
+    {
+      float v[8] = {tc_pool<FAST>(a.x, f), tc_pool<FAST>(a.y, f), tc_pool<FAST>(a.z, f), tc_pool<FAST>(a.w, f),
+                    tc_pool<FAST>(b.x, f), tc_pool<FAST>(b.y, f), tc_pool<FAST>(b.z, f), tc_pool<FAST>(b.w, f)};
+      uint4 hi, lo;
+      split8(v, &hi, &lo);
+      *reinterpret_cast<uint4*>(ph + ckg * kF4Kg + crow * 16) = hi;
+      *reinterpret_cast<uint4*>(ph + kF4Plane + ckg * kF4Kg + crow * 16) = lo;
     }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    asm volatile("bar.arrive %0, %1;" ::"r"(2 + pb), "n"(kF4Sync) : "memory");  // (also releases the box, see issue warp)
+    ++nc;
+  };
+
+  // y = x / (beta + n) for box k (channels 32 k ..) of the tile whose accumulator starts at column `acc`:
+  // thread (r, h) owns pixel row r and the 8 channels 32 k + 8 h ..
+  auto finish_box = [&](int k, uint32_t acc) {
+    const uint32_t slot = ne % 3u, round = ne / 3u;
+    uint8_t* box = smem + L::kOffRing + (3 + slot) * kF4Box;
+    uint32_t nacc[8];
+    tmem_load<8>(tmem_base + acc + lane_sel + (uint32_t)(k * 32 + h * 8), nacc);
+    if (!mbar_wait(bar(L::kBarEfull + slot), round & 1u)) __trap();
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    const float* bs = beta_s + k * 32 + h * 8;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      float4* px = chunk_at(box, r, 2 * h + j);
+      const float4 xv = *px;
+      const float4 bv = *reinterpret_cast<const float4*>(bs + 4 * j);  // same address in every lane: broadcast
+      float4 o;
+      o.x = tc_out<FAST>(xv.x, bv.x + __uint_as_float(nacc[4 * j]), f);
+      o.y = tc_out<FAST>(xv.y, bv.y + __uint_as_float(nacc[4 * j + 1]), f);
+      o.z = tc_out<FAST>(xv.z, bv.z + __uint_as_float(nacc[4 * j + 2]), f);
+      o.w = tc_out<FAST>(xv.w, bv.w + __uint_as_float(nacc[4 * j + 3]), f);
+      *px = o;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // y box -> TMA store
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar(L::kBarY + slot)) : "memory");
+    ++ne;
+  };
+
+  int t = 0;
+  for (long long tile = blockIdx.x;; tile += gridDim.x, ++t) {
+    const bool has_cur = tile < n_tiles;   // tile t: converted now, accumulator (t & 1)
+    const bool has_prev = t > 0;           // tile t - 1: finished now, accumulator ((t - 1) & 1)
+    if (!has_cur && !has_prev) break;
+    const uint32_t acc_prev = (uint32_t)((t - 1) & 1) * 256u;
+    if (!has_cur) {  // drain: the last two commits cover every MMA of the last tile
+#pragma unroll
+      for (int pb = 0; pb < 2; ++pb) {
+        if (!mbar_wait(bar(L::kBarPlane + pb), parp[pb])) __trap();
+        parp[pb] ^= 1u;
+      }
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // Chunks 0 and 1 of this tile first: their plane-buffer waits are the commits of the previous tile's last two
+    // chunks, i.e. after them every MMA of the previous tile has completed.  Then box c - 2 of the previous tile is
+    // finished BEFORE chunk c is converted, which gives the tensor pipe (the slower side) a box worth of slack.
+    if (has_cur) {
+      convert(0, t > 0);
+      convert(1, t > 0);
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+    for (int c = 2; c < NCH; ++c) {
+      if (has_prev) finish_box(c - 2, acc_prev);
+      if (has_cur) convert(c, true);
+    }
+    if (has_prev) {
+      finish_box(NCH - 2, acc_prev);
+      finish_box(NCH - 1, acc_prev);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // accumulator reads precede its next MMAs
+    if (!has_cur) break;
   }
   }  // compute warps
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (tid < 32) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "n"(256));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "n"(512));
   }
 }
 
+// 2-D tensor map of a row-major fp32 [rows, cols] array with [box_rows x box_cols] boxes (zero fill; optionally the
+// 128-byte swizzle: 16-byte chunk j of box row i lands at chunk j ^ (i & 7); needs 128-byte box rows).
+// cuTensorMapEncodeTiled is a driver entry point; it is looked up through the runtime so that the library keeps
+// linking against libcudart only.
+int make_tensor_map_2d(CUtensorMap* map, const float* base, long long rows, int cols, int box_rows, int box_cols,
+                       bool swizzle128 = false) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &st) != cudaSuccess ||
+        st != cudaDriverEntryPointSuccess)
+      fn = nullptr;
+    (void)cudaGetLastError();
+    return reinterpret_cast<EncodeFn>(fn);
+  }();
+  if (!encode) return fail(TFCB_CUDA_ERROR, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUresult rc = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) return fail(TFCB_CUDA_ERROR, "cuTensorMapEncodeTiled failed (%d)", (int)rc);
+  return TFCB_OK;
+}
+
 template <bool FAST>
-int launch_tc_fwd3(const float* x, const float* gamma, const float* beta, float* y, long long n_pix, TcFlags f,
+int launch_tc_fwd4(const float* x, const float* gamma, const float* beta, float* y, long long n_pix, TcFlags f,
                    cudaStream_t s) {
   constexpr int C = 192;
-  using L = Fwd3Smem<C>;
+  using L = Fwd4Smem<C>;
+  CUtensorMap x_map, y_map;
+  TFCB_TRY(make_tensor_map_2d(&x_map, x, n_pix, C, kTileM, 32, true));
+  TFCB_TRY(make_tensor_map_2d(&y_map, y, n_pix, C, kTileM, 32, true));
   __nv_bfloat16* planes = nullptr;
   TFCB_TRY(dev_alloc((void**)&planes, (size_t)2 * C * C * sizeof(__nv_bfloat16), s));
   gdn_tc_prep_kernel<<<((C / 8) * C + 255) / 256, 256, 0, s>>>(gamma, C, planes);
   TFCB_LAUNCHED();
-  bool attr_set = false;  // the attribute is per device: set it on every launch (microseconds)
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gdn_tc_fwd3_kernel<C, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes);
-    if (e != cudaSuccess) {
-      (void)cudaGetLastError();
-      dev_free(planes, s);
-      return fail(TFCB_CUDA_ERROR, "cannot reserve %d bytes of shared memory: %s", L::kBytes, cudaGetErrorString(e));
-    }
-    attr_set = true;
+  cudaError_t e = cudaFuncSetAttribute(gdn_tc_fwd4_kernel<C, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    dev_free(planes, s);
+    return fail(TFCB_CUDA_ERROR, "cannot reserve %d bytes of shared memory: %s", L::kBytes, cudaGetErrorString(e));
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long n_tiles = (n_pix + kTileM - 1) / kTileM;
   const int grid = (int)std::min<long long>(n_tiles, sms);
-  gdn_tc_fwd3_kernel<C, FAST><<<grid, kF3Threads, L::kBytes, s>>>(x, planes, beta, y, n_pix, f);
+  gdn_tc_fwd4_kernel<C, FAST><<<grid, kF4Threads, L::kBytes, s>>>(x_map, y_map, x, planes, beta, n_pix, f);
   TFCB_LAUNCHED();
-  cudaError_t e = cudaGetLastError();
+  e = cudaGetLastError();
   dev_free(planes, s);
   if (e != cudaSuccess) return fail(TFCB_CUDA_ERROR, "GDN tensor-core kernel launch failed: %s", cudaGetErrorString(e));
   return TFCB_OK;
@@ -1693,8 +1820,9 @@ int gdn_tc_forward(const float* x, const float* gamma, const float* beta, float*
   const bool fast = (alpha == 1.f) && (eps == 1.f) && !f.rectify;
   if (C == 128)  // x tile resident in shared memory, bulk async copies
     return fast ? launch_tc_fwd2<true>(x, gamma, beta, y, n_pix, f, s) : launch_tc_fwd2<false>(x, gamma, beta, y, n_pix, f, s);
-  // C == 192: register-fed conversion + MMA-issue warp
-  return fast ? launch_tc_fwd3<true>(x, gamma, beta, y, n_pix, f, s) : launch_tc_fwd3<false>(x, gamma, beta, y, n_pix, f, s);
+  // C == 192: x through rings of 2-D TMA boxes, gamma's lo plane streamed, y through TMA stores
+  if (n_pix >= (1ll << 31)) return fail(TFCB_INVALID_ARGUMENT, "GDN: more than 2^31 pixels in one call");
+  return fast ? launch_tc_fwd4<true>(x, gamma, beta, y, n_pix, f, s) : launch_tc_fwd4<false>(x, gamma, beta, y, n_pix, f, s);
 }
 
 }  // namespace tfcb
