@@ -18,6 +18,7 @@ def __getattr__(name):  # lazy: importing the package must not require torch / t
       "GDN": "gdn", "GDNParameter": "gdn",
       "ContinuousBatchedEntropyModel": "entropy_models", "ContinuousIndexedEntropyModel": "entropy_models",
       "LocationScaleIndexedEntropyModel": "entropy_models", "EntropyBottleneck": "entropy_models",
+      "UniversalBatchedEntropyModel": "entropy_models", "UniversalIndexedEntropyModel": "entropy_models",
       "NoisyDeepFactorized": "distributions", "DeepFactorized": "distributions", "NoisyNormal": "distributions",
       "NoisyLaplace": "distributions", "NoisyLogistic": "distributions",
       "round_st": "math_ops", "lower_bound": "math_ops", "upper_bound": "math_ops",

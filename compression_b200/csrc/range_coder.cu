@@ -2022,9 +2022,11 @@ int launch_decode(tfcb_decoder* h, const int32_t* index, void* out, const float*
   P.n_streams = h->n_streams;
   P.state = h->state;
   P.err = h->err;
-  // Search keys live in shared memory when two CTAs per SM still fit (every stream is its own CTA).
+  // Search keys live in shared memory whenever they fit beside the kernel's static 16 KB: up to 96 KB two CTAs
+  // (streams) still share an SM; up to 200 KB one CTA per SM (cfg3's 64 NoisyNormal tables up to sigma = 256 take
+  // 118 KB: from L1/L2 every slow-path search round cost a global-memory latency on the chain warp).
   const size_t smem = (size_t)((h->lut.n_pairs * 8 + 15) & ~15ll) + (size_t)h->lut.n_rows * sizeof(int4);
-  if (smem <= 96 * 1024) {
+  if (smem <= 200 * 1024) {
     TFCB_CUDA_TRY(cudaFuncSetAttribute(decode_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
     decode_kernel<MODE, true><<<(unsigned)h->n_streams, 96, smem, s>>>(P);

@@ -22,7 +22,8 @@ from compression_b200 import gen_ops, math_ops
 
 __all__ = [
     "ContinuousEntropyModelBase", "ContinuousBatchedEntropyModel", "ContinuousIndexedEntropyModel",
-    "LocationScaleIndexedEntropyModel", "EntropyBottleneck",
+    "LocationScaleIndexedEntropyModel", "UniversalBatchedEntropyModel", "UniversalIndexedEntropyModel",
+    "EntropyBottleneck",
 ]
 
 
@@ -544,6 +545,294 @@ class LocationScaleIndexedEntropyModel(ContinuousIndexedEntropyModel):
 
   def decompress(self, strings, scale_indexes, loc=None, fused=True):
     return super().decompress(strings, scale_indexes, fused=fused, _loc=loc)
+
+
+# ------------------------------------------------------------------------------------------------
+# Universal quantisation (universal.py:30-603): "quantisation" is additive uniform noise whose value is shared by
+# sender and receiver through a stateless pseudo-random stream; coding runs in index mode with one extra leading
+# index, the noise level.
+# ------------------------------------------------------------------------------------------------
+_M32 = 0xFFFFFFFF
+
+
+def _philox4x32(counter, key, rounds=10):
+  """Philox-4x32-10 (Salmon et al., SC'11) on int64 tensors holding uint32 words: counter [n, 4] -> [n, 4]."""
+  c = [counter[:, i].clone() for i in range(4)]
+  k0, k1 = int(key[0]) & _M32, int(key[1]) & _M32
+  for _ in range(rounds):
+    p0, p1 = c[0] * 0xD2511F53, c[2] * 0xCD9E8D57          # < 2^64 as unsigned: split the products by hand
+    hi0 = ((c[0] >> 16) * 0xD2511F53 + (((c[0] & 0xFFFF) * 0xD2511F53) >> 16)) >> 16
+    hi1 = ((c[2] >> 16) * 0xCD9E8D57 + (((c[2] & 0xFFFF) * 0xCD9E8D57) >> 16)) >> 16
+    lo0, lo1 = p0 & _M32, p1 & _M32
+    c = [(hi1 ^ c[1] ^ k0) & _M32, lo1, (hi0 ^ c[3] ^ k1) & _M32, lo0]
+    k0, k1 = (k0 + 0x9E3779B9) & _M32, (k1 + 0xBB67AE85) & _M32
+  return torch.stack(c, dim=1)
+
+
+def stateless_uniform_int(shape, seed, maxval, device=None):
+  """Counter-based stand-in for `tf.random.stateless_uniform(shape, seed, 0, maxval, int32)` (universal.py:33-39):
+  element i is word i % 4 of Philox-4x32-10(counter = i // 4, key = seed), reduced modulo `maxval`.  It depends on
+  nothing but (seed, i), so sender and receiver -- on any device -- draw the same noise levels.  TensorFlow's own
+  key / counter conventions are not reproduced (there is no TF here to pin them against): strings written with
+  universal quantisation decode with THIS implementation, not with the reference's."""
+  shape = tuple(int(d) for d in shape)
+  n = 1
+  for d in shape:
+    n *= d
+  blocks = (n + 3) // 4
+  counter = torch.zeros(blocks, 4, dtype=torch.int64, device=device)
+  idx = torch.arange(blocks, dtype=torch.int64, device=device)
+  counter[:, 0] = idx & _M32
+  counter[:, 1] = idx >> 32
+  words = _philox4x32(counter, seed).reshape(-1)[:n]
+  return (words % int(maxval)).to(torch.int32).reshape(shape)
+
+
+def _add_offset_indexes(indexes, num_noise_levels):
+  """universal.py:30-42: prepends the shared pseudo-random noise-level index to the last axis of `indexes`."""
+  offset_indexes = stateless_uniform_int(indexes.shape[:-1], (1234, 1234), num_noise_levels, indexes.device)
+  return torch.cat((offset_indexes.to(indexes.dtype)[..., None], indexes), dim=-1)
+
+
+def _offset_indexes_to_offset(offset_indexes, num_noise_levels, dtype):
+  """universal.py:45-47: level k of n -> (k + 1) / (n + 1) - 0.5."""
+  return ((offset_indexes.to(torch.float64) + 1) / (num_noise_levels + 1) - 0.5).to(dtype)
+
+
+def _range_coding_offsets(num_noise_levels, prior_rank, dtype):
+  """universal.py:55-62."""
+  offset_indexes = torch.arange(num_noise_levels, dtype=dtype).reshape([-1] + [1] * prior_rank)
+  return _offset_indexes_to_offset(offset_indexes, num_noise_levels, dtype)
+
+
+class UniversalBatchedEntropyModel(ContinuousEntropyModelBase):
+  """universal.py:65-330."""
+
+  def __init__(self, prior, coding_rank, compression=False, laplace_tail_mass=0.0, expected_grads=False,
+               tail_mass=2**-8, range_coder_precision=12, bottleneck_dtype=None, num_noise_levels=15, stateless=False,
+               decode_sanity_check=True):
+    super().__init__(coding_rank=coding_rank, compression=compression, stateless=stateless,
+                     expected_grads=expected_grads, tail_mass=tail_mass, bottleneck_dtype=bottleneck_dtype,
+                     laplace_tail_mass=laplace_tail_mass)
+    self._set_prior(prior)
+    self._num_noise_levels = int(num_noise_levels)
+    self._prior_shape = tuple(int(s) for s in prior.batch_shape)
+    if self.coding_rank < len(self.prior_shape):
+      raise ValueError("`coding_rank` can't be smaller than `prior_shape`.")
+    self.decode_sanity_check = decode_sanity_check
+    if self.compression:
+      offset = _range_coding_offsets(self._num_noise_levels, len(self.prior_shape), self.bottleneck_dtype)
+      cdf, cdf_offset = self._build_tables(self.prior, range_coder_precision, offset=offset)
+      self._init_compression(cdf, cdf_offset, None)
+
+  prior_shape = property(lambda self: self._prior_shape)
+
+  @property
+  def prior_shape_tensor(self):
+    return torch.tensor(self.prior_shape, dtype=torch.int32)
+
+  def _compute_indexes_and_offset(self, broadcast_shape, device):
+    """universal.py:147-170 -> (flat table index, quantisation offset), both of shape broadcast_shape + prior_shape."""
+    broadcast_shape = tuple(int(d) for d in broadcast_shape)
+    prior_size = int(np.prod(self.prior_shape)) if self.prior_shape else 1
+    indexes = torch.arange(prior_size, dtype=torch.int32, device=device)
+    indexes = torch.broadcast_to(indexes, broadcast_shape + (prior_size,))[..., None]
+    indexes = _add_offset_indexes(indexes, self._num_noise_levels)
+    offset = _offset_indexes_to_offset(indexes[..., 0], self._num_noise_levels, self.bottleneck_dtype)
+    flat = indexes[..., 0] * prior_size + indexes[..., 1]          # strides of index_ranges [levels, prior_size]
+    full_shape = broadcast_shape + self.prior_shape
+    return flat.reshape(full_shape).to(torch.int32), offset.reshape(full_shape)
+
+  def forward(self, bottleneck, training=True):
+    """universal.py:172-211."""
+    bottleneck = torch.as_tensor(bottleneck).to(self.bottleneck_dtype)
+    log_prob_fn = functools.partial(self._log_prob, self.prior)
+    if training:
+      log_probs, perturbed = math_ops.perturb_and_apply(log_prob_fn, bottleneck, expected_grads=self.expected_grads)
+    else:
+      coding_shape = tuple(bottleneck.shape[bottleneck.dim() - self.coding_rank:])
+      broadcast_shape = coding_shape[:self.coding_rank - len(self.prior_shape)]
+      _, offset = self._compute_indexes_and_offset(broadcast_shape, bottleneck.device)
+      perturbed = torch.round(bottleneck - offset) + offset
+      log_probs = log_prob_fn(perturbed)
+    axes = tuple(range(-self.coding_rank, 0))
+    return perturbed, log_probs.sum(dim=axes) / -math.log(2.)
+
+  def compress(self, bottleneck, fused=True):
+    """universal.py:213-251."""
+    self._check_compression()
+    dev = _cuda()
+    bottleneck = torch.as_tensor(bottleneck).to(device=dev, dtype=self.bottleneck_dtype)
+    shape = tuple(bottleneck.shape)
+    batch_shape, coding_shape = shape[:len(shape) - self.coding_rank], shape[len(shape) - self.coding_rank:]
+    broadcast_shape = coding_shape[:self.coding_rank - len(self.prior_shape)]
+    indexes, offset = self._compute_indexes_and_offset(broadcast_shape, dev)
+    indexes = torch.broadcast_to(indexes, shape).contiguous()
+    coff = self.cdf_offset.to(dev)
+    handle = gen_ops.create_range_encoder(batch_shape, self._lookup_host())
+    if fused and bottleneck.dtype == torch.float32:
+      F.encode_index_f32(handle, indexes, bottleneck.contiguous(), torch.broadcast_to(offset, shape).contiguous(), coff)
+    else:
+      symbols = torch.round(bottleneck - offset).to(torch.int32) - coff[indexes.long()]
+      gen_ops.entropy_encode_index(handle, indexes, symbols)
+    return gen_ops.entropy_encode_finalize(handle)
+
+  def decompress(self, strings, broadcast_shape, fused=True):
+    """universal.py:253-289."""
+    self._check_compression()
+    if not isinstance(strings, gen_ops.Strings):
+      strings = gen_ops.Strings.from_bytes(strings)
+    dev = strings.bytes_dev.device
+    broadcast_shape = tuple(int(d) for d in np.asarray(broadcast_shape).reshape(-1))
+    decode_shape = broadcast_shape + self.prior_shape
+    output_shape = tuple(strings.shape) + decode_shape
+    indexes, offset = self._compute_indexes_and_offset(broadcast_shape, dev)
+    indexes = torch.broadcast_to(indexes, output_shape).contiguous()
+    offset = torch.broadcast_to(offset, output_shape).contiguous()
+    coff = self.cdf_offset.to(dev)
+    handle = gen_ops.create_range_decoder(strings, self._lookup_host())
+    if fused and self.bottleneck_dtype == torch.float32:
+      outputs = F.decode_index_f32(handle, indexes, offset, coff)
+      symbols = None
+    else:
+      handle, symbols = gen_ops.entropy_decode_index(handle, indexes, decode_shape)
+    sanity = gen_ops.entropy_decode_finalize(handle)
+    if self.decode_sanity_check and not bool(sanity.all()):
+      raise gen_ops.InvalidArgumentError("Sanity check failed.")
+    if symbols is None:
+      return outputs
+    return (symbols + coff[indexes.long()]).to(self.bottleneck_dtype) + offset
+
+  def get_config(self):
+    raise NotImplementedError()
+
+
+class UniversalIndexedEntropyModel(ContinuousEntropyModelBase):
+  """universal.py:292-603."""
+
+  def __init__(self, prior_fn, index_ranges, parameter_fns, coding_rank, compression=False, laplace_tail_mass=0.0,
+               expected_grads=False, tail_mass=2**-8, range_coder_precision=12, bottleneck_dtype=None,
+               prior_dtype=torch.float32, stateless=False, num_noise_levels=15, decode_sanity_check=True):
+    if coding_rank <= 0:
+      raise ValueError("`coding_rank` must be larger than 0.")
+    if not callable(prior_fn):
+      raise TypeError("`prior_fn` must be a class or factory function.")
+    for name, fn in parameter_fns.items():
+      if not isinstance(name, str):
+        raise TypeError("`parameter_fns` must have string keys.")
+      if not callable(fn):
+        raise TypeError(f"`parameter_fns['{name}']` must be callable.")
+    super().__init__(coding_rank=coding_rank, compression=compression, stateless=stateless,
+                     expected_grads=expected_grads, tail_mass=tail_mass, bottleneck_dtype=bottleneck_dtype,
+                     laplace_tail_mass=laplace_tail_mass)
+    self._index_ranges = tuple([int(num_noise_levels)] + [int(r) for r in index_ranges])  # extra index: noise level
+    if len(self._index_ranges) < 2:
+      raise ValueError("`index_ranges` must have at least one element.")
+    self._prior_fn = prior_fn
+    self._parameter_fns = dict(parameter_fns)
+    self._prior_dtype = prior_dtype
+    self._num_noise_levels = int(num_noise_levels)
+    self.decode_sanity_check = decode_sanity_check
+    if self.compression:
+      grids = torch.meshgrid(*[torch.arange(r, dtype=torch.int32) for r in self.index_ranges_without_offsets], indexing="ij")
+      indexes = torch.stack(grids, dim=-1)
+      self._set_prior(self._make_prior(indexes), register=False)
+      offset = _range_coding_offsets(self._num_noise_levels, len(self.prior.batch_shape), self.bottleneck_dtype)
+      cdf, cdf_offset = self._build_tables(self.prior, range_coder_precision, offset=offset)
+      self._init_compression(cdf, cdf_offset, None)
+
+  index_ranges = property(lambda self: self._index_ranges)
+  parameter_fns = property(lambda self: self._parameter_fns)
+  prior_dtype = property(lambda self: self._prior_dtype)
+  prior_fn = property(lambda self: self._prior_fn)
+  index_ranges_without_offsets = property(lambda self: self._index_ranges[1:])
+
+  def _make_prior(self, indexes):
+    indexes = indexes.to(self.prior_dtype)
+    return self.prior_fn(**{k: f(indexes) for k, f in self.parameter_fns.items()})
+
+  def _flatten_indexes(self, indexes):
+    """universal.py:446-449."""
+    strides = np.cumprod((self.index_ranges + (1,))[::-1])[::-1][1:]
+    strides = torch.tensor(strides.copy(), dtype=torch.int32, device=indexes.device)
+    return torch.tensordot(indexes.to(torch.int32), strides, dims=1).to(torch.int32)
+
+  def _normalize_indexes(self, indexes):
+    """universal.py:451-466: clips every index to its range (with or without the leading noise-level index)."""
+    num = indexes.shape[-1]
+    ranges = self.index_ranges if num == len(self.index_ranges) else self.index_ranges_without_offsets
+    assert num == len(ranges)
+    indexes = math_ops.lower_bound(indexes, 0.)
+    bounds = torch.tensor([s - 1 for s in ranges], dtype=indexes.dtype, device=indexes.device)
+    return math_ops.upper_bound(indexes, bounds.reshape([1] * (indexes.dim() - 1) + [num]))
+
+  def _offset_from_indexes(self, indexes_with_offsets):
+    return _offset_indexes_to_offset(indexes_with_offsets[..., 0], self._num_noise_levels, self.bottleneck_dtype)
+
+  def forward(self, bottleneck, indexes, training=True):
+    """universal.py:473-528."""
+    bottleneck = torch.as_tensor(bottleneck).to(self.bottleneck_dtype)
+    indexes = self._normalize_indexes(torch.as_tensor(indexes, dtype=self.prior_dtype, device=bottleneck.device))
+    if training:
+      def log_prob_fn(x, idx):
+        return self._log_prob(self._make_prior(idx), x)
+      log_probs, perturbed = math_ops.perturb_and_apply(log_prob_fn, bottleneck, indexes,
+                                                        expected_grads=self.expected_grads)
+    else:
+      prior = self._make_prior(indexes)
+      offset = self._offset_from_indexes(_add_offset_indexes(indexes, self._num_noise_levels))
+      perturbed = torch.round(bottleneck - offset) + offset
+      log_probs = self._log_prob(prior, perturbed)
+    axes = tuple(range(-self.coding_rank, 0))
+    return perturbed, log_probs.sum(dim=axes) / -math.log(2.)
+
+  def _coding_tensors(self, indexes, dev):
+    indexes = torch.as_tensor(indexes).to(device=dev, dtype=self.prior_dtype)
+    indexes = self._normalize_indexes(_add_offset_indexes(indexes, self._num_noise_levels))
+    return self._flatten_indexes(indexes).contiguous(), self._offset_from_indexes(indexes).contiguous()
+
+  def compress(self, bottleneck, indexes, fused=True):
+    """universal.py:530-566."""
+    self._check_compression()
+    dev = _cuda()
+    bottleneck = torch.as_tensor(bottleneck).to(device=dev, dtype=self.bottleneck_dtype)
+    flat, offset = self._coding_tensors(indexes, dev)
+    fshape = tuple(flat.shape)
+    batch_shape = fshape[:len(fshape) - self.coding_rank]
+    coff = self.cdf_offset.to(dev)
+    handle = gen_ops.create_range_encoder(batch_shape, self._lookup_host())
+    if fused and bottleneck.dtype == torch.float32:
+      F.encode_index_f32(handle, flat, bottleneck.contiguous(), offset, coff)
+    else:
+      symbols = torch.round(bottleneck - offset).to(torch.int32) - coff[flat.long()]
+      gen_ops.entropy_encode_index(handle, flat, symbols)
+    return gen_ops.entropy_encode_finalize(handle)
+
+  def decompress(self, strings, indexes, fused=True):
+    """universal.py:568-598."""
+    self._check_compression()
+    if not isinstance(strings, gen_ops.Strings):
+      strings = gen_ops.Strings.from_bytes(strings)
+    dev = strings.bytes_dev.device
+    flat, offset = self._coding_tensors(indexes, dev)
+    fshape = tuple(flat.shape)
+    decode_shape = fshape[len(fshape) - self.coding_rank:]
+    coff = self.cdf_offset.to(dev)
+    handle = gen_ops.create_range_decoder(strings, self._lookup_host())
+    if fused and self.bottleneck_dtype == torch.float32:
+      outputs = F.decode_index_f32(handle, flat, offset, coff)
+      symbols = None
+    else:
+      handle, symbols = gen_ops.entropy_decode_index(handle, flat, decode_shape)
+    sanity = gen_ops.entropy_decode_finalize(handle)
+    if self.decode_sanity_check and not bool(sanity.all()):
+      raise gen_ops.InvalidArgumentError("Sanity check failed.")
+    if symbols is None:
+      return outputs
+    return (symbols + coff[flat.long()]).to(self.bottleneck_dtype) + offset
+
+  def get_config(self):
+    raise NotImplementedError()
 
 
 def EntropyBottleneck(num_channels=None, prior=None, coding_rank=3, compression=True, **kwargs):

@@ -178,3 +178,42 @@ def test_gdn_layer_matches_reference_closed_form(tfc):
   assert all(p.grad is not None for p in layer.parameters()) and x.grad is not None
   with pytest.raises(RuntimeError):
     layer.inverse = True
+
+
+def test_universal_models_compress_and_decompress_and_match_oracle(tfc):
+  """universal_test.py:29-58 (batched) and :169-188 (indexed): decode(encode(x)) is x up to the shared uniform noise,
+  string length matches the bit estimate, and the strings are the oracle's for the index-mode symbols the model
+  derives (universal.py:213-251,530-566)."""
+  from compression_b200 import entropy_models as E
+  torch.manual_seed(0)
+  prior = tfc.NoisyLogistic(loc=torch.zeros(6), scale=torch.linspace(1., 8., 6))
+  em = tfc.UniversalBatchedEntropyModel(prior, coding_rank=2, compression=True, num_noise_levels=15)
+  assert em.cdf_offset.numel() == 15 * 6
+  x = (torch.randn(3, 4000, 6) * torch.linspace(1., 8., 6) * 1.8).cuda()
+  strings = em.compress(x)
+  assert strings.shape == (3,)
+  x_hat = em.decompress(strings, (4000,))
+  assert float((x_hat - x).abs().max()) <= 0.5 + 1e-5
+  _, bits = em(x, training=False)
+  got_bits = torch.tensor([8 * len(b) for b in strings.tolist()], dtype=torch.float32)
+  assert torch.allclose(bits.cpu(), got_bits, rtol=0.01, atol=16)
+  # literal op sequence == fused kernels; oracle bytes
+  assert em.compress(x, fused=False).tolist() == strings.tolist()
+  assert torch.equal(em.decompress(strings, (4000,), fused=False), x_hat)
+  indexes, offset = em._compute_indexes_and_offset((4000,), x.device)
+  sym = (torch.round(x - offset).to(torch.int32) - em.cdf_offset.cuda()[indexes.long()]).reshape(3, -1).cpu().numpy()
+  idx = torch.broadcast_to(indexes, x.shape).reshape(3, -1).cpu().numpy().astype(np.int32)
+  assert strings.tolist() == oracle.best().encode(em.cdf.cpu().numpy(), sym, idx)
+  # indexed variant: one table per (noise level, scale index)
+  emi = tfc.UniversalIndexedEntropyModel(tfc.NoisyLogistic, (8,), dict(loc=lambda i: 0. * i[..., 0], scale=lambda i: torch.exp(i[..., 0] / 3.)),
+                                         coding_rank=1, compression=True, num_noise_levels=7)
+  assert emi.cdf_offset.numel() == 7 * 8
+  ind = torch.randint(0, 8, (5, 3000, 1)).float().cuda()
+  xi = (torch.randn(5, 3000).cuda() * torch.exp(ind[..., 0] / 3.) * 1.8)
+  si = emi.compress(xi, ind)
+  xi_hat = emi.decompress(si, ind)
+  assert si.shape == (5,) and float((xi_hat - xi).abs().max()) <= 0.5 + 1e-5
+  assert emi.compress(xi, ind, fused=False).tolist() == si.tolist()
+  flat, off = emi._coding_tensors(ind, xi.device)
+  symi = (torch.round(xi - off).to(torch.int32) - emi.cdf_offset.cuda()[flat.long()]).cpu().numpy()
+  assert si.tolist() == oracle.best().encode(emi.cdf.cpu().numpy(), symi, flat.cpu().numpy())
