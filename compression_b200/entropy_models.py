@@ -443,7 +443,7 @@ class ContinuousIndexedEntropyModel(ContinuousEntropyModelBase):
       return indexes
     strides = np.cumprod((self.index_ranges + (1,))[::-1])[::-1][1:]
     strides = torch.tensor(strides.copy(), dtype=torch.int32, device=indexes.device)
-    return torch.tensordot(indexes.movedim(self.channel_axis, -1), strides, dims=1).to(torch.int32)
+    return (indexes.movedim(self.channel_axis, -1) * strides).sum(dim=-1, dtype=torch.int32)  # integer matmul does not exist on CUDA
 
   def forward(self, bottleneck, indexes, training=True):
     """continuous_indexed.py:291-334."""
@@ -755,7 +755,7 @@ class UniversalIndexedEntropyModel(ContinuousEntropyModelBase):
     """universal.py:446-449."""
     strides = np.cumprod((self.index_ranges + (1,))[::-1])[::-1][1:]
     strides = torch.tensor(strides.copy(), dtype=torch.int32, device=indexes.device)
-    return torch.tensordot(indexes.to(torch.int32), strides, dims=1).to(torch.int32)
+    return (indexes.to(torch.int32) * strides).sum(dim=-1, dtype=torch.int32)  # integer matmul does not exist on CUDA
 
   def _normalize_indexes(self, indexes):
     """universal.py:451-466: clips every index to its range (with or without the leading noise-level index)."""

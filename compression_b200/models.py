@@ -279,16 +279,21 @@ class BMSHJ2018Model(_Model):
 # ------------------------------------------------------------------------------------------------
 # bench extra: BASELINE.json configs[1] / [2] as the configs name them (images -> strings, strings -> images)
 # ------------------------------------------------------------------------------------------------
-def _stage_ms(fn, reps=3):
-  fn()
-  a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-  torch.cuda.synchronize()
-  a.record()
-  for _ in range(reps):
+def _stage_ms(fn, reps=5):
+  """Median device time of one call (event between consecutive calls); two warm-up calls that keep the previous
+  result alive like the timed loop, so that no cudaMalloc of an output lands inside the timed region."""
+  out = None
+  for _ in range(2):
     out = fn()
-  b.record()
+  ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
   torch.cuda.synchronize()
-  return a.elapsed_time(b) / reps, out
+  ev[0].record()
+  for i in range(reps):
+    out = fn()
+    ev[i + 1].record()
+  torch.cuda.synchronize()
+  ts = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(reps))
+  return ts[len(ts) // 2], out
 
 
 def bench_model_paths(dev, batch2=256, batch3=128, hw=256):
