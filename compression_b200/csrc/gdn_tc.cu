@@ -1728,6 +1728,463 @@ gdn_tc_bwd_dgamma_kernel(const float* __restrict__ x, const float* __restrict__ 
   }
 }
 
+// =============================================================================================
+// Backward, C = 128, second kernel shape (the default GDN / IGDN: alpha = 1, epsilon = 1, no rectification).
+//
+// Same mathematics and the same operand planes / MN-major views as gdn_tc_bwd_kernel above, rebuilt along the
+// lines of the C = 192 forward: everything that touches HBM is an asynchronous 2-D TMA box, every compute thread
+// (r, h) owns pixel row r (= its TMEM lane) and 8 of the 32 channels of a box, so there are no staging
+// transposes and no CTA-wide barriers, and x and dy are read exactly once:
+//
+//   conv(t)   x boxes -> p = |x| hi / lo planes (whole K)                -> MMA1  n = p . gamma
+//             the raw x values are parked in 128 spare TMEM columns (tcgen05.st) for pass 2
+//   pass2(t)  g boxes + n, x from TMEM -> q planes (32-channel chunks)    -> MMA2  dp += q . gamma^T, MMA3  dgamma += p^T q
+//             the direct term g / n (IGDN: g * n) goes back into n's TMEM columns with sign(x) in the two low
+//             mantissa bits (2 ulp, the contract is 1e-5): the dx pass needs neither x nor g again
+//   pass3(t)  dx = direct + sign(x) * dp  from TMEM only -> box -> TMA store
+//
+// One ring of four 16 KB boxes serves every request in program order: g x 4 (pass 2), output x 4 (pass 3), x x 4
+// (conversion of the CTA's next tile); while the next tile is converted its g boxes are already on their way.
+// TMEM: n | dp | dgamma partial | parked x (4 x 128 columns).  HBM traffic: x, dy in, dx out, nothing else.
+// =============================================================================================
+__device__ __forceinline__ void tmem_store8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
+constexpr int kB3Compute = 512;               // 16 compute warps
+constexpr int kB3Threads = kB3Compute + 96;   // + MMA-issue, copy and store warps
+constexpr int kB3Sync = kB3Compute + 32;      // compute + issue warps (named barriers of the plane hand-offs)
+constexpr int kB3Slots = 4;
+
+struct BwdFusedSmem {
+  static constexpr int C = 128;
+  static constexpr int kOffRing = 0;                              // [4] boxes (1024-byte aligned: swizzle atom)
+  static constexpr int kOffBh = kOffRing + kB3Slots * kF4Box;     // gamma hi, then lo (contiguous, as in global memory)
+  static constexpr int kOffBl = kOffBh + C * C * 2;
+  static constexpr int kPlaneP = (C / 8) * kKg;                   // p hi / lo, whole K
+  static constexpr int kOffPh = kOffBl + C * C * 2;
+  static constexpr int kOffPl = kOffPh + kPlaneP;
+  static constexpr int kPlaneQ = 4 * kKg;                         // q hi / lo, one 32-channel chunk
+  static constexpr int kOffQ = kOffPl + kPlaneP;                  // [2 buffers][hi, lo]
+  static constexpr int kOffBeta = kOffQ + 4 * kPlaneQ;
+  static constexpr int kOffDbeta = kOffBeta + C * 4;
+  static constexpr int kOffBar = kOffDbeta + C * 4;
+  // mbarriers: full[4], empty[4], yready[4], nfull, dpfull, qfree[2]; then the TMEM slot
+  static constexpr int kBarFull = 0, kBarEmpty = 4, kBarY = 8, kBarN = 12, kBarDp = 13, kBarQ = 14, kNumBars = 16;
+  static constexpr int kBytes = kOffBar + kNumBars * 8 + 16;
+  static_assert(kOffBh % 128 == 0 && kOffPh % 16 == 0 && kOffQ % 16 == 0 && kOffBar % 8 == 0, "alignment");
+  static_assert(kBytes <= 232448, "shared memory budget");
+};
+
+__global__ void __launch_bounds__(kB3Threads, 1)
+gdn_tc_bwd3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUtensorMap g_map,
+                   const __grid_constant__ CUtensorMap dx_map, const float* __restrict__ x, const float* __restrict__ dy,
+                   const __nv_bfloat16* __restrict__ planes, const float* __restrict__ beta, float* __restrict__ part_g,
+                   float* __restrict__ part_b, long long n_pix, int inverse) {
+  using L = BwdFusedSmem;
+  constexpr int C = L::C, NCH = C / 32;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float* beta_s = reinterpret_cast<float*>(smem + L::kOffBeta);
+  float* dbeta_s = reinterpret_cast<float*>(smem + L::kOffDbeta);
+  uint64_t* mbars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffBar + L::kNumBars * 8);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r = tid & 127, h = (tid >> 7) & 3, gwarp = warp & 3;  // compute thread (r, h): pixel row r, channel octet h of a box
+  auto bar = [&](int i) { return smem_u32(mbars + i); };
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(planes);  // hi plane, then lo
+    uint4* dst = reinterpret_cast<uint4*>(smem + L::kOffBh);
+    for (int i = tid; i < 2 * C * C * 2 / 16; i += kB3Threads) dst[i] = src[i];
+    for (int i = tid; i < C; i += kB3Threads) {
+      beta_s[i] = beta[i];
+      dbeta_s[i] = 0.f;
+    }
+  }
+  if (tid == 0) {
+    for (int i = 0; i < L::kNumBars; ++i) {
+      const int count = (i >= L::kBarY && i < L::kBarN) ? kB3Compute / 32 : 1;  // y ready: one arrival per compute warp
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar(i)), "r"(count));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_n = *tmem_slot, tmem_dp = tmem_n + C, tmem_dg = tmem_n + 2 * C, tmem_x = tmem_n + 3 * C;
+  const uint32_t lane_sel = (uint32_t)(gwarp * 32) << 16;
+  const uint32_t b_hi = smem_u32(smem + L::kOffBh), b_lo = smem_u32(smem + L::kOffBl);
+  const uint32_t p_hi = smem_u32(smem + L::kOffPh), p_lo = smem_u32(smem + L::kOffPl);
+  const long long n_tiles = (n_pix + kTileM - 1) / kTileM;
+  const long long first = blockIdx.x;
+  // Box requests are numbered in program order; request n uses ring slot n % 4 in its (n / 4)-th round:
+  //   4 x boxes (conversion of the CTA's first tile), then per tile  g x 4, out x 4, (x of the next tile) x 4.
+  constexpr int W0 = kB3Compute / 32;  // first auxiliary warp
+
+  if (warp == W0 + 1) {
+    // ---------------------------------- copy warp ----------------------------------
+    if (lane == 0) {
+      uint32_t n = 0;
+      auto acquire = [&]() {
+        const uint32_t slot = n & 3u, round = n >> 2;
+        if (round > 0) {
+          if (!mbar_wait(bar(L::kBarEmpty + slot), (round - 1u) & 1u)) __trap();
+        }
+        return slot;
+      };
+      auto load = [&](const CUtensorMap* map, int c, int row0) {
+        const uint32_t slot = acquire();
+        const uint32_t full = bar(L::kBarFull + slot);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "n"(kF4Box) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
+                smem_u32(smem + L::kOffRing + slot * kF4Box)),
+            "l"(map), "r"(c * 32), "r"(row0), "r"(full), "l"(kEvictFirst)
+            : "memory");
+        ++n;
+      };
+      auto prefetch_tile = [&](const float* base, long long tile) {  // one contiguous block -> L2
+        const long long p0 = tile * kTileM;
+        const long long rows = min((long long)kTileM, n_pix - p0);
+        if (rows > 0)
+          asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(base + p0 * C),
+                       "r"((uint32_t)(rows * C * 4)), "l"(kEvictLast)
+                       : "memory");
+      };
+      if (first < n_tiles) {
+        prefetch_tile(dy, first);
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c) load(&x_map, c, (int)(first * kTileM));
+      }
+      for (long long tile = first; tile < n_tiles; tile += gridDim.x) {
+        const long long next = tile + gridDim.x;
+        const bool has_next = next < n_tiles;
+        const int row0 = (int)(tile * kTileM);
+        if (has_next) {  // the next tile of this CTA -> L2: its boxes become L2 hits
+          prefetch_tile(x, next);
+          prefetch_tile(dy, next);
+        }
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c) load(&g_map, c, row0);
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c) {
+          const uint32_t slot = acquire();      // output box: nothing to load, the slot only has to be free
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar(L::kBarFull + slot)) : "memory");
+          ++n;
+        }
+        if (has_next) {
+#pragma unroll 1
+          for (int c = 0; c < NCH; ++c) load(&x_map, c, (int)(next * kTileM));
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == W0 + 2) {
+    // ---------------------------------- store warp: dx boxes ----------------------------------
+    if (lane == 0) {
+      uint32_t n = (first < n_tiles) ? (uint32_t)NCH : 0u;
+      uint32_t ypar = 0u;  // per-slot phase of the y-ready barrier (a slot is an output box only now and then)
+      for (long long tile = first; tile < n_tiles; tile += gridDim.x) {
+        const bool has_next = tile + gridDim.x < n_tiles;
+        const int row0 = (int)(tile * kTileM);
+        n += NCH;
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c, ++n) {
+          const uint32_t slot = n & 3u;
+          if (!mbar_wait(bar(L::kBarY + slot), (ypar >> slot) & 1u)) __trap();
+          ypar ^= 1u << slot;
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;" ::"l"(&dx_map),
+                       "r"(c * 32), "r"(row0), "r"(smem_u32(smem + L::kOffRing + slot * kF4Box)), "l"(kEvictFirst)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the box has been read: the slot is free
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar(L::kBarEmpty + slot)) : "memory");
+        }
+        if (has_next) n += NCH;
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
+  } else if (warp == W0) {
+    // ------------------------------- MMA-issue warp -------------------------------
+    constexpr uint32_t kIdesc1 = umma_idesc(kTileM, C);                          // n = p . gamma
+    constexpr uint32_t kIdesc2 = umma_idesc(kTileM, C) | (1u << 16);             // B = gamma^T (MN-major view)
+    constexpr uint32_t kIdesc3 = umma_idesc(C, 32) | (1u << 15) | (1u << 16);    // A = p^T, B = q chunk (both views)
+    uint32_t n = 0;
+    auto release = [&](uint32_t req) {
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar(L::kBarEmpty + (req & 3u))) : "memory");
+    };
+    auto mma1_tile = [&]() {  // n = p . gamma of the tile being converted, K chunk by K chunk
+#pragma unroll 1
+      for (int c = 0; c < NCH; ++c, ++n) {
+        asm volatile("bar.sync %0, %1;" ::"r"(2 + c), "n"(kB3Sync) : "memory");  // p planes of chunk c are written
+        if (lane == 0) {
+          release(n);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+          for (int s2 = 0; s2 < 2; ++s2) {
+            const uint32_t s = (uint32_t)(2 * c + s2);
+            const uint64_t dah = umma_desc(p_hi + 2u * s * kKg, kKg, 128);
+            const uint64_t dal = umma_desc(p_lo + 2u * s * kKg, kKg, 128);
+            const uint64_t dbh = umma_desc(b_hi + 2u * s * (C * 16), C * 16, 128);
+            const uint64_t dbl = umma_desc(b_lo + 2u * s * (C * 16), C * 16, 128);
+            umma_bf16(tmem_n, dah, dbh, kIdesc1, (c | s2) ? 1u : 0u);
+            umma_bf16(tmem_n, dal, dbh, kIdesc1, 1u);
+            umma_bf16(tmem_n, dah, dbl, kIdesc1, 1u);
+          }
+          if (c == NCH - 1) umma_commit(bar(L::kBarN));
+        }
+        __syncwarp();
+      }
+    };
+    if (first < n_tiles) mma1_tile();
+    int t = 0;
+    for (long long tile = first; tile < n_tiles; tile += gridDim.x, ++t) {
+      const bool has_next = tile + gridDim.x < n_tiles;
+#pragma unroll 1
+      for (int c = 0; c < NCH; ++c, ++n) {
+        const int b = c & 1;
+        asm volatile("bar.sync %0, %1;" ::"r"(6 + b), "n"(kB3Sync) : "memory");  // q planes of chunk c are written
+        if (lane == 0) {
+          release(n);  // the g box of this chunk
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t q_hi = smem_u32(smem + L::kOffQ + b * 2 * L::kPlaneQ), q_lo = q_hi + L::kPlaneQ;
+          // MMA2: dp[pix, j] += sum_{i in chunk} q[pix, i] gamma[j, i]   (K = i: 2 steps of 16)
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            const uint64_t dah = umma_desc(q_hi + (uint32_t)(2 * s) * kKg, kKg, 128);
+            const uint64_t dal = umma_desc(q_lo + (uint32_t)(2 * s) * kKg, kKg, 128);
+            const uint32_t koff = (uint32_t)(c * 32 + s * 16) * 16u;
+            const uint64_t dbh = umma_desc(b_hi + koff, 128, C * 16);
+            const uint64_t dbl = umma_desc(b_lo + koff, 128, C * 16);
+            umma_bf16(tmem_dp, dah, dbh, kIdesc2, (c | s) ? 1u : 0u);
+            umma_bf16(tmem_dp, dal, dbh, kIdesc2, 1u);
+            umma_bf16(tmem_dp, dah, dbl, kIdesc2, 1u);
+          }
+          if (c == NCH - 1) umma_commit(bar(L::kBarDp));  // dp is complete: the dx pass may start
+          // MMA3: dgamma[j, i in chunk] += sum_pix p[pix, j] q[pix, i]   (K = pix: 8 steps of 16)
+#pragma unroll
+          for (int s = 0; s < kTileM / 16; ++s) {
+            const uint32_t koff = (uint32_t)(s * 16) * 16u;
+            const uint64_t dah = umma_desc(p_hi + koff, 128, kKg);
+            const uint64_t dal = umma_desc(p_lo + koff, 128, kKg);
+            const uint64_t dbh = umma_desc(q_hi + koff, 128, kKg);
+            const uint64_t dbl = umma_desc(q_lo + koff, 128, kKg);
+            const uint32_t acc_on = ((t % kDgFlush) == 0 && s == 0) ? 0u : 1u;  // restarted after every flush
+            umma_bf16(tmem_dg + (uint32_t)(c * 32), dah, dbh, kIdesc3, acc_on);
+            umma_bf16(tmem_dg + (uint32_t)(c * 32), dal, dbh, kIdesc3, 1u);
+            umma_bf16(tmem_dg + (uint32_t)(c * 32), dah, dbl, kIdesc3, 1u);
+          }
+          umma_commit(bar(L::kBarQ + b));
+        }
+        __syncwarp();
+      }
+      n += NCH;  // the output boxes: handed back by the store warp
+      if (has_next) mma1_tile();
+    }
+  } else if (warp < W0) {
+  // --------------------------------- compute warps ---------------------------------
+  uint32_t n = 0;
+  uint32_t parq[2] = {0u, 0u};
+  float dbeta_acc[NCH][8];  // channels 32 c + 8 h + e, summed over this thread's rows
+#pragma unroll
+  for (int c = 0; c < NCH; ++c)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dbeta_acc[c][e] = 0.f;
+  // 128-byte swizzle: the 16-byte chunk j of box row `row` sits at chunk j ^ (row & 7)
+  auto chunk_at = [](uint8_t* box, int row, int j) { return reinterpret_cast<float4*>(box + row * 128 + ((j ^ (row & 7)) << 4)); };
+  bool flushed = false;  // the global partial holds earlier flushes
+  auto flush_dgamma = [&]() {  // TMEM lane r = input channel j, this thread's 32 columns -> the CTA's partial
+    float* pg = part_g + (long long)blockIdx.x * C * C + (long long)r * C + h * 32;
+#pragma unroll
+    for (int cb = 0; cb < 2; ++cb) {
+      uint32_t a[16];
+      tmem_load<16>(tmem_dg + lane_sel + (uint32_t)(h * 32 + cb * 16), a);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      accum_store16(pg + cb * 16, a, flushed);
+    }
+    flushed = true;
+  };
+
+  // One tile: p = |x| -> hi / lo planes chunk by chunk (each chunk arrives on its own named barrier), raw x -> TMEM
+  auto conv_tile = [&]() {
+#pragma unroll 1
+    for (int c = 0; c < NCH; ++c, ++n) {
+      const uint32_t slot = n & 3u, round = n >> 2;
+      uint8_t* box = smem + L::kOffRing + slot * kF4Box;
+      if (!mbar_wait(bar(L::kBarFull + slot), round & 1u)) __trap();
+      const float4 a = *chunk_at(box, r, 2 * h), b = *chunk_at(box, r, 2 * h + 1);
+      const uint32_t raw[8] = {__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), __float_as_uint(a.w),
+                               __float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w)};
+      tmem_store8(tmem_x + lane_sel + (uint32_t)(c * 32 + h * 8), raw);
+      float v[8] = {fabsf(a.x), fabsf(a.y), fabsf(a.z), fabsf(a.w), fabsf(b.x), fabsf(b.y), fabsf(b.z), fabsf(b.w)};
+      uint4 hi, lo;
+      split8(v, &hi, &lo);
+      *reinterpret_cast<uint4*>(smem + L::kOffPh + (4 * c + h) * kKg + r * 16) = hi;
+      *reinterpret_cast<uint4*>(smem + L::kOffPl + (4 * c + h) * kKg + r * 16) = lo;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("bar.arrive %0, %1;" ::"r"(2 + c), "n"(kB3Sync) : "memory");  // (also releases the box, see issue warp)
+    }
+  };
+
+  if (first < n_tiles) conv_tile();
+  int t = 0;
+  for (long long tile = first; tile < n_tiles; tile += gridDim.x, ++t) {
+    const bool has_next = tile + gridDim.x < n_tiles;
+    if (!mbar_wait(bar(L::kBarN), (uint32_t)t & 1u)) __trap();  // MMA1 of this tile has completed
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // ---- pass 2: q = dL/dn -> q planes; the direct term and sign(x) go back into n's columns ----
+#pragma unroll
+    for (int c = 0; c < NCH; ++c, ++n) {
+      const int b = c & 1;
+      const uint32_t slot = n & 3u;
+      const uint32_t col = lane_sel + (uint32_t)(c * 32 + h * 8);
+      uint32_t nacc[8], xraw[8];
+      tmem_load<8>(tmem_n + col, nacc);
+      tmem_load<8>(tmem_x + col, xraw);
+      if (!mbar_wait(bar(L::kBarFull + slot), (n >> 2) & 1u)) __trap();
+      uint8_t* bg = smem + L::kOffRing + slot * kF4Box;
+      const float4 g0 = *chunk_at(bg, r, 2 * h), g1 = *chunk_at(bg, r, 2 * h + 1);
+      const float4 bv0 = *reinterpret_cast<const float4*>(beta_s + c * 32 + h * 8);      // same address in every lane
+      const float4 bv1 = *reinterpret_cast<const float4*>(beta_s + c * 32 + h * 8 + 4);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const float gs[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bs[8] = {bv0.x, bv0.y, bv0.z, bv0.w, bv1.x, bv1.y, bv1.z, bv1.w};
+      float q[8];
+      uint32_t dbits[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float xe = __uint_as_float(xraw[e]);
+        const float nn = bs[e] + __uint_as_float(nacc[e]);
+        float direct;
+        if (inverse) {
+          direct = gs[e] * nn;
+          q[e] = gs[e] * xe;
+        } else {
+          const float rn = rcp_approx(nn);
+          direct = gs[e] * rn;
+          q[e] = -gs[e] * xe * rn * rn;
+        }
+        const uint32_t code = (xe > 0.f) ? 1u : ((xe < 0.f) ? 2u : 0u);
+        dbits[e] = (__float_as_uint(direct) & ~3u) | code;
+        dbeta_acc[c][e] += q[e];
+      }
+      if (c >= 2) {  // the q buffer was read by the MMAs of chunk c - 2
+        if (!mbar_wait(bar(L::kBarQ + b), parq[b])) __trap();
+        parq[b] ^= 1u;
+      }
+      uint8_t* qh = smem + L::kOffQ + b * 2 * L::kPlaneQ;
+      uint4 hi, lo;
+      split8(q, &hi, &lo);
+      *reinterpret_cast<uint4*>(qh + h * kKg + r * 16) = hi;
+      *reinterpret_cast<uint4*>(qh + L::kPlaneQ + h * kKg + r * 16) = lo;
+      tmem_store8(tmem_n + col, dbits);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("bar.arrive %0, %1;" ::"r"(6 + b), "n"(kB3Sync) : "memory");  // (also releases the g box)
+    }
+    // ---- pass 3: dx = direct + sign(x) * dp, from TMEM only ----
+    if (!mbar_wait(bar(L::kBarDp), (uint32_t)t & 1u)) __trap();  // every MMA2 of this tile has completed
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+    for (int c = 0; c < NCH; ++c, ++n) {
+      const uint32_t slot = n & 3u, round = n >> 2;
+      uint32_t d[8], p[8];
+      tmem_load<8>(tmem_n + lane_sel + (uint32_t)(c * 32 + h * 8), d);
+      tmem_load<8>(tmem_dp + lane_sel + (uint32_t)(c * 32 + h * 8), p);
+      uint8_t* box = smem + L::kOffRing + slot * kF4Box;
+      if (!mbar_wait(bar(L::kBarFull + slot), round & 1u)) __trap();  // the slot's previous user has left
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const uint32_t code = d[e] & 3u;
+        const float s = (code == 1u) ? 1.f : ((code == 2u) ? -1.f : 0.f);
+        o[e] = fmaf(s, __uint_as_float(p[e]), __uint_as_float(d[e]));
+      }
+      *chunk_at(box, r, 2 * h) = make_float4(o[0], o[1], o[2], o[3]);
+      *chunk_at(box, r, 2 * h + 1) = make_float4(o[4], o[5], o[6], o[7]);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // dx box -> TMA store
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar(L::kBarY + slot)) : "memory");
+    }
+    // commits of chunks 2 and 3: every MMA of this tile has completed, the p planes are dead
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      if (!mbar_wait(bar(L::kBarQ + b), parq[b])) __trap();
+      parq[b] ^= 1u;
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if ((t % kDgFlush) == kDgFlush - 1) flush_dgamma();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // TMEM reads precede the next tile's MMAs
+    if (has_next) conv_tile();
+  }
+
+  // ---- this CTA's partial sums ----
+  if (t > 0) {
+    if ((t % kDgFlush) != 0) flush_dgamma();  // tiles since the last flush
+    // dbeta: the 32 lanes of a warp hold the same channels (32 c + 8 h + e) for 32 different rows
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float v = dbeta_acc[c][e];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        if (lane == 0) atomicAdd(dbeta_s + c * 32 + h * 8 + e, v);
+      }
+  }
+  }  // compute warps
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (tid < C) part_b[(long long)blockIdx.x * C + tid] = dbeta_s[tid];
+  if (tid < 32) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "n"(512));
+  }
+}
+
+int launch_tc_bwd3(const float* x, const float* gamma, const float* beta, const float* dy, float* dx, float* part_g,
+                   float* part_b, int* n_parts, long long n_pix, int inverse, cudaStream_t s) {
+  constexpr int C = 128;
+  using L = BwdFusedSmem;
+  CUtensorMap x_map, g_map, dx_map;
+  TFCB_TRY(make_tensor_map_2d(&x_map, x, n_pix, C, kTileM, 32, true));
+  TFCB_TRY(make_tensor_map_2d(&g_map, dy, n_pix, C, kTileM, 32, true));
+  TFCB_TRY(make_tensor_map_2d(&dx_map, dx, n_pix, C, kTileM, 32, true));
+  __nv_bfloat16* planes = nullptr;
+  TFCB_TRY(dev_alloc((void**)&planes, (size_t)2 * C * C * sizeof(__nv_bfloat16), s));
+  gdn_tc_prep_kernel<<<((C / 8) * C + 255) / 256, 256, 0, s>>>(gamma, C, planes);
+  TFCB_LAUNCHED();
+  cudaError_t e = cudaFuncSetAttribute(gdn_tc_bwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    dev_free(planes, s);
+    return fail(TFCB_CUDA_ERROR, "cannot reserve %d bytes of shared memory: %s", L::kBytes, cudaGetErrorString(e));
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long n_tiles = (n_pix + kTileM - 1) / kTileM;
+  const int grid = (int)std::min<long long>(n_tiles, std::min(sms, 148));
+  gdn_tc_bwd3_kernel<<<grid, kB3Threads, L::kBytes, s>>>(x_map, g_map, dx_map, x, dy, planes, beta, part_g, part_b, n_pix,
+                                                        inverse);
+  TFCB_LAUNCHED();
+  e = cudaGetLastError();
+  dev_free(planes, s);
+  if (e != cudaSuccess) return fail(TFCB_CUDA_ERROR, "GDN tensor-core backward launch failed: %s", cudaGetErrorString(e));
+  *n_parts = grid;
+  return TFCB_OK;
+}
+
 template <bool FAST>
 int launch_tc_bwd192(const float* x, const float* gamma, const float* beta, const float* dy, float* dx, float* q_ws,
                      float* part_g, float* part_b, int* n_parts, long long n_pix, TcFlags f, cudaStream_t s) {
@@ -1852,6 +2309,11 @@ int gdn_tc_backward(const float* x, const float* gamma, const float* beta, const
   if (C == 192)
     return fast ? launch_tc_bwd192<true>(x, gamma, beta, dy, dx, q_ws, part_g, part_b, n_parts, n_pix, f, s)
                 : launch_tc_bwd192<false>(x, gamma, beta, dy, dx, q_ws, part_g, part_b, n_parts, n_pix, f, s);
+  // C == 128.  The default GDN / IGDN goes through the box-fed kernel; TFCB_GDN_BWD_V1=1 keeps the register-fed one
+  // (A/B timing), which also serves the alpha = 2 / epsilon = 1/2 / rectified variants.
+  const char* v1 = getenv("TFCB_GDN_BWD_V1");
+  if (fast && n_pix < (1ll << 31) && !(v1 && v1[0] == '1'))
+    return launch_tc_bwd3(x, gamma, beta, dy, dx, part_g, part_b, n_parts, n_pix, f.inverse, s);
   return fast ? launch_tc_bwd<true>(x, gamma, beta, dy, dx, part_g, part_b, n_parts, n_pix, f, s)
               : launch_tc_bwd<false>(x, gamma, beta, dy, dx, part_g, part_b, n_parts, n_pix, f, s);
 }
