@@ -1738,14 +1738,20 @@ gdn_tc_bwd_dgamma_kernel(const float* __restrict__ x, const float* __restrict__ 
 //
 //   conv(t)   x boxes -> p = |x| hi / lo planes (whole K)                -> MMA1  n = p . gamma
 //             the raw x values are parked in 128 spare TMEM columns (tcgen05.st) for pass 2
-//   pass2(t)  g boxes + n, x from TMEM -> q planes (32-channel chunks)    -> MMA2  dp += q . gamma^T, MMA3  dgamma += p^T q
+//   pass2(t)  g boxes + n, x from TMEM -> q hi / lo planes (whole tile, written 32 channels at a time)
+//                                                                         -> MMA2  dp += q_chunk . gamma^T  per chunk
 //             the direct term g / n (IGDN: g * n) goes back into n's TMEM columns with sign(x) in the two low
 //             mantissa bits (2 ulp, the contract is 1e-5): the dx pass needs neither x nor g again
-//   pass3(t)  dx = direct + sign(x) * dp  from TMEM only -> box -> TMA store
+//   pass3(t)  dx = direct + sign(x) * dp  from TMEM only -> box -> TMA store;  meanwhile
+//                                                                         -> MMA3  dgamma += p^T q, 24 full-width MMAs
 //
-// One ring of four 16 KB boxes serves every request in program order: g x 4 (pass 2), output x 4 (pass 3), x x 4
-// (conversion of the CTA's next tile); while the next tile is converted its g boxes are already on their way.
-// TMEM: n | dp | dgamma partial | parked x (4 x 128 columns).  HBM traffic: x, dy in, dx out, nothing else.
+// (With 32-channel q buffers MMA3 was 96 MMAs of N = 32 per tile, each re-reading its 4 KB A operand from shared
+// memory for 16 cycles of math: switching them off saved 20 % of the kernel.)  The whole-tile q planes take the
+// place of the resident gamma planes: gamma (and gamma^T for MMA2) is streamed from L2 in 32-channel K chunks
+// (16 KB hi + lo, double buffered) by a "gamma" warp, 128 KB per tile.
+// One ring of four 16 KB boxes serves every box request in program order: g x 4 (pass 2), output x 4 (pass 3),
+// x x 4 (conversion of the CTA's next tile).  TMEM: n | dp | dgamma partial | parked x (4 x 128 columns).
+// HBM traffic: x, dy in, dx out, nothing else.
 // =============================================================================================
 __device__ __forceinline__ void tmem_store8(uint32_t taddr, const uint32_t (&r)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
@@ -1753,28 +1759,51 @@ __device__ __forceinline__ void tmem_store8(uint32_t taddr, const uint32_t (&r)[
                : "memory");
 }
 
-constexpr int kB3Compute = 512;               // 16 compute warps
-constexpr int kB3Threads = kB3Compute + 96;   // + MMA-issue, copy and store warps
-constexpr int kB3Sync = kB3Compute + 32;      // compute + issue warps (named barriers of the plane hand-offs)
+// gamma [C, C] -> four bf16 planes for the streamed kernel: [j / 8][i][j % 8] hi, lo (MMA1: K = j) and the transposed
+// [i / 8][j][i % 8] hi, lo (MMA2: K = i); a K chunk of 32 channels is 4 contiguous groups = C * 64 bytes of a plane.
+__global__ void gdn_tc_prep2_kernel(const float* __restrict__ gamma, int C, __nv_bfloat16* __restrict__ planes) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over (k / 8, n)
+  if (idx >= (C / 8) * C) return;
+  const int kc = idx / C, n = idx % C;
+  float v[8], w[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    v[e] = gamma[(kc * 8 + e) * C + n];  // k = j (input channel), n = i
+    w[e] = gamma[n * C + kc * 8 + e];    // k = i, n = j
+  }
+  uint4 hi, lo;
+  split8(v, &hi, &lo);
+  reinterpret_cast<uint4*>(planes)[idx] = hi;
+  reinterpret_cast<uint4*>(planes + (size_t)C * C)[idx] = lo;
+  split8(w, &hi, &lo);
+  reinterpret_cast<uint4*>(planes + 2 * (size_t)C * C)[idx] = hi;
+  reinterpret_cast<uint4*>(planes + 3 * (size_t)C * C)[idx] = lo;
+}
+
+constexpr int kB3Compute = 512;                // 16 compute warps
+constexpr int kB3Threads = kB3Compute + 160;   // + two MMA-issue warps, box-copy, gamma and store warps
+constexpr int kB3SyncA = kB3Compute + 32;      // compute + first issue warp
+constexpr int kB3SyncB = kB3Compute + 64;      // compute + both issue warps (last q chunk of a tile)
 constexpr int kB3Slots = 4;
 
 struct BwdFusedSmem {
   static constexpr int C = 128;
+  static constexpr int kGChunk = 4 * C * 16;                      // one 32-channel K chunk of one gamma plane (8 KB)
   static constexpr int kOffRing = 0;                              // [4] boxes (1024-byte aligned: swizzle atom)
-  static constexpr int kOffBh = kOffRing + kB3Slots * kF4Box;     // gamma hi, then lo (contiguous, as in global memory)
-  static constexpr int kOffBl = kOffBh + C * C * 2;
-  static constexpr int kPlaneP = (C / 8) * kKg;                   // p hi / lo, whole K
-  static constexpr int kOffPh = kOffBl + C * C * 2;
-  static constexpr int kOffPl = kOffPh + kPlaneP;
-  static constexpr int kPlaneQ = 4 * kKg;                         // q hi / lo, one 32-channel chunk
-  static constexpr int kOffQ = kOffPl + kPlaneP;                  // [2 buffers][hi, lo]
-  static constexpr int kOffBeta = kOffQ + 4 * kPlaneQ;
+  static constexpr int kOffG = kOffRing + kB3Slots * kF4Box;      // [2 buffers][hi, lo] gamma K chunks
+  static constexpr int kPlane = (C / 8) * kKg;                    // one whole-K operand plane (p or q, hi or lo)
+  static constexpr int kOffPh = kOffG + 4 * kGChunk;
+  static constexpr int kOffPl = kOffPh + kPlane;
+  static constexpr int kOffQh = kOffPl + kPlane;
+  static constexpr int kOffQl = kOffQh + kPlane;
+  static constexpr int kOffBeta = kOffQl + kPlane;
   static constexpr int kOffDbeta = kOffBeta + C * 4;
   static constexpr int kOffBar = kOffDbeta + C * 4;
-  // mbarriers: full[4], empty[4], yready[4], nfull, dpfull, qfree[2]; then the TMEM slot
-  static constexpr int kBarFull = 0, kBarEmpty = 4, kBarY = 8, kBarN = 12, kBarDp = 13, kBarQ = 14, kNumBars = 16;
+  // mbarriers: full[4], empty[4], yready[4], gfull[2], gfree[2], nfull, dpfull, m3done; then the TMEM slot
+  static constexpr int kBarFull = 0, kBarEmpty = 4, kBarY = 8, kBarGfull = 12, kBarGfree = 14, kBarN = 16, kBarDp = 17,
+                       kBarM3 = 18, kNumBars = 19;
   static constexpr int kBytes = kOffBar + kNumBars * 8 + 16;
-  static_assert(kOffBh % 128 == 0 && kOffPh % 16 == 0 && kOffQ % 16 == 0 && kOffBar % 8 == 0, "alignment");
+  static_assert(kOffG % 128 == 0 && kOffPh % 16 == 0 && kOffQh % 16 == 0 && kOffBar % 8 == 0, "alignment");
   static_assert(kBytes <= 232448, "shared memory budget");
 };
 
@@ -1782,7 +1811,7 @@ __global__ void __launch_bounds__(kB3Threads, 1)
 gdn_tc_bwd3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUtensorMap g_map,
                    const __grid_constant__ CUtensorMap dx_map, const float* __restrict__ x, const float* __restrict__ dy,
                    const __nv_bfloat16* __restrict__ planes, const float* __restrict__ beta, float* __restrict__ part_g,
-                   float* __restrict__ part_b, long long n_pix, int inverse) {
+                   float* __restrict__ part_b, long long n_pix, int inverse, int dbg) {
   using L = BwdFusedSmem;
   constexpr int C = L::C, NCH = C / 32;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -1793,18 +1822,13 @@ gdn_tc_bwd3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_const
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r = tid & 127, h = (tid >> 7) & 3, gwarp = warp & 3;  // compute thread (r, h): pixel row r, channel octet h of a box
   auto bar = [&](int i) { return smem_u32(mbars + i); };
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(planes);  // hi plane, then lo
-    uint4* dst = reinterpret_cast<uint4*>(smem + L::kOffBh);
-    for (int i = tid; i < 2 * C * C * 2 / 16; i += kB3Threads) dst[i] = src[i];
-    for (int i = tid; i < C; i += kB3Threads) {
-      beta_s[i] = beta[i];
-      dbeta_s[i] = 0.f;
-    }
+  for (int i = tid; i < C; i += kB3Threads) {
+    beta_s[i] = beta[i];
+    dbeta_s[i] = 0.f;
   }
   if (tid == 0) {
     for (int i = 0; i < L::kNumBars; ++i) {
-      const int count = (i >= L::kBarY && i < L::kBarN) ? kB3Compute / 32 : 1;  // y ready: one arrival per compute warp
+      const int count = (i >= L::kBarY && i < L::kBarGfull) ? kB3Compute / 32 : 1;  // y ready: one arrival per compute warp
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar(i)), "r"(count));
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1819,16 +1843,21 @@ gdn_tc_bwd3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_const
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_n = *tmem_slot, tmem_dp = tmem_n + C, tmem_dg = tmem_n + 2 * C, tmem_x = tmem_n + 3 * C;
   const uint32_t lane_sel = (uint32_t)(gwarp * 32) << 16;
-  const uint32_t b_hi = smem_u32(smem + L::kOffBh), b_lo = smem_u32(smem + L::kOffBl);
   const uint32_t p_hi = smem_u32(smem + L::kOffPh), p_lo = smem_u32(smem + L::kOffPl);
+  const uint32_t q_hi = smem_u32(smem + L::kOffQh), q_lo = smem_u32(smem + L::kOffQl);
   const long long n_tiles = (n_pix + kTileM - 1) / kTileM;
   const long long first = blockIdx.x;
+  // The dgamma accumulator is flushed every kDgFlush tiles; CTAs take turns (all 148 flushing in the same
+  // microsecond made the L2 the bottleneck of the flush)
+  const int fphase = (int)(blockIdx.x % kDgFlush);
   // Box requests are numbered in program order; request n uses ring slot n % 4 in its (n / 4)-th round:
   //   4 x boxes (conversion of the CTA's first tile), then per tile  g x 4, out x 4, (x of the next tile) x 4.
+  // Gamma K chunks likewise, buffer m % 2:  4 chunks of gamma (MMA1 of the first tile), then per tile 4 chunks of
+  // gamma^T (MMA2), 4 chunks of gamma (MMA1 of the next tile).
   constexpr int W0 = kB3Compute / 32;  // first auxiliary warp
 
-  if (warp == W0 + 1) {
-    // ---------------------------------- copy warp ----------------------------------
+  if (warp == W0 + 2) {
+    // ---------------------------------- box-copy warp ----------------------------------
     if (lane == 0) {
       uint32_t n = 0;
       auto acquire = [&]() {
@@ -1885,7 +1914,45 @@ gdn_tc_bwd3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_const
       }
     }
     __syncwarp();
-  } else if (warp == W0 + 2) {
+  } else if (warp == W0 + 3) {
+    // ---------------------------------- gamma warp: K chunks of gamma / gamma^T ----------------------------------
+    if (lane == 0) {
+      const uint8_t* gp = reinterpret_cast<const uint8_t*>(planes);
+      constexpr size_t kPlaneBytes = (size_t)C * C * 2;
+      uint32_t m = 0;
+      auto chunk = [&](int transposed, int c) {
+        const uint32_t buf = m & 1u;
+        if (m >= 2) {  // the MMAs of chunk m - 2 (same buffer) have completed
+          if (!mbar_wait(bar(L::kBarGfree + buf), ((m >> 1) - 1u) & 1u)) __trap();
+        }
+        const uint32_t gfull = bar(L::kBarGfull + buf);
+        const uint32_t dst = smem_u32(smem + L::kOffG + buf * 2 * L::kGChunk);
+        const uint8_t* src = gp + (size_t)(2 * transposed) * kPlaneBytes + (size_t)c * L::kGChunk;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gfull), "n"(2 * L::kGChunk) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+                     "l"(src), "n"(L::kGChunk), "r"(gfull), "l"(kEvictLast)
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                         dst + L::kGChunk),
+                     "l"(src + kPlaneBytes), "n"(L::kGChunk), "r"(gfull), "l"(kEvictLast)
+                     : "memory");
+        ++m;
+      };
+      if (first < n_tiles) {
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c) chunk(0, c);
+      }
+      for (long long tile = first; tile < n_tiles; tile += gridDim.x) {
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c) chunk(1, c);
+        if (tile + gridDim.x < n_tiles) {
+#pragma unroll 1
+          for (int c = 0; c < NCH; ++c) chunk(0, c);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == W0 + 4) {
     // ---------------------------------- store warp: dx boxes ----------------------------------
     if (lane == 0) {
       uint32_t n = (first < n_tiles) ? (uint32_t)NCH : 0u;
@@ -1912,63 +1979,72 @@ gdn_tc_bwd3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_const
     }
     __syncwarp();
   } else if (warp == W0) {
-    // ------------------------------- MMA-issue warp -------------------------------
-    constexpr uint32_t kIdesc1 = umma_idesc(kTileM, C);                          // n = p . gamma
-    constexpr uint32_t kIdesc2 = umma_idesc(kTileM, C) | (1u << 16);             // B = gamma^T (MN-major view)
-    constexpr uint32_t kIdesc3 = umma_idesc(C, 32) | (1u << 15) | (1u << 16);    // A = p^T, B = q chunk (both views)
-    uint32_t n = 0;
+    // ------------------------------- first MMA-issue warp: MMA1, MMA2 (K-chunked, gamma streamed) ------------------
+    constexpr uint32_t kIdesc = umma_idesc(kTileM, C);  // A, B both K-major
+    uint32_t n = 0, m = 0;
+    // six MMAs of one 32-channel K chunk: A planes (hi, lo) x gamma chunk (hi, lo), three products
+    auto chunk_mmas = [&](uint32_t a_hi, uint32_t a_lo, uint32_t acc, bool first_chunk) {
+      const uint32_t buf = m & 1u;
+      if (!mbar_wait(bar(L::kBarGfull + buf), (m >> 1) & 1u)) __trap();
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t g_hi = smem_u32(smem + L::kOffG + buf * 2 * L::kGChunk), g_lo = g_hi + L::kGChunk;
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2) {
+        const uint64_t dah = umma_desc(a_hi + (uint32_t)(2 * s2) * kKg, kKg, 128);
+        const uint64_t dal = umma_desc(a_lo + (uint32_t)(2 * s2) * kKg, kKg, 128);
+        const uint64_t dbh = umma_desc(g_hi + (uint32_t)(2 * s2) * (C * 16), C * 16, 128);
+        const uint64_t dbl = umma_desc(g_lo + (uint32_t)(2 * s2) * (C * 16), C * 16, 128);
+        umma_bf16(acc, dah, dbh, kIdesc, (first_chunk && s2 == 0) ? 0u : 1u);
+        umma_bf16(acc, dal, dbh, kIdesc, 1u);
+        umma_bf16(acc, dah, dbl, kIdesc, 1u);
+      }
+      umma_commit(bar(L::kBarGfree + buf));
+      ++m;
+    };
     auto release = [&](uint32_t req) {
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar(L::kBarEmpty + (req & 3u))) : "memory");
     };
     auto mma1_tile = [&]() {  // n = p . gamma of the tile being converted, K chunk by K chunk
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c, ++n) {
-        asm volatile("bar.sync %0, %1;" ::"r"(2 + c), "n"(kB3Sync) : "memory");  // p planes of chunk c are written
+        asm volatile("bar.sync %0, %1;" ::"r"(2 + c), "n"(kB3SyncA) : "memory");  // p planes of chunk c are written
         if (lane == 0) {
           release(n);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-          for (int s2 = 0; s2 < 2; ++s2) {
-            const uint32_t s = (uint32_t)(2 * c + s2);
-            const uint64_t dah = umma_desc(p_hi + 2u * s * kKg, kKg, 128);
-            const uint64_t dal = umma_desc(p_lo + 2u * s * kKg, kKg, 128);
-            const uint64_t dbh = umma_desc(b_hi + 2u * s * (C * 16), C * 16, 128);
-            const uint64_t dbl = umma_desc(b_lo + 2u * s * (C * 16), C * 16, 128);
-            umma_bf16(tmem_n, dah, dbh, kIdesc1, (c | s2) ? 1u : 0u);
-            umma_bf16(tmem_n, dal, dbh, kIdesc1, 1u);
-            umma_bf16(tmem_n, dah, dbl, kIdesc1, 1u);
-          }
+          chunk_mmas(p_hi + (uint32_t)(4 * c) * kKg, p_lo + (uint32_t)(4 * c) * kKg, tmem_n, c == 0);
           if (c == NCH - 1) umma_commit(bar(L::kBarN));
         }
         __syncwarp();
       }
     };
     if (first < n_tiles) mma1_tile();
-    int t = 0;
-    for (long long tile = first; tile < n_tiles; tile += gridDim.x, ++t) {
+    for (long long tile = first; tile < n_tiles; tile += gridDim.x) {
       const bool has_next = tile + gridDim.x < n_tiles;
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c, ++n) {
-        const int b = c & 1;
-        asm volatile("bar.sync %0, %1;" ::"r"(6 + b), "n"(kB3Sync) : "memory");  // q planes of chunk c are written
+        if (c == NCH - 1) asm volatile("bar.sync %0, %1;" ::"r"(6 + c), "n"(kB3SyncB) : "memory");
+        else asm volatile("bar.sync %0, %1;" ::"r"(6 + c), "n"(kB3SyncA) : "memory");  // q planes of chunk c are written
         if (lane == 0) {
           release(n);  // the g box of this chunk
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t q_hi = smem_u32(smem + L::kOffQ + b * 2 * L::kPlaneQ), q_lo = q_hi + L::kPlaneQ;
-          // MMA2: dp[pix, j] += sum_{i in chunk} q[pix, i] gamma[j, i]   (K = i: 2 steps of 16)
-#pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            const uint64_t dah = umma_desc(q_hi + (uint32_t)(2 * s) * kKg, kKg, 128);
-            const uint64_t dal = umma_desc(q_lo + (uint32_t)(2 * s) * kKg, kKg, 128);
-            const uint32_t koff = (uint32_t)(c * 32 + s * 16) * 16u;
-            const uint64_t dbh = umma_desc(b_hi + koff, 128, C * 16);
-            const uint64_t dbl = umma_desc(b_lo + koff, 128, C * 16);
-            umma_bf16(tmem_dp, dah, dbh, kIdesc2, (c | s) ? 1u : 0u);
-            umma_bf16(tmem_dp, dal, dbh, kIdesc2, 1u);
-            umma_bf16(tmem_dp, dah, dbl, kIdesc2, 1u);
-          }
+          // MMA2: dp[pix, j] += sum_{i in chunk} q[pix, i] gamma[j, i]
+          chunk_mmas(q_hi + (uint32_t)(4 * c) * kKg, q_lo + (uint32_t)(4 * c) * kKg, tmem_dp, c == 0);
           if (c == NCH - 1) umma_commit(bar(L::kBarDp));  // dp is complete: the dx pass may start
-          // MMA3: dgamma[j, i in chunk] += sum_pix p[pix, j] q[pix, i]   (K = pix: 8 steps of 16)
+        }
+        __syncwarp();
+      }
+      n += NCH;  // the output boxes: handed back by the store warp
+      if (has_next) mma1_tile();
+    }
+  } else if (warp == W0 + 1) {
+    // ------------------------------- second MMA-issue warp: MMA3, once per tile -------------------------------
+    constexpr uint32_t kIdesc3 = umma_idesc(C, C) | (1u << 15) | (1u << 16);    // A = p^T, B = q (both MN-major views)
+    int t = 0;
+    for (long long tile = first; tile < n_tiles; tile += gridDim.x, ++t) {
+      asm volatile("bar.sync %0, %1;" ::"r"(6 + NCH - 1), "n"(kB3SyncB) : "memory");  // the whole tile of q is written
+      if (lane == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // dgamma[j, i] += sum_pix p[pix, j] q[pix, i]   (K = pix: 8 steps of 16)
+        if (!(dbg & 1)) {
+          const bool restart = (t == 0) || (((t + fphase) % kDgFlush) == 0);  // first MMA after a flush
 #pragma unroll
           for (int s = 0; s < kTileM / 16; ++s) {
             const uint32_t koff = (uint32_t)(s * 16) * 16u;
@@ -1976,22 +2052,18 @@ gdn_tc_bwd3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_const
             const uint64_t dal = umma_desc(p_lo + koff, 128, kKg);
             const uint64_t dbh = umma_desc(q_hi + koff, 128, kKg);
             const uint64_t dbl = umma_desc(q_lo + koff, 128, kKg);
-            const uint32_t acc_on = ((t % kDgFlush) == 0 && s == 0) ? 0u : 1u;  // restarted after every flush
-            umma_bf16(tmem_dg + (uint32_t)(c * 32), dah, dbh, kIdesc3, acc_on);
-            umma_bf16(tmem_dg + (uint32_t)(c * 32), dal, dbh, kIdesc3, 1u);
-            umma_bf16(tmem_dg + (uint32_t)(c * 32), dah, dbl, kIdesc3, 1u);
+            umma_bf16(tmem_dg, dah, dbh, kIdesc3, (restart && s == 0) ? 0u : 1u);
+            umma_bf16(tmem_dg, dal, dbh, kIdesc3, 1u);
+            umma_bf16(tmem_dg, dah, dbl, kIdesc3, 1u);
           }
-          umma_commit(bar(L::kBarQ + b));
         }
-        __syncwarp();
+        umma_commit(bar(L::kBarM3));
       }
-      n += NCH;  // the output boxes: handed back by the store warp
-      if (has_next) mma1_tile();
+      __syncwarp();
     }
   } else if (warp < W0) {
   // --------------------------------- compute warps ---------------------------------
   uint32_t n = 0;
-  uint32_t parq[2] = {0u, 0u};
   float dbeta_acc[NCH][8];  // channels 32 c + 8 h + e, summed over this thread's rows
 #pragma unroll
   for (int c = 0; c < NCH; ++c)
@@ -2000,14 +2072,33 @@ gdn_tc_bwd3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_const
   // 128-byte swizzle: the 16-byte chunk j of box row `row` sits at chunk j ^ (row & 7)
   auto chunk_at = [](uint8_t* box, int row, int j) { return reinterpret_cast<float4*>(box + row * 128 + ((j ^ (row & 7)) << 4)); };
   bool flushed = false;  // the global partial holds earlier flushes
-  auto flush_dgamma = [&]() {  // TMEM lane r = input channel j, this thread's 32 columns -> the CTA's partial
-    float* pg = part_g + (long long)blockIdx.x * C * C + (long long)r * C + h * 32;
+  // The accumulator (TMEM lane = input channel j, 32 columns per thread) is transposed through the dead q planes
+  // ([128][128] fp32, 16-byte units XOR-swizzled by the row) so that every warp adds 512 contiguous bytes to the CTA's
+  // partial: with one row per lane each vector add touched 32 different L2 lines (8 % of the kernel).
+  auto flush_dgamma = [&]() {
+    uint8_t* stage = smem + L::kOffQh;
 #pragma unroll
     for (int cb = 0; cb < 2; ++cb) {
       uint32_t a[16];
       tmem_load<16>(tmem_dg + lane_sel + (uint32_t)(h * 32 + cb * 16), a);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      accum_store16(pg + cb * 16, a, flushed);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<uint4*>(stage + r * 512 + (((h * 8 + cb * 4 + i) ^ (r & 7)) << 4)) =
+            make_uint4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kB3Compute) : "memory");
+    float* pg = part_g + (long long)blockIdx.x * C * C;
+#pragma unroll
+    for (int it = 0; it < (C * C / 4) / kB3Compute; ++it) {
+      const int item = it * kB3Compute + tid, row = item >> 5, c4 = item & 31;
+      const uint4 v = *reinterpret_cast<const uint4*>(stage + row * 512 + ((c4 ^ (row & 7)) << 4));
+      float* dst = pg + row * C + c4 * 4;
+      // first flush: plain stores; later ones: fire-and-forget vector adds in L2
+      if (!flushed)
+        asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+      else
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
     }
     flushed = true;
   };
@@ -2029,9 +2120,8 @@ gdn_tc_bwd3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_const
       *reinterpret_cast<uint4*>(smem + L::kOffPh + (4 * c + h) * kKg + r * 16) = hi;
       *reinterpret_cast<uint4*>(smem + L::kOffPl + (4 * c + h) * kKg + r * 16) = lo;
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      asm volatile("bar.arrive %0, %1;" ::"r"(2 + c), "n"(kB3Sync) : "memory");  // (also releases the box, see issue warp)
+      asm volatile("bar.arrive %0, %1;" ::"r"(2 + c), "n"(kB3SyncA) : "memory");  // (also releases the box, see issue warp)
     }
   };
 
@@ -2039,12 +2129,12 @@ gdn_tc_bwd3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_const
   int t = 0;
   for (long long tile = first; tile < n_tiles; tile += gridDim.x, ++t) {
     const bool has_next = tile + gridDim.x < n_tiles;
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");  // this thread's parked x values are in TMEM
     if (!mbar_wait(bar(L::kBarN), (uint32_t)t & 1u)) __trap();  // MMA1 of this tile has completed
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     // ---- pass 2: q = dL/dn -> q planes; the direct term and sign(x) go back into n's columns ----
 #pragma unroll
     for (int c = 0; c < NCH; ++c, ++n) {
-      const int b = c & 1;
       const uint32_t slot = n & 3u;
       const uint32_t col = lane_sel + (uint32_t)(c * 32 + h * 8);
       uint32_t nacc[8], xraw[8];
@@ -2077,22 +2167,18 @@ gdn_tc_bwd3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_const
         dbits[e] = (__float_as_uint(direct) & ~3u) | code;
         dbeta_acc[c][e] += q[e];
       }
-      if (c >= 2) {  // the q buffer was read by the MMAs of chunk c - 2
-        if (!mbar_wait(bar(L::kBarQ + b), parq[b])) __trap();
-        parq[b] ^= 1u;
-      }
-      uint8_t* qh = smem + L::kOffQ + b * 2 * L::kPlaneQ;
       uint4 hi, lo;
       split8(q, &hi, &lo);
-      *reinterpret_cast<uint4*>(qh + h * kKg + r * 16) = hi;
-      *reinterpret_cast<uint4*>(qh + L::kPlaneQ + h * kKg + r * 16) = lo;
+      *reinterpret_cast<uint4*>(smem + L::kOffQh + (4 * c + h) * kKg + r * 16) = hi;
+      *reinterpret_cast<uint4*>(smem + L::kOffQl + (4 * c + h) * kKg + r * 16) = lo;
       tmem_store8(tmem_n + col, dbits);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      asm volatile("bar.arrive %0, %1;" ::"r"(6 + b), "n"(kB3Sync) : "memory");  // (also releases the g box)
+      if (c == NCH - 1) asm volatile("bar.arrive %0, %1;" ::"r"(6 + c), "n"(kB3SyncB) : "memory");
+      else asm volatile("bar.arrive %0, %1;" ::"r"(6 + c), "n"(kB3SyncA) : "memory");  // (also releases the g box)
     }
     // ---- pass 3: dx = direct + sign(x) * dp, from TMEM only ----
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");  // this thread's direct terms are in TMEM
     if (!mbar_wait(bar(L::kBarDp), (uint32_t)t & 1u)) __trap();  // every MMA2 of this tile has completed
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
@@ -2117,21 +2203,17 @@ gdn_tc_bwd3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_const
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar(L::kBarY + slot)) : "memory");
     }
-    // commits of chunks 2 and 3: every MMA of this tile has completed, the p planes are dead
-#pragma unroll
-    for (int b = 0; b < 2; ++b) {
-      if (!mbar_wait(bar(L::kBarQ + b), parq[b])) __trap();
-      parq[b] ^= 1u;
-    }
+    // MMA3 of this tile has completed: the p and q planes are dead, the dgamma accumulator is up to date
+    if (!mbar_wait(bar(L::kBarM3), (uint32_t)t & 1u)) __trap();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if ((t % kDgFlush) == kDgFlush - 1) flush_dgamma();
+    if (((t + fphase) % kDgFlush) == kDgFlush - 1 && !(dbg & 4)) flush_dgamma();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // TMEM reads precede the next tile's MMAs
     if (has_next) conv_tile();
   }
 
   // ---- this CTA's partial sums ----
   if (t > 0) {
-    if ((t % kDgFlush) != 0) flush_dgamma();  // tiles since the last flush
+    if (((t + fphase) % kDgFlush) != 0) flush_dgamma();  // tiles since the last flush
     // dbeta: the 32 lanes of a warp hold the same channels (32 c + 8 h + e) for 32 different rows
 #pragma unroll
     for (int c = 0; c < NCH; ++c)
@@ -2161,8 +2243,8 @@ int launch_tc_bwd3(const float* x, const float* gamma, const float* beta, const 
   TFCB_TRY(make_tensor_map_2d(&g_map, dy, n_pix, C, kTileM, 32, true));
   TFCB_TRY(make_tensor_map_2d(&dx_map, dx, n_pix, C, kTileM, 32, true));
   __nv_bfloat16* planes = nullptr;
-  TFCB_TRY(dev_alloc((void**)&planes, (size_t)2 * C * C * sizeof(__nv_bfloat16), s));
-  gdn_tc_prep_kernel<<<((C / 8) * C + 255) / 256, 256, 0, s>>>(gamma, C, planes);
+  TFCB_TRY(dev_alloc((void**)&planes, (size_t)4 * C * C * sizeof(__nv_bfloat16), s));
+  gdn_tc_prep2_kernel<<<((C / 8) * C + 255) / 256, 256, 0, s>>>(gamma, C, planes);
   TFCB_LAUNCHED();
   cudaError_t e = cudaFuncSetAttribute(gdn_tc_bwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes);
   if (e != cudaSuccess) {
@@ -2175,8 +2257,10 @@ int launch_tc_bwd3(const float* x, const float* gamma, const float* beta, const 
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long n_tiles = (n_pix + kTileM - 1) / kTileM;
   const int grid = (int)std::min<long long>(n_tiles, std::min(sms, 148));
+  int dbg = 0;  // timing experiments only (results are wrong with any bit set): 1 no MMA3, 4 no dgamma flushes
+  if (const char* env = getenv("TFCB_GDN_DBG")) dbg = atoi(env);
   gdn_tc_bwd3_kernel<<<grid, kB3Threads, L::kBytes, s>>>(x_map, g_map, dx_map, x, dy, planes, beta, part_g, part_b, n_pix,
-                                                        inverse);
+                                                        inverse, dbg);
   TFCB_LAUNCHED();
   e = cudaGetLastError();
   dev_free(planes, s);
