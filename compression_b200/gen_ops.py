@@ -19,6 +19,7 @@ from compression_b200 import _lib
 from compression_b200._lib import InvalidArgumentError, check
 
 __all__ = [
+    "stochastic_round",
     "create_range_encoder",
     "create_range_decoder",
     "entropy_decode_channel",
@@ -374,4 +375,30 @@ def range_decode(encoded, shape, cdf, precision: int, debug_level: int = 1) -> t
   check(_lib.lib().tfcb_range_decode(
       buf.ctypes.data_as(C.c_void_p), len(encoded), ds.ctypes.data_as(C.c_void_p), len(ds), _ptr(cdf),
       cs.ctypes.data_as(C.c_void_p), cdf.dim(), int(precision), int(debug_level), _ptr(out), _stream()))
+  return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Quantisation ops
+# ------------------------------------------------------------------------------------------------
+_SR_DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+
+
+def stochastic_round(inputs, step_size, seed) -> torch.Tensor:
+  """StochasticRound (cc/ops/quantization_ops.cc:28-53, cc/kernels/quantization_kernels.cc:48-95):
+  int32 floor(inputs / step_size) + Bernoulli(fractional part).  `seed`: int32 tensor / sequence of any shape; the
+  same seed gives the same integers as the reference CPU op; an empty seed seeds from the clock."""
+  if not isinstance(inputs, torch.Tensor):
+    inputs = torch.as_tensor(inputs, dtype=torch.float32)
+  if inputs.dtype not in _SR_DTYPES:
+    raise InvalidArgumentError(f"StochasticRound: unsupported dtype {inputs.dtype} (bfloat16, float16, float32)")
+  step = np.asarray(step_size.cpu() if isinstance(step_size, torch.Tensor) else step_size, dtype=np.float32)
+  if step.ndim != 0:
+    raise InvalidArgumentError("step_size must be a scalar.")
+  inputs = inputs.to(_device()).contiguous()
+  sd = np.ascontiguousarray(np.asarray(seed.cpu() if isinstance(seed, torch.Tensor) else seed, dtype=np.int32).reshape(-1))
+  out = torch.empty(inputs.shape, dtype=torch.int32, device=inputs.device)
+  check(_lib.lib().tfcb_stochastic_round(_ptr(inputs), _SR_DTYPES[inputs.dtype], inputs.numel(), float(step),
+                                         sd.ctypes.data_as(C.c_void_p) if sd.size else None, sd.size, _ptr(out),
+                                         _stream()))
   return out

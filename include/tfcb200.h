@@ -167,6 +167,19 @@ int tfcb_build_lookup(const float* pmf_dev, int64_t rows, int64_t max_len, const
                       int precision, int32_t* lookup_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * StochasticRound:
+ *   op contract   tensorflow_compression/cc/ops/quantization_ops.cc:28-53
+ *   CPU kernel    tensorflow_compression/cc/kernels/quantization_kernels.cc:48-95
+ * outputs[i] = floor(inputs[i] / step_size) + (u_i < frac), u_i the i-th draw of the reference's xoshiro256+
+ * stream seeded through std::seed_seq(seed) -- the same integers as the CPU op for the same seed (the
+ * sequential stream is entered in parallel through GF(2) jump matrices).  `dtype` 0 float32, 1 float16,
+ * 2 bfloat16; `seed_host` int32 [seed_len] in host memory, seed_len == 0 seeds from the clock
+ * (quantization_kernels.cc:71-78).
+ * ---------------------------------------------------------------------------------------------- */
+int tfcb_stochastic_round(const void* inputs_dev, int dtype, int64_t n, float step_size,
+                          const int32_t* seed_host, int64_t seed_len, int32_t* outputs_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * GDN / IGDN (tensorflow_compression/python/layers/gdn.py:371-421), channels-last:
  *   u = rectify ? relu(x) : x;  p = |u|^alpha;  n_i = beta_i + sum_j p_j gamma[j,i];
  *   y_i = u_i / n_i^eps  (GDN)   or   u_i * n_i^eps  (IGDN)

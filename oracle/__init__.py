@@ -169,6 +169,17 @@ class Oracle:
     return out
 
   # ---- PmfToQuantizedCdf ----
+  def stochastic_round(self, inputs, step_size: float, seed) -> np.ndarray:
+    """StochasticRound (quantization_kernels.cc:48-95) with an explicit seed; `inputs` float32 (already promoted)."""
+    x = np.ascontiguousarray(np.asarray(inputs, dtype=np.float32))
+    sd = _i32(np.asarray(seed).reshape(-1))
+    out = np.empty(x.shape, np.int32)
+    if not hasattr(self, "_stochastic_round"):
+      self._fn("stochastic_round", C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_int64, C.c_void_p])
+    if self._stochastic_round(x.ctypes.data, x.size, float(step_size), sd.ctypes.data, sd.size, out.ctypes.data) != 0:
+      raise OracleError(self._err())
+    return out
+
   def pmf_to_cdf(self, pmf, precision: int) -> np.ndarray:
     pmf = np.ascontiguousarray(pmf, dtype=np.float32)
     n = pmf.shape[-1]

@@ -26,6 +26,7 @@
 #include <atomic>
 #include <cmath>
 #include <condition_variable>
+#include <random>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -664,6 +665,38 @@ int tfcref_pmf_to_cdf(const float* pmf, int64_t rows, int64_t n, int precision, 
       return Fail("`pmf` has non-finite or negative element: " + std::to_string(pmf[i]));
   }
   for (int64_t r = 0; r < rows; ++r) PmfRow(pmf + r * n, n, precision, cdf + r * (n + 1));
+  return 0;
+}
+
+// StochasticRound, quantization_kernels.cc:35-95 restated: one xoshiro256+ stream seeded through std::seed_seq,
+// one draw per element in element order.  `inputs` are the op's inputs already promoted to float32 (the op does
+// static_cast<float>, exact for float16 / bfloat16).  An empty seed (clock seeding) is not reproducible and is
+// rejected here.
+int tfcref_stochastic_round(const float* inputs, int64_t n, float step_size, const int32_t* seed, int64_t seed_len,
+                            int32_t* outputs) {
+  if (seed_len <= 0) return Fail("the oracle needs an explicit seed");
+  uint64_t state[4];
+  std::seed_seq seq(seed, seed + seed_len);
+  seq.generate(reinterpret_cast<uint32_t*>(state), reinterpret_cast<uint32_t*>(state + 4));
+  auto next = [&state]() {
+    const uint64_t result = state[0] + state[3];
+    const uint64_t t = state[1] << 17;
+    state[2] ^= state[0];
+    state[3] ^= state[1];
+    state[1] ^= state[2];
+    state[0] ^= state[3];
+    state[2] ^= t;
+    state[3] = (state[3] << 45) | (state[3] >> (64 - 45));
+    return result;
+  };
+  for (int64_t i = 0; i < n; ++i) {
+    float number = inputs[i] / step_size;
+    float integral = std::floor(number);
+    outputs[i] = integral;
+    float fractional = number - integral;
+    float random = (next() >> 40) * 0x1.0p-24f;
+    if (random < fractional) ++outputs[i];
+  }
   return 0;
 }
 

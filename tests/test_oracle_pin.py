@@ -112,3 +112,22 @@ def test_pmf_to_cdf_invariants_and_tie_rule():
     assert (cdf[:, 0] == 0).all() and (cdf[:, -1] == 1 << p).all() and (np.diff(cdf, axis=-1) >= 1).all()
   with pytest.raises(oracle.OracleError):
     O.pmf_to_cdf(np.asarray([[0.5, np.nan]], np.float32), 8)
+
+
+def test_stochastic_round_port_equals_reference_flavour():
+  """quantization_kernels.cc:48-95: the C restatement of std::seed_seq + xoshiro256+ against libstdc++'s own
+  seed_seq driving the same loop (oracle/ref/ref_driver.cc), and the reference's invariants
+  (python/ops/quantization_ops_test.py:28-83) on the oracle itself."""
+  if not oracle.have_ref():
+    pytest.skip("reference flavour of the oracle not built")
+  P, R = oracle.port(), oracle.ref()
+  rng = np.random.default_rng(0)
+  for seed in ([1], [123, 456], [5] * 9, [-7, 2**31 - 1, 0, 3, 4, 5, 6, 7, 8, 9, 10]):
+    x = rng.uniform(-100, 100, 20000).astype(np.float32)
+    a, b = P.stochastic_round(x, 0.75, seed), R.stochastic_round(x, 0.75, seed)
+    assert np.array_equal(a, b)
+    assert np.all(np.abs(a * np.float32(0.75) - x) <= 0.75 + 1e-4)
+  ints = rng.integers(-100, 100, 100).astype(np.float32)
+  assert np.array_equal(P.stochastic_round(ints * np.float32(0.75), 0.75, [3]), ints.astype(np.int32))
+  rep = np.broadcast_to(rng.uniform(-100, 100, 20).astype(np.float32), (20000, 20))
+  assert np.abs(P.stochastic_round(rep, 1.0, [9]).mean(0) - rep[0]).max() < 3e-2
