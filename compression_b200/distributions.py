@@ -17,31 +17,45 @@ __all__ = [
 # ------------------------------------------------------------------------------------------------
 # helpers.py
 # ------------------------------------------------------------------------------------------------
-def estimate_tails(func, target, shape, dtype=torch.float32, device=None):
-  """Adam-style root finding of func(x) == target (helpers.py:29-102), vectorised over `shape`."""
+def estimate_tails(func, target, shape, dtype=torch.float32, device=None, check_every=16):
+  """Adam-style root finding of func(x) == target (helpers.py:29-102), vectorised over `shape`.
+
+  The reference's `tf.while_loop` condition (max loss > 1e-8 and min count < 100) is evaluated on the device: the
+  loop state is frozen by a 0-d `active` flag once the condition turns false, and the host looks at that flag only
+  every `check_every` iterations -- the result is the one of the sequential loop, without two host round trips
+  per iteration (the loop runs 100-300 iterations per table build)."""
   shape = tuple(int(s) for s in shape)
   target = torch.as_tensor(target, dtype=dtype, device=device)
   tails = torch.zeros(shape, dtype=dtype, device=device)
+  if tails.numel() == 0:
+    return tails
   m = torch.zeros_like(tails)
   v = torch.ones_like(tails)
   loss = torch.full_like(tails, torch.finfo(dtype).max)
-  count = torch.zeros(shape, dtype=torch.int32, device=device)
+  count = torch.zeros(shape, dtype=torch.int32, device=tails.device)
   best_tails, best_loss = tails.clone(), loss.clone()
-  while bool(loss.max() > 1e-8) and bool(count.min() < 100):
-    t = tails.detach().requires_grad_(True)
-    with torch.enable_grad():
-      loss = (func(t) - target).abs()
-      grad, = torch.autograd.grad(loss.sum(), t)
-    loss = loss.detach()
-    better = loss < best_loss
-    best_tails = torch.where(better, tails, best_tails)
-    best_loss = torch.where(better, loss, best_loss)
-    prev_m = m
-    m = (prev_m + grad) / 2
-    v = (v + grad.square()) / 2
-    k = torch.sqrt((count + 1).to(dtype))
-    tails = tails - 0.1 * m / (k * torch.sqrt(v) + 1e-20)
-    count = torch.where((count > 0) | (prev_m * grad < 0), count + 1, count)
+  active = torch.ones((), dtype=torch.bool, device=tails.device)
+  keep = lambda new, old: torch.where(active, new, old)
+  while True:
+    for _ in range(check_every):
+      active = active & (loss.max() > 1e-8) & (count.min() < 100)  # loop_cond, helpers.py:61-66
+      t = tails.detach().requires_grad_(True)
+      with torch.enable_grad():
+        new_loss = (func(t) - target).abs()
+        grad, = torch.autograd.grad(new_loss.sum(), t)
+      new_loss = new_loss.detach()
+      better = active & (new_loss < best_loss)
+      best_tails = torch.where(better, tails, best_tails)
+      best_loss = torch.where(better, new_loss, best_loss)
+      new_m = (m + grad) / 2
+      new_v = (v + grad.square()) / 2
+      k = torch.sqrt((count + 1).to(dtype))
+      new_tails = tails - 0.1 * new_m / (k * torch.sqrt(new_v) + 1e-20)
+      new_count = torch.where((count > 0) | (m * grad < 0), count + 1, count)
+      tails, m, v, loss, count = (keep(new_tails, tails), keep(new_m, m), keep(new_v, v), keep(new_loss, loss),
+                                  keep(new_count, count))
+    if not bool(active):  # the only host synchronisation
+      break
   return best_tails
 
 
