@@ -389,6 +389,56 @@ __global__ void gdn_bwd_generic_dgamma_kernel(const float* __restrict__ x, const
   }
 }
 
+// Gradients of the two scalar exponents (only needed when they are trainable, gdn.py:345-367): one warp per pixel,
+//   n_i = beta_i + sum_j p_j gamma[j, i],   q_i = dL/dn_i,   dp_j = sum_i gamma[j, i] q_i
+//   dL/depsilon = sum q_i n_i ln(n_i) / epsilon        (m = n^epsilon:  dL/dm * dm/depsilon = q * n * ln n / epsilon)
+//   dL/dalpha   = sum dp_j p_j ln(u_j)                 (p = u^alpha, u > 0)
+// Self-contained (recomputes n and q): the fused tensor-core backward does not keep q.  Per-block partials
+// [blocks][2], reduced in a fixed order by reduce_partials_kernel.
+__global__ void __launch_bounds__(128) gdn_bwd_exponents_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, const float* __restrict__ dy,
+                                                                float* __restrict__ part, long long n_pix, int C,
+                                                                GdnFlags f) {
+  extern __shared__ float qs[];  // [4 warps][C]
+  __shared__ float red[4][2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* q = qs + warp * C;
+  float dal = 0.f, dep = 0.f;
+  for (long long pix = blockIdx.x * 4ll + warp; pix < n_pix; pix += 4ll * gridDim.x) {
+    const float* xr = x + pix * C;
+    for (int i = lane; i < C; i += 32) {
+      float n = 0.f;
+      for (int j = 0; j < C; ++j) n = fmaf(pool_of(xr[j], f), gamma[(long long)j * C + i], n);
+      n = beta[i] + n;
+      const float u = f.rectify ? fmaxf(xr[i], 0.f) : xr[i];
+      const float qi = dl_dn(dy[pix * C + i], u, n, f);
+      q[i] = qi;
+      dep += qi * n * logf(n) / f.eps;
+    }
+    __syncwarp();
+    for (int j = lane; j < C; j += 32) {
+      float dp = 0.f;
+      for (int i = 0; i < C; ++i) dp = fmaf(gamma[(long long)j * C + i], q[i], dp);
+      const float u = f.rectify ? fmaxf(xr[j], 0.f) : xr[j];
+      if (u > 0.f) dal += dp * pool_of(xr[j], f) * logf(u);
+    }
+    __syncwarp();
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    dal += __shfl_xor_sync(0xFFFFFFFFu, dal, o);
+    dep += __shfl_xor_sync(0xFFFFFFFFu, dep, o);
+  }
+  if (lane == 0) {
+    red[warp][0] = dal;
+    red[warp][1] = dep;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2)
+    part[(long long)blockIdx.x * 2 + threadIdx.x] = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
+}
+
+constexpr int kExpGrid = 1184;  // blocks of the exponent-gradient kernel (8 per SM)
+
 int parse_flags(int flags, float alpha, float eps, GdnFlags* f) {
   f->inverse = (flags & TFCB_GDN_INVERSE) != 0;
   f->rectify = (flags & TFCB_GDN_RECTIFY) != 0;
@@ -396,6 +446,10 @@ int parse_flags(int flags, float alpha, float eps, GdnFlags* f) {
   f->eps = eps;
   f->alpha_mode = (alpha == 1.f) ? 1 : ((alpha == 2.f) ? 2 : 0);
   f->eps_mode = (eps == 1.f) ? 1 : ((eps == 0.5f) ? 2 : 0);
+  // trainable exponents: the reference takes `inputs ** alpha` / `norm_pool ** epsilon` whatever the current value
+  // (gdn.py:380-388,406-411: the fixed-exponent shortcuts apply only when the parameter is not callable)
+  if (flags & TFCB_GDN_POW_ALPHA) f->alpha_mode = 0;
+  if (flags & TFCB_GDN_POW_EPSILON) f->eps_mode = 0;
   return TFCB_OK;
 }
 
@@ -538,6 +592,32 @@ int tfcb_gdn_backward(const float* x_dev, const float* gamma_dev, const float* b
     TFCB_LAUNCHED();
     TFCB_LAUNCHED();
   }
+  TFCB_CUDA_TRY(cudaGetLastError());
+  return TFCB_OK;
+}
+
+int64_t tfcb_gdn_exponent_grads_workspace_bytes(void) { return (int64_t)kExpGrid * 2 * (int64_t)sizeof(float); }
+
+int tfcb_gdn_exponent_grads(const float* x_dev, const float* gamma_dev, const float* beta_dev, const float* dy_dev,
+                            float* dalpha_depsilon_dev, void* workspace_dev, int64_t n_pix, int C, int flags,
+                            float alpha, float epsilon, void* stream) {
+  if (n_pix < 0 || C <= 0) return fail(TFCB_INVALID_ARGUMENT, "bad GDN shape: n_pix=%lld C=%d", (long long)n_pix, C);
+  if (!x_dev || !gamma_dev || !beta_dev || !dy_dev || !dalpha_depsilon_dev || !workspace_dev)
+    return fail(TFCB_INVALID_ARGUMENT, "null pointer");
+  if ((size_t)C * 4 * sizeof(float) > 48 * 1024) return fail(TFCB_INVALID_ARGUMENT, "GDN exponent gradients: C too large");
+  cudaStream_t s = as_stream(stream);
+  GdnFlags f;
+  parse_flags(flags, alpha, epsilon, &f);
+  if (n_pix == 0) {
+    TFCB_CUDA_TRY(cudaMemsetAsync(dalpha_depsilon_dev, 0, 2 * sizeof(float), s));
+    return TFCB_OK;
+  }
+  const int grid = (int)std::min<long long>((n_pix + 3) / 4, kExpGrid);
+  float* part = reinterpret_cast<float*>(workspace_dev);
+  gdn_bwd_exponents_kernel<<<grid, 128, (size_t)C * 4 * sizeof(float), s>>>(x_dev, gamma_dev, beta_dev, dy_dev, part, n_pix, C, f);
+  reduce_partials_kernel<<<1, 32, 0, s>>>(part, grid, 2, dalpha_depsilon_dev);
+  TFCB_LAUNCHED();
+  TFCB_LAUNCHED();
   TFCB_CUDA_TRY(cudaGetLastError());
   return TFCB_OK;
 }

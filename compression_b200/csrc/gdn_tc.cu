@@ -2269,6 +2269,409 @@ int launch_tc_bwd3(const float* x, const float* gamma, const float* beta, const 
   return TFCB_OK;
 }
 
+// =============================================================================================
+// Backward, C = 192, first of the two kernels (dx and q), box-fed like gdn_tc_bwd3_kernel.
+//
+// n, dp and a dgamma accumulator need 3 x 192 TMEM columns and whole-tile p and q planes 198 KB of shared memory, so
+// C = 192 keeps the two-kernel split: this kernel produces dx and q = dL/dn (fp32, to the workspace), and
+// gdn_tc_bwd_dgamma_kernel contracts x and q into dgamma / dbeta.  Per 128-pixel tile:
+//
+//   conv(t)   x boxes -> p = |x| hi / lo planes, one 32-channel K chunk at a time (two chunk buffers)  -> MMA1  n += p_c . gamma_c
+//   pass2(t)  x (L2 hit), g boxes + n from TMEM -> q: fp32 into an output box (TMA store to the workspace) and hi / lo
+//             planes of the chunk                                                                      -> MMA2  dp += q_c . gammaT_c
+//             the direct term g / n (IGDN: g * n) goes back into n's columns with sign(x) in the two low mantissa bits
+//   pass3(t)  dx = direct + sign(x) * dp, from TMEM only -> output box -> TMA store
+//
+// gamma and gamma^T arrive as K chunks (24 KB hi + lo, double buffered) from a "gamma" warp; chunk m of the stream
+// uses operand buffer and gamma buffer m % 2, so ONE commit per chunk frees both.  A ring of seven 16 KB boxes
+// serves every box request in program order.  TMEM: n | dp (2 x 192 columns).
+// =============================================================================================
+constexpr int kD2Compute = 512;
+constexpr int kD2Threads = kD2Compute + 128;   // + MMA-issue, box-copy, gamma and store warps
+constexpr int kD2Sync = kD2Compute + 32;
+constexpr int kD2Slots = 7;
+
+struct BwdDx2Smem {
+  static constexpr int C = 192;
+  static constexpr int kGChunk = 4 * C * 16;                      // one 32-channel K chunk of one gamma plane (12 KB)
+  static constexpr int kOpPlane = 4 * kKg;                        // hi or lo plane of one 32-channel operand chunk
+  static constexpr int kOffRing = 0;                              // [7] boxes (1024-byte aligned: swizzle atom)
+  static constexpr int kOffG = kOffRing + kD2Slots * kF4Box;      // [2 buffers][hi, lo] gamma K chunks
+  static constexpr int kOffOp = kOffG + 4 * kGChunk;              // [2 buffers][hi, lo] operand (p or q) chunks
+  static constexpr int kOffBeta = kOffOp + 4 * kOpPlane;
+  static constexpr int kOffBar = kOffBeta + C * 4;
+  // mbarriers: full[7], empty[7], yready[7], gfull[2], cfree[2], nfull, dpfull; then the TMEM slot
+  static constexpr int kBarFull = 0, kBarEmpty = 7, kBarY = 14, kBarGfull = 21, kBarCfree = 23, kBarN = 25, kBarDp = 26,
+                       kNumBars = 27;
+  static constexpr int kBytes = kOffBar + kNumBars * 8 + 16;
+  static_assert(kOffG % 128 == 0 && kOffOp % 16 == 0 && kOffBar % 8 == 0, "alignment");
+  static_assert(kBytes <= 232448, "shared memory budget");
+};
+
+__global__ void __launch_bounds__(kD2Threads, 1)
+gdn_tc_bwd_dx2_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUtensorMap g_map,
+                      const __grid_constant__ CUtensorMap dx_map, const __grid_constant__ CUtensorMap q_map,
+                      const float* __restrict__ x, const float* __restrict__ dy, const __nv_bfloat16* __restrict__ planes,
+                      const float* __restrict__ beta, long long n_pix, int inverse) {
+  using L = BwdDx2Smem;
+  constexpr int C = L::C, NCH = C / 32;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float* beta_s = reinterpret_cast<float*>(smem + L::kOffBeta);
+  uint64_t* mbars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffBar + L::kNumBars * 8);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r = tid & 127, h = (tid >> 7) & 3, gwarp = warp & 3;  // compute thread (r, h): pixel row r, channel octet h of a box
+  auto bar = [&](int i) { return smem_u32(mbars + i); };
+  for (int i = tid; i < C; i += kD2Threads) beta_s[i] = beta[i];
+  if (tid == 0) {
+    for (int i = 0; i < L::kNumBars; ++i) {
+      const int count = (i >= L::kBarY && i < L::kBarGfull) ? kD2Compute / 32 : 1;  // y ready: one arrival per compute warp
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar(i)), "r"(count));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_n = *tmem_slot, tmem_dp = tmem_n + C;
+  const uint32_t lane_sel = (uint32_t)(gwarp * 32) << 16;
+  const long long n_tiles = (n_pix + kTileM - 1) / kTileM;
+  const long long first = blockIdx.x;
+  // Box request n uses ring slot n % 7 in its (n / 7)-th round:
+  //   6 x boxes (conversion of the CTA's first tile), then per tile {x, g, q-out} x 6 (pass 2), dx-out x 6 (pass 3),
+  //   (x of the next tile) x 6.
+  // Chunk m of the operand / gamma stream uses buffers m % 2: 6 conversion chunks of the first tile, then per tile 6 q
+  // chunks, 6 conversion chunks of the next tile.
+  constexpr int W0 = kD2Compute / 32;  // first auxiliary warp
+  auto slot_of = [](uint32_t n) { return n % (uint32_t)kD2Slots; };
+  auto round_of = [](uint32_t n) { return n / (uint32_t)kD2Slots; };
+
+  if (warp == W0 + 1) {
+    // ---------------------------------- box-copy warp ----------------------------------
+    if (lane == 0) {
+      uint32_t n = 0;
+      auto acquire = [&]() {
+        const uint32_t slot = slot_of(n), round = round_of(n);
+        if (round > 0) {
+          if (!mbar_wait(bar(L::kBarEmpty + slot), (round - 1u) & 1u)) __trap();
+        }
+        return slot;
+      };
+      auto load = [&](const CUtensorMap* map, int c, int row0) {
+        const uint32_t slot = acquire();
+        const uint32_t full = bar(L::kBarFull + slot);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "n"(kF4Box) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
+                smem_u32(smem + L::kOffRing + slot * kF4Box)),
+            "l"(map), "r"(c * 32), "r"(row0), "r"(full), "l"(kEvictFirst)
+            : "memory");
+        ++n;
+      };
+      auto reserve = [&]() {  // output box: nothing to load, the slot only has to be free
+        const uint32_t slot = acquire();
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar(L::kBarFull + slot)) : "memory");
+        ++n;
+      };
+      auto prefetch_tile = [&](const float* base, long long tile) {  // one contiguous block -> L2
+        const long long p0 = tile * kTileM;
+        const long long rows = min((long long)kTileM, n_pix - p0);
+        if (rows > 0)
+          asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(base + p0 * C),
+                       "r"((uint32_t)(rows * C * 4)), "l"(kEvictLast)
+                       : "memory");
+      };
+      if (first < n_tiles) {
+        prefetch_tile(x, first);
+        prefetch_tile(dy, first);
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c) load(&x_map, c, (int)(first * kTileM));
+      }
+      for (long long tile = first; tile < n_tiles; tile += gridDim.x) {
+        const long long next = tile + gridDim.x;
+        const bool has_next = next < n_tiles;
+        const int row0 = (int)(tile * kTileM);
+        if (has_next) {  // the next tile of this CTA -> L2: its boxes become L2 hits
+          prefetch_tile(x, next);
+          prefetch_tile(dy, next);
+        }
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c) {
+          load(&x_map, c, row0);  // second read of x: an L2 hit
+          load(&g_map, c, row0);
+          reserve();              // q out
+        }
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c) reserve();  // dx out
+        if (has_next) {
+#pragma unroll 1
+          for (int c = 0; c < NCH; ++c) load(&x_map, c, (int)(next * kTileM));
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == W0 + 2) {
+    // ---------------------------------- gamma warp: K chunks of gamma / gamma^T ----------------------------------
+    if (lane == 0) {
+      const uint8_t* gp = reinterpret_cast<const uint8_t*>(planes);
+      constexpr size_t kPlaneBytes = (size_t)C * C * 2;
+      uint32_t m = 0;
+      auto chunk = [&](int transposed, int c) {
+        const uint32_t buf = m & 1u;
+        if (m >= 2) {  // the MMAs of chunk m - 2 (same buffers) have completed
+          if (!mbar_wait(bar(L::kBarCfree + buf), ((m >> 1) - 1u) & 1u)) __trap();
+        }
+        const uint32_t gfull = bar(L::kBarGfull + buf);
+        const uint32_t dst = smem_u32(smem + L::kOffG + buf * 2 * L::kGChunk);
+        const uint8_t* src = gp + (size_t)(2 * transposed) * kPlaneBytes + (size_t)c * L::kGChunk;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gfull), "n"(2 * L::kGChunk) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+                     "l"(src), "n"(L::kGChunk), "r"(gfull), "l"(kEvictLast)
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                         dst + L::kGChunk),
+                     "l"(src + kPlaneBytes), "n"(L::kGChunk), "r"(gfull), "l"(kEvictLast)
+                     : "memory");
+        ++m;
+      };
+      if (first < n_tiles) {
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c) chunk(0, c);
+      }
+      for (long long tile = first; tile < n_tiles; tile += gridDim.x) {
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c) chunk(1, c);
+        if (tile + gridDim.x < n_tiles) {
+#pragma unroll 1
+          for (int c = 0; c < NCH; ++c) chunk(0, c);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == W0 + 3) {
+    // ---------------------------------- store warp: q and dx boxes ----------------------------------
+    if (lane == 0) {
+      uint32_t n = (first < n_tiles) ? (uint32_t)NCH : 0u;
+      uint32_t ypar = 0u;  // per-slot phase of the y-ready barrier (a slot is an output box only now and then)
+      auto store = [&](const CUtensorMap* map, int c, int row0) {
+        const uint32_t slot = slot_of(n);
+        if (!mbar_wait(bar(L::kBarY + slot), (ypar >> slot) & 1u)) __trap();
+        ypar ^= 1u << slot;
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;" ::"l"(map),
+                     "r"(c * 32), "r"(row0), "r"(smem_u32(smem + L::kOffRing + slot * kF4Box)), "l"(kEvictFirst)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the box has been read: the slot is free
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar(L::kBarEmpty + slot)) : "memory");
+      };
+      for (long long tile = first; tile < n_tiles; tile += gridDim.x) {
+        const bool has_next = tile + gridDim.x < n_tiles;
+        const int row0 = (int)(tile * kTileM);
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c) {
+          n += 2;  // x, g
+          store(&q_map, c, row0);
+          ++n;
+        }
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c, ++n) store(&dx_map, c, row0);
+        if (has_next) n += NCH;
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
+  } else if (warp == W0) {
+    // ------------------------------- MMA-issue warp: MMA1, MMA2 (K-chunked, everything streamed) -------------------
+    constexpr uint32_t kIdesc = umma_idesc(kTileM, C);  // A, B both K-major
+    uint32_t n = 0, m = 0;
+    auto chunk_mmas = [&](uint32_t acc, bool first_chunk) {  // six MMAs of chunk m: operand buffer x gamma buffer
+      const uint32_t buf = m & 1u;
+      if (!mbar_wait(bar(L::kBarGfull + buf), (m >> 1) & 1u)) __trap();
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a_hi = smem_u32(smem + L::kOffOp + buf * 2 * L::kOpPlane), a_lo = a_hi + L::kOpPlane;
+      const uint32_t g_hi = smem_u32(smem + L::kOffG + buf * 2 * L::kGChunk), g_lo = g_hi + L::kGChunk;
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2) {
+        const uint64_t dah = umma_desc(a_hi + (uint32_t)(2 * s2) * kKg, kKg, 128);
+        const uint64_t dal = umma_desc(a_lo + (uint32_t)(2 * s2) * kKg, kKg, 128);
+        const uint64_t dbh = umma_desc(g_hi + (uint32_t)(2 * s2) * (C * 16), C * 16, 128);
+        const uint64_t dbl = umma_desc(g_lo + (uint32_t)(2 * s2) * (C * 16), C * 16, 128);
+        umma_bf16(acc, dah, dbh, kIdesc, (first_chunk && s2 == 0) ? 0u : 1u);
+        umma_bf16(acc, dal, dbh, kIdesc, 1u);
+        umma_bf16(acc, dah, dbl, kIdesc, 1u);
+      }
+      umma_commit(bar(L::kBarCfree + buf));
+      ++m;
+    };
+    auto release = [&](uint32_t req) {
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar(L::kBarEmpty + slot_of(req))) : "memory");
+    };
+    auto mma1_tile = [&]() {
+#pragma unroll 1
+      for (int c = 0; c < NCH; ++c, ++n) {
+        asm volatile("bar.sync %0, %1;" ::"r"(2 + (int)(m & 1u)), "n"(kD2Sync) : "memory");  // p planes of this chunk are written
+        if (lane == 0) {
+          release(n);
+          chunk_mmas(tmem_n, c == 0);
+          if (c == NCH - 1) umma_commit(bar(L::kBarN));
+        } else {
+          ++m;
+        }
+        m = __shfl_sync(0xFFFFFFFFu, m, 0);
+      }
+    };
+    if (first < n_tiles) mma1_tile();
+    for (long long tile = first; tile < n_tiles; tile += gridDim.x) {
+      const bool has_next = tile + gridDim.x < n_tiles;
+#pragma unroll 1
+      for (int c = 0; c < NCH; ++c, n += 3) {
+        asm volatile("bar.sync %0, %1;" ::"r"(4 + (int)(m & 1u)), "n"(kD2Sync) : "memory");  // q planes of this chunk are written
+        if (lane == 0) {
+          release(n);      // x box
+          release(n + 1);  // g box   (the q-out box n + 2 is handed back by the store warp)
+          chunk_mmas(tmem_dp, c == 0);
+          if (c == NCH - 1) umma_commit(bar(L::kBarDp));  // dp is complete: the dx pass may start
+        } else {
+          ++m;
+        }
+        m = __shfl_sync(0xFFFFFFFFu, m, 0);
+      }
+      n += NCH;  // dx-out boxes
+      if (has_next) mma1_tile();
+    }
+  } else if (warp < W0) {
+  // --------------------------------- compute warps ---------------------------------
+  uint32_t n = 0, m = 0;
+  // 128-byte swizzle: the 16-byte chunk j of box row `row` sits at chunk j ^ (row & 7)
+  auto chunk_at = [](uint8_t* box, int row, int j) { return reinterpret_cast<float4*>(box + row * 128 + ((j ^ (row & 7)) << 4)); };
+  auto wait_full = [&](uint32_t req) {
+    if (!mbar_wait(bar(L::kBarFull + slot_of(req)), round_of(req) & 1u)) __trap();
+    return smem + L::kOffRing + slot_of(req) * kF4Box;
+  };
+  // this thread's 16-byte rows of the hi / lo planes of operand chunk m (waits until the MMAs of chunk m - 2 are done)
+  auto operand_rows = [&](uint4** hi, uint4** lo) {
+    const uint32_t buf = m & 1u;
+    if (m >= 2) {
+      if (!mbar_wait(bar(L::kBarCfree + buf), ((m >> 1) - 1u) & 1u)) __trap();
+    }
+    uint8_t* base = smem + L::kOffOp + buf * 2 * L::kOpPlane + h * kKg + r * 16;
+    *hi = reinterpret_cast<uint4*>(base);
+    *lo = reinterpret_cast<uint4*>(base + L::kOpPlane);
+  };
+
+  auto conv_tile = [&]() {
+#pragma unroll 1
+    for (int c = 0; c < NCH; ++c, ++n) {
+      uint8_t* box = wait_full(n);
+      const float4 a = *chunk_at(box, r, 2 * h), b = *chunk_at(box, r, 2 * h + 1);
+      float v[8] = {fabsf(a.x), fabsf(a.y), fabsf(a.z), fabsf(a.w), fabsf(b.x), fabsf(b.y), fabsf(b.z), fabsf(b.w)};
+      uint4 hi, lo, *ph, *pl;
+      split8(v, &hi, &lo);
+      operand_rows(&ph, &pl);
+      *ph = hi;
+      *pl = lo;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("bar.arrive %0, %1;" ::"r"(2 + (int)(m & 1u)), "n"(kD2Sync) : "memory");  // (also releases the box, see issue warp)
+      ++m;
+    }
+  };
+
+  if (first < n_tiles) conv_tile();
+  int t = 0;
+  for (long long tile = first; tile < n_tiles; tile += gridDim.x, ++t) {
+    const bool has_next = tile + gridDim.x < n_tiles;
+    if (!mbar_wait(bar(L::kBarN), (uint32_t)t & 1u)) __trap();  // MMA1 of this tile has completed
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // ---- pass 2: q = dL/dn -> output box + q planes; the direct term and sign(x) go back into n's columns ----
+#pragma unroll 1
+    for (int c = 0; c < NCH; ++c, n += 3) {
+      const uint32_t col = tmem_n + lane_sel + (uint32_t)(c * 32 + h * 8);
+      uint32_t nacc[8];
+      tmem_load<8>(col, nacc);
+      uint8_t* bx = wait_full(n);
+      uint8_t* bg = wait_full(n + 1);
+      uint8_t* bq = wait_full(n + 2);
+      const float4 x0 = *chunk_at(bx, r, 2 * h), x1 = *chunk_at(bx, r, 2 * h + 1);
+      const float4 g0 = *chunk_at(bg, r, 2 * h), g1 = *chunk_at(bg, r, 2 * h + 1);
+      const float4 bv0 = *reinterpret_cast<const float4*>(beta_s + c * 32 + h * 8);      // same address in every lane
+      const float4 bv1 = *reinterpret_cast<const float4*>(beta_s + c * 32 + h * 8 + 4);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      const float gs[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bs[8] = {bv0.x, bv0.y, bv0.z, bv0.w, bv1.x, bv1.y, bv1.z, bv1.w};
+      float q[8];
+      uint32_t dbits[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float nn = bs[e] + __uint_as_float(nacc[e]);
+        float direct;
+        if (inverse) {
+          direct = gs[e] * nn;
+          q[e] = gs[e] * xs[e];
+        } else {
+          const float rn = rcp_approx(nn);
+          direct = gs[e] * rn;
+          q[e] = -gs[e] * xs[e] * rn * rn;
+        }
+        const uint32_t code = (xs[e] > 0.f) ? 1u : ((xs[e] < 0.f) ? 2u : 0u);
+        dbits[e] = (__float_as_uint(direct) & ~3u) | code;
+      }
+      *chunk_at(bq, r, 2 * h) = make_float4(q[0], q[1], q[2], q[3]);
+      *chunk_at(bq, r, 2 * h + 1) = make_float4(q[4], q[5], q[6], q[7]);
+      uint4 hi, lo, *qh, *ql;
+      split8(q, &hi, &lo);
+      operand_rows(&qh, &ql);
+      *qh = hi;
+      *ql = lo;
+      tmem_store8(col, dbits);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // q planes -> MMA, q box -> TMA store
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("bar.arrive %0, %1;" ::"r"(4 + (int)(m & 1u)), "n"(kD2Sync) : "memory");  // (also releases the x and g boxes)
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar(L::kBarY + slot_of(n + 2))) : "memory");
+      ++m;
+    }
+    // ---- pass 3: dx = direct + sign(x) * dp, from TMEM only ----
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");  // this thread's direct terms are in TMEM
+    if (!mbar_wait(bar(L::kBarDp), (uint32_t)t & 1u)) __trap();  // every MMA2 of this tile has completed
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+    for (int c = 0; c < NCH; ++c, ++n) {
+      uint32_t d[8], p[8];
+      tmem_load<8>(tmem_n + lane_sel + (uint32_t)(c * 32 + h * 8), d);
+      tmem_load<8>(tmem_dp + lane_sel + (uint32_t)(c * 32 + h * 8), p);
+      uint8_t* box = wait_full(n);  // the slot's previous user has left
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const uint32_t code = d[e] & 3u;
+        const float s = (code == 1u) ? 1.f : ((code == 2u) ? -1.f : 0.f);
+        o[e] = fmaf(s, __uint_as_float(p[e]), __uint_as_float(d[e]));
+      }
+      *chunk_at(box, r, 2 * h) = make_float4(o[0], o[1], o[2], o[3]);
+      *chunk_at(box, r, 2 * h + 1) = make_float4(o[4], o[5], o[6], o[7]);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // dx box -> TMA store
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar(L::kBarY + slot_of(n))) : "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // TMEM reads precede the next tile's MMAs
+    if (has_next) conv_tile();
+  }
+  }  // compute warps
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (tid < 32) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "n"(512));
+  }
+}
+
 template <bool FAST>
 int launch_tc_bwd192(const float* x, const float* gamma, const float* beta, const float* dy, float* dx, float* q_ws,
                      float* part_g, float* part_b, int* n_parts, long long n_pix, TcFlags f, cudaStream_t s) {
@@ -2296,8 +2699,34 @@ int launch_tc_bwd192(const float* x, const float* gamma, const float* beta, cons
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long n_tiles = (n_pix + kTileM - 1) / kTileM;
   const int grid = (int)std::min<long long>(n_tiles, std::min(sms, 148));
-  gdn_tc_bwd_dx_kernel<C, FAST><<<grid, kBwdThreads, Bwd2Smem<C>::kBytes, s>>>(x, dy, planes, beta, dx, q_ws, n_pix, f);
-  TFCB_LAUNCHED();
+  const char* v1 = getenv("TFCB_GDN_BWD_V1");  // A/B timing: the register-fed dx kernel
+  if (FAST && n_pix < (1ll << 31) && !(v1 && v1[0] == '1')) {
+    using L2 = BwdDx2Smem;
+    CUtensorMap x_map, g_map, dx_map, q_map;
+    __nv_bfloat16* planes4 = nullptr;
+    int rc = make_tensor_map_2d(&x_map, x, n_pix, C, kTileM, 32, true);
+    if (rc == TFCB_OK) rc = make_tensor_map_2d(&g_map, dy, n_pix, C, kTileM, 32, true);
+    if (rc == TFCB_OK) rc = make_tensor_map_2d(&dx_map, dx, n_pix, C, kTileM, 32, true);
+    if (rc == TFCB_OK) rc = make_tensor_map_2d(&q_map, q_ws, n_pix, C, kTileM, 32, true);
+    if (rc == TFCB_OK) rc = dev_alloc((void**)&planes4, (size_t)4 * C * C * sizeof(__nv_bfloat16), s);
+    if (rc == TFCB_OK && cudaFuncSetAttribute(gdn_tc_bwd_dx2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L2::kBytes) != cudaSuccess) {
+      (void)cudaGetLastError();
+      rc = fail(TFCB_CUDA_ERROR, "cannot reserve %d bytes of shared memory", L2::kBytes);
+    }
+    if (rc != TFCB_OK) {
+      dev_free(planes4, s);
+      dev_free(planes, s);
+      return rc;
+    }
+    gdn_tc_prep2_kernel<<<((C / 8) * C + 255) / 256, 256, 0, s>>>(gamma, C, planes4);
+    TFCB_LAUNCHED();
+    gdn_tc_bwd_dx2_kernel<<<grid, kD2Threads, L2::kBytes, s>>>(x_map, g_map, dx_map, q_map, x, dy, planes4, beta, n_pix, f.inverse);
+    TFCB_LAUNCHED();
+    dev_free(planes4, s);
+  } else {
+    gdn_tc_bwd_dx_kernel<C, FAST><<<grid, kBwdThreads, Bwd2Smem<C>::kBytes, s>>>(x, dy, planes, beta, dx, q_ws, n_pix, f);
+    TFCB_LAUNCHED();
+  }
   gdn_tc_bwd_dgamma_kernel<C, FAST><<<grid, kBwdThreads, Bwd3Smem<C>::kBytes, s>>>(x, q_ws, part_g, part_b, n_pix, f);
   TFCB_LAUNCHED();
   cudaError_t e = cudaGetLastError();
@@ -2348,6 +2777,7 @@ int gdn_tc_forward(const float* x, const float* gamma, const float* beta, float*
   *handled = false;
   if (!(C == 128 || C == 192)) return TFCB_OK;
   if (!(alpha == 1.f || alpha == 2.f) || !(eps == 1.f || eps == 0.5f)) return TFCB_OK;
+  if (flags & (TFCB_GDN_POW_ALPHA | TFCB_GDN_POW_EPSILON)) return TFCB_OK;  // trainable exponents: literal pow
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(beta)) & 15) return TFCB_OK;  // 16-byte rows
   if (const char* env = getenv("TFCB_GDN_FP32")) {
     if (env[0] == '1') return TFCB_OK;  // debugging aid: force the CUDA-core kernels
@@ -2379,6 +2809,7 @@ int gdn_tc_backward(const float* x, const float* gamma, const float* beta, const
   if (C != 128 && C != 192) return TFCB_OK;
   if (C == 192 && (reinterpret_cast<uintptr_t>(q_ws) & 15)) return TFCB_OK;
   if (!(alpha == 1.f || alpha == 2.f) || !(eps == 1.f || eps == 0.5f)) return TFCB_OK;
+  if (flags & (TFCB_GDN_POW_ALPHA | TFCB_GDN_POW_EPSILON)) return TFCB_OK;  // trainable exponents: literal pow
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) return TFCB_OK;
   if (const char* env = getenv("TFCB_GDN_FP32")) {
     if (env[0] == '1') return TFCB_OK;

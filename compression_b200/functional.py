@@ -20,64 +20,102 @@ def _p(t):
   return None if t is None else C.c_void_p(t.data_ptr())
 
 
-def _flags(inverse, rectify):
-  return (GDN_INVERSE if inverse else 0) | (GDN_RECTIFY if rectify else 0)
+GDN_POW_ALPHA = 4      # trainable alpha: literal u ** alpha (no |u| / u^2 shortcut), gdn.py:380-388
+GDN_POW_EPSILON = 8    # trainable epsilon: literal n ** epsilon, gdn.py:406-411
 
 
-def gdn_forward(x, gamma, beta, inverse=False, rectify=False, alpha=1.0, epsilon=1.0):
-  """x: float32 CUDA [..., C] (channels-last, contiguous) -> y of the same shape."""
+def _flags(inverse, rectify, pow_alpha=False, pow_epsilon=False):
+  return ((GDN_INVERSE if inverse else 0) | (GDN_RECTIFY if rectify else 0) | (GDN_POW_ALPHA if pow_alpha else 0) |
+          (GDN_POW_EPSILON if pow_epsilon else 0))
+
+
+def _gdn_args(x, gamma, beta):
   assert x.is_cuda and x.dtype == torch.float32
   x = x.contiguous()
   C_ = x.shape[-1]
   gamma = gamma.to(device=x.device, dtype=torch.float32).contiguous()
   beta = beta.to(device=x.device, dtype=torch.float32).contiguous()
   assert gamma.shape == (C_, C_) and beta.shape == (C_,)
+  return x, gamma, beta, C_, x.numel() // C_
+
+
+def gdn_forward(x, gamma, beta, inverse=False, rectify=False, alpha=1.0, epsilon=1.0, pow_alpha=False,
+                pow_epsilon=False):
+  """x: float32 CUDA [..., C] (channels-last, contiguous) -> y of the same shape."""
+  x, gamma, beta, C_, n_pix = _gdn_args(x, gamma, beta)
   y = torch.empty_like(x)
-  n_pix = x.numel() // C_
-  check(_lib.lib().tfcb_gdn_forward(_p(x), _p(gamma), _p(beta), _p(y), n_pix, C_, _flags(inverse, rectify),
-                                    float(alpha), float(epsilon), _stream()))
+  check(_lib.lib().tfcb_gdn_forward(_p(x), _p(gamma), _p(beta), _p(y), n_pix, C_,
+                                    _flags(inverse, rectify, pow_alpha, pow_epsilon), float(alpha), float(epsilon),
+                                    _stream()))
   return y
 
 
-def gdn_backward(x, gamma, beta, dy, inverse=False, rectify=False, alpha=1.0, epsilon=1.0):
+def gdn_backward(x, gamma, beta, dy, inverse=False, rectify=False, alpha=1.0, epsilon=1.0, pow_alpha=False,
+                 pow_epsilon=False):
   """Returns (dx, dgamma, dbeta) for upstream gradient dy."""
-  assert x.is_cuda and x.dtype == torch.float32
-  x = x.contiguous()
+  x, gamma, beta, C_, n_pix = _gdn_args(x, gamma, beta)
   dy = dy.to(dtype=torch.float32).contiguous()
-  C_ = x.shape[-1]
-  gamma = gamma.to(device=x.device, dtype=torch.float32).contiguous()
-  beta = beta.to(device=x.device, dtype=torch.float32).contiguous()
-  n_pix = x.numel() // C_
   dx = torch.empty_like(x)
   dgamma = torch.empty_like(gamma)
   dbeta = torch.empty_like(beta)
   ws_bytes = int(_lib.lib().tfcb_gdn_backward_workspace_bytes(n_pix, C_))
   ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
   check(_lib.lib().tfcb_gdn_backward(_p(x), _p(gamma), _p(beta), _p(dy), _p(dx), _p(dgamma), _p(dbeta), _p(ws),
-                                     n_pix, C_, _flags(inverse, rectify), float(alpha), float(epsilon),
-                                     _stream()))
+                                     n_pix, C_, _flags(inverse, rectify, pow_alpha, pow_epsilon), float(alpha),
+                                     float(epsilon), _stream()))
   return dx, dgamma, dbeta
 
 
+def gdn_exponent_grads(x, gamma, beta, dy, inverse=False, rectify=False, alpha=1.0, epsilon=1.0, pow_alpha=True,
+                       pow_epsilon=True):
+  """(dL/dalpha, dL/depsilon) as a float32 [2] tensor: the gradients TF autodiff produces through `inputs ** alpha`
+  and `norm_pool ** epsilon` when the exponents are trainable GDNParameters (gdn.py:345-367,388,411)."""
+  x, gamma, beta, C_, n_pix = _gdn_args(x, gamma, beta)
+  dy = dy.to(dtype=torch.float32).contiguous()
+  out = torch.empty(2, dtype=torch.float32, device=x.device)
+  ws = torch.empty(int(_lib.lib().tfcb_gdn_exponent_grads_workspace_bytes()), dtype=torch.uint8, device=x.device)
+  check(_lib.lib().tfcb_gdn_exponent_grads(_p(x), _p(gamma), _p(beta), _p(dy), _p(out), _p(ws), n_pix, C_,
+                                           _flags(inverse, rectify, pow_alpha, pow_epsilon), float(alpha),
+                                           float(epsilon), _stream()))
+  return out
+
+
 class _GDNFunction(torch.autograd.Function):
+  """alpha_t / epsilon_t: 0-d tensors when the exponent is trainable (their value is read on the host: the kernels
+  take the exponents as scalars), else None and the fixed value travels in `alpha` / `epsilon`."""
 
   @staticmethod
-  def forward(ctx, x, gamma, beta, inverse, rectify, alpha, epsilon):
+  def forward(ctx, x, gamma, beta, alpha_t, epsilon_t, inverse, rectify, alpha, epsilon):
+    pa, pe = alpha_t is not None, epsilon_t is not None
+    if pa:
+      alpha = float(alpha_t)
+    if pe:
+      epsilon = float(epsilon_t)
     ctx.save_for_backward(x, gamma, beta)
-    ctx.cfg = (inverse, rectify, alpha, epsilon)
-    return gdn_forward(x, gamma, beta, inverse, rectify, alpha, epsilon)
+    ctx.cfg = (inverse, rectify, alpha, epsilon, pa, pe)
+    return gdn_forward(x, gamma, beta, inverse, rectify, alpha, epsilon, pa, pe)
 
   @staticmethod
   def backward(ctx, dy):
     x, gamma, beta = ctx.saved_tensors
-    inverse, rectify, alpha, epsilon = ctx.cfg
-    dx, dgamma, dbeta = gdn_backward(x, gamma, beta, dy, inverse, rectify, alpha, epsilon)
-    return dx, dgamma, dbeta, None, None, None, None
+    inverse, rectify, alpha, epsilon, pa, pe = ctx.cfg
+    dx, dgamma, dbeta = gdn_backward(x, gamma, beta, dy, inverse, rectify, alpha, epsilon, pa, pe)
+    dalpha = depsilon = None
+    if (pa and ctx.needs_input_grad[3]) or (pe and ctx.needs_input_grad[4]):
+      g2 = gdn_exponent_grads(x, gamma, beta, dy, inverse, rectify, alpha, epsilon, pa, pe)
+      dalpha = g2[0] if pa else None
+      depsilon = g2[1] if pe else None
+    return dx, dgamma, dbeta, dalpha, depsilon, None, None, None, None
 
 
 def gdn(x, gamma, beta, inverse=False, rectify=False, alpha=1.0, epsilon=1.0):
-  """Differentiable GDN/IGDN on channels-last float32 CUDA tensors."""
-  return _GDNFunction.apply(x, gamma, beta, bool(inverse), bool(rectify), float(alpha), float(epsilon))
+  """Differentiable GDN/IGDN on channels-last float32 CUDA tensors.  `alpha` / `epsilon`: Python numbers (fixed
+  exponents: |u|, u^2, sqrt shortcuts and the tensor-core kernels apply) or 0-d tensors (trainable: literal pow, with
+  gradients)."""
+  at = alpha if isinstance(alpha, torch.Tensor) else None
+  et = epsilon if isinstance(epsilon, torch.Tensor) else None
+  return _GDNFunction.apply(x, gamma, beta, at, et, bool(inverse), bool(rectify),
+                            1.0 if at is not None else float(alpha), 1.0 if et is not None else float(epsilon))
 
 
 # ------------------------------------------------------------------------------------------------

@@ -144,18 +144,17 @@ class GDN(nn.Module):
     out_dtype = x.dtype
     x32 = x.to(torch.float32).contiguous()
     alpha, epsilon = self.alpha_parameter, self.epsilon_parameter
-    if callable(alpha) or callable(epsilon):
-      # trainable exponents: the reference differentiates through pow; that path is composed from torch
-      # ops (the CUDA kernels cover fixed exponents, which is what bls2017 / bmshj2018 use).
-      y = self._torch_graph(x32, dev)
-    else:
-      y = F.gdn(x32, self._param("gamma", device=dev), self._param("beta", device=dev), self.inverse,
-                self.rectify, float(alpha), float(epsilon))
+    # trainable exponents travel as 0-d tensors: literal pow in the kernels plus the two scalar gradients
+    # (gdn.py:345-367,388,411); fixed ones as Python numbers (|u| / u^2 / sqrt shortcuts, tensor-core kernels)
+    a = self._param("alpha", device=dev) if callable(alpha) else float(alpha)
+    e = self._param("epsilon", device=dev) if callable(epsilon) else float(epsilon)
+    y = F.gdn(x32, self._param("gamma", device=dev), self._param("beta", device=dev), self.inverse, self.rectify, a, e)
     y = y.to(out_dtype)
     return y.movedim(-1, 1) if self.data_format == "channels_first" else y
 
   def _torch_graph(self, x, dev):
-    """gdn.py:377-415 literally: the fixed-exponent special cases are kept even when the OTHER exponent is
+    """NOT on the product path (forward() runs the CUDA kernels for every exponent configuration): the reference's
+    graph, kept as the checker of the trainable-exponent kernels in the tests.  gdn.py:377-415 literally: the fixed-exponent special cases are kept even when the OTHER exponent is
     trainable (|x| for alpha == 1 without rectify, square for alpha == 2, sqrt for epsilon == .5)."""
     u = torch.relu(x) if self.rectify else x
     alpha, epsilon = self.alpha_parameter, self.epsilon_parameter

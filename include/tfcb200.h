@@ -193,6 +193,10 @@ int tfcb_stochastic_round(const void* inputs_dev, int dtype, int64_t n, float st
  * ---------------------------------------------------------------------------------------------- */
 #define TFCB_GDN_INVERSE 1
 #define TFCB_GDN_RECTIFY 2
+/* trainable exponents: compute `u ** alpha` / `n ** epsilon` literally even when the current value is 1, 2 or 1/2
+ * (gdn.py:380-388,406-411 take the |u| / u^2 / sqrt shortcuts only for fixed exponents) */
+#define TFCB_GDN_POW_ALPHA 4
+#define TFCB_GDN_POW_EPSILON 8
 
 int tfcb_gdn_forward(const float* x_dev, const float* gamma_dev, const float* beta_dev, float* y_dev,
                      int64_t n_pix, int C, int flags, float alpha, float epsilon, void* stream);
@@ -207,6 +211,14 @@ int tfcb_gdn_backward(const float* x_dev, const float* gamma_dev, const float* b
                       float epsilon, void* stream);
 
 /* Number of kernel launches issued by this library since load (bench.py's `gpu_launches`). */
+/* Gradients of the loss with respect to the scalar exponents alpha and epsilon (gdn.py:345-367 makes them
+ * trainable GDNParameters; TF autodiff differentiates through pow): dalpha_depsilon_dev float32 [2].
+ * workspace_dev: tfcb_gdn_exponent_grads_workspace_bytes() bytes. */
+int64_t tfcb_gdn_exponent_grads_workspace_bytes(void);
+int tfcb_gdn_exponent_grads(const float* x_dev, const float* gamma_dev, const float* beta_dev,
+                            const float* dy_dev, float* dalpha_depsilon_dev, void* workspace_dev,
+                            int64_t n_pix, int C, int flags, float alpha, float epsilon, void* stream);
+
 int64_t tfcb_launch_count(void);
 
 #ifdef __cplusplus

@@ -163,3 +163,66 @@ def test_backward_at_two_million_pixels_vs_fp64_oracle(F, C, n_pix):
   want = gdn_oracle.gdn_reference(x, gamma, beta)
   got = F.gdn_forward(x.cuda(), gamma.cuda(), beta.cuda())
   assert _relerr(got, want) < RTOL
+
+
+def _graph64(x, gamma, beta, alpha, epsilon, inverse, rectify, pow_alpha, pow_epsilon):
+  """gdn.py:377-415 in float64; alpha / epsilon None-able shortcuts as in the reference."""
+  u = torch.relu(x) if rectify else x
+  if not pow_alpha and float(alpha) == 1:
+    pool = u if rectify else u.abs()
+  elif not pow_alpha and float(alpha) == 2:
+    pool = u.square()
+  else:
+    pool = u**alpha
+  n = pool @ gamma + beta
+  if not pow_epsilon and float(epsilon) == 1:
+    pass
+  elif not pow_epsilon and float(epsilon) == .5:
+    n = n.sqrt()
+  else:
+    n = n**epsilon
+  return u * n if inverse else u / n
+
+
+@pytest.mark.parametrize("C,n_pix", [(5, 300), (32, 1000), (128, 3000)])
+@pytest.mark.parametrize("alpha,epsilon,train_a,train_e,rectify,inverse", [
+    (1.3, 1.0, True, False, True, False), (1.0, 0.8, False, True, False, False), (1.3, 0.8, True, True, True, False),
+    (2.0, 0.6, False, True, False, True), (1.0, 1.0, True, True, True, True)])
+def test_trainable_exponents_vs_fp64_graph(F, C, n_pix, alpha, epsilon, train_a, train_e, rectify, inverse):
+  """gdn.py:345-367: alpha / epsilon as trainable parameters.  Forward and all five gradients (x, gamma, beta, alpha,
+  epsilon) come from the CUDA kernels (literal pow + the exponent-gradient kernel) and agree with the reference's
+  graph differentiated by autograd in float64; a FIXED exponent of a mixed configuration keeps its |u| / u^2 / sqrt
+  shortcut (gdn.py:380-388), a trainable one sitting at 1.0 does not."""
+  gamma, beta = _params(C, 31)
+  x = (_x(n_pix, C, 32) * 1.5).cuda().requires_grad_(True)
+  g = gamma.cuda().requires_grad_(True)
+  b = beta.cuda().requires_grad_(True)
+  a_t = torch.tensor(alpha, device="cuda", requires_grad=True) if train_a else alpha
+  e_t = torch.tensor(epsilon, device="cuda", requires_grad=True) if train_e else epsilon
+  y = F.gdn(x, g, b, inverse, rectify, a_t, e_t)
+  dy = torch.randn(n_pix, C, generator=torch.Generator().manual_seed(33)).cuda()
+  leaves = [x, g, b] + ([a_t] if train_a else []) + ([e_t] if train_e else [])
+  got = torch.autograd.grad(y, leaves, dy)
+  x64, g64, b64 = (t.detach().double().requires_grad_(True) for t in (x, g, b))
+  a64 = torch.tensor(alpha, dtype=torch.float64, device="cuda", requires_grad=True) if train_a else alpha
+  e64 = torch.tensor(epsilon, dtype=torch.float64, device="cuda", requires_grad=True) if train_e else epsilon
+  y64 = _graph64(x64, g64, b64, a64, e64, inverse, rectify, train_a, train_e)
+  want = torch.autograd.grad(y64, [x64, g64, b64] + ([a64] if train_a else []) + ([e64] if train_e else []), dy.double())
+  assert float(((y.double() - y64).abs() / (y64.abs() + 1e-6)).max()) < 2e-5
+  for gt, w in zip(got, want):
+    w = torch.nan_to_num(w, nan=0.0, posinf=0.0, neginf=0.0)
+    scale = float(w.abs().max()) + 1e-12
+    assert float((gt.double() - w).abs().max()) / scale < 1e-4, (tuple(gt.shape), float((gt.double() - w).abs().max()), scale)
+
+
+def test_layer_with_trainable_exponents_uses_the_kernels(tfc_mod=None):
+  import compression_b200 as tfc
+  from compression_b200 import _lib
+  layer = tfc.GDN(alpha_parameter=None, epsilon_parameter=None, rectify=True)
+  x = torch.rand(200, 16).cuda() + 0.1
+  n0 = _lib.launch_count()
+  y = layer(x)
+  y.square().sum().backward()
+  assert _lib.launch_count() >= n0 + 3
+  grads = {n: p.grad for n, p in layer.named_parameters()}
+  assert len(grads) == 4 and all(v is not None and torch.isfinite(v).all() for v in grads.values())
