@@ -480,6 +480,8 @@ constexpr int kDgammaGrid = 148;
 
 int gdn_tc_forward(const float* x, const float* gamma, const float* beta, float* y, long long n_pix, int C,
                    int flags, float alpha, float eps, cudaStream_t s, bool* handled);
+int gdn_tc_forward16(const void* x, const float* gamma, const float* beta, void* y, long long n_pix, int C, int flags,
+                     float alpha, float eps, int dtype, cudaStream_t s, bool* handled);
 int gdn_tc_backward(const float* x, const float* gamma, const float* beta, const float* dy, float* dx, float* q_ws,
                     float* part_g, float* part_b, int* n_parts, long long n_pix, int C, int flags, float alpha,
                     float eps, cudaStream_t s, bool* handled);
@@ -525,6 +527,21 @@ int tfcb_gdn_forward(const float* x_dev, const float* gamma_dev, const float* be
     gdn_fwd_generic_kernel<<<(unsigned)blocks, 128, 0, s>>>(x_dev, gamma_dev, beta_dev, y_dev, n_pix, C, f);
   }
   TFCB_LAUNCHED();
+  TFCB_CUDA_TRY(cudaGetLastError());
+  return TFCB_OK;
+}
+
+int tfcb_gdn_forward_16bit(const void* x_dev, const float* gamma_dev, const float* beta_dev, void* y_dev, int64_t n_pix,
+                           int C, int dtype, int flags, float alpha, float epsilon, void* stream) {
+  if (n_pix < 0 || C <= 0) return fail(TFCB_INVALID_ARGUMENT, "bad GDN shape: n_pix=%lld C=%d", (long long)n_pix, C);
+  if (dtype != 1 && dtype != 2) return fail(TFCB_INVALID_ARGUMENT, "GDN 16-bit: dtype must be 1 (float16) or 2 (bfloat16)");
+  if (!x_dev || !gamma_dev || !beta_dev || !y_dev) return fail(TFCB_INVALID_ARGUMENT, "null pointer");
+  if (n_pix == 0) return TFCB_OK;
+  bool handled = false;
+  TFCB_TRY(gdn_tc_forward16(x_dev, gamma_dev, beta_dev, y_dev, n_pix, C, flags, alpha, epsilon, dtype, as_stream(stream), &handled));
+  if (!handled)
+    return fail(TFCB_INVALID_ARGUMENT, "GDN 16-bit: only C = 128 with alpha in {1, 2}, epsilon in {1, 1/2} has a native 16-bit kernel; "
+                "convert to float32 for this configuration");
   TFCB_CUDA_TRY(cudaGetLastError());
   return TFCB_OK;
 }

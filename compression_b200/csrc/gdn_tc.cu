@@ -19,6 +19,7 @@
 // Everything outside {C in {128, 192}, alpha in {1, 2}, eps in {1, 0.5}} falls back to the fp32 kernels in gdn.cu.
 #include <cuda.h>  // CUtensorMap (types only; cuTensorMapEncodeTiled is fetched through the runtime)
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -231,12 +232,53 @@ struct Fwd2Smem {
   static_assert(kBytes <= 232448, "shared memory budget");
 };
 
-template <bool FAST>
+// Element type of x / y in memory: 0 float32, 1 float16, 2 bfloat16 (the reference's mixed-precision policy keeps the
+// variables in float32 and the activations in 16 bits, gdn_test.py:200-210; arithmetic is float32 here either way).
+template <int IO>
+struct IoBytes { static constexpr int value = IO == 0 ? 4 : 2; };
+
+template <int IO>
+__device__ __forceinline__ void io_load8(const uint8_t* src, float (&v)[8]) {  // 8 consecutive 16-bit elements
+  const uint4 raw = *reinterpret_cast<const uint4*>(src);
+  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (IO == 2) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    } else {
+      const __half2 hh = *reinterpret_cast<const __half2*>(&w[i]);
+      const float2 ff = __half22float2(hh);
+      v[2 * i] = ff.x;
+      v[2 * i + 1] = ff.y;
+    }
+  }
+}
+
+template <int IO>
+__device__ __forceinline__ void io_store8(uint8_t* dst, const float (&v)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (IO == 2) {
+      w[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+    } else {
+      const __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    }
+  }
+  *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+template <bool FAST, int IO>
 __global__ void __launch_bounds__(kF2Threads, 1)
-gdn_tc_fwd2_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ planes,
-                   const float* __restrict__ beta, float* __restrict__ y, long long n_pix, TcFlags f) {
+gdn_tc_fwd2_kernel(const void* __restrict__ x_, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, void* __restrict__ y_, long long n_pix, TcFlags f) {
   using L = Fwd2Smem;
   constexpr int C = 128;
+  constexpr int EB = IoBytes<IO>::value, kRowB = C * EB;  // bytes per element / per pixel row
+  const uint8_t* x = static_cast<const uint8_t*>(x_);
+  uint8_t* y = static_cast<uint8_t*>(y_);
   extern __shared__ __align__(1024) uint8_t smem[];
   float* stage = reinterpret_cast<float*>(smem + L::kOffP);          // [128][68] fp32, only during the epilogue
   uint64_t* mbars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);  // [0,1] full, [2,3] plane, [4,5] y tile ready
@@ -245,10 +287,17 @@ gdn_tc_fwd2_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict_
   const int r = tid & 127, h = tid >> 7, gwarp = warp & 3;
   constexpr uint32_t kIdesc = umma_idesc(kTileM, C);
 
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(planes);
-    uint4* dst = reinterpret_cast<uint4*>(smem + L::kOffBh);
-    for (int i = tid; i < 2 * C * C * 2 / 16; i += kF2Threads) dst[i] = src[i];
+  // gamma [C, C] fp32 (64 KB, L2 resident) -> hi / lo bf16 planes [j / 8][i][j % 8], converted by every CTA in its
+  // prologue: no per-call allocation and no separate preparation launch (they cost the small shapes 10 %)
+  for (int idx = tid; idx < (C / 8) * C; idx += kF2Threads) {
+    const int jc = idx / C, i = idx % C;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = __ldg(gamma + (jc * 8 + e) * C + i);
+    uint4 hi, lo;
+    split8(v, &hi, &lo);
+    reinterpret_cast<uint4*>(smem + L::kOffBh)[idx] = hi;
+    reinterpret_cast<uint4*>(smem + L::kOffBl)[idx] = lo;
   }
   if (tid == 0) {
     for (int i = 0; i < 6; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbars + i)));
@@ -272,12 +321,12 @@ gdn_tc_fwd2_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict_
   // thread 0 moves the tiles: a tile is one contiguous block of rows * 512 bytes
   auto issue_load = [&](long long tile, int b) {
     const long long p0 = tile * kTileM;
-    const uint32_t bytes = (uint32_t)min((long long)kTileM, n_pix - p0) * 512u;
+    const uint32_t bytes = (uint32_t)min((long long)kTileM, n_pix - p0) * (uint32_t)kRowB;
     const uint32_t mbar = smem_u32(mbars + b);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      xs + b * kF2XBuf),
-                 "l"(x + p0 * C), "r"(bytes), "r"(mbar)
+                 "l"(x + p0 * kRowB), "r"(bytes), "r"(mbar)
                  : "memory");
   };
   if (warp == kF2Compute / 32) {
@@ -292,10 +341,10 @@ gdn_tc_fwd2_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict_
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const int b = it & 1;
         const long long p0 = tile * kTileM;
-        const uint32_t bytes = (uint32_t)min((long long)kTileM, n_pix - p0) * 512u;
+        const uint32_t bytes = (uint32_t)min((long long)kTileM, n_pix - p0) * (uint32_t)kRowB;
         if (!mbar_wait(smem_u32(mbars + 4 + b), par_y[b])) __trap();
         par_y[b] ^= 1u;
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(y + p0 * C),
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(y + p0 * kRowB),
                      "r"(xs + b * kF2XBuf), "r"(bytes)
                      : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -367,12 +416,19 @@ gdn_tc_fwd2_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict_
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int row = crow + 64 * i;
-        const uint8_t* src = xt + row * 512 + (c * 32 + ckg * 8) * 4;
-        const float4 va = *reinterpret_cast<const float4*>(src + (swap ? 16 : 0));
-        const float4 vb = *reinterpret_cast<const float4*>(src + (swap ? 0 : 16));
-        const float4 v0 = swap ? vb : va, v1 = swap ? va : vb;
-        float v[8] = {tc_pool<FAST>(v0.x, f), tc_pool<FAST>(v0.y, f), tc_pool<FAST>(v0.z, f), tc_pool<FAST>(v0.w, f),
-                      tc_pool<FAST>(v1.x, f), tc_pool<FAST>(v1.y, f), tc_pool<FAST>(v1.z, f), tc_pool<FAST>(v1.w, f)};
+        const uint8_t* src = xt + row * kRowB + (c * 32 + ckg * 8) * EB;
+        float v[8];
+        if (IO == 0) {
+          const float4 va = *reinterpret_cast<const float4*>(src + (swap ? 16 : 0));
+          const float4 vb = *reinterpret_cast<const float4*>(src + (swap ? 0 : 16));
+          const float4 v0 = swap ? vb : va, v1 = swap ? va : vb;
+          v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w;
+          v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
+        } else {
+          io_load8<IO>(src, v);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = tc_pool<FAST>(v[e], f);
         uint4 hi, lo;
         split8(v, &hi, &lo);
         *reinterpret_cast<uint4*>(ph + ckg * kF2Kg + row * 16) = hi;
@@ -412,8 +468,19 @@ gdn_tc_fwd2_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict_
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int row = erow + 32 * i;
-        uint8_t* src = xt + row * 512 + (cc * 64 + ekg * 8) * 4;
+        uint8_t* src = xt + row * kRowB + (cc * 64 + ekg * 8) * EB;
         const uint8_t* nsrc = reinterpret_cast<const uint8_t*>(stage + row * kF2StLd + ekg * 8);
+        if (IO != 0) {  // 16-bit elements: one 16-byte load and store per item
+          float xv[8], o[8];
+          io_load8<IO>(src, xv);
+          const float4 na = *reinterpret_cast<const float4*>(nsrc), nb = *reinterpret_cast<const float4*>(nsrc + 16);
+          const float nn[8] = {bv0.x + na.x, bv0.y + na.y, bv0.z + na.z, bv0.w + na.w,
+                               bv1.x + nb.x, bv1.y + nb.y, bv1.z + nb.z, bv1.w + nb.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = tc_out<FAST>(xv[e], nn[e], f);
+          io_store8<IO>(src, o);
+          continue;
+        }
         float4* pa = reinterpret_cast<float4*>(src + (eswap ? 16 : 0));
         float4* pb2 = reinterpret_cast<float4*>(src + (eswap ? 0 : 16));
         const float4 va = *pa, vb = *pb2;
@@ -447,34 +514,26 @@ gdn_tc_fwd2_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict_
   }
 }
 
-template <bool FAST>
-int launch_tc_fwd2(const float* x, const float* gamma, const float* beta, float* y, long long n_pix, TcFlags f,
+template <bool FAST, int IO>
+int launch_tc_fwd2(const void* x, const float* gamma, const float* beta, void* y, long long n_pix, TcFlags f,
                    cudaStream_t s) {
   constexpr int C = 128;
   using L = Fwd2Smem;
-  __nv_bfloat16* planes = nullptr;
-  TFCB_TRY(dev_alloc((void**)&planes, (size_t)2 * C * C * sizeof(__nv_bfloat16), s));
-  gdn_tc_prep_kernel<<<((C / 8) * C + 255) / 256, 256, 0, s>>>(gamma, C, planes);
-  TFCB_LAUNCHED();
-  bool attr_set = false;  // the attribute is per device: set it on every launch (microseconds)
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gdn_tc_fwd2_kernel<FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes);
+  {  // the attribute is per device: set it on every launch (microseconds)
+    cudaError_t e = cudaFuncSetAttribute(gdn_tc_fwd2_kernel<FAST, IO>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes);
     if (e != cudaSuccess) {
       (void)cudaGetLastError();
-      dev_free(planes, s);
       return fail(TFCB_CUDA_ERROR, "cannot reserve %d bytes of shared memory: %s", L::kBytes, cudaGetErrorString(e));
     }
-    attr_set = true;
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long n_tiles = (n_pix + kTileM - 1) / kTileM;
   const int grid = (int)std::min<long long>(n_tiles, sms);
-  gdn_tc_fwd2_kernel<FAST><<<grid, kF2Threads, L::kBytes, s>>>(x, planes, beta, y, n_pix, f);
+  gdn_tc_fwd2_kernel<FAST, IO><<<grid, kF2Threads, L::kBytes, s>>>(x, gamma, beta, y, n_pix, f);
   TFCB_LAUNCHED();
   cudaError_t e = cudaGetLastError();
-  dev_free(planes, s);
   if (e != cudaSuccess) return fail(TFCB_CUDA_ERROR, "GDN tensor-core kernel launch failed: %s", cudaGetErrorString(e));
   return TFCB_OK;
 }
@@ -2790,10 +2849,31 @@ int gdn_tc_forward(const float* x, const float* gamma, const float* beta, float*
   *handled = true;
   const bool fast = (alpha == 1.f) && (eps == 1.f) && !f.rectify;
   if (C == 128)  // x tile resident in shared memory, bulk async copies
-    return fast ? launch_tc_fwd2<true>(x, gamma, beta, y, n_pix, f, s) : launch_tc_fwd2<false>(x, gamma, beta, y, n_pix, f, s);
+    return fast ? launch_tc_fwd2<true, 0>(x, gamma, beta, y, n_pix, f, s) : launch_tc_fwd2<false, 0>(x, gamma, beta, y, n_pix, f, s);
   // C == 192: x through rings of 2-D TMA boxes, gamma's lo plane streamed, y through TMA stores
   if (n_pix >= (1ll << 31)) return fail(TFCB_INVALID_ARGUMENT, "GDN: more than 2^31 pixels in one call");
   return fast ? launch_tc_fwd4<true>(x, gamma, beta, y, n_pix, f, s) : launch_tc_fwd4<false>(x, gamma, beta, y, n_pix, f, s);
+}
+
+// 16-bit activations (float16 / bfloat16 in, same type out; parameters and arithmetic float32): the C = 128 resident
+// tile kernel with 256-byte rows.  *handled = false -> the caller converts and runs the float32 path.
+int gdn_tc_forward16(const void* x, const float* gamma, const float* beta, void* y, long long n_pix, int C, int flags,
+                     float alpha, float eps, int dtype, cudaStream_t s, bool* handled) {
+  *handled = false;
+  if (C != 128 || (dtype != 1 && dtype != 2)) return TFCB_OK;
+  if (!(alpha == 1.f || alpha == 2.f) || !(eps == 1.f || eps == 0.5f)) return TFCB_OK;
+  if (flags & (TFCB_GDN_POW_ALPHA | TFCB_GDN_POW_EPSILON)) return TFCB_OK;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(beta)) & 15) return TFCB_OK;
+  TcFlags f;
+  f.inverse = (flags & TFCB_GDN_INVERSE) ? 1 : 0;
+  f.rectify = (flags & TFCB_GDN_RECTIFY) ? 1 : 0;
+  f.alpha_mode = (alpha == 2.f) ? 2 : 1;
+  f.eps_mode = (eps == 0.5f) ? 2 : 1;
+  *handled = true;
+  const bool fast = (alpha == 1.f) && (eps == 1.f) && !f.rectify;
+  if (dtype == 1)
+    return fast ? launch_tc_fwd2<true, 1>(x, gamma, beta, y, n_pix, f, s) : launch_tc_fwd2<false, 1>(x, gamma, beta, y, n_pix, f, s);
+  return fast ? launch_tc_fwd2<true, 2>(x, gamma, beta, y, n_pix, f, s) : launch_tc_fwd2<false, 2>(x, gamma, beta, y, n_pix, f, s);
 }
 
 }  // namespace tfcb

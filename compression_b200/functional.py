@@ -29,8 +29,11 @@ def _flags(inverse, rectify, pow_alpha=False, pow_epsilon=False):
           (GDN_POW_EPSILON if pow_epsilon else 0))
 
 
+_IO16 = {torch.float16: 1, torch.bfloat16: 2}
+
+
 def _gdn_args(x, gamma, beta):
-  assert x.is_cuda and x.dtype == torch.float32
+  assert x.is_cuda and x.dtype in (torch.float32, torch.float16, torch.bfloat16)
   x = x.contiguous()
   C_ = x.shape[-1]
   gamma = gamma.to(device=x.device, dtype=torch.float32).contiguous()
@@ -43,6 +46,17 @@ def gdn_forward(x, gamma, beta, inverse=False, rectify=False, alpha=1.0, epsilon
                 pow_epsilon=False):
   """x: float32 CUDA [..., C] (channels-last, contiguous) -> y of the same shape."""
   x, gamma, beta, C_, n_pix = _gdn_args(x, gamma, beta)
+  if x.dtype in _IO16:
+    # mixed precision (gdn_test.py:200-210): 16-bit activations, float32 parameters and arithmetic.  C = 128 with the
+    # fixed exponents has a kernel that reads and writes 16-bit elements; everything else converts to float32.
+    native = (C_ == 128 and not pow_alpha and not pow_epsilon and float(alpha) in (1.0, 2.0) and
+              float(epsilon) in (1.0, 0.5) and n_pix > 0)
+    if native:
+      y = torch.empty_like(x)
+      check(_lib.lib().tfcb_gdn_forward_16bit(_p(x), _p(gamma), _p(beta), _p(y), n_pix, C_, _IO16[x.dtype],
+                                              _flags(inverse, rectify), float(alpha), float(epsilon), _stream()))
+      return y
+    return gdn_forward(x.float(), gamma, beta, inverse, rectify, alpha, epsilon, pow_alpha, pow_epsilon).to(x.dtype)
   y = torch.empty_like(x)
   check(_lib.lib().tfcb_gdn_forward(_p(x), _p(gamma), _p(beta), _p(y), n_pix, C_,
                                     _flags(inverse, rectify, pow_alpha, pow_epsilon), float(alpha), float(epsilon),
@@ -54,6 +68,9 @@ def gdn_backward(x, gamma, beta, dy, inverse=False, rectify=False, alpha=1.0, ep
                  pow_epsilon=False):
   """Returns (dx, dgamma, dbeta) for upstream gradient dy."""
   x, gamma, beta, C_, n_pix = _gdn_args(x, gamma, beta)
+  if x.dtype in _IO16:  # the backward kernels are float32: convert, run, hand dx back in the activations' type
+    dx, dgamma, dbeta = gdn_backward(x.float(), gamma, beta, dy, inverse, rectify, alpha, epsilon, pow_alpha, pow_epsilon)
+    return dx.to(x.dtype), dgamma, dbeta
   dy = dy.to(dtype=torch.float32).contiguous()
   dx = torch.empty_like(x)
   dgamma = torch.empty_like(gamma)
@@ -70,7 +87,7 @@ def gdn_exponent_grads(x, gamma, beta, dy, inverse=False, rectify=False, alpha=1
                        pow_epsilon=True):
   """(dL/dalpha, dL/depsilon) as a float32 [2] tensor: the gradients TF autodiff produces through `inputs ** alpha`
   and `norm_pool ** epsilon` when the exponents are trainable GDNParameters (gdn.py:345-367,388,411)."""
-  x, gamma, beta, C_, n_pix = _gdn_args(x, gamma, beta)
+  x, gamma, beta, C_, n_pix = _gdn_args(x.float(), gamma, beta)
   dy = dy.to(dtype=torch.float32).contiguous()
   out = torch.empty(2, dtype=torch.float32, device=x.device)
   ws = torch.empty(int(_lib.lib().tfcb_gdn_exponent_grads_workspace_bytes()), dtype=torch.uint8, device=x.device)
@@ -109,7 +126,7 @@ class _GDNFunction(torch.autograd.Function):
 
 
 def gdn(x, gamma, beta, inverse=False, rectify=False, alpha=1.0, epsilon=1.0):
-  """Differentiable GDN/IGDN on channels-last float32 CUDA tensors.  `alpha` / `epsilon`: Python numbers (fixed
+  """Differentiable GDN/IGDN on channels-last float32 / float16 / bfloat16 CUDA tensors (float32 parameters).  `alpha` / `epsilon`: Python numbers (fixed
   exponents: |u|, u^2, sqrt shortcuts and the tensor-core kernels apply) or 0-d tensors (trainable: literal pow, with
   gradients)."""
   at = alpha if isinstance(alpha, torch.Tensor) else None

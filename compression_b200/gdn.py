@@ -142,7 +142,8 @@ class GDN(nn.Module):
     dev = inputs.device
     x = inputs.movedim(1, -1) if self.data_format == "channels_first" else inputs
     out_dtype = x.dtype
-    x32 = x.to(torch.float32).contiguous()
+    # float16 / bfloat16 activations go to the kernels as they are (mixed precision, gdn_test.py:200-210)
+    x32 = (x if x.dtype in (torch.float32, torch.float16, torch.bfloat16) else x.to(torch.float32)).contiguous()
     alpha, epsilon = self.alpha_parameter, self.epsilon_parameter
     # trainable exponents travel as 0-d tensors: literal pow in the kernels plus the two scalar gradients
     # (gdn.py:345-367,388,411); fixed ones as Python numbers (|u| / u^2 / sqrt shortcuts, tensor-core kernels)

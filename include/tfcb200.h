@@ -204,6 +204,13 @@ int tfcb_gdn_forward(const float* x_dev, const float* gamma_dev, const float* be
 /* Gradients for upstream dy: dx [n_pix, C], dgamma [C, C], dbeta [C] (dgamma / dbeta are
  * OVERWRITTEN, reduced over all pixels).  `workspace_dev` must hold
  * tfcb_gdn_backward_workspace_bytes(n_pix, C) bytes. */
+/* Mixed-precision variant (gdn_test.py:200-210: float32 variables, float16 / bfloat16 activations): x and y in
+ * 16 bits (dtype 1 float16, 2 bfloat16), arithmetic in float32 -- 4 bytes of HBM traffic per element instead of 8.
+ * Native kernel for C = 128 with alpha in {1, 2}, epsilon in {1, 1/2}; TFCB_INVALID_ARGUMENT otherwise (the caller
+ * converts to float32). */
+int tfcb_gdn_forward_16bit(const void* x_dev, const float* gamma_dev, const float* beta_dev, void* y_dev,
+                           int64_t n_pix, int C, int dtype, int flags, float alpha, float epsilon, void* stream);
+
 int64_t tfcb_gdn_backward_workspace_bytes(int64_t n_pix, int C);
 int tfcb_gdn_backward(const float* x_dev, const float* gamma_dev, const float* beta_dev,
                       const float* dy_dev, float* dx_dev, float* dgamma_dev, float* dbeta_dev,

@@ -226,3 +226,43 @@ def test_layer_with_trainable_exponents_uses_the_kernels(tfc_mod=None):
   assert _lib.launch_count() >= n0 + 3
   grads = {n: p.grad for n, p in layer.named_parameters()}
   assert len(grads) == 4 and all(v is not None and torch.isfinite(v).all() for v in grads.values())
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("n_pix", [1, 129, 128 * 148 * 2 + 5])
+@pytest.mark.parametrize("inverse,alpha,epsilon,rectify", [(False, 1, 1, False), (True, 1, 1, False), (False, 2, 0.5, False),
+                                                           (False, 1, 1, True)])
+def test_sixteen_bit_activations_native_kernel(F, dtype, n_pix, inverse, alpha, epsilon, rectify):
+  """Mixed precision (gdn_test.py:200-210): x, y in 16 bits, float32 parameters.  The C = 128 kernel reads and writes the
+  16-bit elements itself; its result is the float32 result of the same (already rounded) inputs, rounded once."""
+  from compression_b200 import _lib
+  C = 128
+  gamma, beta = _params(C, 41)
+  x = _x(n_pix, C, 42).to(dtype).cuda()
+  n0 = _lib.launch_count()
+  y = F.gdn_forward(x, gamma.cuda(), beta.cuda(), inverse, rectify, alpha, epsilon)
+  assert _lib.launch_count() == n0 + 1 and y.dtype == dtype  # one kernel, no conversion passes
+  # it is exactly the float32 kernel's output (same inputs) rounded to the activation type ...
+  y32 = F.gdn_forward(x.float(), gamma.cuda(), beta.cuda(), inverse, rectify, alpha, epsilon)
+  assert torch.equal(y, y32.to(dtype))
+  # ... i.e. within half an ulp of the activation type of the float64 oracle (normal range of float16)
+  want = gdn_oracle.gdn_reference(x.float().cpu(), gamma, beta, inverse, rectify, alpha, epsilon)
+  eps_io = 2.0**-11 if dtype == torch.float16 else 2.0**-8
+  big = want.abs() >= 1e-3
+  err = ((y.double().cpu() - want).abs() / (want.abs() + 1e-30))[big].max().item() if bool(big.any()) else 0.0
+  assert err <= eps_io * 1.01 + 2e-5
+
+
+def test_sixteen_bit_module_and_gradients(F):
+  import compression_b200 as tfc
+  layer = tfc.GDN()
+  x = (torch.randn(500, 128) * 2).to(torch.bfloat16).cuda().requires_grad_(True)
+  y = layer(x)
+  assert y.dtype == torch.bfloat16
+  for p in layer.parameters():
+    assert p.dtype == torch.float32  # gdn_test.py:205-206
+  y.float().square().sum().backward()
+  assert x.grad is not None and x.grad.dtype == torch.bfloat16
+  # other widths convert and still return the activation type
+  y2 = tfc.GDN()(torch.randn(70, 192).half().cuda())
+  assert y2.dtype == torch.float16
