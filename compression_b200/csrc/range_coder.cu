@@ -1,24 +1,25 @@
-// Range coder for sm_100a: one warp per code stream.
+// Range coder for sm_100a: one CTA per code stream, the serial recurrence alone on one warp.
 //
 // Replaces (paths relative to /root/reference/tensorflow_compression):
 //   cc/lib/range_coder.cc:37-307, cc/lib/range_coder.h:79-282          the coder
 //   cc/kernels/range_coder_kernels.cc:110-164,168-322,334-471           multi-stream ops
 //   cc/kernels/range_coding_kernels.cc:60-379 (+ _util.cc:34-91)        legacy single-stream ops
 //
-// ENCODER DESIGN.  The reference emits bytes through a delayed-carry state machine.  Its output is
-// exactly the big-number sum  SUM_k a_k * 2^-(16 r_k + 32)  of the per-symbol interval offsets a_k
-// (r_k = number of 16-bit renormalisations before symbol k) followed by a short flush.  Only the
-// recurrence on the interval size is inherently serial.  So per stream (= per warp):
-//   * all 32 lanes cooperatively gather the (lower, upper, precision) triples of the next 32 symbols
-//     (coalesced symbol load + table gather, fused quantisation, Elias-gamma preparation);
-//   * every lane then runs the same serial recurrence (size', base', carry-out) over those triples,
-//     fetched with warp shuffles; a renormalisation appends one *unresolved* 16-bit word plus one
-//     carry bit ("a carry left the 32-bit window while this word was its top half");
-//   * words are staged one per lane and flushed as 64-byte coalesced stores;
-//   * finalize resolves all carries at once with a warp-wide carry-lookahead over 32-word groups,
-//     applies RangeEncoder::Finalize's tail rule and compacts all strings into one buffer.
-// DECODER DESIGN.  Same recurrence; the CDF search is a warp-parallel k-ary search (each lane tests
-// one candidate per round, ballot picks the bracket), the byte window is prefetched 64 B at a time.
+// ENCODER.  The reference emits bytes through a delayed-carry state machine.  Its output is exactly the
+// big-number sum  SUM_k a_k * 2^-(16 r_k + 32)  of the per-symbol interval offsets a_k (r_k = number of 16-bit
+// renormalisations before symbol k) followed by a short flush; only the recurrence on the interval size is
+// inherently serial.  Per stream (encode_kernel, six warps):
+//   * gather warps: coalesced symbol loads three passes ahead, fused quantisation, range checks, escape expansion
+//     (an escaping symbol is followed by the records of its Elias-gamma bits), table gathers, operand pre-scaling;
+//   * chain warp: nothing but the recurrence on the UN-renormalised span (EncChain::step: IADD3 -> IMAD.WIDE ->
+//     funnel shift -> IADD3, no select between the multiplies), one entry {L, s'} per Encode;
+//   * drain warp: base, carries, emitted 16-bit words and word count are prefix computations over those entries
+//     (EncDrain: a warp scan over the maps x -> (x << S) + A), written as unresolved words + one carry bit each;
+//   * finalize: warp-wide carry-lookahead over 32-word groups, RangeEncoder::Finalize's tail rule, compaction.
+// DECODER.  Same recurrence plus a CDF search per symbol (decode_kernel, three warps: prepare / chain / resolve):
+// pre-scaled search keys, a 64-key window per row around its median evaluated two keys per lane with one IMAD.HI
+// each and two warp reductions; the symbol index itself is recovered off the chain by the resolve warp.
+// The one-warp-per-stream helpers further down (ByteWindow, dec_symbol) serve the legacy single-stream ops only.
 #include <algorithm>
 #include <cstring>
 #include <vector>

@@ -42,7 +42,8 @@ const char* tfcb_last_error(void);
  *   op contract   tensorflow_compression/cc/ops/range_coder_ops.cc:28-135
  *   CPU kernels   tensorflow_compression/cc/kernels/range_coder_kernels.cc:168-322,484-592
  *   coder         tensorflow_compression/cc/lib/range_coder.cc:37-307
- * One CUDA warp drives one code stream; streams = prod(handle shape).
+ * One CTA per code stream (gather / chain / drain warps); streams = prod(handle shape); a stream holds < 2^31
+ * 16-bit words (4 GB).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct tfcb_encoder tfcb_encoder;
 
