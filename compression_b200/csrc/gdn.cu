@@ -547,7 +547,7 @@ int tfcb_gdn_forward_16bit(const void* x_dev, const float* gamma_dev, const floa
 }
 
 int64_t tfcb_gdn_backward_workspace_bytes(int64_t n_pix, int C) {
-  const int64_t q = n_pix * C * (int64_t)sizeof(float);
+  const int64_t q = ((n_pix + 127) / 128 * 128) * C * (int64_t)sizeof(float);  // whole 128-pixel tiles (the C = 192 tensor-core pair hands q over tile by tile)
   const int64_t parts = (int64_t)kDgammaGrid * ((int64_t)C * C + C) * (int64_t)sizeof(float);
   return q + parts + 256;
 }
@@ -567,7 +567,7 @@ int tfcb_gdn_backward(const float* x_dev, const float* gamma_dev, const float* b
     return TFCB_OK;
   }
   float* q = reinterpret_cast<float*>(workspace_dev);
-  float* part_g = q + (((size_t)n_pix * C + 63) & ~(size_t)63);
+  float* part_g = q + (size_t)((n_pix + 127) / 128 * 128) * C;
   float* part_b = part_g + (size_t)kDgammaGrid * C * C;
   bool handled = false;
   int n_parts = 0;

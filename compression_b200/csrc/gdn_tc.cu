@@ -2332,36 +2332,40 @@ int launch_tc_bwd3(const float* x, const float* gamma, const float* beta, const 
 // Backward, C = 192, first of the two kernels (dx and q), box-fed like gdn_tc_bwd3_kernel.
 //
 // n, dp and a dgamma accumulator need 3 x 192 TMEM columns and whole-tile p and q planes 198 KB of shared memory, so
-// C = 192 keeps the two-kernel split: this kernel produces dx and q = dL/dn (fp32, to the workspace), and
-// gdn_tc_bwd_dgamma_kernel contracts x and q into dgamma / dbeta.  Per 128-pixel tile:
+// C = 192 keeps the two-kernel split: this kernel produces dx and q = dL/dn, and gdn_tc_bwd_dgamma2_kernel contracts
+// x and q into dgamma / dbeta.  q travels through the workspace AS THE bf16 hi / lo OPERAND PLANES the second kernel
+// needs ([tile][hi, lo][24 groups][128 rows][8], 4 B/element like fp32): this kernel's q chunk buffers are bulk-stored
+// as they are, the second kernel bulk-loads a tile's planes with one copy and converts nothing.  Per 128-pixel tile:
 //
 //   conv(t)   x boxes -> p = |x| hi / lo planes, one 32-channel K chunk at a time (two chunk buffers)  -> MMA1  n += p_c . gamma_c
-//   pass2(t)  x (L2 hit), g boxes + n from TMEM -> q: fp32 into an output box (TMA store to the workspace) and hi / lo
-//             planes of the chunk                                                                      -> MMA2  dp += q_c . gammaT_c
+//   pass2(t)  x (L2 hit), g boxes + n from TMEM -> q hi / lo planes of the chunk (also bulk-stored to the workspace)
+//                                                                                                      -> MMA2  dp += q_c . gammaT_c
 //             the direct term g / n (IGDN: g * n) goes back into n's columns with sign(x) in the two low mantissa bits
 //   pass3(t)  dx = direct + sign(x) * dp, from TMEM only -> output box -> TMA store
 //
 // gamma and gamma^T arrive as K chunks (24 KB hi + lo, double buffered) from a "gamma" warp; chunk m of the stream
-// uses operand buffer and gamma buffer m % 2, so ONE commit per chunk frees both.  A ring of seven 16 KB boxes
-// serves every box request in program order.  TMEM: n | dp (2 x 192 columns).
+// uses operand buffer and gamma buffer m % 2, so ONE commit per chunk frees both (a q chunk's buffer additionally
+// waits for its bulk store to have read it).  A ring of seven 16 KB boxes serves every box request in program order.
+// TMEM: n | dp (2 x 192 columns).
 // =============================================================================================
 constexpr int kD2Compute = 512;
 constexpr int kD2Threads = kD2Compute + 128;   // + MMA-issue, box-copy, gamma and store warps
 constexpr int kD2Sync = kD2Compute + 32;
 constexpr int kD2Slots = 7;
+constexpr int kDKg = kTileM * 16;  // dense group stride of the operand planes (row-per-lane stores need no padding)
 
 struct BwdDx2Smem {
   static constexpr int C = 192;
   static constexpr int kGChunk = 4 * C * 16;                      // one 32-channel K chunk of one gamma plane (12 KB)
-  static constexpr int kOpPlane = 4 * kKg;                        // hi or lo plane of one 32-channel operand chunk
+  static constexpr int kOpPlane = 4 * kDKg;                       // hi or lo plane of one 32-channel operand chunk (8 KB)
   static constexpr int kOffRing = 0;                              // [7] boxes (1024-byte aligned: swizzle atom)
   static constexpr int kOffG = kOffRing + kD2Slots * kF4Box;      // [2 buffers][hi, lo] gamma K chunks
   static constexpr int kOffOp = kOffG + 4 * kGChunk;              // [2 buffers][hi, lo] operand (p or q) chunks
   static constexpr int kOffBeta = kOffOp + 4 * kOpPlane;
   static constexpr int kOffBar = kOffBeta + C * 4;
-  // mbarriers: full[7], empty[7], yready[7], gfull[2], cfree[2], nfull, dpfull; then the TMEM slot
+  // mbarriers: full[7], empty[7], yready[7], gfull[2], cfree[2], nfull, dpfull, qready[2], sfree[2]; then the TMEM slot
   static constexpr int kBarFull = 0, kBarEmpty = 7, kBarY = 14, kBarGfull = 21, kBarCfree = 23, kBarN = 25, kBarDp = 26,
-                       kNumBars = 27;
+                       kBarQready = 27, kBarSfree = 29, kNumBars = 31;
   static constexpr int kBytes = kOffBar + kNumBars * 8 + 16;
   static_assert(kOffG % 128 == 0 && kOffOp % 16 == 0 && kOffBar % 8 == 0, "alignment");
   static_assert(kBytes <= 232448, "shared memory budget");
@@ -2369,9 +2373,9 @@ struct BwdDx2Smem {
 
 __global__ void __launch_bounds__(kD2Threads, 1)
 gdn_tc_bwd_dx2_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUtensorMap g_map,
-                      const __grid_constant__ CUtensorMap dx_map, const __grid_constant__ CUtensorMap q_map,
-                      const float* __restrict__ x, const float* __restrict__ dy, const __nv_bfloat16* __restrict__ planes,
-                      const float* __restrict__ beta, long long n_pix, int inverse) {
+                      const __grid_constant__ CUtensorMap dx_map, const float* __restrict__ x,
+                      const float* __restrict__ dy, const __nv_bfloat16* __restrict__ planes,
+                      const float* __restrict__ beta, uint8_t* __restrict__ q_planes, long long n_pix, int inverse) {
   using L = BwdDx2Smem;
   constexpr int C = L::C, NCH = C / 32;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -2384,7 +2388,8 @@ gdn_tc_bwd_dx2_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_co
   for (int i = tid; i < C; i += kD2Threads) beta_s[i] = beta[i];
   if (tid == 0) {
     for (int i = 0; i < L::kNumBars; ++i) {
-      const int count = (i >= L::kBarY && i < L::kBarGfull) ? kD2Compute / 32 : 1;  // y ready: one arrival per compute warp
+      // y ready / q ready: one arrival per compute warp
+      const int count = ((i >= L::kBarY && i < L::kBarGfull) || (i >= L::kBarQready && i < L::kBarSfree)) ? kD2Compute / 32 : 1;
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar(i)), "r"(count));
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -2402,7 +2407,7 @@ gdn_tc_bwd_dx2_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_co
   const long long n_tiles = (n_pix + kTileM - 1) / kTileM;
   const long long first = blockIdx.x;
   // Box request n uses ring slot n % 7 in its (n / 7)-th round:
-  //   6 x boxes (conversion of the CTA's first tile), then per tile {x, g, q-out} x 6 (pass 2), dx-out x 6 (pass 3),
+  //   6 x boxes (conversion of the CTA's first tile), then per tile {x, g} x 6 (pass 2), dx-out x 6 (pass 3),
   //   (x of the next tile) x 6.
   // Chunk m of the operand / gamma stream uses buffers m % 2: 6 conversion chunks of the first tile, then per tile 6 q
   // chunks, 6 conversion chunks of the next tile.
@@ -2463,7 +2468,6 @@ gdn_tc_bwd_dx2_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_co
         for (int c = 0; c < NCH; ++c) {
           load(&x_map, c, row0);  // second read of x: an L2 hit
           load(&g_map, c, row0);
-          reserve();              // q out
         }
 #pragma unroll 1
         for (int c = 0; c < NCH; ++c) reserve();  // dx out
@@ -2513,33 +2517,49 @@ gdn_tc_bwd_dx2_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_co
     }
     __syncwarp();
   } else if (warp == W0 + 3) {
-    // ---------------------------------- store warp: q and dx boxes ----------------------------------
+    // ---------------------------------- store warp: q planes and dx boxes ----------------------------------
     if (lane == 0) {
       uint32_t n = (first < n_tiles) ? (uint32_t)NCH : 0u;
+      uint32_t m = (first < n_tiles) ? (uint32_t)NCH : 0u;  // operand chunk counter (q chunks are stored, p chunks skipped)
       uint32_t ypar = 0u;  // per-slot phase of the y-ready barrier (a slot is an output box only now and then)
-      auto store = [&](const CUtensorMap* map, int c, int row0) {
-        const uint32_t slot = slot_of(n);
-        if (!mbar_wait(bar(L::kBarY + slot), (ypar >> slot) & 1u)) __trap();
-        ypar ^= 1u << slot;
-        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;" ::"l"(map),
-                     "r"(c * 32), "r"(row0), "r"(smem_u32(smem + L::kOffRing + slot * kF4Box)), "l"(kEvictFirst)
-                     : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the box has been read: the slot is free
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar(L::kBarEmpty + slot)) : "memory");
-      };
+      uint32_t qcnt[2] = {0u, 0u};
       for (long long tile = first; tile < n_tiles; tile += gridDim.x) {
         const bool has_next = tile + gridDim.x < n_tiles;
         const int row0 = (int)(tile * kTileM);
+        uint8_t* qt = q_planes + (size_t)tile * (2 * (C / 8) * kDKg);  // this tile's [hi, lo][24][128][8] planes
 #pragma unroll 1
-        for (int c = 0; c < NCH; ++c) {
-          n += 2;  // x, g
-          store(&q_map, c, row0);
-          ++n;
+        for (int c = 0; c < NCH; ++c, ++m) {
+          const uint32_t buf = m & 1u;
+          if (!mbar_wait(bar(L::kBarQready + buf), qcnt[buf] & 1u)) __trap();
+          ++qcnt[buf];
+          const uint32_t src = smem_u32(smem + L::kOffOp + buf * 2 * L::kOpPlane);
+#pragma unroll
+          for (int pl = 0; pl < 2; ++pl)
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(
+                             qt + (size_t)pl * ((C / 8) * kDKg) + (size_t)c * L::kOpPlane),
+                         "r"(src + pl * L::kOpPlane), "n"(L::kOpPlane), "l"(kEvictLast)
+                         : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the buffer has been read
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar(L::kBarSfree + buf)) : "memory");
         }
+        n += 2 * NCH;  // x and g boxes of pass 2
 #pragma unroll 1
-        for (int c = 0; c < NCH; ++c, ++n) store(&dx_map, c, row0);
-        if (has_next) n += NCH;
+        for (int c = 0; c < NCH; ++c, ++n) {
+          const uint32_t slot = slot_of(n);
+          if (!mbar_wait(bar(L::kBarY + slot), (ypar >> slot) & 1u)) __trap();
+          ypar ^= 1u << slot;
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;" ::"l"(&dx_map),
+                       "r"(c * 32), "r"(row0), "r"(smem_u32(smem + L::kOffRing + slot * kF4Box)), "l"(kEvictFirst)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the box has been read: the slot is free
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar(L::kBarEmpty + slot)) : "memory");
+        }
+        if (has_next) {
+          n += NCH;
+          m += NCH;
+        }
       }
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
@@ -2556,8 +2576,8 @@ gdn_tc_bwd_dx2_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_co
       const uint32_t g_hi = smem_u32(smem + L::kOffG + buf * 2 * L::kGChunk), g_lo = g_hi + L::kGChunk;
 #pragma unroll
       for (int s2 = 0; s2 < 2; ++s2) {
-        const uint64_t dah = umma_desc(a_hi + (uint32_t)(2 * s2) * kKg, kKg, 128);
-        const uint64_t dal = umma_desc(a_lo + (uint32_t)(2 * s2) * kKg, kKg, 128);
+        const uint64_t dah = umma_desc(a_hi + (uint32_t)(2 * s2) * kDKg, kDKg, 128);
+        const uint64_t dal = umma_desc(a_lo + (uint32_t)(2 * s2) * kDKg, kDKg, 128);
         const uint64_t dbh = umma_desc(g_hi + (uint32_t)(2 * s2) * (C * 16), C * 16, 128);
         const uint64_t dbl = umma_desc(g_lo + (uint32_t)(2 * s2) * (C * 16), C * 16, 128);
         umma_bf16(acc, dah, dbh, kIdesc, (first_chunk && s2 == 0) ? 0u : 1u);
@@ -2588,11 +2608,11 @@ gdn_tc_bwd_dx2_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_co
     for (long long tile = first; tile < n_tiles; tile += gridDim.x) {
       const bool has_next = tile + gridDim.x < n_tiles;
 #pragma unroll 1
-      for (int c = 0; c < NCH; ++c, n += 3) {
+      for (int c = 0; c < NCH; ++c, n += 2) {
         asm volatile("bar.sync %0, %1;" ::"r"(4 + (int)(m & 1u)), "n"(kD2Sync) : "memory");  // q planes of this chunk are written
         if (lane == 0) {
           release(n);      // x box
-          release(n + 1);  // g box   (the q-out box n + 2 is handed back by the store warp)
+          release(n + 1);  // g box
           chunk_mmas(tmem_dp, c == 0);
           if (c == NCH - 1) umma_commit(bar(L::kBarDp));  // dp is complete: the dx pass may start
         } else {
@@ -2612,18 +2632,24 @@ gdn_tc_bwd_dx2_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_co
     if (!mbar_wait(bar(L::kBarFull + slot_of(req)), round_of(req) & 1u)) __trap();
     return smem + L::kOffRing + slot_of(req) * kF4Box;
   };
-  // this thread's 16-byte rows of the hi / lo planes of operand chunk m (waits until the MMAs of chunk m - 2 are done)
-  auto operand_rows = [&](uint4** hi, uint4** lo) {
+  // this thread's 16-byte rows of the hi / lo planes of operand chunk m: waits until the MMAs of chunk m - 2 are done
+  // and, if that chunk was a q chunk, until its bulk store has read the buffer
+  uint32_t scnt[2] = {0u, 0u};
+  auto operand_rows = [&](uint4** hi, uint4** lo, bool prev_was_q) {
     const uint32_t buf = m & 1u;
     if (m >= 2) {
       if (!mbar_wait(bar(L::kBarCfree + buf), ((m >> 1) - 1u) & 1u)) __trap();
     }
-    uint8_t* base = smem + L::kOffOp + buf * 2 * L::kOpPlane + h * kKg + r * 16;
+    if (prev_was_q) {
+      if (!mbar_wait(bar(L::kBarSfree + buf), scnt[buf] & 1u)) __trap();
+      ++scnt[buf];
+    }
+    uint8_t* base = smem + L::kOffOp + buf * 2 * L::kOpPlane + h * kDKg + r * 16;
     *hi = reinterpret_cast<uint4*>(base);
     *lo = reinterpret_cast<uint4*>(base + L::kOpPlane);
   };
 
-  auto conv_tile = [&]() {
+  auto conv_tile = [&](bool after_pass2) {
 #pragma unroll 1
     for (int c = 0; c < NCH; ++c, ++n) {
       uint8_t* box = wait_full(n);
@@ -2631,7 +2657,7 @@ gdn_tc_bwd_dx2_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_co
       float v[8] = {fabsf(a.x), fabsf(a.y), fabsf(a.z), fabsf(a.w), fabsf(b.x), fabsf(b.y), fabsf(b.z), fabsf(b.w)};
       uint4 hi, lo, *ph, *pl;
       split8(v, &hi, &lo);
-      operand_rows(&ph, &pl);
+      operand_rows(&ph, &pl, after_pass2 && c < 2);  // chunks 0, 1 reuse the buffers of the tile's last two q chunks
       *ph = hi;
       *pl = lo;
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -2641,7 +2667,7 @@ gdn_tc_bwd_dx2_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_co
     }
   };
 
-  if (first < n_tiles) conv_tile();
+  if (first < n_tiles) conv_tile(false);
   int t = 0;
   for (long long tile = first; tile < n_tiles; tile += gridDim.x, ++t) {
     const bool has_next = tile + gridDim.x < n_tiles;
@@ -2649,13 +2675,12 @@ gdn_tc_bwd_dx2_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_co
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     // ---- pass 2: q = dL/dn -> output box + q planes; the direct term and sign(x) go back into n's columns ----
 #pragma unroll 1
-    for (int c = 0; c < NCH; ++c, n += 3) {
+    for (int c = 0; c < NCH; ++c, n += 2) {
       const uint32_t col = tmem_n + lane_sel + (uint32_t)(c * 32 + h * 8);
       uint32_t nacc[8];
       tmem_load<8>(col, nacc);
       uint8_t* bx = wait_full(n);
       uint8_t* bg = wait_full(n + 1);
-      uint8_t* bq = wait_full(n + 2);
       const float4 x0 = *chunk_at(bx, r, 2 * h), x1 = *chunk_at(bx, r, 2 * h + 1);
       const float4 g0 = *chunk_at(bg, r, 2 * h), g1 = *chunk_at(bg, r, 2 * h + 1);
       const float4 bv0 = *reinterpret_cast<const float4*>(beta_s + c * 32 + h * 8);      // same address in every lane
@@ -2681,19 +2706,17 @@ gdn_tc_bwd_dx2_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_co
         const uint32_t code = (xs[e] > 0.f) ? 1u : ((xs[e] < 0.f) ? 2u : 0u);
         dbits[e] = (__float_as_uint(direct) & ~3u) | code;
       }
-      *chunk_at(bq, r, 2 * h) = make_float4(q[0], q[1], q[2], q[3]);
-      *chunk_at(bq, r, 2 * h + 1) = make_float4(q[4], q[5], q[6], q[7]);
       uint4 hi, lo, *qh, *ql;
       split8(q, &hi, &lo);
-      operand_rows(&qh, &ql);
+      operand_rows(&qh, &ql, c >= 2);
       *qh = hi;
       *ql = lo;
       tmem_store8(col, dbits);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // q planes -> MMA, q box -> TMA store
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // q planes -> MMA and -> bulk store
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       asm volatile("bar.arrive %0, %1;" ::"r"(4 + (int)(m & 1u)), "n"(kD2Sync) : "memory");  // (also releases the x and g boxes)
       __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar(L::kBarY + slot_of(n + 2))) : "memory");
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar(L::kBarQready + (m & 1u))) : "memory");
       ++m;
     }
     // ---- pass 3: dx = direct + sign(x) * dp, from TMEM only ----
@@ -2721,11 +2744,269 @@ gdn_tc_bwd_dx2_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_co
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar(L::kBarY + slot_of(n))) : "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // TMEM reads precede the next tile's MMAs
-    if (has_next) conv_tile();
+    if (has_next) conv_tile(true);
   }
   }  // compute warps
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (tid < 32) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "n"(512));
+  }
+}
+
+// =============================================================================================
+// Backward, C = 192, second kernel: dgamma += p^T q, dbeta += column sums of q, box-fed.
+//
+// Per 128-pixel tile: the tile's q hi / lo planes arrive from the workspace with ONE bulk copy (96 KB, written in
+// exactly this layout by gdn_tc_bwd_dx2_kernel); x arrives as six TMA boxes through a two-slot ring and is converted
+// into the p = |x| planes by the compute threads (thread (r, h): pixel row r, 8 channels of a box); 48 MMAs
+// (two overlapping M = 128 row blocks [0,128) and [64,192) of p^T, N = 192, K = 128 pixels) accumulate into TMEM.
+// The planes are single buffered (4 x 48 KB): the next tile's conversion starts when the MMAs have completed, its q
+// planes and first two x boxes are already on their way.  dbeta comes from the planes (q = hi + lo to 2^-17).
+// The accumulator is flushed every kDgFlush tiles (CTAs take turns), transposed through the dead p planes one row
+// block at a time into coalesced L2 adds.
+// =============================================================================================
+constexpr int kG2Compute = 512;
+constexpr int kG2Threads = kG2Compute + 64;   // + MMA-issue and copy warps
+constexpr int kG2Sync = kG2Compute + 32;
+
+struct BwdDg2Smem {
+  static constexpr int C = 192;
+  static constexpr int kPlane = (C / 8) * kDKg;          // 49 152: one whole-K plane, dense groups
+  static constexpr int kOffRing = 0;                     // [2] x boxes
+  static constexpr int kOffPh = kOffRing + 2 * kF4Box;
+  static constexpr int kOffPl = kOffPh + kPlane;
+  static constexpr int kOffQh = kOffPl + kPlane;         // q hi, lo contiguous: one bulk copy per tile
+  static constexpr int kOffQl = kOffQh + kPlane;
+  static constexpr int kOffDbeta = kOffQl + kPlane;
+  static constexpr int kOffBar = kOffDbeta + C * 4;
+  // mbarriers: full[2], empty[2], qfull, qdone, m3done; then the TMEM slot
+  static constexpr int kBarFull = 0, kBarEmpty = 2, kBarQfull = 4, kBarQdone = 5, kBarM3 = 6, kNumBars = 7;
+  static constexpr int kBytes = kOffBar + kNumBars * 8 + 16;
+  static_assert(kBytes <= 232448, "shared memory budget");
+  static_assert(2 * kPlane >= kTileM * C * 4, "flush staging of one row block fits in the p planes");
+};
+
+__global__ void __launch_bounds__(kG2Threads, 1)
+gdn_tc_bwd_dgamma2_kernel(const __grid_constant__ CUtensorMap x_map, const float* __restrict__ x,
+                          const uint8_t* __restrict__ q_planes, float* __restrict__ part_g, float* __restrict__ part_b,
+                          long long n_pix) {
+  using L = BwdDg2Smem;
+  constexpr int C = L::C, NCH = C / 32;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float* dbeta_s = reinterpret_cast<float*>(smem + L::kOffDbeta);
+  uint64_t* mbars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffBar + L::kNumBars * 8);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r = tid & 127, h = (tid >> 7) & 3, gwarp = warp & 3;
+  auto bar = [&](int i) { return smem_u32(mbars + i); };
+  for (int i = tid; i < C; i += kG2Threads) dbeta_s[i] = 0.f;
+  if (tid == 0) {
+    for (int i = 0; i < L::kNumBars; ++i) {
+      const int count = (i == L::kBarQdone) ? kG2Compute / 32 : 1;
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar(i)), "r"(count));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_a = *tmem_slot, tmem_b = tmem_a + C;  // rows j in [0,128) | rows j in [64,192)
+  const uint32_t lane_sel = (uint32_t)(gwarp * 32) << 16;
+  const long long n_tiles = (n_pix + kTileM - 1) / kTileM;
+  const long long first = blockIdx.x;
+  const int fphase = (int)(blockIdx.x % kDgFlush);
+  constexpr int W0 = kG2Compute / 32;
+
+  if (warp == W0 + 1) {
+    // ---------------------------------- copy warp: q planes and x boxes ----------------------------------
+    if (lane == 0) {
+      uint32_t n = 0;
+      int t = 0;
+      for (long long tile = first; tile < n_tiles; tile += gridDim.x, ++t) {
+        const long long next = tile + gridDim.x;
+        if (next < n_tiles) {  // the next tile of this CTA -> L2
+          const long long p0 = next * kTileM;
+          const long long rows = min((long long)kTileM, n_pix - p0);
+          asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(x + p0 * C),
+                       "r"((uint32_t)(rows * C * 4)), "l"(kEvictLast)
+                       : "memory");
+          asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(q_planes + (size_t)next * (2 * L::kPlane)),
+                       "n"(2 * L::kPlane), "l"(kEvictLast)
+                       : "memory");
+        }
+        if (t > 0) {  // the q planes are free once the previous tile's MMAs and dbeta reads are done
+          if (!mbar_wait(bar(L::kBarM3), (uint32_t)(t - 1) & 1u)) __trap();
+          if (!mbar_wait(bar(L::kBarQdone), (uint32_t)(t - 1) & 1u)) __trap();
+        }
+        const uint32_t qfull = bar(L::kBarQfull);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(qfull), "n"(2 * L::kPlane) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                         smem_u32(smem + L::kOffQh)),
+                     "l"(q_planes + (size_t)tile * (2 * L::kPlane)), "n"(2 * L::kPlane), "r"(qfull), "l"(kEvictFirst)
+                     : "memory");
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c, ++n) {
+          const uint32_t slot = n & 1u, round = n >> 1;
+          if (round > 0) {
+            if (!mbar_wait(bar(L::kBarEmpty + slot), (round - 1u) & 1u)) __trap();
+          }
+          const uint32_t full = bar(L::kBarFull + slot);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "n"(kF4Box) : "memory");
+          asm volatile(
+              "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
+                  smem_u32(smem + L::kOffRing + slot * kF4Box)),
+              "l"(&x_map), "r"(c * 32), "r"((int)(tile * kTileM)), "r"(full), "l"(kEvictFirst)
+              : "memory");
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == W0) {
+    // ------------------------------- MMA-issue warp -------------------------------
+    constexpr uint32_t kIdesc = umma_idesc(kTileM, C) | (1u << 15) | (1u << 16);  // A = p^T, B = q, both MN-major views
+    const uint32_t p_hi = smem_u32(smem + L::kOffPh), p_lo = smem_u32(smem + L::kOffPl);
+    const uint32_t q_hi = smem_u32(smem + L::kOffQh), q_lo = smem_u32(smem + L::kOffQl);
+    uint32_t n = 0;
+    int t = 0;
+    for (long long tile = first; tile < n_tiles; tile += gridDim.x, ++t) {
+#pragma unroll 1
+      for (int c = 0; c < NCH; ++c, ++n) {
+        asm volatile("bar.sync %0, %1;" ::"r"(2 + (c & 1)), "n"(kG2Sync) : "memory");  // p planes of chunk c are written
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar(L::kBarEmpty + (n & 1u))) : "memory");
+        __syncwarp();
+      }
+      if (lane == 0) {
+        if (!mbar_wait(bar(L::kBarQfull), (uint32_t)t & 1u)) __trap();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const bool restart = (t == 0) || (((t + fphase) % kDgFlush) == 0);
+#pragma unroll 1
+        for (int blk = 0; blk < 2; ++blk) {
+          const uint32_t moff = (uint32_t)(blk * 8) * kDKg;  // second block starts at channel 64 = m group 8
+          const uint32_t td = blk ? tmem_b : tmem_a;
+#pragma unroll
+          for (int s = 0; s < kTileM / 16; ++s) {
+            const uint32_t koff = (uint32_t)(s * 16) * 16u;
+            const uint64_t dah = umma_desc(p_hi + moff + koff, 128, kDKg);
+            const uint64_t dal = umma_desc(p_lo + moff + koff, 128, kDKg);
+            const uint64_t dbh = umma_desc(q_hi + koff, 128, kDKg);
+            const uint64_t dbl = umma_desc(q_lo + koff, 128, kDKg);
+            umma_bf16(td, dah, dbh, kIdesc, (restart && s == 0) ? 0u : 1u);
+            umma_bf16(td, dal, dbh, kIdesc, 1u);
+            umma_bf16(td, dah, dbl, kIdesc, 1u);
+          }
+        }
+        umma_commit(bar(L::kBarM3));
+      }
+      __syncwarp();
+    }
+  } else if (warp < W0) {
+  // --------------------------------- compute warps ---------------------------------
+  uint32_t n = 0;
+  float dbeta_acc[NCH][8];  // channels 32 c + 8 h + e, summed over this thread's rows
+#pragma unroll
+  for (int c = 0; c < NCH; ++c)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dbeta_acc[c][e] = 0.f;
+  auto chunk_at = [](uint8_t* box, int row, int j) { return reinterpret_cast<float4*>(box + row * 128 + ((j ^ (row & 7)) << 4)); };
+  bool flushed = false;
+  // one row block of the accumulator (lane r = row, 48 columns per thread) -> swizzled [128][192] fp32 staging in
+  // the dead p planes -> 768 contiguous bytes per row added to the CTA's partial
+  auto flush_dgamma = [&]() {
+    uint8_t* stage = smem + L::kOffPh;
+#pragma unroll 1
+    for (int blk = 0; blk < 2; ++blk) {
+#pragma unroll
+      for (int cb = 0; cb < 3; ++cb) {
+        uint32_t a[16];
+        tmem_load<16>((blk ? tmem_b : tmem_a) + lane_sel + (uint32_t)(h * 48 + cb * 16), a);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<uint4*>(stage + r * 768 + (((h * 12 + cb * 4 + i) ^ (r & 7)) << 4)) =
+              make_uint4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kG2Compute) : "memory");
+      float* pg = part_g + (long long)blockIdx.x * C * C + (long long)(blk * 64) * C;  // block b: lane r = channel 64 + r
+#pragma unroll 1
+      for (int it = 0; it < (kTileM * C / 4) / kG2Compute; ++it) {
+        const int item = it * kG2Compute + tid, row = item / 48, u = item % 48;
+        if (blk && row < 64) continue;  // rows [64,128) of block b repeat block a's
+        const uint4 v = *reinterpret_cast<const uint4*>(stage + row * 768 + ((u ^ (row & 7)) << 4));
+        float* dst = pg + row * C + u * 4;
+        if (!flushed)
+          asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+        else
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kG2Compute) : "memory");  // the staging is rewritten (next block / next tile's p)
+    }
+    flushed = true;
+  };
+
+  int t = 0;
+  for (long long tile = first; tile < n_tiles; tile += gridDim.x, ++t) {
+    if (t > 0) {  // the previous tile's MMAs have completed: the p planes are dead, the accumulator is up to date
+      if (!mbar_wait(bar(L::kBarM3), (uint32_t)(t - 1) & 1u)) __trap();
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (((t - 1 + fphase) % kDgFlush) == kDgFlush - 1) flush_dgamma();
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    // p = |x| -> hi / lo planes, chunk by chunk
+#pragma unroll 1
+    for (int c = 0; c < NCH; ++c, ++n) {
+      const uint32_t slot = n & 1u, round = n >> 1;
+      uint8_t* box = smem + L::kOffRing + slot * kF4Box;
+      if (!mbar_wait(bar(L::kBarFull + slot), round & 1u)) __trap();
+      const float4 a = *chunk_at(box, r, 2 * h), b = *chunk_at(box, r, 2 * h + 1);
+      float v[8] = {fabsf(a.x), fabsf(a.y), fabsf(a.z), fabsf(a.w), fabsf(b.x), fabsf(b.y), fabsf(b.z), fabsf(b.w)};
+      uint4 hi, lo;
+      split8(v, &hi, &lo);
+      *reinterpret_cast<uint4*>(smem + L::kOffPh + (4 * c + h) * kDKg + r * 16) = hi;
+      *reinterpret_cast<uint4*>(smem + L::kOffPl + (4 * c + h) * kDKg + r * 16) = lo;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("bar.arrive %0, %1;" ::"r"(2 + (c & 1)), "n"(kG2Sync) : "memory");  // (also releases the box, see issue warp)
+    }
+    // dbeta from the q planes (q = hi + lo to 2^-17 relative)
+    if (!mbar_wait(bar(L::kBarQfull), (uint32_t)t & 1u)) __trap();
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const uint4 qh = *reinterpret_cast<const uint4*>(smem + L::kOffQh + (4 * c + h) * kDKg + r * 16);
+      const uint4 ql = *reinterpret_cast<const uint4*>(smem + L::kOffQl + (4 * c + h) * kDKg + r * 16);
+      const uint32_t wh[4] = {qh.x, qh.y, qh.z, qh.w}, wl[4] = {ql.x, ql.y, ql.z, ql.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        dbeta_acc[c][2 * i] += __uint_as_float(wh[i] << 16) + __uint_as_float(wl[i] << 16);
+        dbeta_acc[c][2 * i + 1] += __uint_as_float(wh[i] & 0xFFFF0000u) + __uint_as_float(wl[i] & 0xFFFF0000u);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar(L::kBarQdone)) : "memory");
+  }
+  if (t > 0) {
+    if (!mbar_wait(bar(L::kBarM3), (uint32_t)(t - 1) & 1u)) __trap();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    flush_dgamma();  // the tiles since the last restart (a turn that falls on the last tile is flushed here as well)
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float v = dbeta_acc[c][e];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        if (lane == 0) atomicAdd(dbeta_s + c * 32 + h * 8 + e, v);
+      }
+  }
+  }  // compute warps
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  for (int i = tid; i < C; i += kG2Threads) part_b[(long long)blockIdx.x * C + i] = dbeta_s[i];
   if (tid < 32) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "n"(512));
   }
@@ -2758,19 +3039,22 @@ int launch_tc_bwd192(const float* x, const float* gamma, const float* beta, cons
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long n_tiles = (n_pix + kTileM - 1) / kTileM;
   const int grid = (int)std::min<long long>(n_tiles, std::min(sms, 148));
-  const char* v1 = getenv("TFCB_GDN_BWD_V1");  // A/B timing: the register-fed dx kernel
+  const char* v1 = getenv("TFCB_GDN_BWD_V1");  // A/B timing: the register-fed kernels
   if (FAST && n_pix < (1ll << 31) && !(v1 && v1[0] == '1')) {
+    // box-fed pair: q travels as bf16 hi / lo planes ([tile][2][24][128][8], 4 B/element; the workspace is sized in
+    // whole tiles, tfcb_gdn_backward_workspace_bytes)
     using L2 = BwdDx2Smem;
-    CUtensorMap x_map, g_map, dx_map, q_map;
+    using L3 = BwdDg2Smem;
+    CUtensorMap x_map, g_map, dx_map;
     __nv_bfloat16* planes4 = nullptr;
     int rc = make_tensor_map_2d(&x_map, x, n_pix, C, kTileM, 32, true);
     if (rc == TFCB_OK) rc = make_tensor_map_2d(&g_map, dy, n_pix, C, kTileM, 32, true);
     if (rc == TFCB_OK) rc = make_tensor_map_2d(&dx_map, dx, n_pix, C, kTileM, 32, true);
-    if (rc == TFCB_OK) rc = make_tensor_map_2d(&q_map, q_ws, n_pix, C, kTileM, 32, true);
     if (rc == TFCB_OK) rc = dev_alloc((void**)&planes4, (size_t)4 * C * C * sizeof(__nv_bfloat16), s);
-    if (rc == TFCB_OK && cudaFuncSetAttribute(gdn_tc_bwd_dx2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L2::kBytes) != cudaSuccess) {
+    if (rc == TFCB_OK && (cudaFuncSetAttribute(gdn_tc_bwd_dx2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L2::kBytes) != cudaSuccess ||
+                          cudaFuncSetAttribute(gdn_tc_bwd_dgamma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L3::kBytes) != cudaSuccess)) {
       (void)cudaGetLastError();
-      rc = fail(TFCB_CUDA_ERROR, "cannot reserve %d bytes of shared memory", L2::kBytes);
+      rc = fail(TFCB_CUDA_ERROR, "cannot reserve shared memory for the C=192 backward");
     }
     if (rc != TFCB_OK) {
       dev_free(planes4, s);
@@ -2779,13 +3063,21 @@ int launch_tc_bwd192(const float* x, const float* gamma, const float* beta, cons
     }
     gdn_tc_prep2_kernel<<<((C / 8) * C + 255) / 256, 256, 0, s>>>(gamma, C, planes4);
     TFCB_LAUNCHED();
-    gdn_tc_bwd_dx2_kernel<<<grid, kD2Threads, L2::kBytes, s>>>(x_map, g_map, dx_map, q_map, x, dy, planes4, beta, n_pix, f.inverse);
+    gdn_tc_bwd_dx2_kernel<<<grid, kD2Threads, L2::kBytes, s>>>(x_map, g_map, dx_map, x, dy, planes4, beta,
+                                                              reinterpret_cast<uint8_t*>(q_ws), n_pix, f.inverse);
     TFCB_LAUNCHED();
+    gdn_tc_bwd_dgamma2_kernel<<<grid, kG2Threads, L3::kBytes, s>>>(x_map, x, reinterpret_cast<const uint8_t*>(q_ws), part_g,
+                                                                   part_b, n_pix);
+    TFCB_LAUNCHED();
+    cudaError_t e2 = cudaGetLastError();
     dev_free(planes4, s);
-  } else {
-    gdn_tc_bwd_dx_kernel<C, FAST><<<grid, kBwdThreads, Bwd2Smem<C>::kBytes, s>>>(x, dy, planes, beta, dx, q_ws, n_pix, f);
-    TFCB_LAUNCHED();
+    dev_free(planes, s);
+    if (e2 != cudaSuccess) return fail(TFCB_CUDA_ERROR, "GDN tensor-core backward (C=192) launch failed: %s", cudaGetErrorString(e2));
+    *n_parts = grid;
+    return TFCB_OK;
   }
+  gdn_tc_bwd_dx_kernel<C, FAST><<<grid, kBwdThreads, Bwd2Smem<C>::kBytes, s>>>(x, dy, planes, beta, dx, q_ws, n_pix, f);
+  TFCB_LAUNCHED();
   gdn_tc_bwd_dgamma_kernel<C, FAST><<<grid, kBwdThreads, Bwd3Smem<C>::kBytes, s>>>(x, q_ws, part_g, part_b, n_pix, f);
   TFCB_LAUNCHED();
   cudaError_t e = cudaGetLastError();
