@@ -2758,13 +2758,13 @@ gdn_tc_bwd_dx2_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_co
 // Backward, C = 192, second kernel: dgamma += p^T q, dbeta += column sums of q, box-fed.
 //
 // Per 128-pixel tile: the tile's q hi / lo planes arrive from the workspace with ONE bulk copy (96 KB, written in
-// exactly this layout by gdn_tc_bwd_dx2_kernel); x arrives as six TMA boxes through a two-slot ring and is converted
-// into the p = |x| planes by the compute threads (thread (r, h): pixel row r, 8 channels of a box); 48 MMAs
-// (two overlapping M = 128 row blocks [0,128) and [64,192) of p^T, N = 192, K = 128 pixels) accumulate into TMEM.
-// The planes are single buffered (4 x 48 KB): the next tile's conversion starts when the MMAs have completed, its q
-// planes and first two x boxes are already on their way.  dbeta comes from the planes (q = hi + lo to 2^-17).
-// The accumulator is flushed every kDgFlush tiles (CTAs take turns), transposed through the dead p planes one row
-// block at a time into coalesced L2 adds.
+// exactly this layout by gdn_tc_bwd_dx2_kernel); the x tile (six TMA boxes, 96 KB) lands IN THE MEMORY OF THE p PLANES
+// (same size), every compute thread (r, h) takes its 48 values into registers, and after a barrier the p = |x| hi / lo
+// planes are written over the boxes; 48 MMAs (two overlapping M = 128 row blocks [0,128) and [64,192) of p^T, N = 192,
+// K = 128 pixels) accumulate into TMEM.  Nothing is double buffered (4 x 48 KB of planes): a tile costs one load
+// latency + the conversion + the MMAs.  dbeta comes from the planes (q = hi + lo to 2^-17): warp w sums 8-channel
+// groups w and w + 16, lane = pixel row mod 32.  The accumulator is flushed every kDgFlush tiles (CTAs take turns),
+// transposed through the dead p planes one row block at a time into coalesced L2 adds.
 // =============================================================================================
 constexpr int kG2Compute = 512;
 constexpr int kG2Threads = kG2Compute + 64;   // + MMA-issue and copy warps
@@ -2773,18 +2773,17 @@ constexpr int kG2Sync = kG2Compute + 32;
 struct BwdDg2Smem {
   static constexpr int C = 192;
   static constexpr int kPlane = (C / 8) * kDKg;          // 49 152: one whole-K plane, dense groups
-  static constexpr int kOffRing = 0;                     // [2] x boxes
-  static constexpr int kOffPh = kOffRing + 2 * kF4Box;
+  static constexpr int kOffPh = 0;                       // p hi, lo: also the landing area of the six x boxes
   static constexpr int kOffPl = kOffPh + kPlane;
   static constexpr int kOffQh = kOffPl + kPlane;         // q hi, lo contiguous: one bulk copy per tile
   static constexpr int kOffQl = kOffQh + kPlane;
   static constexpr int kOffDbeta = kOffQl + kPlane;
   static constexpr int kOffBar = kOffDbeta + C * 4;
-  // mbarriers: full[2], empty[2], qfull, qdone, m3done; then the TMEM slot
-  static constexpr int kBarFull = 0, kBarEmpty = 2, kBarQfull = 4, kBarQdone = 5, kBarM3 = 6, kNumBars = 7;
+  // mbarriers: xfull, pfree, qfull, qdone, m3done; then the TMEM slot
+  static constexpr int kBarXfull = 0, kBarPfree = 1, kBarQfull = 2, kBarQdone = 3, kBarM3 = 4, kNumBars = 5;
   static constexpr int kBytes = kOffBar + kNumBars * 8 + 16;
   static_assert(kBytes <= 232448, "shared memory budget");
-  static_assert(2 * kPlane >= kTileM * C * 4, "flush staging of one row block fits in the p planes");
+  static_assert(2 * kPlane == 6 * kF4Box && 2 * kPlane >= kTileM * C * 4, "x tile / flush staging fit in the p planes");
 };
 
 __global__ void __launch_bounds__(kG2Threads, 1)
@@ -2803,7 +2802,7 @@ gdn_tc_bwd_dgamma2_kernel(const __grid_constant__ CUtensorMap x_map, const float
   for (int i = tid; i < C; i += kG2Threads) dbeta_s[i] = 0.f;
   if (tid == 0) {
     for (int i = 0; i < L::kNumBars; ++i) {
-      const int count = (i == L::kBarQdone) ? kG2Compute / 32 : 1;
+      const int count = (i == L::kBarQdone || i == L::kBarPfree) ? kG2Compute / 32 : 1;
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar(i)), "r"(count));
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -2824,9 +2823,8 @@ gdn_tc_bwd_dgamma2_kernel(const __grid_constant__ CUtensorMap x_map, const float
   constexpr int W0 = kG2Compute / 32;
 
   if (warp == W0 + 1) {
-    // ---------------------------------- copy warp: q planes and x boxes ----------------------------------
+    // ---------------------------------- copy warp: q planes and the x tile ----------------------------------
     if (lane == 0) {
-      uint32_t n = 0;
       int t = 0;
       for (long long tile = first; tile < n_tiles; tile += gridDim.x, ++t) {
         const long long next = tile + gridDim.x;
@@ -2850,20 +2848,17 @@ gdn_tc_bwd_dgamma2_kernel(const __grid_constant__ CUtensorMap x_map, const float
                          smem_u32(smem + L::kOffQh)),
                      "l"(q_planes + (size_t)tile * (2 * L::kPlane)), "n"(2 * L::kPlane), "r"(qfull), "l"(kEvictFirst)
                      : "memory");
+        // the p planes are free once the compute warps say so (previous MMAs done, flush staging consumed)
+        if (!mbar_wait(bar(L::kBarPfree), (uint32_t)t & 1u)) __trap();
+        const uint32_t xfull = bar(L::kBarXfull);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(xfull), "n"(6 * kF4Box) : "memory");
 #pragma unroll 1
-        for (int c = 0; c < NCH; ++c, ++n) {
-          const uint32_t slot = n & 1u, round = n >> 1;
-          if (round > 0) {
-            if (!mbar_wait(bar(L::kBarEmpty + slot), (round - 1u) & 1u)) __trap();
-          }
-          const uint32_t full = bar(L::kBarFull + slot);
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "n"(kF4Box) : "memory");
+        for (int c = 0; c < NCH; ++c)
           asm volatile(
               "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
-                  smem_u32(smem + L::kOffRing + slot * kF4Box)),
-              "l"(&x_map), "r"(c * 32), "r"((int)(tile * kTileM)), "r"(full), "l"(kEvictFirst)
+                  smem_u32(smem + L::kOffPh + c * kF4Box)),
+              "l"(&x_map), "r"(c * 32), "r"((int)(tile * kTileM)), "r"(xfull), "l"(kEvictFirst)
               : "memory");
-        }
       }
     }
     __syncwarp();
@@ -2872,15 +2867,9 @@ gdn_tc_bwd_dgamma2_kernel(const __grid_constant__ CUtensorMap x_map, const float
     constexpr uint32_t kIdesc = umma_idesc(kTileM, C) | (1u << 15) | (1u << 16);  // A = p^T, B = q, both MN-major views
     const uint32_t p_hi = smem_u32(smem + L::kOffPh), p_lo = smem_u32(smem + L::kOffPl);
     const uint32_t q_hi = smem_u32(smem + L::kOffQh), q_lo = smem_u32(smem + L::kOffQl);
-    uint32_t n = 0;
     int t = 0;
     for (long long tile = first; tile < n_tiles; tile += gridDim.x, ++t) {
-#pragma unroll 1
-      for (int c = 0; c < NCH; ++c, ++n) {
-        asm volatile("bar.sync %0, %1;" ::"r"(2 + (c & 1)), "n"(kG2Sync) : "memory");  // p planes of chunk c are written
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar(L::kBarEmpty + (n & 1u))) : "memory");
-        __syncwarp();
-      }
+      asm volatile("bar.sync 2, %0;" ::"n"(kG2Sync) : "memory");  // the p planes are written
       if (lane == 0) {
         if (!mbar_wait(bar(L::kBarQfull), (uint32_t)t & 1u)) __trap();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -2907,12 +2896,11 @@ gdn_tc_bwd_dgamma2_kernel(const __grid_constant__ CUtensorMap x_map, const float
     }
   } else if (warp < W0) {
   // --------------------------------- compute warps ---------------------------------
-  uint32_t n = 0;
-  float dbeta_acc[NCH][8];  // channels 32 c + 8 h + e, summed over this thread's rows
+  float dbeta_acc[2][8];  // 8-channel groups warp and warp + 16, summed over rows lane, lane + 32, ...
 #pragma unroll
-  for (int c = 0; c < NCH; ++c)
+  for (int k = 0; k < 2; ++k)
 #pragma unroll
-    for (int e = 0; e < 8; ++e) dbeta_acc[c][e] = 0.f;
+    for (int e = 0; e < 8; ++e) dbeta_acc[k][e] = 0.f;
   auto chunk_at = [](uint8_t* box, int row, int j) { return reinterpret_cast<float4*>(box + row * 128 + ((j ^ (row & 7)) << 4)); };
   bool flushed = false;
   // one row block of the accumulator (lane r = row, 48 columns per thread) -> swizzled [128][192] fp32 staging in
@@ -2944,7 +2932,7 @@ gdn_tc_bwd_dgamma2_kernel(const __grid_constant__ CUtensorMap x_map, const float
         else
           asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(kG2Compute) : "memory");  // the staging is rewritten (next block / next tile's p)
+      asm volatile("bar.sync 1, %0;" ::"n"(kG2Compute) : "memory");  // the staging is rewritten (next block / the x tile)
     }
     flushed = true;
   };
@@ -2957,33 +2945,49 @@ gdn_tc_bwd_dgamma2_kernel(const __grid_constant__ CUtensorMap x_map, const float
       if (((t - 1 + fphase) % kDgFlush) == kDgFlush - 1) flush_dgamma();
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
-    // p = |x| -> hi / lo planes, chunk by chunk
-#pragma unroll 1
-    for (int c = 0; c < NCH; ++c, ++n) {
-      const uint32_t slot = n & 1u, round = n >> 1;
-      uint8_t* box = smem + L::kOffRing + slot * kF4Box;
-      if (!mbar_wait(bar(L::kBarFull + slot), round & 1u)) __trap();
-      const float4 a = *chunk_at(box, r, 2 * h), b = *chunk_at(box, r, 2 * h + 1);
-      float v[8] = {fabsf(a.x), fabsf(a.y), fabsf(a.z), fabsf(a.w), fabsf(b.x), fabsf(b.y), fabsf(b.z), fabsf(b.w)};
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic accesses of the p planes precede the TMA writes
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar(L::kBarPfree)) : "memory");
+    // the x tile has landed in the p planes: take this thread's 48 values, then overwrite the boxes with the planes
+    if (!mbar_wait(bar(L::kBarXfull), (uint32_t)t & 1u)) __trap();
+    float4 xa[NCH], xb[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      uint8_t* box = smem + L::kOffPh + c * kF4Box;
+      xa[c] = *chunk_at(box, r, 2 * h);
+      xb[c] = *chunk_at(box, r, 2 * h + 1);
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kG2Compute) : "memory");  // every thread holds its values
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      float v[8] = {fabsf(xa[c].x), fabsf(xa[c].y), fabsf(xa[c].z), fabsf(xa[c].w),
+                    fabsf(xb[c].x), fabsf(xb[c].y), fabsf(xb[c].z), fabsf(xb[c].w)};
       uint4 hi, lo;
       split8(v, &hi, &lo);
       *reinterpret_cast<uint4*>(smem + L::kOffPh + (4 * c + h) * kDKg + r * 16) = hi;
       *reinterpret_cast<uint4*>(smem + L::kOffPl + (4 * c + h) * kDKg + r * 16) = lo;
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      asm volatile("bar.arrive %0, %1;" ::"r"(2 + (c & 1)), "n"(kG2Sync) : "memory");  // (also releases the box, see issue warp)
     }
-    // dbeta from the q planes (q = hi + lo to 2^-17 relative)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    asm volatile("bar.arrive 2, %0;" ::"n"(kG2Sync) : "memory");
+    // dbeta from the q planes (q = hi + lo to 2^-17 relative): groups warp and warp + 16, rows lane + 32 k
     if (!mbar_wait(bar(L::kBarQfull), (uint32_t)t & 1u)) __trap();
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      const uint4 qh = *reinterpret_cast<const uint4*>(smem + L::kOffQh + (4 * c + h) * kDKg + r * 16);
-      const uint4 ql = *reinterpret_cast<const uint4*>(smem + L::kOffQl + (4 * c + h) * kDKg + r * 16);
-      const uint32_t wh[4] = {qh.x, qh.y, qh.z, qh.w}, wl[4] = {ql.x, ql.y, ql.z, ql.w};
+    for (int k = 0; k < 2; ++k) {
+      const int grp = warp + 16 * k;
+      if (grp < C / 8) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        dbeta_acc[c][2 * i] += __uint_as_float(wh[i] << 16) + __uint_as_float(wl[i] << 16);
-        dbeta_acc[c][2 * i + 1] += __uint_as_float(wh[i] & 0xFFFF0000u) + __uint_as_float(wl[i] & 0xFFFF0000u);
+        for (int rq = 0; rq < 4; ++rq) {
+          const int row = lane + 32 * rq;
+          const uint4 qh = *reinterpret_cast<const uint4*>(smem + L::kOffQh + grp * kDKg + row * 16);
+          const uint4 ql = *reinterpret_cast<const uint4*>(smem + L::kOffQl + grp * kDKg + row * 16);
+          const uint32_t wh[4] = {qh.x, qh.y, qh.z, qh.w}, wl[4] = {ql.x, ql.y, ql.z, ql.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            dbeta_acc[k][2 * i] += __uint_as_float(wh[i] << 16) + __uint_as_float(wl[i] << 16);
+            dbeta_acc[k][2 * i + 1] += __uint_as_float(wh[i] & 0xFFFF0000u) + __uint_as_float(wl[i] & 0xFFFF0000u);
+          }
+        }
       }
     }
     __syncwarp();
@@ -2994,13 +2998,14 @@ gdn_tc_bwd_dgamma2_kernel(const __grid_constant__ CUtensorMap x_map, const float
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     flush_dgamma();  // the tiles since the last restart (a turn that falls on the last tile is flushed here as well)
 #pragma unroll
-    for (int c = 0; c < NCH; ++c)
+    for (int k = 0; k < 2; ++k)
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        float v = dbeta_acc[c][e];
+        float v = dbeta_acc[k][e];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-        if (lane == 0) atomicAdd(dbeta_s + c * 32 + h * 8 + e, v);
+        const int grp = warp + 16 * k;
+        if (lane == 0 && grp < C / 8) dbeta_s[grp * 8 + e] = v;  // one warp per group: no atomics
       }
   }
   }  // compute warps
