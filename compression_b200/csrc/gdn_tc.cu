@@ -2343,15 +2343,17 @@ int launch_tc_bwd3(const float* x, const float* gamma, const float* beta, const 
 //             the direct term g / n (IGDN: g * n) goes back into n's columns with sign(x) in the two low mantissa bits
 //   pass3(t)  dx = direct + sign(x) * dp, from TMEM only -> output box -> TMA store
 //
-// gamma and gamma^T arrive as K chunks (24 KB hi + lo, double buffered) from a "gamma" warp; chunk m of the stream
-// uses operand buffer and gamma buffer m % 2, so ONE commit per chunk frees both (a q chunk's buffer additionally
-// waits for its bulk store to have read it).  A ring of seven 16 KB boxes serves every box request in program order.
+// gamma's hi plane is resident (72 KB; MMA2 reads it through the MN-major view); the lo planes of gamma (MMA1) and
+// gamma^T (MMA2) arrive as 12 KB K chunks, double buffered, from a "gamma" warp, and each chunk's two hi products are
+// issued before the one that needs the streamed chunk.  Chunk m of the stream uses operand buffer and gamma buffer
+// m % 2, so ONE commit per chunk frees both (a q chunk's buffer additionally waits for its bulk store to have read
+// it).  A ring of six 16 KB boxes serves every box request in program order.
 // TMEM: n | dp (2 x 192 columns).
 // =============================================================================================
 constexpr int kD2Compute = 512;
 constexpr int kD2Threads = kD2Compute + 128;   // + MMA-issue, box-copy, gamma and store warps
 constexpr int kD2Sync = kD2Compute + 32;
-constexpr int kD2Slots = 7;
+constexpr int kD2Slots = 6;
 constexpr int kDKg = kTileM * 16;  // dense group stride of the operand planes (row-per-lane stores need no padding)
 
 struct BwdDx2Smem {
@@ -2359,15 +2361,16 @@ struct BwdDx2Smem {
   static constexpr int kGChunk = 4 * C * 16;                      // one 32-channel K chunk of one gamma plane (12 KB)
   static constexpr int kOpPlane = 4 * kDKg;                       // hi or lo plane of one 32-channel operand chunk (8 KB)
   static constexpr int kOffRing = 0;                              // [7] boxes (1024-byte aligned: swizzle atom)
-  static constexpr int kOffG = kOffRing + kD2Slots * kF4Box;      // [2 buffers][hi, lo] gamma K chunks
-  static constexpr int kOffOp = kOffG + 4 * kGChunk;              // [2 buffers][hi, lo] operand (p or q) chunks
+  static constexpr int kOffGh = kOffRing + kD2Slots * kF4Box;     // gamma hi plane [j / 8][i][8], resident
+  static constexpr int kOffG = kOffGh + C * C * 2;                // [2 buffers] lo K chunks of gamma / gamma^T
+  static constexpr int kOffOp = kOffG + 2 * kGChunk;              // [2 buffers][hi, lo] operand (p or q) chunks
   static constexpr int kOffBeta = kOffOp + 4 * kOpPlane;
   static constexpr int kOffBar = kOffBeta + C * 4;
   // mbarriers: full[7], empty[7], yready[7], gfull[2], cfree[2], nfull, dpfull, qready[2], sfree[2]; then the TMEM slot
   static constexpr int kBarFull = 0, kBarEmpty = 7, kBarY = 14, kBarGfull = 21, kBarCfree = 23, kBarN = 25, kBarDp = 26,
                        kBarQready = 27, kBarSfree = 29, kNumBars = 31;
   static constexpr int kBytes = kOffBar + kNumBars * 8 + 16;
-  static_assert(kOffG % 128 == 0 && kOffOp % 16 == 0 && kOffBar % 8 == 0, "alignment");
+  static_assert(kOffGh % 128 == 0 && kOffG % 128 == 0 && kOffOp % 16 == 0 && kOffBar % 8 == 0, "alignment");
   static_assert(kBytes <= 232448, "shared memory budget");
 };
 
@@ -2386,6 +2389,11 @@ gdn_tc_bwd_dx2_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_co
   const int r = tid & 127, h = (tid >> 7) & 3, gwarp = warp & 3;  // compute thread (r, h): pixel row r, channel octet h of a box
   auto bar = [&](int i) { return smem_u32(mbars + i); };
   for (int i = tid; i < C; i += kD2Threads) beta_s[i] = beta[i];
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(planes);  // first plane: gamma hi, [j / 8][i][8]
+    uint4* dst = reinterpret_cast<uint4*>(smem + L::kOffGh);
+    for (int i = tid; i < C * C * 2 / 16; i += kD2Threads) dst[i] = src[i];
+  }
   if (tid == 0) {
     for (int i = 0; i < L::kNumBars; ++i) {
       // y ready / q ready: one arrival per compute warp
@@ -2490,15 +2498,11 @@ gdn_tc_bwd_dx2_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_co
           if (!mbar_wait(bar(L::kBarCfree + buf), ((m >> 1) - 1u) & 1u)) __trap();
         }
         const uint32_t gfull = bar(L::kBarGfull + buf);
-        const uint32_t dst = smem_u32(smem + L::kOffG + buf * 2 * L::kGChunk);
-        const uint8_t* src = gp + (size_t)(2 * transposed) * kPlaneBytes + (size_t)c * L::kGChunk;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gfull), "n"(2 * L::kGChunk) : "memory");
+        const uint32_t dst = smem_u32(smem + L::kOffG + buf * L::kGChunk);
+        const uint8_t* src = gp + (size_t)(2 * transposed + 1) * kPlaneBytes + (size_t)c * L::kGChunk;  // the lo plane
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gfull), "n"(L::kGChunk) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
                      "l"(src), "n"(L::kGChunk), "r"(gfull), "l"(kEvictLast)
-                     : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-                         dst + L::kGChunk),
-                     "l"(src + kPlaneBytes), "n"(L::kGChunk), "r"(gfull), "l"(kEvictLast)
                      : "memory");
         ++m;
       };
@@ -2568,20 +2572,32 @@ gdn_tc_bwd_dx2_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_co
     // ------------------------------- MMA-issue warp: MMA1, MMA2 (K-chunked, everything streamed) -------------------
     constexpr uint32_t kIdesc = umma_idesc(kTileM, C);  // A, B both K-major
     uint32_t n = 0, m = 0;
-    auto chunk_mmas = [&](uint32_t acc, bool first_chunk) {  // six MMAs of chunk m: operand buffer x gamma buffer
+    constexpr uint32_t kIdescT = umma_idesc(kTileM, C) | (1u << 16);  // B = resident gamma hi read transposed (MMA2)
+    const uint32_t gh = smem_u32(smem + L::kOffGh);
+    // Six MMAs of chunk m (K chunk c of the tile): the four that only need the resident hi plane first, then the two
+    // against the streamed lo chunk.  MMA1: B = gamma[j in chunk, :] (K-major); MMA2: B = gamma[:, i in chunk]^T, the
+    // same plane through the MN-major view (hi) / the gamma^T lo chunk (K-major).
+    auto chunk_mmas = [&](uint32_t acc, int c, bool transposed) {
       const uint32_t buf = m & 1u;
-      if (!mbar_wait(bar(L::kBarGfull + buf), (m >> 1) & 1u)) __trap();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t a_hi = smem_u32(smem + L::kOffOp + buf * 2 * L::kOpPlane), a_lo = a_hi + L::kOpPlane;
-      const uint32_t g_hi = smem_u32(smem + L::kOffG + buf * 2 * L::kGChunk), g_lo = g_hi + L::kGChunk;
+      const uint32_t g_lo = smem_u32(smem + L::kOffG + buf * L::kGChunk);
 #pragma unroll
       for (int s2 = 0; s2 < 2; ++s2) {
         const uint64_t dah = umma_desc(a_hi + (uint32_t)(2 * s2) * kDKg, kDKg, 128);
         const uint64_t dal = umma_desc(a_lo + (uint32_t)(2 * s2) * kDKg, kDKg, 128);
-        const uint64_t dbh = umma_desc(g_hi + (uint32_t)(2 * s2) * (C * 16), C * 16, 128);
+        const uint64_t dbh = transposed ? umma_desc(gh + (uint32_t)(c * 32 + s2 * 16) * 16u, 128, C * 16)
+                                        : umma_desc(gh + (uint32_t)(c * 4 + 2 * s2) * (C * 16), C * 16, 128);
+        const uint32_t idesc = transposed ? kIdescT : kIdesc;
+        umma_bf16(acc, dah, dbh, idesc, (c == 0 && s2 == 0) ? 0u : 1u);
+        umma_bf16(acc, dal, dbh, idesc, 1u);
+      }
+      if (!mbar_wait(bar(L::kBarGfull + buf), (m >> 1) & 1u)) __trap();
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2) {
+        const uint64_t dah = umma_desc(a_hi + (uint32_t)(2 * s2) * kDKg, kDKg, 128);
         const uint64_t dbl = umma_desc(g_lo + (uint32_t)(2 * s2) * (C * 16), C * 16, 128);
-        umma_bf16(acc, dah, dbh, kIdesc, (first_chunk && s2 == 0) ? 0u : 1u);
-        umma_bf16(acc, dal, dbh, kIdesc, 1u);
         umma_bf16(acc, dah, dbl, kIdesc, 1u);
       }
       umma_commit(bar(L::kBarCfree + buf));
@@ -2596,7 +2612,7 @@ gdn_tc_bwd_dx2_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_co
         asm volatile("bar.sync %0, %1;" ::"r"(2 + (int)(m & 1u)), "n"(kD2Sync) : "memory");  // p planes of this chunk are written
         if (lane == 0) {
           release(n);
-          chunk_mmas(tmem_n, c == 0);
+          chunk_mmas(tmem_n, c, false);
           if (c == NCH - 1) umma_commit(bar(L::kBarN));
         } else {
           ++m;
@@ -2613,7 +2629,7 @@ gdn_tc_bwd_dx2_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_co
         if (lane == 0) {
           release(n);      // x box
           release(n + 1);  // g box
-          chunk_mmas(tmem_dp, c == 0);
+          chunk_mmas(tmem_dp, c, true);
           if (c == NCH - 1) umma_commit(bar(L::kBarDp));  // dp is complete: the dx pass may start
         } else {
           ++m;
