@@ -879,6 +879,36 @@ int make_tensor_map_2d(CUtensorMap* map, const float* base, long long rows, int 
   return TFCB_OK;
 }
 
+// 3-D view of a row-major fp32 [rows, cols] array as (32 channels, rows, cols / 32 chunks) with boxes of
+// [chunks_per_box][box_rows][32 channels], 128-byte swizzle: ONE copy instruction moves several of the kernels'
+// [128 rows x 32 channels] boxes, which land back to back in shared memory exactly as separate 2-D boxes would.
+// (The SM's async-copy engine retires ~2.5 copy instructions per microsecond whatever their size -- 0.39 us per 16 KB
+// box, tools/tma_probe.py -- so the number of instructions per tile, not the bytes, bounded the box-fed kernels.)
+int make_tensor_map_3d(CUtensorMap* map, const float* base, long long rows, int cols, int box_rows, int chunks_per_box) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &st) != cudaSuccess ||
+        st != cudaDriverEntryPointSuccess)
+      fn = nullptr;
+    (void)cudaGetLastError();
+    return reinterpret_cast<EncodeFn>(fn);
+  }();
+  if (!encode) return fail(TFCB_CUDA_ERROR, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[3] = {32u, (cuuint64_t)rows, (cuuint64_t)(cols / 32)};
+  const cuuint64_t strides[2] = {(cuuint64_t)cols * sizeof(float), 32u * sizeof(float)};  // row stride, chunk stride
+  const cuuint32_t box[3] = {32u, (cuuint32_t)box_rows, (cuuint32_t)chunks_per_box};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  const CUresult rc = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) return fail(TFCB_CUDA_ERROR, "cuTensorMapEncodeTiled (3-D) failed (%d)", (int)rc);
+  return TFCB_OK;
+}
+
 template <bool FAST>
 int launch_tc_fwd4(const float* x, const float* gamma, const float* beta, float* y, long long n_pix, TcFlags f,
                    cudaStream_t s) {
@@ -1818,8 +1848,11 @@ __device__ __forceinline__ void tmem_store8(uint32_t taddr, const uint32_t (&r)[
                : "memory");
 }
 
-// gamma [C, C] -> four bf16 planes for the streamed kernel: [j / 8][i][j % 8] hi, lo (MMA1: K = j) and the transposed
-// [i / 8][j][i % 8] hi, lo (MMA2: K = i); a K chunk of 32 channels is 4 contiguous groups = C * 64 bytes of a plane.
+// gamma [C, C] -> bf16 K chunks for the streamed kernels: for t in {gamma (MMA1: K = j), gamma^T (MMA2: K = i)} and each
+// 32-channel K chunk c one block [hi: 4 groups x C x 8][lo: the same], i.e. chunk (t, c) is ONE contiguous copy of
+// C * 128 bytes (a copy instruction costs the SM's copy engine ~0.35 us whatever its size).  INTERLEAVED = false keeps
+// four whole planes [gamma hi, gamma lo, gamma^T hi, gamma^T lo] (the C = 192 dx kernel keeps a whole hi plane resident).
+template <bool INTERLEAVED>
 __global__ void gdn_tc_prep2_kernel(const float* __restrict__ gamma, int C, __nv_bfloat16* __restrict__ planes) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over (k / 8, n)
   if (idx >= (C / 8) * C) return;
@@ -1830,13 +1863,25 @@ __global__ void gdn_tc_prep2_kernel(const float* __restrict__ gamma, int C, __nv
     v[e] = gamma[(kc * 8 + e) * C + n];  // k = j (input channel), n = i
     w[e] = gamma[n * C + kc * 8 + e];    // k = i, n = j
   }
+  uint4* out = reinterpret_cast<uint4*>(planes);
+  const size_t plane16 = (size_t)C * C / 8;  // 16-byte units per plane
   uint4 hi, lo;
   split8(v, &hi, &lo);
-  reinterpret_cast<uint4*>(planes)[idx] = hi;
-  reinterpret_cast<uint4*>(planes + (size_t)C * C)[idx] = lo;
-  split8(w, &hi, &lo);
-  reinterpret_cast<uint4*>(planes + 2 * (size_t)C * C)[idx] = hi;
-  reinterpret_cast<uint4*>(planes + 3 * (size_t)C * C)[idx] = lo;
+  if (INTERLEAVED) {
+    const size_t chunk16 = (size_t)4 * C;  // units of one chunk of one plane
+    const size_t at = ((size_t)(kc / 4) * 2) * chunk16 + (size_t)(kc % 4) * C + n;
+    out[at] = hi;
+    out[at + chunk16] = lo;
+    split8(w, &hi, &lo);
+    out[2 * plane16 + at] = hi;
+    out[2 * plane16 + at + chunk16] = lo;
+  } else {
+    out[idx] = hi;
+    out[plane16 + idx] = lo;
+    split8(w, &hi, &lo);
+    out[2 * plane16 + idx] = hi;
+    out[3 * plane16 + idx] = lo;
+  }
 }
 
 constexpr int kB3Compute = 512;                // 16 compute warps
@@ -1986,14 +2031,11 @@ gdn_tc_bwd3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_const
         }
         const uint32_t gfull = bar(L::kBarGfull + buf);
         const uint32_t dst = smem_u32(smem + L::kOffG + buf * 2 * L::kGChunk);
-        const uint8_t* src = gp + (size_t)(2 * transposed) * kPlaneBytes + (size_t)c * L::kGChunk;
+        // chunk (t, c) = [hi 8 KB][lo 8 KB], contiguous in the prepared buffer: one copy
+        const uint8_t* src = gp + (size_t)(2 * transposed) * kPlaneBytes + (size_t)c * (2 * L::kGChunk);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gfull), "n"(2 * L::kGChunk) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
-                     "l"(src), "n"(L::kGChunk), "r"(gfull), "l"(kEvictLast)
-                     : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-                         dst + L::kGChunk),
-                     "l"(src + kPlaneBytes), "n"(L::kGChunk), "r"(gfull), "l"(kEvictLast)
+                     "l"(src), "n"(2 * L::kGChunk), "r"(gfull), "l"(kEvictLast)
                      : "memory");
         ++m;
       };
@@ -2303,7 +2345,7 @@ int launch_tc_bwd3(const float* x, const float* gamma, const float* beta, const 
   TFCB_TRY(make_tensor_map_2d(&dx_map, dx, n_pix, C, kTileM, 32, true));
   __nv_bfloat16* planes = nullptr;
   TFCB_TRY(dev_alloc((void**)&planes, (size_t)4 * C * C * sizeof(__nv_bfloat16), s));
-  gdn_tc_prep2_kernel<<<((C / 8) * C + 255) / 256, 256, 0, s>>>(gamma, C, planes);
+  gdn_tc_prep2_kernel<true><<<((C / 8) * C + 255) / 256, 256, 0, s>>>(gamma, C, planes);
   TFCB_LAUNCHED();
   cudaError_t e = cudaFuncSetAttribute(gdn_tc_bwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes);
   if (e != cudaSuccess) {
@@ -2868,13 +2910,13 @@ gdn_tc_bwd_dgamma2_kernel(const __grid_constant__ CUtensorMap x_map, const float
         if (!mbar_wait(bar(L::kBarPfree), (uint32_t)t & 1u)) __trap();
         const uint32_t xfull = bar(L::kBarXfull);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(xfull), "n"(6 * kF4Box) : "memory");
-#pragma unroll 1
-        for (int c = 0; c < NCH; ++c)
-          asm volatile(
-              "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
-                  smem_u32(smem + L::kOffPh + c * kF4Box)),
-              "l"(&x_map), "r"(c * 32), "r"((int)(tile * kTileM)), "r"(xfull), "l"(kEvictFirst)
-              : "memory");
+        // ONE 3-D box: all six [128 x 32] boxes of the tile, back to back (a copy instruction costs the SM's copy
+        // engine ~0.35 us whatever its size, tools/tma_probe.py)
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(
+                smem_u32(smem + L::kOffPh)),
+            "l"(&x_map), "r"(0), "r"((int)(tile * kTileM)), "r"(0), "r"(xfull), "l"(kEvictFirst)
+            : "memory");
       }
     }
     __syncwarp();
@@ -3082,12 +3124,19 @@ int launch_tc_bwd192(const float* x, const float* gamma, const float* beta, cons
       dev_free(planes, s);
       return rc;
     }
-    gdn_tc_prep2_kernel<<<((C / 8) * C + 255) / 256, 256, 0, s>>>(gamma, C, planes4);
+    gdn_tc_prep2_kernel<false><<<((C / 8) * C + 255) / 256, 256, 0, s>>>(gamma, C, planes4);
     TFCB_LAUNCHED();
     gdn_tc_bwd_dx2_kernel<<<grid, kD2Threads, L2::kBytes, s>>>(x_map, g_map, dx_map, x, dy, planes4, beta,
                                                               reinterpret_cast<uint8_t*>(q_ws), n_pix, f.inverse);
     TFCB_LAUNCHED();
-    gdn_tc_bwd_dgamma2_kernel<<<grid, kG2Threads, L3::kBytes, s>>>(x_map, x, reinterpret_cast<const uint8_t*>(q_ws), part_g,
+    CUtensorMap x_map3;  // the whole [128 x 192] x tile as one 3-D box
+    rc = make_tensor_map_3d(&x_map3, x, n_pix, C, kTileM, C / 32);
+    if (rc != TFCB_OK) {
+      dev_free(planes4, s);
+      dev_free(planes, s);
+      return rc;
+    }
+    gdn_tc_bwd_dgamma2_kernel<<<grid, kG2Threads, L3::kBytes, s>>>(x_map3, x, reinterpret_cast<const uint8_t*>(q_ws), part_g,
                                                                    part_b, n_pix);
     TFCB_LAUNCHED();
     cudaError_t e2 = cudaGetLastError();

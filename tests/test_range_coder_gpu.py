@@ -205,3 +205,47 @@ def test_truncated_stream_fails_sanity(ops):
   assert dec.shape == (4, 1000) and ok.shape == (4,)
   d = dec.cpu().numpy()
   assert d.min() >= 0 and d.max() < 30
+
+
+@pytest.mark.parametrize("mode", ["index", "channel"])
+def test_wide_rows(ops, mode):
+  """Rows wider than the decoder's 64-key window (generic search path): flat and peaked
+  tables of 65 ... 4000 bins (stride 2 ... 63), with and without overflow, uniform symbols (every bin is hit, both
+  window edges, first and last bins, escapes); streams and decoded symbols against the oracle."""
+  rng = np.random.default_rng(7 if mode == "index" else 8)
+  sizes = [65, 66, 127, 128, 129, 191, 640, 1000, 1501, 2048, 4000, 40, 64]
+  cdfs, precs, ovf = [], [], []
+  for i, nb in enumerate(sizes):
+    p = 16 if nb > 1500 else (12 if nb <= 1000 else 14)
+    cdfs.append(util.random_cdf(rng, nb, p, peaky=1.0 if i % 2 else 6.0))
+    precs.append(p)
+    ovf.append(i % 3 == 0)
+  lookup = util.make_lookup_1d(cdfs, precs, ovf)
+  S, N = 6, 5000 if mode == "index" else 13 * 400
+  if mode == "index":
+    index = rng.integers(0, len(sizes), (S, N)).astype(np.int32)
+  else:
+    index = np.broadcast_to(np.arange(N, dtype=np.int32) % len(sizes), (S, N)).copy()
+  hi = np.asarray([len(c) - 1 for c in cdfs])[index]           # bins per symbol's row
+  ov = np.asarray(ovf)[index]
+  value = (rng.random((S, N)) * (hi - ov)).astype(np.int32)    # overflow rows: regular symbols are [0, bins - 1)
+  esc = ov & (rng.random((S, N)) < 0.02)
+  value[esc] = rng.integers(-300, 3000, int(esc.sum())).astype(np.int32)
+  edge = rng.random((S, N)) < 0.05
+  value[edge & ~esc] = np.where(rng.random(int((edge & ~esc).sum())) < 0.5, 0, (hi - ov - 1)[edge & ~esc])
+  O = oracle.best()
+  want = O.encode(lookup, value, index if mode == "index" else None)
+  h = ops.create_range_encoder([S], lookup)
+  if mode == "index":
+    ops.entropy_encode_index(h, torch.from_numpy(index).cuda(), torch.from_numpy(value).cuda())
+  else:
+    ops.entropy_encode_channel(h, torch.from_numpy(value).cuda())
+  got = ops.entropy_encode_finalize(h)
+  assert got.tolist() == want
+  hd = ops.create_range_decoder(got, lookup)
+  if mode == "index":
+    hd, dec = ops.entropy_decode_index(hd, torch.from_numpy(index).cuda(), [N])
+  else:
+    hd, dec = ops.entropy_decode_channel(hd, [N])
+  assert bool(ops.entropy_decode_finalize(hd).all())
+  assert np.array_equal(dec.cpu().numpy(), value)
