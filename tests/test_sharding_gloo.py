@@ -38,7 +38,15 @@ def _worker(rank, world, port, q):
                                                cdf_shapes=(1, 1), quantization_offset=True)
     sharding.broadcast_tables(model, src=0)
     lo, hi = sharding.shard_range(257, rank, world)
-    q.put((rank, model.cdf.clone(), model.cdf_offset.clone(), model.quantization_offset.clone(), lo, hi))
+    # data-parallel training: the per-rank parameter gradients of a layer are averaged with one all-reduce
+    lin = torch.nn.Linear(3, 2)
+    with torch.no_grad():
+      lin.weight.fill_(1.0)
+      lin.bias.fill_(0.0)
+    lin(torch.full((4, 3), float(rank + 1))).sum().backward()
+    n_red = sharding.allreduce_gradients(lin)
+    q.put((rank, model.cdf.clone(), model.cdf_offset.clone(), model.quantization_offset.clone(), lo, hi,
+           n_red, lin.weight.grad.clone(), lin.bias.grad.clone()))
   finally:
     dist.barrier()
     dist.destroy_process_group()
@@ -74,8 +82,10 @@ def test_table_broadcast_and_batch_shards():
       last = e
   assert got is not None, f"gloo rendezvous failed three times: {last!r}"
   cdf, coff, qoff = _tables()
-  for rank, c, o, qo, lo, hi in got:
+  for rank, c, o, qo, lo, hi, n_red, gw, gb in got:
     assert torch.equal(c, cdf.to(torch.int32)) and torch.equal(o, coff) and torch.allclose(qo, qoff)
+    # rank r's own gradient is 4 (r + 1) per weight and 4 per bias: the average over two ranks is 6 and 4
+    assert n_red == 8 and torch.allclose(gw, torch.full((2, 3), 6.0)) and torch.allclose(gb, torch.full((2,), 4.0))
   assert got[0][4] == 0 and got[0][5] == got[1][4] and got[1][5] == 257
   assert abs((got[0][5] - got[0][4]) - (got[1][5] - got[1][4])) <= 1
 
