@@ -24,7 +24,7 @@ from compression_b200.gdn import GDN
 from compression_b200.packed_tensors import PackedTensors
 from compression_b200.signal_conv import SignalConv2D
 
-__all__ = ["BLS2017Model", "BMSHJ2018Model", "AnalysisTransform", "SynthesisTransform", "HyperAnalysisTransform",
+__all__ = ["BLS2017Model", "BMSHJ2018Model", "MS2020Model", "AnalysisTransform", "SynthesisTransform", "HyperAnalysisTransform",
            "HyperSynthesisTransform", "bench_model_paths"]
 
 
@@ -273,6 +273,152 @@ class BMSHJ2018Model(_Model):
 
   def decompress_from_tfci(self, data):
     dtypes = [bytes, bytes, torch.int32, torch.int32, torch.int32]
+    return self.decompress(*PackedTensors(data).unpack(dtypes))
+
+
+class _MS2020SliceTransform(nn.Sequential):
+  """ms2020.py:139-166: channel-conditional parameter / latent-residual-prediction transform of one slice."""
+
+  def __init__(self, slice_depth):
+    conv = lambda f, k, name, act: _conv(f, k, name, corr=False, kernel_parameter="variable", activation=act)
+    super().__init__(conv(224, 5, "layer_0", torch.relu), conv(128, 5, "layer_1", torch.relu),
+                     conv(slice_depth, 3, "layer_2", None))
+
+
+class MS2020Model(_Model):
+  """models/ms2020.py:169-440 (channel-wise autoregressive entropy model with latent residual prediction): the
+  callers' side of the index-mode coder -- every slice of y is coded by one `LocationScaleIndexedEntropyModel`
+  call conditioned on the hyperprior and on the slices decoded before it, so compress() issues num_slices + 1
+  encodes AND the matching decodes (ms2020.py:334-389)."""
+
+  def __init__(self, lmbda=0.01, num_filters=192, latent_depth=320, hyperprior_depth=192, num_slices=10,
+               max_support_slices=5, num_scales=64, scale_min=.11, scale_max=256.):
+    super().__init__()
+    if latent_depth % num_slices:
+      raise ValueError("Slices do not evenly divide latent depth (%d / %d)" % (latent_depth, num_slices))
+    self.lmbda = lmbda
+    self.num_scales, self.num_slices, self.max_support_slices = int(num_scales), int(num_slices), int(max_support_slices)
+    offset = math.log(scale_min)
+    factor = (math.log(scale_max) - math.log(scale_min)) / (num_scales - 1.)
+    self.scale_fn = lambda i: torch.exp(offset + factor * i)
+    f = num_filters
+    self.analysis_transform = nn.Sequential(                                       # ms2020.py:53-71
+        _Scale(1 / 255.), *[_conv(f, 5, f"layer_{i}", down=2, activation=GDN(name=f"gdn_{i}")) for i in range(3)],
+        _conv(latent_depth, 5, "layer_3", down=2))
+    self.synthesis_transform = nn.Sequential(                                      # ms2020.py:74-95
+        *[_conv(f, 5, f"layer_{i}", up=2, corr=False, activation=GDN(name=f"igdn_{i}", inverse=True)) for i in range(3)],
+        _conv(3, 5, "layer_3", up=2, corr=False), _Scale(255.))
+    self.hyper_analysis_transform = nn.Sequential(                                 # ms2020.py:98-115
+        _conv(320, 3, "layer_0", activation=torch.relu), _conv(256, 5, "layer_1", down=2, activation=torch.relu),
+        _conv(hyperprior_depth, 5, "layer_2", down=2, use_bias=False))
+    hs = lambda: nn.Sequential(                                                    # ms2020.py:118-136
+        _conv(192, 5, "layer_0", up=2, corr=False, kernel_parameter="variable", activation=torch.relu),
+        _conv(256, 5, "layer_1", up=2, corr=False, kernel_parameter="variable", activation=torch.relu),
+        _conv(320, 3, "layer_2", corr=False, kernel_parameter="variable", activation=torch.relu))
+    self.hyper_synthesis_mean_transform, self.hyper_synthesis_scale_transform = hs(), hs()
+    sd = latent_depth // num_slices
+    self.cc_mean_transforms = nn.ModuleList([_MS2020SliceTransform(sd) for _ in range(num_slices)])
+    self.cc_scale_transforms = nn.ModuleList([_MS2020SliceTransform(sd) for _ in range(num_slices)])
+    self.lrp_transforms = nn.ModuleList([_MS2020SliceTransform(sd) for _ in range(num_slices)])
+    self.hyperprior = D.NoisyDeepFactorized(batch_shape=(hyperprior_depth,))
+    self.em_z = self.em_y = None
+
+  def _slice_params(self, i, latent_means, latent_scales, y_hat_slices, y_hw):
+    """mu, scale indexes and the LRP support of slice i (ms2020.py:241-253)."""
+    support = y_hat_slices if self.max_support_slices < 0 else y_hat_slices[:self.max_support_slices]
+    mean_support = torch.cat([latent_means] + support, dim=-1)
+    mu = self.cc_mean_transforms[i](mean_support)[:, :y_hw[0], :y_hw[1], :]
+    scale_support = torch.cat([latent_scales] + support, dim=-1)
+    sigma = self.cc_scale_transforms[i](scale_support)[:, :y_hw[0], :y_hw[1], :]
+    return mu, sigma, mean_support
+
+  def _lrp(self, i, mean_support, y_hat_slice):
+    return y_hat_slice + 0.5 * torch.tanh(self.lrp_transforms[i](torch.cat([mean_support, y_hat_slice], dim=-1)))
+
+  def forward(self, x, training=True):
+    """ms2020.py:200-286 -> (loss, bpp, mse)."""
+    x = x.to(torch.float32)
+    y = self.analysis_transform(x)
+    y_hw = tuple(y.shape[1:-1])
+    z = self.hyper_analysis_transform(y)
+    num_pixels = float(np.prod(x.shape[1:-1]))
+    em_z = E.ContinuousBatchedEntropyModel(self.hyperprior, coding_rank=3, compression=False, offset_heuristic=False)
+    _, z_bits = em_z(z, training=training)
+    z_hat = em_z.quantize(z)
+    latent_scales = self.hyper_synthesis_scale_transform(z_hat)
+    latent_means = self.hyper_synthesis_mean_transform(z_hat)
+    em_y = E.LocationScaleIndexedEntropyModel(D.NoisyNormal, self.num_scales, self.scale_fn, coding_rank=3,
+                                              compression=False)
+    y_hat_slices, bpp = [], z_bits.mean() / num_pixels
+    for i, y_slice in enumerate(torch.chunk(y, self.num_slices, dim=-1)):
+      mu, sigma, mean_support = self._slice_params(i, latent_means, latent_scales, y_hat_slices, y_hw)
+      _, slice_bits = em_y(y_slice, sigma, loc=mu, training=training)
+      bpp = bpp + slice_bits.mean() / num_pixels
+      y_hat_slices.append(self._lrp(i, mean_support, em_y.quantize(y_slice, loc=mu)))
+    x_hat = self.synthesis_transform(torch.cat(y_hat_slices, dim=-1))
+    mse = torch.mean((x - x_hat[:, :x.shape[1], :x.shape[2], :])**2)
+    return bpp + self.lmbda * mse, bpp, mse
+
+  def fix_tables(self):
+    """ms2020.py:321-329."""
+    dev = self._device()
+    self.em_z = E.ContinuousBatchedEntropyModel(self.hyperprior, coding_rank=3, compression=True,
+                                                offset_heuristic=False).to(dev)
+    self.em_y = E.LocationScaleIndexedEntropyModel(D.NoisyNormal, self.num_scales, self.scale_fn, coding_rank=3,
+                                                   compression=True).to(dev)
+    return self
+
+  @torch.no_grad()
+  def compress_batch(self, x):
+    """ms2020.py:331-389 for B images: (x_shape, y_shape, z_shape, z_strings, y_strings[0], ..., y_strings[S - 1])."""
+    x = _as_batch(x).to(device=self._device(), dtype=torch.float32)
+    y = self.analysis_transform(x)
+    y_hw = tuple(y.shape[1:-1])
+    z = self.hyper_analysis_transform(y)
+    z_string = self.em_z.compress(z)
+    z_hat = self.em_z.decompress(z_string, tuple(z.shape[1:-1]))
+    latent_scales = self.hyper_synthesis_scale_transform(z_hat)
+    latent_means = self.hyper_synthesis_mean_transform(z_hat)
+    y_strings, y_hat_slices = [], []
+    for i, y_slice in enumerate(torch.chunk(y, self.num_slices, dim=-1)):
+      mu, sigma, mean_support = self._slice_params(i, latent_means, latent_scales, y_hat_slices, y_hw)
+      y_strings.append(self.em_y.compress(y_slice.contiguous(), sigma, mu))
+      y_hat_slices.append(self._lrp(i, mean_support, self.em_y.decompress(y_strings[-1], sigma, mu)))
+    shapes = [torch.tensor(t.shape[1:-1], dtype=torch.int32) for t in (x, y, z)]
+    return tuple(shapes) + (z_string,) + tuple(y_strings)
+
+  @torch.no_grad()
+  def decompress_batch(self, x_shape, y_shape, z_shape, z_string, *y_strings):
+    """ms2020.py:391-433."""
+    assert len(y_strings) == self.num_slices
+    y_hw = (int(y_shape[0]), int(y_shape[1]))
+    z_hat = self.em_z.decompress(z_string, tuple(int(v) for v in z_shape))
+    latent_scales = self.hyper_synthesis_scale_transform(z_hat)
+    latent_means = self.hyper_synthesis_mean_transform(z_hat)
+    y_hat_slices = []
+    for i, y_string in enumerate(y_strings):
+      mu, sigma, mean_support = self._slice_params(i, latent_means, latent_scales, y_hat_slices, y_hw)
+      y_hat_slices.append(self._lrp(i, mean_support, self.em_y.decompress(y_string, sigma, loc=mu)))
+    x_hat = self.synthesis_transform(torch.cat(y_hat_slices, dim=-1))
+    return _to_uint8(x_hat[:, :int(x_shape[0]), :int(x_shape[1]), :])
+
+  def compress(self, x):
+    """One image uint8 [H, W, 3], the reference's signature (ms2020.py:331-389)."""
+    x = torch.as_tensor(x)
+    if x.dim() != 3 or x.shape[-1] != 3:
+      raise ValueError(f"expected one image [H, W, 3], received shape {tuple(x.shape)}")
+    return self.compress_batch(x[None])
+
+  def decompress(self, x_shape, y_shape, z_shape, z_string, *y_strings):
+    return self.decompress_batch(x_shape, y_shape, z_shape, z_string, *y_strings)[0]
+
+  def compress_to_tfci(self, x):
+    packed = PackedTensors()
+    packed.pack(self.compress(x))
+    return packed.string
+
+  def decompress_from_tfci(self, data):
+    dtypes = [torch.int32] * 3 + [bytes] * (self.num_slices + 1)
     return self.decompress(*PackedTensors(data).unpack(dtypes))
 
 

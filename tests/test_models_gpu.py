@@ -89,3 +89,51 @@ def test_bmshj2018_two_level_image_to_tfci_and_back():
   loss, bpp, mse = m(torch.rand(2, 64, 64, 3).cuda() * 255, training=True)
   loss.backward()
   assert float(bpp) > 0 and torch.isfinite(loss)
+
+
+def test_ms2020_slice_loop_image_to_tfci_and_back():
+  """models/ms2020.py:331-433: the hyperprior string plus one string per channel slice, each slice coded in index mode
+  with `loc` conditioned on the slices decoded before it.  Checked: the container layout (three shapes, then
+  num_slices + 1 strings), every slice string against the oracle for the symbols this model derives, decompress ==
+  the synthesis of the latents the encoder itself reconstructed, batches, and the training graph."""
+  from compression_b200 import models, PackedTensors
+  torch.manual_seed(4)
+  S = 4
+  m = models.MS2020Model(num_filters=24, latent_depth=32, hyperprior_depth=16, num_slices=S, max_support_slices=2)
+  m.build("cuda", patch=(64, 64)).fix_tables()
+  # (ms2020.py concatenates the un-cropped hyper-synthesis output with the slices: image sides must be multiples of 64,
+  # which is what models/tfci.py pads to)
+  for h, w in ((64, 64), (128, 64)):
+    x = _image(h, w, h + w)
+    out = m.compress(x)
+    x_shape, y_shape, z_shape, z_string = out[:4]
+    y_strings = out[4:]
+    assert len(y_strings) == S and x_shape.tolist() == [h, w] and y_shape.tolist() == [-(-h // 16), -(-w // 16)]
+    data = m.compress_to_tfci(x)
+    feats = PackedTensors(data).unpack([torch.int32] * 3 + [bytes] * (S + 1))
+    assert feats[0].tolist() == [h, w] and feats[3] == z_string.tolist() and feats[4 + S - 1] == y_strings[-1].tolist()
+    x_hat = m.decompress_from_tfci(data)
+    assert x_hat.dtype == torch.uint8 and tuple(x_hat.shape) == (h, w, 3)
+    # replay the encoder's slice loop and compare every string with the oracle
+    y = m.analysis_transform(x[None].cuda().float())
+    z = m.hyper_analysis_transform(y)
+    zs = (torch.round(z).to(torch.int32) - m.em_z.cdf_offset).reshape(1, -1).cpu().numpy()   # offset_heuristic=False
+    assert z_string.tolist() == oracle.best().encode(m.em_z.cdf.cpu().numpy(), zs)
+    z_hat = m.em_z.quantize(z)
+    lm, ls = m.hyper_synthesis_mean_transform(z_hat), m.hyper_synthesis_scale_transform(z_hat)
+    y_hat_slices = []
+    for i, y_slice in enumerate(torch.chunk(y, S, dim=-1)):
+      mu, sigma, support = m._slice_params(i, lm, ls, y_hat_slices, tuple(y.shape[1:-1]))
+      flat = torch.clamp(sigma, 0, m.num_scales - 1).to(torch.int32)
+      sym = (torch.round(y_slice - mu).to(torch.int32) - m.em_y.cdf_offset.cuda()[flat.long()]).reshape(1, -1).cpu().numpy()
+      assert y_strings[i].tolist() == oracle.best().encode(m.em_y.cdf.cpu().numpy(), sym, flat.reshape(1, -1).cpu().numpy())
+      y_hat_slices.append(m._lrp(i, support, m.em_y.quantize(y_slice, loc=mu)))
+    want = m.synthesis_transform(torch.cat(y_hat_slices, dim=-1))[0, :h, :w]
+    assert torch.equal(x_hat, torch.clamp(torch.round(want), 0, 255).to(torch.uint8))
+  xb = torch.stack([_image(64, 128, s) for s in range(3)])
+  outb = m.compress_batch(xb)
+  assert outb[3].shape == (3,) and all(s.shape == (3,) for s in outb[4:])
+  assert tuple(m.decompress_batch(*outb).shape) == (3, 64, 128, 3)
+  loss, bpp, mse = m(torch.rand(2, 64, 64, 3).cuda() * 255, training=True)
+  loss.backward()
+  assert float(bpp) > 0 and torch.isfinite(loss)
