@@ -786,12 +786,20 @@ __global__ void exclusive_scan_kernel(const long long* lens, long long n, long l
 }
 
 // One warp per stream: resolve carries right-to-left, 32 words per step, and write the bytes.
-__global__ void __launch_bounds__(128) enc_write_kernel(const EncState* state, const uint16_t* words,
-                                                        const uint32_t* cbits, long long cap,
-                                                        long long n_streams,
-                                                        const long long* offsets, uint8_t* out) {
-  const long long s = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
+// One CTA of kWriteWarps warps per stream.  The carry chain runs right to left over 32-word groups; it is cut into
+// kWriteWarps segments: every warp first runs its segment's chain for BOTH possible carries entering it (two adds per
+// group instead of one), the segments' carry-ins are then resolved through shared memory (a chain of kWriteWarps
+// steps), and each warp resolves and writes its own segment.  (One warp per stream walked 200 groups serially:
+// 46 us of the 714 us cfg2 step.)
+constexpr int kWriteWarps = 8;
+
+__global__ void __launch_bounds__(32 * kWriteWarps) enc_write_kernel(const EncState* state, const uint16_t* words,
+                                                                    const uint32_t* cbits, long long cap,
+                                                                    long long n_streams,
+                                                                    const long long* offsets, uint8_t* out) {
+  __shared__ uint32_t seg_out[kWriteWarps][2];
+  const long long s = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (s >= n_streams) return;
   const EncState st = state[s];
   const uint16_t* w = words + s * cap;
@@ -803,51 +811,69 @@ __global__ void __launch_bounds__(128) enc_write_kernel(const EncState* state, c
   const long long len = enc_final_length(st, w, &straddle, &tail, &ntail);
   const long long body = straddle ? len : 2ll * st.cnt;  // bytes that come from resolved words
 
-  // carry entering the right-most word (index cnt-1)
-  uint32_t x = straddle ? 1u : ((cb[st.cnt >> 5] >> (st.cnt & 31u)) & 1u);
   const long long n_groups = ((long long)st.cnt + 31) >> 5;
+  const long long per = (n_groups + kWriteWarps - 1) / kWriteWarps;
+  const long long g_lo = min((long long)warp * per, n_groups), g_hi = min(g_lo + per, n_groups);  // this warp's groups
   const bool even = ((reinterpret_cast<uintptr_t>(dst)) & 1) == 0;
   constexpr int kBatch = 8;  // groups whose (independent) loads are in flight together
-  for (long long gt = n_groups; gt > 0; gt -= kBatch) {
-    uint32_t word[kBatch], F[kBatch];
+
+  // One pass over the segment [g_lo, g_hi), right to left.  WRITE = false: only the carries leaving the segment for a
+  // carry of 0 and of 1 entering it; WRITE = true: resolve with the real carry `x0` and store the bytes.
+  auto pass = [&](uint32_t& x0, uint32_t& x1, const bool write) {
+    for (long long gt = g_hi; gt > g_lo; gt -= kBatch) {
+      uint32_t word[kBatch], F[kBatch];
 #pragma unroll
-    for (int i = 0; i < kBatch; ++i) {
-      const long long g = gt - 1 - i;
-      const uint32_t idx = (uint32_t)(g << 5) + lane;
-      word[i] = (g >= 0 && idx < st.cnt) ? (uint32_t)w[idx] : 0u;
-      F[i] = (g >= 0) ? cb[g] : 0u;
-    }
+      for (int i = 0; i < kBatch; ++i) {
+        const long long g = gt - 1 - i;
+        const uint32_t idx = (uint32_t)(g << 5) + lane;
+        word[i] = (g >= g_lo && idx < st.cnt) ? (uint32_t)w[idx] : 0u;
+        F[i] = (g >= g_lo) ? cb[g] : 0u;
+      }
 #pragma unroll
-    for (int i = 0; i < kBatch; ++i) {
-      const long long g = gt - 1 - i;
-      if (g < 0) break;
-      const uint32_t idx = (uint32_t)(g << 5) + lane;
-      const bool live = idx < st.cnt;
-      uint32_t Fm = F[i];
-      const uint32_t fill = st.cnt - (uint32_t)(g << 5);
-      if (fill < 32u) Fm &= (1u << fill) - 1u;
-      // P: word propagates a carry.  Dead lanes right of the last word must pass `x` through.
-      const uint32_t Pm = __ballot_sync(kFull, live ? (word[i] == 0xFFFFu) : true);
-      // position j = 31 - lane (bit 0 = right-most word); c[j+1] = F[31-j] | (P[31-j] & c[j])
-      const uint32_t G = __brev(Fm);
-      const uint32_t A = G | __brev(Pm);
-      const unsigned long long sum = (unsigned long long)A + G + x;
-      const uint32_t cin = (uint32_t)sum ^ A ^ G;  // bit j = carry into position j
-      const uint32_t my_c = (cin >> (31 - lane)) & 1u;
-      x = (uint32_t)(sum >> 32) & 1u;
-      if (live) {
-        const uint32_t r = (word[i] + my_c) & 0xFFFFu;
-        const long long b0 = 2ll * idx;
-        if (even && b0 + 1 < body) {
-          *reinterpret_cast<uint16_t*>(dst + b0) = (uint16_t)((r >> 8) | ((r & 0xFFu) << 8));  // big endian
-        } else {
-          if (b0 < body) dst[b0] = (uint8_t)(r >> 8);
-          if (b0 + 1 < body) dst[b0 + 1] = (uint8_t)r;
+      for (int i = 0; i < kBatch; ++i) {
+        const long long g = gt - 1 - i;
+        if (g < g_lo) break;
+        const uint32_t idx = (uint32_t)(g << 5) + lane;
+        const bool live = idx < st.cnt;
+        uint32_t Fm = F[i];
+        const uint32_t fill = st.cnt - (uint32_t)(g << 5);
+        if (fill < 32u) Fm &= (1u << fill) - 1u;
+        // P: word propagates a carry.  Dead lanes right of the last word must pass the carry through.
+        const uint32_t Pm = __ballot_sync(kFull, live ? (word[i] == 0xFFFFu) : true);
+        // position j = 31 - lane (bit 0 = right-most word); c[j+1] = F[31-j] | (P[31-j] & c[j])
+        const uint32_t G = __brev(Fm);
+        const uint32_t A = G | __brev(Pm);
+        const unsigned long long sum = (unsigned long long)A + G + x0;
+        if (!write) x1 = (uint32_t)(((unsigned long long)A + G + x1) >> 32) & 1u;
+        const uint32_t cin = (uint32_t)sum ^ A ^ G;  // bit j = carry into position j
+        const uint32_t my_c = (cin >> (31 - lane)) & 1u;
+        x0 = (uint32_t)(sum >> 32) & 1u;
+        if (write && live) {
+          const uint32_t r = (word[i] + my_c) & 0xFFFFu;
+          const long long b0 = 2ll * idx;
+          if (even && b0 + 1 < body) {
+            *reinterpret_cast<uint16_t*>(dst + b0) = (uint16_t)((r >> 8) | ((r & 0xFFu) << 8));  // big endian
+          } else {
+            if (b0 < body) dst[b0] = (uint8_t)(r >> 8);
+            if (b0 + 1 < body) dst[b0 + 1] = (uint8_t)r;
+          }
         }
       }
     }
+  };
+  uint32_t o0 = 0u, o1 = 1u;
+  pass(o0, o1, false);
+  if (lane == 0) {
+    seg_out[warp][0] = o0;
+    seg_out[warp][1] = o1;
   }
-  if (!straddle && lane == 0) {
+  __syncthreads();
+  // carry entering the right-most word (index cnt - 1), then through the segments to the right of this one
+  uint32_t x = straddle ? 1u : ((cb[st.cnt >> 5] >> (st.cnt & 31u)) & 1u);
+  for (int k = kWriteWarps - 1; k > warp; --k) x = seg_out[k][x];
+  uint32_t unused = 0u;
+  pass(x, unused, true);
+  if (!straddle && threadIdx.x == 0) {
     if (ntail >= 1) dst[body] = (uint8_t)(tail >> 8);
     if (ntail == 2) dst[body + 1] = (uint8_t)tail;
   }
@@ -1931,7 +1957,7 @@ int tfcb_encode_finalize(tfcb_encoder* h, void* stream, int64_t* total_bytes_hos
   h->total = total;
   TFCB_TRY(dev_alloc((void**)&h->out, (size_t)std::max<long long>(total, 1), s));
   if (S > 0) {
-    enc_write_kernel<<<(unsigned)((S + 3) / 4), 128, 0, s>>>(h->state, h->words, h->cbits, h->cap, S,
+    enc_write_kernel<<<(unsigned)S, 32 * kWriteWarps, 0, s>>>(h->state, h->words, h->cbits, h->cap, S,
                                                              h->offsets, h->out);
     TFCB_LAUNCHED();
     TFCB_CUDA_TRY(cudaGetLastError());
@@ -2235,7 +2261,7 @@ int tfcb_range_encode(const int16_t* data_dev, const int64_t* data_shape_host, i
   }
   enc_lengths_kernel<<<1, 32, 0, s>>>(state, words, cap, 1, lens);
   exclusive_scan_kernel<<<1, 32, 0, s>>>(lens, 1, lens + 1);
-  enc_write_kernel<<<1, 128, 0, s>>>(state, words, cbits, cap, 1, lens + 1, out);
+  enc_write_kernel<<<1, 32 * kWriteWarps, 0, s>>>(state, words, cbits, cap, 1, lens + 1, out);
   TFCB_LAUNCHED();
   TFCB_LAUNCHED();
   TFCB_LAUNCHED();
