@@ -13,6 +13,7 @@ timeout 600 ncu --set full --import-source on --clock-control none -k regex:enco
 timeout 600 ncu --set full --import-source on --clock-control none -k regex:decode_kernel -s 1 -c 1 -o gpurun_out/${TAG}_decode_full -f python tools/prof_encode.py > gpurun_out/${TAG}_ncu_decode.log 2>&1; echo "ncu decode rc=$?"
 timeout 600 ncu --set full --import-source on --clock-control none -k regex:gdn_tc_fwd2_kernel -s 1 -c 1 -o gpurun_out/${TAG}_gdn_fwd_full -f python tools/prof_gdn.py > gpurun_out/${TAG}_ncu_gdn_fwd.log 2>&1; echo "ncu gdn fwd rc=$?"
 timeout 600 ncu --set full --import-source on --clock-control none -k regex:gdn_tc_fwd4_kernel -s 1 -c 1 -o gpurun_out/${TAG}_gdn_fwd192_full -f python tools/prof_gdn.py > gpurun_out/${TAG}_ncu_gdn_fwd192.log 2>&1; echo "ncu gdn fwd C=192 rc=$?"
-timeout 600 ncu --set full --import-source on --clock-control none -k regex:gdn_tc_bwd_kernel -s 1 -c 1 -o gpurun_out/${TAG}_gdn_bwd_full -f python tools/prof_gdn.py > gpurun_out/${TAG}_ncu_gdn_bwd.log 2>&1; echo "ncu gdn bwd rc=$?"
-timeout 600 ncu --set full --import-source on --clock-control none -k regex:gdn_tc_bwd_dx_kernel -s 1 -c 1 -o gpurun_out/${TAG}_gdn_bwd192_dx_full -f python tools/prof_gdn.py > gpurun_out/${TAG}_ncu_gdn_bwd192_dx.log 2>&1; echo "ncu gdn bwd dx C=192 rc=$?"
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:gdn_tc_bwd3_kernel -s 1 -c 1 -o gpurun_out/${TAG}_gdn_bwd128_full -f python tools/prof_gdn_bwd128.py > gpurun_out/${TAG}_ncu_gdn_bwd128.log 2>&1; echo "ncu gdn bwd C=128 rc=$?"
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:gdn_tc_bwd_dx2_kernel -s 1 -c 1 -o gpurun_out/${TAG}_gdn_bwd192_dx2_full -f python tools/prof_gdn_bwd192.py > gpurun_out/${TAG}_ncu_gdn_bwd192_dx2.log 2>&1; echo "ncu gdn bwd dx C=192 rc=$?"
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:gdn_tc_bwd_dgamma2_kernel -s 1 -c 1 -o gpurun_out/${TAG}_gdn_bwd192_dgamma2_full -f python tools/prof_gdn_bwd192.py > gpurun_out/${TAG}_ncu_gdn_bwd192_dgamma2.log 2>&1; echo "ncu gdn bwd dgamma C=192 rc=$?"
 ls -la gpurun_out | tail -20
