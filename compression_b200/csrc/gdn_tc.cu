@@ -2142,6 +2142,11 @@ gdn_tc_bwd3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_const
     for (long long tile = first; tile < n_tiles; tile += gridDim.x, ++t) {
       asm volatile("bar.sync %0, %1;" ::"r"(6 + NCH - 1), "n"(kB3SyncB) : "memory");  // the whole tile of q is written
       if (lane == 0) {
+        // let the tile's last MMA2s through first: the dx pass waits for them, nothing waits for MMA3 until the next
+        // conversion (both issue warps leave the same barrier; 24 MMAs ahead of 6 cost the dx pass ~0.8 us per tile)
+        if (!(dbg & 8)) {
+          if (!mbar_wait(bar(L::kBarDp), (uint32_t)t & 1u)) __trap();
+        }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // dgamma[j, i] += sum_pix p[pix, j] q[pix, i]   (K = pix: 8 steps of 16)
         if (!(dbg & 1)) {
