@@ -61,6 +61,8 @@ SIGNATURES = {
     "tfcb_range_decode": (_int, [_vp, _i64, _vp, _int, _vp, _vp, _int, _int, _int, _vp, _vp]),
     "tfcb_pmf_to_quantized_cdf": (_int, [_vp, _i64, _i64, _int, _vp, _vp]),
     "tfcb_build_lookup": (_int, [_vp, _i64, _i64, _vp, _int, _vp, _vp]),
+    "tfcb_run_length_encode": (_int, [_vp, _i64, _int, _int, _int, _vp, _i64, _p(_i64), _vp]),
+    "tfcb_run_length_decode": (_int, [_vp, _i64, _int, _int, _int, _vp, _i64, _vp]),
     "tfcb_stochastic_round": (_int, [_vp, _int, _i64, _f32, _vp, _i64, _vp, _vp]),
     "tfcb_gdn_forward": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _int, _f32, _f32, _vp]),
     "tfcb_gdn_forward_16bit": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _int, _int, _f32, _f32, _vp]),

@@ -20,6 +20,10 @@ from compression_b200._lib import InvalidArgumentError, check
 
 __all__ = [
     "stochastic_round",
+    "run_length_encode",
+    "run_length_decode",
+    "run_length_gamma_encode",
+    "run_length_gamma_decode",
     "create_range_encoder",
     "create_range_decoder",
     "entropy_decode_channel",
@@ -402,3 +406,55 @@ def stochastic_round(inputs, step_size, seed) -> torch.Tensor:
                                          sd.ctypes.data_as(C.c_void_p) if sd.size else None, sd.size, _ptr(out),
                                          _stream()))
   return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Run-length / Rice / gamma bit coding (cc/ops/run_length_ops.cc:28-84, run_length_gamma_ops.cc)
+# ------------------------------------------------------------------------------------------------
+def run_length_encode(data, run_length_code: int, magnitude_code: int, use_run_length_for_non_zeros: bool) -> bytes:
+  """RunLengthEncode: int32 tensor of any shape -> one bit string (zeros as run lengths, non-zeros as sign +
+  magnitude; Rice codes for parameters >= 0, Elias gamma otherwise)."""
+  data = _dev(data, torch.int32).reshape(-1)
+  n = data.numel()
+  if n == 0:
+    return b""
+  cap = 4 * ((2 * n + 64 + 3) // 4)
+  while True:
+    code = torch.empty(cap, dtype=torch.uint8, device=data.device)
+    nb = C.c_int64(0)
+    rc = _lib.lib().tfcb_run_length_encode(_ptr(data), n, int(run_length_code), int(magnitude_code),
+                                           int(bool(use_run_length_for_non_zeros)), _ptr(code), cap, C.byref(nb),
+                                           _stream())
+    if rc == _lib.INVALID_ARGUMENT and nb.value > cap - 4:   # the code is longer than the first guess: once more
+      cap = 4 * ((nb.value + 3) // 4) + 4
+      continue
+    check(rc)
+    return code[:nb.value].cpu().numpy().tobytes()
+
+
+def run_length_decode(code, shape, run_length_code: int, magnitude_code: int, use_run_length_for_non_zeros: bool):
+  """RunLengthDecode: the inverse; `shape` of the encoded tensor must be known (cc/ops/run_length_ops.cc:50-84)."""
+  if isinstance(code, Strings):
+    if code.shape != ():
+      raise InvalidArgumentError(f"Invalid `code` shape: {list(code.shape)}")
+    code = code.tolist()[0]
+  if not isinstance(code, (bytes, bytearray)):
+    raise InvalidArgumentError("Invalid `code` shape: expected a scalar string")
+  shape_np = np.asarray(shape.cpu() if isinstance(shape, torch.Tensor) else shape)
+  if shape_np.ndim != 1:
+    raise InvalidArgumentError(f"Invalid `shape` shape: {list(shape_np.shape)}")
+  dims = tuple(int(d) for d in shape_np)
+  out = torch.empty(dims, dtype=torch.int32, device=_device())
+  buf = torch.from_numpy(np.frombuffer(bytes(code) + b"\0\0\0\0", dtype=np.uint8).copy()).to(out.device)
+  check(_lib.lib().tfcb_run_length_decode(_ptr(buf), len(code), int(run_length_code), int(magnitude_code),
+                                          int(bool(use_run_length_for_non_zeros)), _ptr(out), out.numel(), _stream()))
+  return out
+
+
+def run_length_gamma_encode(data) -> bytes:
+  """RunLengthGammaEncode = RunLengthEncode(-1, -1, False) (cc/ops/run_length_ops.cc:34-37)."""
+  return run_length_encode(data, -1, -1, False)
+
+
+def run_length_gamma_decode(code, shape):
+  return run_length_decode(code, shape, -1, -1, False)

@@ -168,6 +168,22 @@ int tfcb_build_lookup(const float* pmf_dev, int64_t rows, int64_t max_len, const
                       int precision, int32_t* lookup_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * RunLengthEncode / RunLengthDecode (and RunLengthGammaEncode/Decode = codes (-1, -1), use_run_length_for_non_zeros 0):
+ *   op contract   tensorflow_compression/cc/ops/run_length_ops.cc:28-84
+ *   CPU kernels   tensorflow_compression/cc/kernels/run_length_kernels.cc:52-262, bit packing cc/lib/bit_coder.cc:50-191
+ * data int32 [n] (flattened) <-> one bit string.  run_length_code / magnitude_code >= 0: Rice code with that parameter,
+ * < 0: Elias gamma.  Encode: `code_dev` has room for `capacity` bytes (a multiple of 4 is used); *n_bytes_host receives
+ * the length of the code; TFCB_INVALID_ARGUMENT with the needed size in the message (and in *n_bytes_host) when it
+ * does not fit.  The encoder is data parallel (scans + atomics); the decoder is serial, as in the reference.
+ * Decode errors carry the reference's DataLoss messages.
+ * ---------------------------------------------------------------------------------------------- */
+int tfcb_run_length_encode(const int32_t* data_dev, int64_t n, int run_length_code, int magnitude_code,
+                           int use_run_length_for_non_zeros, uint8_t* code_dev, int64_t capacity,
+                           int64_t* n_bytes_host, void* stream);
+int tfcb_run_length_decode(const uint8_t* code_dev, int64_t n_bytes, int run_length_code, int magnitude_code,
+                           int use_run_length_for_non_zeros, int32_t* data_dev, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * StochasticRound:
  *   op contract   tensorflow_compression/cc/ops/quantization_ops.cc:28-53
  *   CPU kernel    tensorflow_compression/cc/kernels/quantization_kernels.cc:48-95

@@ -180,6 +180,34 @@ class Oracle:
       raise OracleError(self._err())
     return out
 
+  def run_length_encode(self, data, run_length_code=-1, magnitude_code=-1, use_run_length_for_non_zeros=False) -> bytes:
+    """RunLengthEncode (cc/kernels/run_length_kernels.cc:52-139), sequential C restatement (port only)."""
+    d = _i32(np.asarray(data).reshape(-1))
+    cap = int(16 + 20 * d.size)
+    while True:
+      out = np.zeros(cap, np.uint8)
+      if not hasattr(self, "_run_length_encode"):
+        self._fn("run_length_encode", C.c_int64, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64])
+      nb = self._run_length_encode(d.ctypes.data, d.size, int(run_length_code), int(magnitude_code),
+                                   int(bool(use_run_length_for_non_zeros)), out.ctypes.data, cap)
+      if nb >= 0:
+        return out[:nb].tobytes()
+      cap *= 8
+
+  def run_length_decode(self, code: bytes, shape, run_length_code=-1, magnitude_code=-1,
+                        use_run_length_for_non_zeros=False) -> np.ndarray:
+    """RunLengthDecode (cc/kernels/run_length_kernels.cc:141-258); raises OracleError with the reference's messages."""
+    n = int(np.prod(shape))
+    buf = np.frombuffer(bytes(code) + b"\0", np.uint8)
+    out = np.zeros(max(n, 1), np.int32)
+    if not hasattr(self, "_run_length_decode"):
+      self._fn("run_length_decode", C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64])
+    e = self._run_length_decode(buf.ctypes.data, len(code), int(run_length_code), int(magnitude_code),
+                                int(bool(use_run_length_for_non_zeros)), out.ctypes.data, n)
+    if e:
+      raise OracleError({1: "Out of bits to read.", 2: "Exceeded maximum gamma bit width.", 3: "Decoded past end of tensor."}[e])
+    return out[:n].reshape(shape)
+
   def pmf_to_cdf(self, pmf, precision: int) -> np.ndarray:
     pmf = np.ascontiguousarray(pmf, dtype=np.float32)
     n = pmf.shape[-1]

@@ -131,3 +131,19 @@ def test_stochastic_round_port_equals_reference_flavour():
   assert np.array_equal(P.stochastic_round(ints * np.float32(0.75), 0.75, [3]), ints.astype(np.int32))
   rep = np.broadcast_to(rng.uniform(-100, 100, 20).astype(np.float32), (20000, 20))
   assert np.abs(P.stochastic_round(rep, 1.0, [9]).mean(0) - rep[0]).max() < 3e-2
+
+
+def test_run_length_port_reproduces_the_reference_literal():
+  """cc/kernels/run_length_kernels_test.cc:272-305 holds the one literal bit string of the run-length ops:
+  [-6, 3, 0, 0] <-> {0b11010001, 0b01101101} (gamma / gamma / zeros only); plus round trips over every code flavour."""
+  P = oracle.port()
+  assert P.run_length_encode([-6, 3, 0, 0]) == bytes([0b11010001, 0b01101101])
+  assert P.run_length_decode(bytes([0b11010001, 0b01101101]), (4,)).tolist() == [-6, 3, 0, 0]
+  rng = np.random.default_rng(1)
+  for rl, mg, nz in ((-1, -1, False), (-1, -1, True), (2, 3, True), (0, 0, False), (5, -1, False), (-1, 4, True)):
+    for density in (0.02, 0.5, 1.0):
+      d = (rng.integers(-300, 300, 5000) * (rng.random(5000) < density)).astype(np.int32)
+      code = P.run_length_encode(d, rl, mg, nz)
+      assert np.array_equal(P.run_length_decode(code, d.shape, rl, mg, nz), d)
+  with pytest.raises(oracle.OracleError, match="Out of bits"):
+    P.run_length_decode(b"\x01", (9,))
