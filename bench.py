@@ -68,7 +68,11 @@ def synth_latents(rank, n_rot, batch=None):
   out = []
   for _ in range(n_rot):
     u = torch.rand(B, HW, HW, C, generator=g) - 0.5
-    y = -scales * torch.sign(u) * torch.log1p(-2 * u.abs())
+    # rand() returns exactly 0 about once per 2^24 draws, i.e. u = -0.5 and log1p(-1) = -inf: an infinite latent
+    # quantises to INT32_MIN, whose Elias-gamma payload the reference's width loop never finishes
+    # (range_coder_kernels.cc:310-315).  Every other draw has 1 - 2|u| >= 2^-23 (log >= -15.95), so the clamp
+    # touches only those draws.
+    y = -scales * torch.sign(u) * torch.log1p(-2 * u.abs()).clamp_min(-17.0)
     out.append(y.contiguous())
   return scales, out
 
@@ -476,6 +480,18 @@ def main():
   world = int(os.environ.get("WORLD_SIZE", "1"))
   local = int(os.environ.get("LOCAL_RANK", "0"))
   assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+  # A rank stuck outside a collective leaves the others waiting in NCCL for ever: every rank arms a watchdog
+  # that prints all its Python stacks and exits non-zero instead (re-armed before each phase).
+  import faulthandler
+  watchdog_s = int(os.environ.get("TFCB_BENCH_WATCHDOG_S", "900"))
+
+  def phase(name):
+    faulthandler.cancel_dump_traceback_later()
+    faulthandler.dump_traceback_later(watchdog_s, exit=True)
+    if os.environ.get("TFCB_BENCH_TRACE"):
+      print(f"[bench rank {rank}] {name}", file=sys.stderr, flush=True)
+
+  phase("setup")
   torch.cuda.set_device(local)
   dev = torch.device("cuda", local)
   warm_oracle_pool()                      # before pinning: the checker's workers keep the whole machine
@@ -514,12 +530,14 @@ def main():
       dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
 
+  phase("warm-up")
   for i in range(max(args.warmup, 3)):
     strings = step(i)
   barrier()
   bits_per_symbol = 8.0 * strings.nbytes() / sym_per_step
 
   # ---- parity, outside the timed region: every rank, its own first batch, byte for byte against the oracle ----
+  phase("parity")
   threads = max(1, (os.cpu_count() or 1) // world)
   ok, parity = parity_check(model, ys_host[0], model.compress(ys[0]), threads)
   flag = torch.tensor([1 if ok else 0], device=dev)
@@ -540,6 +558,7 @@ def main():
     barrier()
     return allmax(ev0.elapsed_time(ev1))
 
+  phase("timed region")
   launches0 = _lib.launch_count()
   # clocks are sampled by rank 0 only (its own GPU, in-process NVML): one sampler per rank disturbed the others
   clocks = ClockSampler(local, str(torch.cuda.get_device_properties(dev).uuid)) if rank == 0 else None
@@ -557,6 +576,7 @@ def main():
   # Two staging buffers and a copy stream: the H2D copy of batch i+1 runs while batch i is encoded (compress()
   # blocks the host at its finalize, so the next copy has to be queued before it).  Every step's H2D and D2H
   # happen inside the timed region; the result (bytes + offsets) lands in pinned host memory.
+  phase("e2e")
   out_cap = 2 * strings.nbytes() + 4096
   host_bytes = [torch.empty(out_cap, dtype=torch.uint8).pin_memory() for _ in range(2)]
   host_offs = [torch.empty(S + 1, dtype=torch.int64).pin_memory() for _ in range(2)]
@@ -630,6 +650,9 @@ def main():
   if rank == 0:
     result["clocks"] = clocks.summary()
 
+  phase("extras")
+  if rank != 0:
+    faulthandler.cancel_dump_traceback_later()   # waiting for rank 0's side measurements; torchrun ends us if it dies
   if rank == 0 and not args.no_extras:
     try:
       extras(result, model, ys, ys_host, strings, dev, args, sym_per_step, S, N)
@@ -641,6 +664,7 @@ def main():
   if world > 1:
     dist.barrier()
     dist.destroy_process_group()
+  faulthandler.cancel_dump_traceback_later()
 
 
 def extras(result, model, ys, ys_host, strings, dev, args, sym_per_step, S, N):

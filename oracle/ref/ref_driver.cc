@@ -318,6 +318,17 @@ int tfcref_encoder_encode(void* h, const int32_t* index, const int32_t* value, i
           }
           enc.Encode(row.p[val + 1], row.p[val + 2], row.p[0], sink);
         } else {
+          // The reference's Elias-gamma width loop (`while (gamma >= (1 << n))`, :310-315, "TODO Clamp gamma")
+          // never ends once the payload reaches 2^30: `1 << 31` is negative and wider shifts wrap.  A checker
+          // must not hang on such input, so it is refused here; below 2^30 the loop is the reference's.
+          const int64_t payload = val < 0 ? -static_cast<int64_t>(val)
+                                          : static_cast<int64_t>(val) - (static_cast<int64_t>(row.size) - 3) + 1;
+          if (payload >= (int64_t{1} << 30)) {
+            std::lock_guard<std::mutex> g(mu);
+            err = "value=" + std::to_string(val) +
+                  " has an Elias-gamma payload >= 2^30; the reference's width loop does not terminate on it";
+            return;
+          }
           OverflowEncode(enc, sink, row, val);
         }
       }

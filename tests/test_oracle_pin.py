@@ -147,3 +147,31 @@ def test_run_length_port_reproduces_the_reference_literal():
       assert np.array_equal(P.run_length_decode(code, d.shape, rl, mg, nz), d)
   with pytest.raises(oracle.OracleError, match="Out of bits"):
     P.run_length_decode(b"\x01", (9,))
+
+
+@pytest.mark.parametrize("flavour", FLAVOURS)
+def test_escape_payloads_the_reference_cannot_finish_are_refused(flavour):
+  """OverflowEncode's width loop `while (gamma >= (1 << n))` (range_coder_kernels.cc:310-315, "TODO Clamp gamma")
+  never ends once the payload reaches 2^30.  The checker refuses such a symbol instead of hanging (bench.py found
+  this through an infinite synthetic latent); the largest payloads below the limit still round-trip."""
+  O = _o(flavour)
+  lookup = np.asarray([-4, 0, 5, 11, 16], np.int32)  # overflow row, escape symbol 2: payload = v - 1 for v >= 2
+  fine = np.asarray([[0, 1, 1 << 30, -((1 << 30) - 1), 7, -3]], np.int32)
+  s = O.encode(lookup, fine)
+  back, ok = O.decode(lookup, s, fine.shape[1])
+  assert np.array_equal(back, fine) and ok.all()
+  for v in ((1 << 30) + 1, -(1 << 30), np.iinfo(np.int32).min, np.iinfo(np.int32).max):
+    with pytest.raises(oracle.OracleError, match="Elias-gamma payload"):
+      O.encode(lookup, np.asarray([[0, v, 0]], np.int32))
+
+
+def test_bench_latents_are_finite_on_every_rank():
+  """bench.synth_latents: rand() == 0 used to give log1p(-1) = -inf, i.e. a latent that quantises to INT32_MIN;
+  rank 1's first batch had one, and the per-rank parity check then waited for ever inside the oracle."""
+  import torch
+  import bench
+  for rank in (0, 1, 7):
+    _, ys = bench.synth_latents(rank, 2, batch=64)
+    assert all(bool(torch.isfinite(y).all()) and float(y.abs().max()) < 8.0 * 17.0 + 1e-3 for y in ys)
+  _, full = bench.synth_latents(1, 1)   # the batch that hung the 2-GPU run
+  assert bool(torch.isfinite(full[0]).all())
