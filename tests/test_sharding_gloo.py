@@ -45,8 +45,20 @@ def _worker(rank, world, port, q):
       lin.bias.fill_(0.0)
     lin(torch.full((4, 3), float(rank + 1))).sum().backward()
     n_red = sharding.allreduce_gradients(lin)
+    # the CPU half of bench.py's per-rank parity check: every rank codes ITS OWN first cfg2 batch with the oracle
+    # and the verdicts are MIN-reduced (round 2: rank 1's batch held an infinite latent and never came back)
+    import bench
+    import oracle
+    fx = bench.load_fixture()
+    _, ys = bench.synth_latents(rank, 1)
+    value = bench.symbols_of(fx["cdf_offset"], None if fx["qoff"] is None else torch.from_numpy(fx["qoff"]), ys[0])
+    O = oracle.best()
+    want = O.encode(fx["lookup"], value, None, 2)
+    back, ok = O.decode(fx["lookup"], want, value.shape[1], None, 2)
+    flag = torch.tensor([1 if (np.array_equal(back, value) and ok.all()) else 0])
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     q.put((rank, model.cdf.clone(), model.cdf_offset.clone(), model.quantization_offset.clone(), lo, hi,
-           n_red, lin.weight.grad.clone(), lin.bias.grad.clone()))
+           n_red, lin.weight.grad.clone(), lin.bias.grad.clone(), int(flag.item()), int(np.abs(value).max())))
   finally:
     dist.barrier()
     dist.destroy_process_group()
@@ -82,7 +94,8 @@ def test_table_broadcast_and_batch_shards():
       last = e
   assert got is not None, f"gloo rendezvous failed three times: {last!r}"
   cdf, coff, qoff = _tables()
-  for rank, c, o, qo, lo, hi, n_red, gw, gb in got:
+  for rank, c, o, qo, lo, hi, n_red, gw, gb, parity, sym_max in got:
+    assert parity == 1 and sym_max < 1000
     assert torch.equal(c, cdf.to(torch.int32)) and torch.equal(o, coff) and torch.allclose(qo, qoff)
     # rank r's own gradient is 4 (r + 1) per weight and 4 per bias: the average over two ranks is 6 and 4
     assert n_red == 8 and torch.allclose(gw, torch.full((2, 3), 6.0)) and torch.allclose(gb, torch.full((2,), 4.0))
