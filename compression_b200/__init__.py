@@ -11,7 +11,7 @@ from compression_b200._lib import InvalidArgumentError
 def __getattr__(name):  # lazy: importing the package must not require torch / the built library
   import importlib
   modules = ("gen_ops", "functional", "math_ops", "distributions", "entropy_models", "gdn", "packed_tensors",
-             "signal_conv", "models", "sharding")
+             "signal_conv", "models", "sharding", "run_length_models")
   if name in modules:
     return importlib.import_module("compression_b200." + name)
   exported = {
@@ -24,7 +24,8 @@ def __getattr__(name):  # lazy: importing the package must not require torch / t
       "round_st": "math_ops", "lower_bound": "math_ops", "upper_bound": "math_ops",
       "perturb_and_apply": "math_ops", "PackedTensors": "packed_tensors",
       "SignalConv2D": "signal_conv", "RDFTParameter": "signal_conv", "same_padding_for_kernel": "signal_conv",
-      "BLS2017Model": "models", "BMSHJ2018Model": "models",
+      "BLS2017Model": "models", "BMSHJ2018Model": "models", "MS2020Model": "models",
+      "PowerLawEntropyModel": "run_length_models", "LaplaceEntropyModel": "run_length_models",
   }
   if name in exported:
     return getattr(importlib.import_module("compression_b200." + exported[name]), name)

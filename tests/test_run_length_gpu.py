@@ -80,3 +80,25 @@ def test_decode_errors_carry_the_reference_messages(ops):
   with pytest.raises(ValueError, match="shape"):
     ops.run_length_gamma_decode(code, [[6]])
   assert ops.run_length_gamma_encode(torch.zeros(0, dtype=torch.int32)) == b""
+
+
+def test_power_law_and_laplace_entropy_models_on_the_cuda_coder():
+  """power_law_test.py:50-56 / laplace_test.py:52-58 through the product path: every coding unit's string is the
+  sequential restatement's, and decompress(compress(x)) == quantize(x)."""
+  from compression_b200 import run_length_models as M
+  O = oracle.port()
+  g = torch.Generator().manual_seed(9)
+  x = (torch.randn(3, 2, 500, generator=g) * 4 * (torch.rand(3, 2, 500, generator=g) < 0.3)).cuda()
+  want = torch.round(x).cpu().numpy().astype(np.int32)
+  for em, params in ((M.PowerLawEntropyModel(coding_rank=1), (-1, -1, False)),
+                     (M.LaplaceEntropyModel(coding_rank=1), (-1, 0, False)),
+                     (M.LaplaceEntropyModel(coding_rank=1, run_length_code=2, magnitude_code=3,
+                                            use_run_length_for_non_zeros=True), (2, 3, True))):
+    strings = em.compress(x)
+    assert strings.shape == (3, 2)
+    for i in range(3):
+      for j in range(2):
+        assert strings[i, j] == O.run_length_encode(want[i, j], *params)
+    back = em.decompress(strings, (500,))
+    assert back.dtype == torch.float32 and back.shape == (3, 2, 500)
+    assert torch.equal(back.cpu(), em.quantize(x).cpu())
