@@ -11,7 +11,7 @@ from compression_b200._lib import InvalidArgumentError
 def __getattr__(name):  # lazy: importing the package must not require torch / the built library
   import importlib
   modules = ("gen_ops", "functional", "math_ops", "distributions", "entropy_models", "gdn", "packed_tensors",
-             "signal_conv", "models", "sharding", "run_length_models")
+             "signal_conv", "models", "sharding", "run_length_models", "soft_round_layers")
   if name in modules:
     return importlib.import_module("compression_b200." + name)
   exported = {
@@ -23,6 +23,15 @@ def __getattr__(name):  # lazy: importing the package must not require torch / t
       "NoisyLaplace": "distributions", "NoisyLogistic": "distributions",
       "round_st": "math_ops", "lower_bound": "math_ops", "upper_bound": "math_ops",
       "perturb_and_apply": "math_ops", "PackedTensors": "packed_tensors",
+      "soft_round_inverse": "math_ops", "soft_round_conditional_mean": "math_ops",
+      "SoftRound": "soft_round_layers", "SoftRoundConditionalMean": "soft_round_layers",
+      "soft_round": "math_ops",
+      "UniformNoiseAdapter": "distributions", "MonotonicAdapter": "distributions", "RoundAdapter": "distributions",
+      "NoisyRoundAdapter": "distributions", "NoisyRoundedNormal": "distributions",
+      "NoisyRoundedDeepFactorized": "distributions", "SoftRoundAdapter": "distributions",
+      "NoisySoftRoundAdapter": "distributions", "NoisySoftRoundedNormal": "distributions",
+      "NoisySoftRoundedDeepFactorized": "distributions", "estimate_tails": "distributions",
+      "quantization_offset": "distributions", "lower_tail": "distributions", "upper_tail": "distributions",
       "SignalConv2D": "signal_conv", "RDFTParameter": "signal_conv", "same_padding_for_kernel": "signal_conv",
       "BLS2017Model": "models", "BMSHJ2018Model": "models", "MS2020Model": "models",
       "PowerLawEntropyModel": "run_length_models", "LaplaceEntropyModel": "run_length_models",

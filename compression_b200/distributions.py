@@ -1,5 +1,6 @@
 """Priors used to derive range-coding tables, mirroring tensorflow_compression/python/distributions:
-helpers.py:29-219 (tail / offset estimation), deep_factorized.py:50-267 and uniform_noise.py:50-262.
+helpers.py:29-219 (tail / offset estimation), deep_factorized.py:50-267, uniform_noise.py:50-262 and
+round_adapters.py:36-288.
 TensorFlow Probability is replaced by a minimal scalar-distribution protocol on PyTorch:
 ``cdf / survival_function / log_cdf / log_survival_function / quantile / batch_shape / dtype``."""
 import math
@@ -10,7 +11,9 @@ from torch import nn
 __all__ = [
     "estimate_tails", "quantization_offset", "lower_tail", "upper_tail", "DeepFactorized",
     "NoisyDeepFactorized", "UniformNoiseAdapter", "Normal", "Laplace", "Logistic", "NoisyNormal",
-    "NoisyLaplace", "NoisyLogistic",
+    "NoisyLaplace", "NoisyLogistic", "MonotonicAdapter", "RoundAdapter", "NoisyRoundAdapter",
+    "NoisyRoundedNormal", "NoisyRoundedDeepFactorized", "SoftRoundAdapter", "NoisySoftRoundAdapter",
+    "NoisySoftRoundedNormal", "NoisySoftRoundedDeepFactorized",
 ]
 
 
@@ -267,6 +270,13 @@ class _LocScale:
     q = torch.as_tensor(q, dtype=self.dtype, device=self.device)
     return self.loc + self.scale * self._std_quantile(q)
 
+  def sample(self, sample_shape=(), generator=None):
+    """Inverse-CDF sampling; shape sample_shape + batch_shape."""
+    shape = tuple(sample_shape) + self.batch_shape
+    u = torch.rand(shape, dtype=self.dtype, device=self.device, generator=generator)
+    tiny = torch.finfo(self.dtype).tiny
+    return self.quantile(u.clamp(tiny, 1 - torch.finfo(self.dtype).eps / 2))
+
 
 class Normal(_LocScale):
   _std_cdf = staticmethod(torch.special.ndtr)
@@ -341,6 +351,22 @@ class UniformNoiseAdapter(nn.Module):
   def mean(self):
     return self.base.mean()
 
+  def sample(self, sample_shape=(), generator=None):
+    """base sample + U(-.5, .5) (uniform_noise.py:103-112)."""
+    x = self.base.sample(sample_shape, generator=generator)
+    return x + torch.rand(x.shape, dtype=x.dtype, device=x.device, generator=generator) - .5
+
+  # the noisy density has no closed-form mode / quantile / survival function (uniform_noise.py leaves the tfp
+  # defaults, which raise)
+  def mode(self):
+    raise NotImplementedError("mode is not implemented for UniformNoiseAdapter")
+
+  def quantile(self, value):
+    raise NotImplementedError("quantile is not implemented for UniformNoiseAdapter")
+
+  def survival_function(self, y):
+    raise NotImplementedError("survival_function is not implemented for UniformNoiseAdapter")
+
   def _quantization_offset(self):
     return quantization_offset(self.base)
 
@@ -375,3 +401,164 @@ class NoisyLaplace(UniformNoiseAdapter):
 
   def __init__(self, loc, scale, dtype=torch.float32):
     super().__init__(Laplace(loc, scale, dtype))
+
+
+# ------------------------------------------------------------------------------------------------
+# round_adapters.py
+# ------------------------------------------------------------------------------------------------
+class MonotonicAdapter(nn.Module):
+  """A continuous distribution seen through an ascending monotonic function (round_adapters.py:36-147;
+  Agustsson & Theis 2020, appendix E): cdf_Y(y) = cdf_X(inverse_transform(y))."""
+  invertible = True  # False: quantile / mode / tails of the base cannot be pushed through `transform`
+
+  def __init__(self, base):
+    super().__init__()
+    self.base = base
+
+  @property
+  def dtype(self):
+    return self.base.dtype
+
+  @property
+  def batch_shape(self):
+    return self.base.batch_shape
+
+  @property
+  def device(self):
+    return self.base.device
+
+  def transform(self, x):
+    raise NotImplementedError()
+
+  def inverse_transform(self, y):
+    raise NotImplementedError()
+
+  def sample(self, sample_shape=(), generator=None):
+    return self.transform(self.base.sample(sample_shape, generator=generator))
+
+  def prob(self, *args, **kwargs):
+    raise NotImplementedError
+
+  def log_prob(self, *args, **kwargs):
+    raise NotImplementedError
+
+  def _y(self, y):
+    return torch.as_tensor(y, dtype=self.dtype, device=self.device)
+
+  def cdf(self, y):
+    return self.base.cdf(self.inverse_transform(self._y(y)))
+
+  def log_cdf(self, y):
+    return self.base.log_cdf(self.inverse_transform(self._y(y)))
+
+  def survival_function(self, y):
+    return self.base.survival_function(self.inverse_transform(self._y(y)))
+
+  def log_survival_function(self, y):
+    return self.base.log_survival_function(self.inverse_transform(self._y(y)))
+
+  def _require_invertible(self):
+    if not self.invertible:
+      raise NotImplementedError()
+
+  def quantile(self, value):
+    self._require_invertible()
+    return self.transform(self.base.quantile(value))
+
+  def mode(self):
+    self._require_invertible()
+    return self.transform(self.base.mode())
+
+  def _quantization_offset(self):
+    self._require_invertible()
+    return self.transform(quantization_offset(self.base))
+
+  def _lower_tail(self, tail_mass):
+    self._require_invertible()
+    return self.transform(lower_tail(self.base, tail_mass))
+
+  def _upper_tail(self, tail_mass):
+    self._require_invertible()
+    return self.transform(upper_tail(self.base, tail_mass))
+
+
+class RoundAdapter(MonotonicAdapter):
+  """Continuous density + round (round_adapters.py:150-169): cdf_Y(y) = cdf_X(ceil(y) - 1/2)."""
+  invertible = False
+
+  def transform(self, x):
+    return torch.round(x)
+
+  def inverse_transform(self, y):
+    return torch.ceil(y) - .5
+
+  def _quantization_offset(self):
+    return torch.zeros((), dtype=self.dtype)
+
+  def _lower_tail(self, tail_mass):
+    return torch.floor(lower_tail(self.base, tail_mass))
+
+  def _upper_tail(self, tail_mass):
+    return torch.ceil(upper_tail(self.base, tail_mass))
+
+
+class NoisyRoundAdapter(UniformNoiseAdapter):
+  """Uniform noise + round (round_adapters.py:172-183)."""
+
+  def __init__(self, base):
+    super().__init__(RoundAdapter(base))
+
+
+class NoisyRoundedDeepFactorized(NoisyRoundAdapter):
+  """round_adapters.py:186-191."""
+
+  def __init__(self, **kwargs):
+    super().__init__(DeepFactorized(**kwargs))
+
+
+class NoisyRoundedNormal(NoisyRoundAdapter):
+  """round_adapters.py:194-198."""
+
+  def __init__(self, loc, scale, dtype=torch.float32):
+    super().__init__(Normal(loc, scale, dtype))
+
+
+class SoftRoundAdapter(MonotonicAdapter):
+  """Differentiable approximation of round (round_adapters.py:201-221)."""
+
+  def __init__(self, base, alpha):
+    super().__init__(base)
+    self._alpha = alpha
+
+  @property
+  def alpha(self):
+    return self._alpha
+
+  def transform(self, x):
+    from compression_b200 import math_ops
+    return math_ops.soft_round(x, self._alpha)
+
+  def inverse_transform(self, y):
+    from compression_b200 import math_ops
+    return math_ops.soft_round_inverse(y, self._alpha)
+
+
+class NoisySoftRoundAdapter(UniformNoiseAdapter):
+  """Uniform noise + soft round (round_adapters.py:224-236)."""
+
+  def __init__(self, base, alpha):
+    super().__init__(SoftRoundAdapter(base, alpha))
+
+
+class NoisySoftRoundedNormal(NoisySoftRoundAdapter):
+  """round_adapters.py:239-247."""
+
+  def __init__(self, alpha=5.0, loc=0., scale=1., dtype=torch.float32):
+    super().__init__(Normal(loc, scale, dtype), alpha)
+
+
+class NoisySoftRoundedDeepFactorized(NoisySoftRoundAdapter):
+  """round_adapters.py:250-260."""
+
+  def __init__(self, alpha=5.0, **kwargs):
+    super().__init__(DeepFactorized(**kwargs), alpha)

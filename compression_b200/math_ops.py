@@ -1,8 +1,9 @@
-"""Bound / perturbation helpers, mirroring tensorflow_compression/python/ops/math_ops.py:27-216 and
-round_ops.py:28-43 on PyTorch autograd."""
+"""Bound / perturbation / rounding helpers, mirroring tensorflow_compression/python/ops/math_ops.py:27-216 and
+round_ops.py:28-130 on PyTorch autograd."""
 import torch
 
-__all__ = ["upper_bound", "lower_bound", "perturb_and_apply", "round_st"]
+__all__ = ["upper_bound", "lower_bound", "perturb_and_apply", "round_st", "soft_round", "soft_round_inverse",
+           "soft_round_conditional_mean"]
 
 _GRADIENTS = ("identity_if_towards", "identity", "disconnected")
 
@@ -83,3 +84,36 @@ def perturb_and_apply(f, x, *args, u=None, x_plus_u=None, expected_grads=True):
   # y + (x - x.detach()) * dydx has value y and d/dx = dydx
   y = y + (x - x.detach()) * dydx
   return y, x_plus_u
+
+
+def _alpha_like(alpha, x):
+  return torch.as_tensor(alpha, dtype=x.dtype, device=x.device)
+
+
+def soft_round(x, alpha, eps=1e-3):
+  """Differentiable approximation of round (round_ops.py:44-74; Agustsson & Theis 2020, sec. 4.1):
+  m + tanh(alpha r) / (2 tanh(alpha / 2)) with m = floor(x) + 1/2, r = x - m; the identity for alpha < eps.  alpha
+  is bounded below by eps inside the formula so that the branch not taken has finite gradients."""
+  x = torch.as_tensor(x)
+  alpha = _alpha_like(alpha, x)
+  bounded = torch.clamp_min(alpha, eps)
+  m = torch.floor(x) + .5
+  y = m + torch.tanh(bounded * (x - m)) / (torch.tanh(bounded / 2.) * 2.)
+  return torch.where(alpha < eps, x, y)
+
+
+def soft_round_inverse(y, alpha, eps=1e-3):
+  """Inverse of `soft_round` (round_ops.py:77-108): r = atanh(2 tanh(alpha / 2) (y - m)) / alpha clipped to
+  [-1/2, 1/2] (atanh overflows first for large alpha), result m + r; the identity for alpha < eps."""
+  y = torch.as_tensor(y)
+  alpha = _alpha_like(alpha, y)
+  bounded = torch.clamp_min(alpha, eps)
+  m = torch.floor(y) + .5
+  r = torch.atanh((y - m) * (torch.tanh(bounded / 2.) * 2.)) / bounded
+  r = torch.clamp(r, -.5, .5)
+  return torch.where(alpha < eps, y, m + r)
+
+
+def soft_round_conditional_mean(y, alpha):
+  """E[Y | soft_round(Y) + U = y], U ~ U(-1/2, 1/2), Y locally uniform (round_ops.py:111-130)."""
+  return soft_round_inverse(torch.as_tensor(y) - .5, alpha) + .5
