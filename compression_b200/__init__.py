@@ -33,6 +33,10 @@ def __getattr__(name):  # lazy: importing the package must not require torch / t
       "NoisySoftRoundedDeepFactorized": "distributions", "estimate_tails": "distributions",
       "quantization_offset": "distributions", "lower_tail": "distributions", "upper_tail": "distributions",
       "SignalConv2D": "signal_conv", "RDFTParameter": "signal_conv", "same_padding_for_kernel": "signal_conv",
+      "IdentityInitializer": "signal_conv",
+      "MixtureSameFamily": "distributions", "NoisyMixtureSameFamily": "distributions",
+      "NoisyNormalMixture": "distributions", "NoisyLogisticMixture": "distributions", "Normal": "distributions",
+      "Logistic": "distributions", "Laplace": "distributions",
       "BLS2017Model": "models", "BMSHJ2018Model": "models", "MS2020Model": "models",
       "PowerLawEntropyModel": "run_length_models", "LaplaceEntropyModel": "run_length_models",
   }

@@ -13,7 +13,8 @@ __all__ = [
     "NoisyDeepFactorized", "UniformNoiseAdapter", "Normal", "Laplace", "Logistic", "NoisyNormal",
     "NoisyLaplace", "NoisyLogistic", "MonotonicAdapter", "RoundAdapter", "NoisyRoundAdapter",
     "NoisyRoundedNormal", "NoisyRoundedDeepFactorized", "SoftRoundAdapter", "NoisySoftRoundAdapter",
-    "NoisySoftRoundedNormal", "NoisySoftRoundedDeepFactorized",
+    "NoisySoftRoundedNormal", "NoisySoftRoundedDeepFactorized", "MixtureSameFamily", "NoisyMixtureSameFamily",
+    "NoisyNormalMixture", "NoisyLogisticMixture",
 ]
 
 
@@ -401,6 +402,136 @@ class NoisyLaplace(UniformNoiseAdapter):
 
   def __init__(self, loc, scale, dtype=torch.float32):
     super().__init__(Laplace(loc, scale, dtype))
+
+
+class MixtureSameFamily:
+  """Stand-in for `tfp.distributions.MixtureSameFamily` over a scalar family: `probs[..., K]` weights the K
+  components held in the last batch axis of `components`; that axis is summed out."""
+
+  def __init__(self, probs, components):
+    self.components = components
+    self.dtype = components.dtype
+    self.probs = torch.as_tensor(probs, dtype=self.dtype, device=components.device)
+    full = torch.broadcast_shapes(tuple(self.probs.shape), tuple(components.batch_shape))
+    self._batch_shape = tuple(full[:-1])
+
+  @property
+  def batch_shape(self):
+    return self._batch_shape
+
+  @property
+  def device(self):
+    return self.components.device
+
+  def _x(self, x):
+    return torch.as_tensor(x, dtype=self.dtype, device=self.device).unsqueeze(-1)
+
+  def cdf(self, x):
+    return (self.probs * self.components.cdf(self._x(x))).sum(-1)
+
+  def survival_function(self, x):
+    return (self.probs * self.components.survival_function(self._x(x))).sum(-1)
+
+  def log_cdf(self, x):
+    return torch.logsumexp(torch.log(self.probs) + self.components.log_cdf(self._x(x)), -1)
+
+  def log_survival_function(self, x):
+    return torch.logsumexp(torch.log(self.probs) + self.components.log_survival_function(self._x(x)), -1)
+
+  def mean(self):
+    return (self.probs * self.components.mean()).sum(-1)
+
+  def mode(self):
+    raise NotImplementedError("mode is not implemented for MixtureSameFamily")
+
+  def quantile(self, value):
+    raise NotImplementedError("quantile is not implemented for MixtureSameFamily")
+
+  def sample(self, sample_shape=(), generator=None):
+    x = self.components.sample(sample_shape, generator=generator)            # sample_shape + batch + [K]
+    x = x.expand(tuple(sample_shape) + self.batch_shape + x.shape[-1:])
+    w = self.probs.expand(x.shape).reshape(-1, x.shape[-1])
+    k = torch.multinomial(w, 1, generator=generator).reshape(x.shape[:-1] + (1,))
+    return torch.gather(x, -1, k).squeeze(-1)
+
+
+class NoisyMixtureSameFamily(nn.Module):
+  """Mixture of distributions with additive uniform noise (uniform_noise.py:200-244): the noise is added to every
+  component, tails come from the noiseless mixture, the quantisation offset is that of the component under which
+  its own offset is most probable."""
+
+  def __init__(self, mixture_probs, components_distribution):
+    super().__init__()
+    self.components_distribution = UniformNoiseAdapter(components_distribution)
+    self.base = MixtureSameFamily(mixture_probs, components_distribution)
+
+  @property
+  def mixture_probs(self):
+    return self.base.probs
+
+  @property
+  def dtype(self):
+    return self.base.dtype
+
+  @property
+  def batch_shape(self):
+    return self.base.batch_shape
+
+  @property
+  def device(self):
+    return self.base.device
+
+  def log_prob(self, y):
+    y = torch.as_tensor(y, dtype=self.dtype, device=self.device).unsqueeze(-1)
+    return torch.logsumexp(torch.log(self.mixture_probs) + self.components_distribution.log_prob(y), -1)
+
+  def prob(self, y):
+    y = torch.as_tensor(y, dtype=self.dtype, device=self.device).unsqueeze(-1)
+    return (self.mixture_probs * self.components_distribution.prob(y)).sum(-1)
+
+  def mean(self):
+    return self.base.mean()
+
+  def sample(self, sample_shape=(), generator=None):
+    x = self.base.sample(sample_shape, generator=generator)
+    return x + torch.rand(x.shape, dtype=x.dtype, device=x.device, generator=generator) - .5
+
+  def mode(self):
+    raise NotImplementedError("mode is not implemented for NoisyMixtureSameFamily")
+
+  def quantile(self, value):
+    raise NotImplementedError("quantile is not implemented for NoisyMixtureSameFamily")
+
+  def survival_function(self, y):
+    raise NotImplementedError("survival_function is not implemented for NoisyMixtureSameFamily")
+
+  def _quantization_offset(self):
+    """uniform_noise.py:231-237."""
+    offsets = quantization_offset(self.components_distribution)
+    offsets = offsets.expand(self.batch_shape + offsets.shape[-1:])
+    at = offsets.movedim(-1, 0)                                # [K] + batch: every component's offset as a point
+    component = torch.argmax(self.log_prob(at), dim=0)          # batch
+    return torch.gather(offsets, -1, component.unsqueeze(-1)).squeeze(-1)
+
+  def _lower_tail(self, tail_mass):
+    return lower_tail(self.base, tail_mass)
+
+  def _upper_tail(self, tail_mass):
+    return upper_tail(self.base, tail_mass)
+
+
+class NoisyNormalMixture(NoisyMixtureSameFamily):
+  """uniform_noise.py:268-285."""
+
+  def __init__(self, loc, scale, weight, dtype=torch.float32):
+    super().__init__(weight, Normal(loc, scale, dtype))
+
+
+class NoisyLogisticMixture(NoisyMixtureSameFamily):
+  """uniform_noise.py:288-305."""
+
+  def __init__(self, loc, scale, weight, dtype=torch.float32):
+    super().__init__(weight, Logistic(loc, scale, dtype))
 
 
 # ------------------------------------------------------------------------------------------------

@@ -15,7 +15,28 @@ import torch
 import torch.nn.functional as Fnn
 from torch import nn
 
-__all__ = ["same_padding_for_kernel", "RDFTParameter", "SignalConv2D"]
+__all__ = ["same_padding_for_kernel", "RDFTParameter", "SignalConv2D", "IdentityInitializer"]
+
+
+class IdentityInitializer:
+  """Initialises an n-D `SignalConv*` kernel (spatial..., in, out) to the identity (initializers.py:25-66): `gain`
+  at the centre tap `s // 2` of every spatial axis, times the in x out identity matrix."""
+
+  def __init__(self, gain=1):
+    self.gain = gain
+
+  def __call__(self, shape, dtype=None):
+    shape = tuple(int(d) for d in shape)
+    if len(shape) <= 2:
+      raise ValueError(f"shape must be at least rank 3, got {shape}.")
+    dtype = torch.float32 if dtype is None else dtype
+    kernel = torch.zeros(shape, dtype=dtype)
+    centre = tuple(s // 2 for s in shape[:-2])
+    kernel[centre] = self.gain * torch.eye(shape[-2], shape[-1], dtype=dtype)
+    return kernel
+
+  def get_config(self):
+    return dict(gain=self.gain)
 
 
 def same_padding_for_kernel(shape, corr, strides_up=None):

@@ -89,3 +89,24 @@ def test_lazy_build_default_parameters_and_activation_order():
   assert .5 / 75 < var < 2. / 75                                                           # variance_scaling: 1 / fan_in
   with pytest.raises(ValueError):
     layer(torch.randn(9, 8, 3))
+
+
+def test_identity_initializer_kernels():
+  """initializers_test.py:22-50."""
+  from compression_b200.signal_conv import IdentityInitializer, SignalConv2D
+  k = IdentityInitializer(gain=3)((3, 4, 3), dtype=torch.int32)
+  want = torch.zeros(3, 4, 3, dtype=torch.int32)
+  for i in range(3):
+    want[1, i, i] = 3
+  assert torch.equal(k, want)
+  k = IdentityInitializer()((4, 5, 1, 1))
+  want = torch.zeros(4, 5, 1, 1)
+  want[2, 2, 0, 0] = 1
+  assert torch.equal(k, want) and k.dtype == torch.float32
+  with pytest.raises(ValueError):
+    IdentityInitializer()((2, 3))
+  # what it is for: a `same`-padded layer initialised with it copies its input
+  layer = SignalConv2D(3, (5, 5), corr=True, padding="same_zeros", use_bias=False, kernel_parameter="variable",
+                       kernel_initializer=IdentityInitializer())
+  x = torch.randn(2, 9, 8, 3)
+  assert torch.allclose(layer(x), x, atol=1e-6)

@@ -171,3 +171,43 @@ def test_rounded_prior_builds_integer_aligned_tables():
   assert torch.equal(D.quantization_offset(d), torch.zeros(()))
   lo, hi = D.lower_tail(d, 2**-8), D.upper_tail(d, 2**-8)
   assert torch.equal(lo, torch.round(lo)) and torch.equal(hi, torch.round(hi))
+
+
+@pytest.mark.parametrize("cls", [D.NoisyNormalMixture, D.NoisyLogisticMixture])
+def test_noisy_mixtures(cls):
+  """uniform_noise_test.py:105-172 (MixtureTest)."""
+  assert cls(loc=[3., -3.], scale=[5., 2.5], weight=[.3, .7]).batch_shape == ()
+  assert cls(loc=[[3., -3.], [2., -2.]], scale=[5., 2.5], weight=[.3, .7]).batch_shape == (2,)
+  loc = torch.ones(2, requires_grad=True)
+  log_scale = torch.zeros(2, requires_grad=True)
+  logit = torch.tensor([.3, .7], requires_grad=True)
+  x = torch.randn(20, generator=torch.Generator().manual_seed(0))
+  loss = -cls(loc=loc, scale=torch.exp(log_scale), weight=torch.softmax(logit, 0)).log_prob(x).mean()
+  assert all(g is not None and bool(torch.isfinite(g).all()) for g in torch.autograd.grad(loss, [loc, log_scale, logit]))
+  # scales -> 0: a mixture of unit-width uniform densities
+  dist = cls(loc=[2.5, -1.], scale=[1e-7, 1e-7], weight=[.3, .7])
+  box = torch.tensor([0, 0, 0, 1, 1, 1, 1, 0, 0, 0.])
+  assert torch.allclose(dist.prob(torch.linspace(1.5, 3.5, 10)), .3 * box, atol=1e-5)
+  assert torch.allclose(dist.prob(torch.linspace(-2., 0., 10)), .7 * box, atol=1e-5)
+  assert cls(loc=[[0.]], scale=[3., 5.], weight=[.2, .8]).sample((5, 4)).shape == (5, 4, 1)
+  dist = cls(loc=[5.4, 8.6], scale=[1.4, 2.], weight=[.6, .4])
+  assert float(D.upper_tail(dist, 2**-8)) > float(D.lower_tail(dist, 2**-8))
+  assert math.isclose(float(D.quantization_offset(dist)), 0.4, abs_tol=1e-5)   # decimal part of the peakiest mode
+  assert float(dist.base.cdf(D.lower_tail(dist, 2**-8))) <= 2**-8 * 0.51
+  dist = cls(loc=[1., 0.], scale=2., weight=[.1, .9])
+  for call in (dist.mode, lambda: dist.quantile(.5), lambda: dist.survival_function(.5)):
+    with pytest.raises(NotImplementedError):
+      call()
+  dist = cls(loc=[0., 0.], scale=[0., 0.], weight=[.5, .5])   # all mass at 0
+  assert torch.allclose(dist.prob([0.]), torch.ones(1)) and torch.allclose(dist.prob([1.]), torch.zeros(1))
+
+
+def test_mixture_prior_trains_an_entropy_model_on_cpu():
+  import compression_b200 as tfc
+  prior = tfc.NoisyNormalMixture(loc=torch.tensor([[-2., 2.]] * 3), scale=torch.tensor([[1., 1.5]] * 3),
+                                 weight=torch.tensor([.4, .6]))
+  assert prior.batch_shape == (3,)
+  em = tfc.ContinuousBatchedEntropyModel(prior, coding_rank=1, compression=False)
+  x = torch.randn(5, 3, generator=torch.Generator().manual_seed(0)) * 2
+  xt, bits = em(x, training=True)
+  assert xt.shape == x.shape and bits.shape == (5,) and bool((bits > 0).all())
