@@ -32,7 +32,7 @@ def __getattr__(name):  # lazy: importing the package must not require torch / t
       "NoisySoftRoundAdapter": "distributions", "NoisySoftRoundedNormal": "distributions",
       "NoisySoftRoundedDeepFactorized": "distributions", "estimate_tails": "distributions",
       "quantization_offset": "distributions", "lower_tail": "distributions", "upper_tail": "distributions",
-      "SignalConv2D": "signal_conv", "RDFTParameter": "signal_conv", "same_padding_for_kernel": "signal_conv",
+      "SignalConv1D": "signal_conv", "SignalConv2D": "signal_conv", "SignalConv3D": "signal_conv", "RDFTParameter": "signal_conv", "same_padding_for_kernel": "signal_conv",
       "IdentityInitializer": "signal_conv",
       "MixtureSameFamily": "distributions", "NoisyMixtureSameFamily": "distributions",
       "NoisyNormalMixture": "distributions", "NoisyLogisticMixture": "distributions", "Normal": "distributions",

@@ -110,3 +110,161 @@ def test_identity_initializer_kernels():
                        kernel_initializer=IdentityInitializer())
   x = torch.randn(2, 9, 8, 3)
   assert torch.allclose(layer(x), x, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------
+# 1-D / 3-D layers, `same_reflect`, `channel_separable`: against the layer's definition computed with scipy
+# ------------------------------------------------------------------------------------------------
+def _definition_nd(x, kernel, corr, up, down, padding, extra_pad_end=True, separable=False):
+  """x [B, *L, Ci], kernel [*k, Ci, Co | m] -> [B, *L', Co | Ci*m] (signal_conv.py:61-215 docstring): upsample by
+  zero insertion, convolve / correlate with the kernel centred at K // 2, downsample.  `same_*` padding is applied to
+  the signal BEFORE the zero insertion (that is what makes `same_reflect` well defined, :884-905), in the amounts of
+  ops/padding_ops.py:22-51."""
+  from scipy import signal
+  r = x.ndim - 2
+  k = kernel.shape[:r]
+  mode = {"same_zeros": "constant", "same_reflect": "reflect", "valid": None}[padding]
+  if corr and any(u > 1 for u in up):          # correlation == convolution with the reversed kernel (odd supports)
+    assert all(s % 2 == 1 for s in k)
+    kernel = np.flip(kernel, axis=tuple(range(r)))
+    corr = False
+  B, Ci = x.shape[0], x.shape[-1]
+  nout = kernel.shape[-1]
+  pairs = [(c, j, c * nout + j) for c in range(Ci) for j in range(nout)] if separable else \
+      [(c, j, j) for c in range(Ci) for j in range(nout)]
+  n_out_channels = Ci * nout if separable else nout
+  if corr:
+    xp = x
+    if mode:
+      xp = np.pad(x, [(0, 0)] + [(s // 2, (s - 1) // 2) for s in k] + [(0, 0)], mode=mode)
+    out = None
+    for c, j, o in pairs:
+      for b in range(B):
+        y = signal.correlate(xp[b, ..., c], kernel[..., c, j], mode="valid")
+        if out is None:
+          out = np.zeros((B,) + y.shape + (n_out_channels,))
+        out[b, ..., o] += y
+  else:
+    P = r * [(0, 0)]
+    if mode:
+      P = [(((s - 1) // 2 - 1) // u + 1, (s // 2 - 1) // u + 1) for s, u in zip(k, up)]
+    xp = np.pad(x, [(0, 0)] + P + [(0, 0)], mode=mode) if mode else x
+    Lp = xp.shape[1:-1]
+    Lu = [n * u if extra_pad_end else (n - 1) * u + 1 for n, u in zip(Lp, up)]
+    us = np.zeros((B,) + tuple(Lu) + (Ci,))
+    us[(slice(None),) + tuple(slice(0, None, u) for u in up)] = xp
+    crop = []
+    for i in range(r):
+      if padding == "valid":
+        a = z = k[i] - 1
+      else:
+        a, z = P[i][0] * up[i] + k[i] // 2, P[i][1] * up[i] + (k[i] - 1) // 2
+      crop.append(slice(a, Lu[i] + k[i] - 1 - z))
+    out = None
+    for c, j, o in pairs:
+      for b in range(B):
+        y = signal.convolve(us[b, ..., c], kernel[..., c, j], mode="full")[tuple(crop)]
+        if out is None:
+          out = np.zeros((B,) + y.shape + (n_out_channels,))
+        out[b, ..., o] += y
+  return out[(slice(None),) + tuple(slice(None, None, d) for d in down)]
+
+
+def _layer_cls(rank):
+  from compression_b200 import signal_conv
+  return {1: signal_conv.SignalConv1D, 2: signal_conv.SignalConv2D, 3: signal_conv.SignalConv3D}[rank]
+
+
+ND_CASES = [
+    # rank, support, corr, up, down, padding, extra_pad_end, separable
+    (1, (5,), True, 1, 2, "same_zeros", True, False),
+    (1, (4,), False, 2, 1, "same_zeros", True, False),
+    (1, (3,), False, 2, 1, "valid", False, False),
+    (1, (5,), True, 1, 2, "same_reflect", True, False),
+    (1, (5,), False, 2, 1, "same_reflect", False, False),
+    (1, (4,), False, 3, 2, "same_reflect", True, False),
+    (1, (5,), True, 1, 1, "same_zeros", True, True),
+    (1, (3,), False, 2, 1, "same_zeros", True, True),
+    (2, (5, 3), True, 1, 2, "same_reflect", True, False),
+    (2, (3, 5), False, (2, 1), 1, "same_reflect", True, False),
+    (2, (5, 5), True, 2, 1, "same_reflect", False, False),
+    (2, (4, 3), False, 1, 1, "same_reflect", True, False),
+    (2, (5, 5), True, 1, (2, 2), "same_zeros", True, True),
+    (2, (3, 3), False, 2, 1, "valid", True, True),
+    (2, (3, 4), False, 1, 1, "same_reflect", True, True),
+    (3, (3, 3, 3), True, 1, 2, "same_zeros", True, False),
+    (3, (3, 2, 3), False, 2, 1, "same_zeros", True, False),
+    (3, (3, 3, 3), True, 1, 1, "valid", True, False),
+    (3, (3, 3, 3), False, (1, 2, 2), (2, 1, 1), "same_reflect", True, False),
+]
+
+
+@pytest.mark.parametrize("rank,k,corr,up,down,padding,extra,separable", ND_CASES)
+def test_nd_layers_match_the_definition(rank, k, corr, up, down, padding, extra, separable):
+  rng = np.random.default_rng(hash((rank, k, corr, str(up), str(down), padding, extra, separable)) % 2**32)
+  up_t = rank * (up,) if isinstance(up, int) else up
+  down_t = rank * (down,) if isinstance(down, int) else down
+  L = {1: (11,), 2: (9, 8), 3: (6, 5, 7)}[rank]
+  Ci, F = 3, 2
+  x = rng.normal(size=(2,) + L + (Ci,))
+  kernel = rng.normal(size=k + (Ci, F))
+  layer = _layer_cls(rank)(F, k, corr=corr, strides_up=up, strides_down=down, padding=padding, extra_pad_end=extra,
+                           channel_separable=separable, kernel_parameter=torch.tensor(kernel))
+  y = layer(torch.tensor(x))
+  want = _definition_nd(x, kernel, corr, up_t, down_t, padding, extra, separable)
+  assert tuple(y.shape) == want.shape == layer.compute_output_shape(x.shape)
+  np.testing.assert_allclose(y.numpy(), want, rtol=1e-9, atol=1e-9)
+  cf = _layer_cls(rank)(F, k, corr=corr, strides_up=up, strides_down=down, padding=padding, extra_pad_end=extra,
+                        channel_separable=separable, data_format="channels_first", kernel_parameter=torch.tensor(kernel))
+  yc = cf(torch.tensor(x).movedim(-1, 1))
+  assert tuple(yc.shape) == cf.compute_output_shape((2, Ci) + L)
+  np.testing.assert_allclose(yc.movedim(1, -1).numpy(), want, rtol=1e-9, atol=1e-9)
+
+
+def test_definition_agrees_with_the_2d_loop_restatement():
+  """The scipy definition used for the N-D cases is the same function as the loop restatement above."""
+  rng = np.random.default_rng(0)
+  x, kernel = rng.normal(size=(2, 7, 6, 3)), rng.normal(size=(4, 5, 3, 4))
+  for corr, up, down, padding in ((False, 2, 1, "same_zeros"), (True, 1, 2, "same_zeros"), (False, 1, 1, "valid"),
+                                  (False, 4, 2, "valid")):
+    np.testing.assert_allclose(_definition_nd(x, kernel, corr, (up, up), (down, down), padding),
+                               _definition(x, kernel, corr, up, down, padding), rtol=1e-10, atol=1e-10)
+
+
+def test_equivalent_kernels_of_the_docstring_give_the_same_output():
+  """signal_conv.py:92-104: with `same_*` padding, convolving with [1,2,3], [0,1,2,3,0], [0,1,2,3] and correlating
+  with [3,2,1], [0,3,2,1,0], [0,3,2,1] are all the same operation (the kernel centre is at K // 2)."""
+  from compression_b200.signal_conv import SignalConv1D
+  x = torch.randn(2, 12, 1, dtype=torch.float64, generator=torch.Generator().manual_seed(0))
+  outs = []
+  for corr, taps in ((False, [1, 2, 3]), (False, [0, 1, 2, 3, 0]), (False, [0, 1, 2, 3]),
+                     (True, [3, 2, 1]), (True, [0, 3, 2, 1, 0]), (True, [0, 3, 2, 1])):
+    for padding in ("same_zeros", "same_reflect"):
+      k = torch.tensor(taps, dtype=torch.float64).reshape(-1, 1, 1)
+      outs.append((padding, SignalConv1D(1, len(taps), corr=corr, padding=padding, kernel_parameter=k)(x)))
+  for padding in ("same_zeros", "same_reflect"):
+    same = [o for p, o in outs if p == padding]
+    for o in same[1:]:
+      torch.testing.assert_close(o, same[0], rtol=1e-12, atol=1e-12)
+
+
+def test_rdft_parameter_for_1d_and_3d_kernels():
+  for shape in ((7, 3, 4), (3, 4, 5, 2, 3)):
+    k = torch.randn(shape, generator=torch.Generator().manual_seed(len(shape)))
+    p = RDFTParameter(k)
+    assert p.shape == shape and p.real.shape[:2] == shape[-2:] and p.real.shape[-1] == shape[len(shape) - 3] // 2 + 1
+    torch.testing.assert_close(p(), k, rtol=1e-5, atol=1e-5)
+  with pytest.raises(ValueError):
+    RDFTParameter(torch.zeros(3, 3))
+
+
+def test_argument_errors():
+  from compression_b200.signal_conv import SignalConv1D, SignalConv3D
+  with pytest.raises(ValueError):
+    SignalConv2D(4, (3, 3), padding="same_wrap")
+  with pytest.raises(ValueError):
+    SignalConv3D(4, (3, 3))
+  with pytest.raises(ValueError):
+    SignalConv1D(4, 3)(torch.zeros(2, 5, 5, 3))
+  with pytest.raises(NotImplementedError):   # correlation + upsampling of an even-length kernel (:946-947)
+    SignalConv1D(2, 4, corr=True, strides_up=2, kernel_parameter="variable")(torch.zeros(1, 8, 3))
