@@ -498,7 +498,8 @@ def main():
   numa = pin_to_gpu_numa_node(local)
   if world > 1:
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    dist.init_process_group("nccl", device_id=dev)
+    import datetime
+    dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(minutes=30))
 
   n_rot = CFG["n_rot"]
   scales, ys_host = synth_latents(rank, n_rot)
@@ -720,6 +721,12 @@ def extras(result, model, ys, ys_host, strings, dev, args, sym_per_step, S, N):
   dec_ms, out = _time_ms(lambda: model.decompress(strings, (CFG["hw"], CFG["hw"])), max(3, min(args.steps, 10)), warm=2)
   result["decode"] = {"value": sym_per_step / (dec_ms * 1e-3) / 1e6, "unit": "Msymbols/s", "ms_per_step": dec_ms,
                       "roundtrip_equals_quantize": bool(torch.equal(out, model.quantize(ys[0])))}
+  if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    # N > 1 is the scaling measurement: the other ranks wait at a barrier while rank 0 is here, so the long side
+    # measurements (cfg3, GDN at 12 GiB tensors, the model path, the CPU baselines -- rank 0 at N = 1 only) stay
+    # with the single-GPU run
+    result["extras_note"] = "N > 1: cfg3 / GDN / model-path / CPU side measurements are taken by the N = 1 run"
+    return
   # --- configs[2]: bmshj2018 hyperprior, both levels, encode and decode
   try:
     w = cfg3_workload(dev)
