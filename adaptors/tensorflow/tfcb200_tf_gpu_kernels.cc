@@ -6,6 +6,8 @@
 //                                      CreateRangeDecoder, EntropyDecode{Channel,Index,Finalize}
 //   cc/ops/pmf_to_cdf_ops.cc:28-57     PmfToQuantizedCdf
 //   cc/ops/quantization_ops.cc:28-53   StochasticRound
+//   cc/ops/run_length_ops.cc:28-84, run_length_gamma_ops.cc:26-58   RunLength{,Gamma}{Encode,Decode}
+//   cc/ops/range_coding_ops.cc:30-124  RangeEncode, RangeDecode (legacy single-stream ops)
 // and their CPU kernels stay registered (cc/kernels/range_coder_kernels.cc:505-700 etc.); TensorFlow's placer picks
 // the GPU kernel when the data tensors live on the GPU, so python/ops/gen_ops.py and models/*.py are unchanged.
 // GDN has no op in the reference (python/layers/gdn.py:371-421 composes TF ops): GdnForward / GdnBackward are
@@ -310,6 +312,160 @@ TFCB_REGISTER_SR(float, 0);
 TFCB_REGISTER_SR(Eigen::half, 1);
 TFCB_REGISTER_SR(tf::bfloat16, 2);
 #undef TFCB_REGISTER_SR
+
+// ---- RunLengthEncode / RunLengthGammaEncode (run_length_kernels.cc:52-139, run_length_gamma_kernels.cc:51-101) ----
+// `data` on the device, `code` (a scalar tf.string) in host memory: the bits are packed on the device into a
+// temporary and copied out once the length is known (tfcb_run_length_encode synchronises to report it).
+class RunLengthEncodeGpuOp : public tf::OpKernel {
+ public:
+  explicit RunLengthEncodeGpuOp(tf::OpKernelConstruction* c) : tf::OpKernel(c) {
+    if (c->HasAttr("run_length_code")) {   // RunLengthGammaEncode has no attributes: gamma / gamma / false
+      OP_REQUIRES_OK(c, c->GetAttr("run_length_code", &run_length_code_));
+      OP_REQUIRES_OK(c, c->GetAttr("magnitude_code", &magnitude_code_));
+      OP_REQUIRES_OK(c, c->GetAttr("use_run_length_for_non_zeros", &non_zero_runs_));
+    }
+  }
+  void Compute(tf::OpKernelContext* ctx) override {
+    const tf::Tensor& data = ctx->input(0);
+    tf::Tensor* code;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, tf::TensorShape({}), &code));
+    const int64_t n = data.NumElements();
+    if (n == 0) return;
+    int64_t cap = 4 * ((2 * n + 64 + 3) / 4), n_bytes = 0;
+    tf::Tensor tmp;
+    for (int attempt = 0; attempt < 2; ++attempt) {       // a second pass only if the first guess was too small
+      OP_REQUIRES_OK(ctx, ctx->allocate_temp(tf::DT_UINT8, tf::TensorShape({cap}), &tmp));
+      const int rc = tfcb_run_length_encode(data.flat<int32_t>().data(), n, run_length_code_, magnitude_code_,
+                                            non_zero_runs_ ? 1 : 0, tmp.flat<uint8_t>().data(), cap, &n_bytes,
+                                            CudaStream(ctx));
+      if (rc == TFCB_INVALID_ARGUMENT && n_bytes > cap - 4 && attempt == 0) {
+        cap = 4 * ((n_bytes + 3) / 4) + 4;
+        continue;
+      }
+      OP_REQUIRES_OK(ctx, FromRc(rc));
+      break;
+    }
+    std::string host(static_cast<size_t>(n_bytes), '\0');
+    auto* stream = ctx->op_device_context()->stream();
+    stream_executor::DeviceMemoryBase src(tmp.flat<uint8_t>().data(), static_cast<uint64_t>(n_bytes));
+    OP_REQUIRES_OK(ctx, stream->Memcpy(&host[0], src, static_cast<uint64_t>(n_bytes)));
+    OP_REQUIRES_OK(ctx, stream->BlockHostUntilDone());
+    code->scalar<tf::tstring>()() = std::move(host);
+  }
+ private:
+  int run_length_code_ = -1, magnitude_code_ = -1;
+  bool non_zero_runs_ = false;
+};
+REGISTER_KERNEL_BUILDER(Name("RunLengthEncode").Device(tf::DEVICE_GPU).HostMemory("code"), RunLengthEncodeGpuOp);
+REGISTER_KERNEL_BUILDER(Name("RunLengthGammaEncode").Device(tf::DEVICE_GPU).HostMemory("code"), RunLengthEncodeGpuOp);
+
+// ---- RunLengthDecode / RunLengthGammaDecode (run_length_kernels.cc:141-262) ----
+class RunLengthDecodeGpuOp : public tf::OpKernel {
+ public:
+  explicit RunLengthDecodeGpuOp(tf::OpKernelConstruction* c) : tf::OpKernel(c) {
+    if (c->HasAttr("run_length_code")) {
+      OP_REQUIRES_OK(c, c->GetAttr("run_length_code", &run_length_code_));
+      OP_REQUIRES_OK(c, c->GetAttr("magnitude_code", &magnitude_code_));
+      OP_REQUIRES_OK(c, c->GetAttr("use_run_length_for_non_zeros", &non_zero_runs_));
+    }
+  }
+  void Compute(tf::OpKernelContext* ctx) override {
+    const tf::Tensor& code = ctx->input(0);   // host memory
+    OP_REQUIRES(ctx, tf::TensorShapeUtils::IsScalar(code.shape()),
+                InvalidArgument("Invalid `code` shape: ", code.shape().DebugString()));
+    OP_REQUIRES(ctx, tf::TensorShapeUtils::IsVector(ctx->input(1).shape()),
+                InvalidArgument("Invalid `shape` shape: ", ctx->input(1).shape().DebugString()));
+    tf::TensorShape shape;
+    OP_REQUIRES_OK(ctx, tf::tensor::MakeShape(ctx->input(1), &shape));
+    tf::Tensor* data;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, shape, &data));
+    const tf::tstring& bytes = code.scalar<tf::tstring>()();
+    tf::Tensor dev;                            // the string on the device, padded so that word reads stay inside
+    OP_REQUIRES_OK(ctx, ctx->allocate_temp(tf::DT_UINT8, tf::TensorShape({static_cast<int64_t>(bytes.size()) + 4}), &dev));
+    auto* stream = ctx->op_device_context()->stream();
+    stream_executor::DeviceMemoryBase dst(dev.flat<uint8_t>().data(), bytes.size());
+    if (!bytes.empty()) OP_REQUIRES_OK(ctx, stream->Memcpy(&dst, bytes.data(), bytes.size()));
+    // decode errors come back as the reference's DataLoss messages ("Out of bits to read." ...)
+    const int rc = tfcb_run_length_decode(dev.flat<uint8_t>().data(), static_cast<int64_t>(bytes.size()), run_length_code_,
+                                          magnitude_code_, non_zero_runs_ ? 1 : 0, data->flat<int32_t>().data(),
+                                          data->NumElements(), CudaStream(ctx));
+    OP_REQUIRES(ctx, rc == TFCB_OK, rc == TFCB_INVALID_ARGUMENT ? tf::errors::DataLoss(tfcb_last_error())
+                                                                : FromRc(rc));
+  }
+ private:
+  int run_length_code_ = -1, magnitude_code_ = -1;
+  bool non_zero_runs_ = false;
+};
+REGISTER_KERNEL_BUILDER(Name("RunLengthDecode").Device(tf::DEVICE_GPU).HostMemory("code").HostMemory("shape"),
+                        RunLengthDecodeGpuOp);
+REGISTER_KERNEL_BUILDER(Name("RunLengthGammaDecode").Device(tf::DEVICE_GPU).HostMemory("code").HostMemory("shape"),
+                        RunLengthDecodeGpuOp);
+
+// ---- RangeEncode / RangeDecode, the legacy single-stream ops (range_coding_kernels.cc:176-379) ----
+std::vector<int64_t> Dims(const tf::TensorShape& shape) {
+  std::vector<int64_t> d(shape.dims());
+  for (int i = 0; i < shape.dims(); ++i) d[i] = shape.dim_size(i);
+  return d;
+}
+
+class RangeEncodeGpuOp : public tf::OpKernel {
+ public:
+  explicit RangeEncodeGpuOp(tf::OpKernelConstruction* c) : tf::OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("precision", &precision_));
+    OP_REQUIRES_OK(c, c->GetAttr("debug_level", &debug_level_));
+    OP_REQUIRES(c, 0 < precision_ && precision_ <= 16, InvalidArgument("`precision` must be in [1, 16]: ", precision_));
+  }
+  void Compute(tf::OpKernelContext* ctx) override {
+    const tf::Tensor& data = ctx->input(0);
+    const tf::Tensor& cdf = ctx->input(1);
+    const std::vector<int64_t> ds = Dims(data.shape()), cs = Dims(cdf.shape());
+    tf::Tensor* out;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, tf::TensorShape({}), &out));
+    // a symbol costs at most `precision` <= 16 bits; the coder flushes at most four more bytes
+    std::string host(static_cast<size_t>(2 * data.NumElements() + 16), '\0');
+    int64_t n_bytes = 0;
+    OP_REQUIRES_OK(ctx, FromRc(tfcb_range_encode(data.flat<int16_t>().data(), ds.data(), data.dims(),
+                                                cdf.flat<int32_t>().data(), cs.data(), cdf.dims(), precision_, debug_level_,
+                                                reinterpret_cast<uint8_t*>(&host[0]), static_cast<int64_t>(host.size()),
+                                                &n_bytes, CudaStream(ctx))));
+    host.resize(static_cast<size_t>(n_bytes));
+    out->scalar<tf::tstring>()() = std::move(host);
+  }
+ private:
+  int precision_, debug_level_;
+};
+REGISTER_KERNEL_BUILDER(Name("RangeEncode").Device(tf::DEVICE_GPU).HostMemory("encoded"), RangeEncodeGpuOp);
+
+class RangeDecodeGpuOp : public tf::OpKernel {
+ public:
+  explicit RangeDecodeGpuOp(tf::OpKernelConstruction* c) : tf::OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("precision", &precision_));
+    OP_REQUIRES_OK(c, c->GetAttr("debug_level", &debug_level_));
+    OP_REQUIRES(c, 0 < precision_ && precision_ <= 16, InvalidArgument("`precision` must be in [1, 16]: ", precision_));
+  }
+  void Compute(tf::OpKernelContext* ctx) override {
+    const tf::Tensor& encoded = ctx->input(0);   // host memory
+    const tf::Tensor& cdf = ctx->input(2);
+    OP_REQUIRES(ctx, tf::TensorShapeUtils::IsScalar(encoded.shape()),
+                InvalidArgument("Invalid `encoded` shape: ", encoded.shape().DebugString()));
+    OP_REQUIRES(ctx, tf::TensorShapeUtils::IsVector(ctx->input(1).shape()),
+                InvalidArgument("Invalid `shape` shape: ", ctx->input(1).shape().DebugString()));
+    tf::TensorShape shape;
+    OP_REQUIRES_OK(ctx, tf::tensor::MakeShape(ctx->input(1), &shape));
+    const std::vector<int64_t> ds = Dims(shape), cs = Dims(cdf.shape());
+    tf::Tensor* out;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, shape, &out));
+    const tf::tstring& bytes = encoded.scalar<tf::tstring>()();
+    OP_REQUIRES_OK(ctx, FromRc(tfcb_range_decode(reinterpret_cast<const uint8_t*>(bytes.data()),
+                                                static_cast<int64_t>(bytes.size()), ds.data(), shape.dims(),
+                                                cdf.flat<int32_t>().data(), cs.data(), cdf.dims(), precision_, debug_level_,
+                                                out->flat<int16_t>().data(), CudaStream(ctx))));
+  }
+ private:
+  int precision_, debug_level_;
+};
+REGISTER_KERNEL_BUILDER(Name("RangeDecode").Device(tf::DEVICE_GPU).HostMemory("encoded").HostMemory("shape"),
+                        RangeDecodeGpuOp);
 
 // ---- GDN: two new ops (the reference has none); see gdn_custom_gradient.py in this directory ----
 REGISTER_OP("GdnForward")
