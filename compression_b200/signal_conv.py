@@ -263,7 +263,8 @@ class _SignalConv(nn.Module):
       else:
         start = prepad[i][0] * s[i] + k[i] // 2
         stop = prepad[i][1] * s[i] + (k[i] - 1) // 2
-      extend.append((0, total - full.shape[2 + i]))       # the zeros of `extra_pad_end`
+      # the zeros of `extra_pad_end` are materialised only where the crop reaches into them (short kernels)
+      extend.append((0, max(0, total - stop - full.shape[2 + i])))
       sl.append(slice(start, total - stop, self.strides_down[i]))
     if any(e != (0, 0) for e in extend):
       full = Fnn.pad(full, _pad_spec(extend))
