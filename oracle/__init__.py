@@ -181,7 +181,8 @@ class Oracle:
     return out
 
   def run_length_encode(self, data, run_length_code=-1, magnitude_code=-1, use_run_length_for_non_zeros=False) -> bytes:
-    """RunLengthEncode (cc/kernels/run_length_kernels.cc:52-139), sequential C restatement (port only)."""
+    """RunLengthEncode (cc/kernels/run_length_kernels.cc:52-139): the C port restates the bit packing too; the
+    reference flavour runs the op loop around the reference's own BitWriter (cc/lib/bit_coder.cc compiled in place)."""
     d = _i32(np.asarray(data).reshape(-1))
     cap = int(16 + 20 * d.size)
     while True:

@@ -13,6 +13,8 @@
 //                         cc/kernels/range_coding_kernels.cc:60-132, 134-173, 232-269, 345-373
 //                         cc/kernels/range_coding_kernels_util.cc:34-91 (MergeAxes)
 //   PmfToQuantizedCdf     cc/kernels/pmf_to_cdf_kernels.cc:58-101, 104-208
+//   RunLengthEncode/Decode op loops  cc/kernels/run_length_kernels.cc:69-135, 158-250  (around the reference's own
+//                         BitWriter / BitReader, cc/lib/bit_coder.cc, compiled in place like the range coder)
 //
 // Every arithmetic step of the coder itself is executed by the reference's
 // tensorflow_compression::RangeEncoder / RangeDecoder objects.  Streams are sharded
@@ -38,6 +40,7 @@
 #include <thread>
 #include <vector>
 
+#include "tensorflow_compression/cc/lib/bit_coder.h"
 #include "tensorflow_compression/cc/lib/range_coder.h"
 
 namespace tfc = tensorflow_compression;
@@ -707,6 +710,139 @@ int tfcref_stochastic_round(const float* inputs, int64_t n, float step_size, con
     float fractional = number - integral;
     float random = (next() >> 40) * 0x1.0p-24f;
     if (random < fractional) ++outputs[i];
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// RunLengthEncode / RunLengthDecode (cc/kernels/run_length_kernels.cc:52-262): the op loops restated around the
+// reference's BitWriter / BitReader objects, which do every bit of the packing.
+// ------------------------------------------------------------------------------------------
+}  // extern "C"
+
+namespace {
+struct RunLengthCodes {
+  int run_length_code, magnitude_code;
+  bool non_zero_runs;
+};
+
+// :69-75
+void WriteRunLength(const RunLengthCodes& c, tfc::BitWriter& enc, int32_t run_length) {
+  if (c.run_length_code >= 0) {
+    enc.WriteRice(run_length, c.run_length_code);
+  } else {
+    enc.WriteGamma(run_length + 1);
+  }
+}
+
+// :77-92
+void WriteNonZero(const RunLengthCodes& c, tfc::BitWriter& enc, int32_t sample) {
+  const int32_t sign = sample > 0;
+  enc.WriteOneBit(sign);
+  if (c.magnitude_code >= 0) {
+    enc.WriteRice(sign ? sample - 1 : -(sample + 1), c.magnitude_code);
+  } else if (sample == std::numeric_limits<int32_t>::min()) {
+    enc.WriteGamma(-(std::numeric_limits<int32_t>::min() + 1));   // not representable: the closest value instead
+  } else {
+    enc.WriteGamma(sign ? sample : -sample);
+  }
+}
+
+// :158-168
+absl::StatusOr<int32_t> ReadRunLength(const RunLengthCodes& c, tfc::BitReader& dec) {
+  if (c.run_length_code >= 0) return dec.ReadRice(c.run_length_code);
+  auto gamma = dec.ReadGamma();
+  if (!gamma.ok()) return gamma;
+  return *gamma - 1;
+}
+
+// :170-184
+absl::StatusOr<int32_t> ReadNonZero(const RunLengthCodes& c, tfc::BitReader& dec) {
+  auto positive = dec.ReadOneBit();
+  if (!positive.ok()) return positive;
+  if (c.magnitude_code >= 0) {
+    auto rice = dec.ReadRice(c.magnitude_code);
+    if (!rice.ok()) return rice;
+    return *positive ? *rice + 1 : -*rice - 1;
+  }
+  auto gamma = dec.ReadGamma();
+  if (!gamma.ok()) return gamma;
+  return *positive ? *gamma : -*gamma;
+}
+}  // namespace
+
+extern "C" {
+
+// Returns the number of code bytes, or -(needed) if `cap` is too small.  :94-135
+int64_t tfcref_run_length_encode(const int32_t* data, int64_t n, int rl_code, int mag_code, int rl_nz, uint8_t* out,
+                                 int64_t cap) {
+  const RunLengthCodes c{rl_code, mag_code, rl_nz != 0};
+  tfc::BitWriter enc;
+  const int32_t* const end = data + n;
+  const int32_t* p = data;
+  int32_t run_length_offset = 0;   // with runs of non-zeros too, only the first zero run can be empty
+  while (p < end) {
+    const int32_t* q = std::find_if_not(p, end, [](int32_t x) { return x == 0; });
+    WriteRunLength(c, enc, static_cast<int32_t>(q - p) - run_length_offset);
+    p = q;
+    if (!(p < end)) break;
+    if (c.non_zero_runs) {
+      q = std::find_if(p, end, [](int32_t x) { return x == 0; });
+      WriteRunLength(c, enc, static_cast<int32_t>(q - p) - 1);
+      while (p < q) WriteNonZero(c, enc, *p++);
+      run_length_offset = 1;
+    } else {
+      WriteNonZero(c, enc, *p++);
+    }
+  }
+  const auto encoded = enc.GetData();
+  const int64_t nb = static_cast<int64_t>(encoded.size());
+  if (nb > cap) return -nb;
+  std::memcpy(out, encoded.data(), encoded.size());
+  return nb;
+}
+
+// 0 ok; 1 "Out of bits to read."; 2 "Exceeded maximum gamma bit width."; 3 "Decoded past end of tensor."
+// (the same codes as the C port; the message is also left in tfcref_last_error()).  :186-250
+int tfcref_run_length_decode(const uint8_t* code, int64_t n_bytes, int rl_code, int mag_code, int rl_nz, int32_t* data,
+                             int64_t n) {
+  const RunLengthCodes c{rl_code, mag_code, rl_nz != 0};
+  auto fail = [](const absl::Status& st) {
+    g_error = st.message();
+    return g_error == "Out of bits to read." ? 1 : (g_error == "Exceeded maximum gamma bit width." ? 2 : 3);
+  };
+  const absl::Status past_end = absl::DataLossError("Decoded past end of tensor.");
+  tfc::BitReader dec(absl::string_view(reinterpret_cast<const char*>(code), static_cast<size_t>(n_bytes)));
+  std::memset(data, 0, static_cast<size_t>(n) * sizeof(int32_t));
+  int32_t* const end = data + n;
+  int32_t* p = data;
+  int32_t run_length_offset = 0;
+  while (p < end) {
+    auto run_length = ReadRunLength(c, dec);
+    if (!run_length.ok()) return fail(run_length.status());
+    // the reference advances the pointer itself (p += ...); an index keeps a corrupt run length inside the language
+    const int64_t at = (p - data) + static_cast<int64_t>(*run_length) + run_length_offset;
+    if (!(at < n)) {
+      if (at != n) return fail(past_end);
+      break;
+    }
+    p = data + at;
+    if (c.non_zero_runs) {
+      run_length = ReadRunLength(c, dec);
+      if (!run_length.ok()) return fail(run_length.status());
+      const int64_t next_zero = at + static_cast<int64_t>(*run_length) + 1;
+      if (next_zero > n) return fail(past_end);
+      while (p < data + next_zero) {
+        auto nonzero = ReadNonZero(c, dec);
+        if (!nonzero.ok()) return fail(nonzero.status());
+        *p++ = *nonzero;
+      }
+      run_length_offset = 1;
+    } else {
+      auto nonzero = ReadNonZero(c, dec);
+      if (!nonzero.ok()) return fail(nonzero.status());
+      *p++ = *nonzero;
+    }
   }
   return 0;
 }

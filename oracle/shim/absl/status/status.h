@@ -15,4 +15,5 @@ class Status {
 };
 inline Status OkStatus() { return Status(); }
 inline Status InvalidArgumentError(const std::string& m) { return Status(m); }
+inline Status DataLossError(const std::string& m) { return Status(m); }
 }  // namespace absl

@@ -133,20 +133,101 @@ def test_stochastic_round_port_equals_reference_flavour():
   assert np.abs(P.stochastic_round(rep, 1.0, [9]).mean(0) - rep[0]).max() < 3e-2
 
 
-def test_run_length_port_reproduces_the_reference_literal():
+def _runs(mask):
+  """Lengths of the maximal runs of True in a boolean vector."""
+  edges = np.flatnonzero(np.diff(np.concatenate(([0], mask.astype(np.int8), [0]))))
+  return edges[1::2] - edges[0::2]
+
+
+def _inside_the_reference_writer(d, rl, mg, nz):
+  """Keeps every Rice-coded quantity's unary part below 57 zeros (see the fuzz test below for why)."""
+  d = d.copy()
+  if mg >= 0:
+    d = np.clip(d, -(56 << mg), 56 << mg).astype(np.int32)
+  if rl >= 0:
+    step = 56 << rl
+    d[step - 1::step] = np.where(d[step - 1::step] == 0, 1, d[step - 1::step])
+    if nz:
+      d[step // 2::step] = 0
+      assert _runs(d != 0).max(initial=0) <= step
+    assert _runs(d == 0).max(initial=0) <= step
+  return d
+
+
+@pytest.mark.parametrize("flavour", FLAVOURS)
+def test_run_length_oracles_reproduce_the_reference_literal(flavour):
   """cc/kernels/run_length_kernels_test.cc:272-305 holds the one literal bit string of the run-length ops:
   [-6, 3, 0, 0] <-> {0b11010001, 0b01101101} (gamma / gamma / zeros only); plus round trips over every code flavour."""
-  P = oracle.port()
+  P = _o(flavour)
   assert P.run_length_encode([-6, 3, 0, 0]) == bytes([0b11010001, 0b01101101])
   assert P.run_length_decode(bytes([0b11010001, 0b01101101]), (4,)).tolist() == [-6, 3, 0, 0]
   rng = np.random.default_rng(1)
   for rl, mg, nz in ((-1, -1, False), (-1, -1, True), (2, 3, True), (0, 0, False), (5, -1, False), (-1, 4, True)):
     for density in (0.02, 0.5, 1.0):
       d = (rng.integers(-300, 300, 5000) * (rng.random(5000) < density)).astype(np.int32)
+      d = _inside_the_reference_writer(d, rl, mg, nz)
       code = P.run_length_encode(d, rl, mg, nz)
       assert np.array_equal(P.run_length_decode(code, d.shape, rl, mg, nz), d)
   with pytest.raises(oracle.OracleError, match="Out of bits"):
     P.run_length_decode(b"\x01", (9,))
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="compiled reference not present")
+def test_run_length_port_equals_the_compiled_bit_coder_fuzz():
+  """The C port's own bit packing against the reference's BitWriter / BitReader (cc/lib/bit_coder.cc compiled in
+  place; only the op loops of run_length_kernels.cc are restated around it): same bytes, same decoded tensors, same
+  error classes on truncated and over-long codes, over every code flavour, densities from all-zero to dense,
+  magnitudes up to the int32 limits.
+
+  Inputs are kept where the reference is defined: `BitWriter::WriteRice` emits a unary part of 57 zeros or more in
+  chunks of up to 57 (bit_coder.cc:88-92), and a 57-bit chunk that lands on bit offset 7 makes `WriteBits` shift its
+  64-bit buffer by 64 (bit_coder.cc:60-68, undefined; on x86 the seven old bits are written twice) -- the reference
+  then cannot decode its own string.  The port and the CUDA coder write the intended code there (next test)."""
+  P, R = oracle.port(), oracle.ref()
+  rng = np.random.default_rng(11)
+  big = np.iinfo(np.int32)
+  for rl, mg, nz in ((-1, -1, False), (-1, -1, True), (0, 0, False), (2, 3, True), (5, -1, False), (-1, 4, True),
+                     (3, 0, True), (7, 12, False)):
+    for trial in range(12):
+      n = int(rng.integers(1, 3000))
+      mag = int(rng.choice([2, 40, 5000, 2**20]))
+      d = (rng.integers(-mag, mag + 1, n) * (rng.random(n) < rng.choice([0.0, 0.03, 0.5, 1.0]))).astype(np.int32)
+      d = _inside_the_reference_writer(d, rl, mg, nz)
+      if trial == 3 and mg < 0:        # the gamma magnitude code clamps INT32_MIN to the closest value (:84-87)
+        d[rng.integers(0, n)] = big.min
+        d[rng.integers(0, n)] = big.max
+      code = P.run_length_encode(d, rl, mg, nz)
+      assert code == R.run_length_encode(d, rl, mg, nz), (rl, mg, nz, trial)
+      want = np.where(d == big.min, big.min + 1, d) if mg < 0 else d
+      for O in (P, R):
+        assert np.array_equal(O.run_length_decode(code, d.shape, rl, mg, nz), want)
+      # damaged codes: both flavours fail in the same class or decode the same tensor
+      for damaged, shape in ((code[:len(code) // 2], d.shape), (code, (n + 5,)), (code, (max(n - 3, 1),))):
+        outcome = []
+        for O in (P, R):
+          try:
+            outcome.append(O.run_length_decode(damaged, shape, rl, mg, nz).tolist())
+          except oracle.OracleError as e:
+            outcome.append(str(e))
+        assert outcome[0] == outcome[1], (rl, mg, nz, trial, outcome[0] if isinstance(outcome[0], str) else "data")
+
+
+def test_run_length_port_writes_long_rice_codes_as_specified():
+  """Where the reference's writer is undefined (unary parts longer than 57 zeros, see above) the port follows the
+  code's definition -- q zeros, a one, k low bits -- and the reference's own READER, which has no such limit, decodes
+  the port's string (when the compiled reference is present)."""
+  P = oracle.port()
+  d = np.zeros(5000, np.int32)
+  d[[3, 700, 701, 4999]] = [9, -300, 1, 77]
+  for rl, mg in ((0, 0), (1, 2), (0, -1)):
+    code = P.run_length_encode(d, rl, mg, False)
+    assert np.array_equal(P.run_length_decode(code, d.shape, rl, mg, False), d)
+    if oracle.have_ref():
+      assert np.array_equal(oracle.ref().run_length_decode(code, d.shape, rl, mg, False), d)
+  # by hand: zeros-only run of 3 then 9 with Rice(0) magnitudes: "0001" run, sign 1, 8 zeros + "1"
+  code = P.run_length_encode(np.asarray([0, 0, 0, 9], np.int32), 0, 0, False)
+  bits = "".join(format(b, "08b")[::-1] for b in code)       # LSB-first packing (bit_coder.cc:60)
+  assert bits.startswith("0001" + "1" + "000000001")
 
 
 @pytest.mark.parametrize("flavour", FLAVOURS)
@@ -175,3 +256,20 @@ def test_bench_latents_are_finite_on_every_rank():
     assert all(bool(torch.isfinite(y).all()) and float(y.abs().max()) < 8.0 * 17.0 + 1e-3 for y in ys)
   _, full = bench.synth_latents(1, 1)   # the batch that hung the 2-GPU run
   assert bool(torch.isfinite(full[0]).all())
+
+
+@pytest.mark.parametrize("flavour", FLAVOURS)
+def test_run_length_golden_vectors(flavour):
+  """tests/golden/run_length_golden.npz (oracle/make_run_length_golden.py: strings written by the reference's own
+  BitWriter): every oracle flavour reproduces the bytes and decodes them."""
+  import os
+  g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "run_length_golden.npz"))
+  O = _o(flavour)
+  at_d = at_c = 0
+  for (rl, mg, nz), nd, nc in zip(g["params"], g["data_len"], g["code_len"]):
+    d = g["data"][at_d:at_d + nd]
+    code = bytes(g["code"][at_c:at_c + nc])
+    at_d, at_c = at_d + nd, at_c + nc
+    assert O.run_length_encode(d, int(rl), int(mg), bool(nz)) == code
+    assert np.array_equal(O.run_length_decode(code, d.shape, int(rl), int(mg), bool(nz)), d)
+  assert bytes(g["code"][:2]) == bytes([0b11010001, 0b01101101])   # the reference test's literal

@@ -102,3 +102,17 @@ def test_power_law_and_laplace_entropy_models_on_the_cuda_coder():
     back = em.decompress(strings, (500,))
     assert back.dtype == torch.float32 and back.shape == (3, 2, 500)
     assert torch.equal(back.cpu(), em.quantize(x).cpu())
+
+
+def test_golden_vectors_written_by_the_reference_bit_writer(ops):
+  """tests/golden/run_length_golden.npz: strings produced by the reference's own BitWriter (compiled in place,
+  oracle/make_run_length_golden.py); the CUDA coder writes the same bytes and reads them back."""
+  import os
+  g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "run_length_golden.npz"))
+  at_d = at_c = 0
+  for (rl, mg, nz), nd, nc in zip(g["params"], g["data_len"], g["code_len"]):
+    d = np.ascontiguousarray(g["data"][at_d:at_d + nd]).astype(np.int32)
+    code = bytes(g["code"][at_c:at_c + nc])
+    at_d, at_c = at_d + nd, at_c + nc
+    assert ops.run_length_encode(torch.from_numpy(d), int(rl), int(mg), bool(nz)) == code
+    assert np.array_equal(ops.run_length_decode(code, [int(nd)], int(rl), int(mg), bool(nz)).cpu().numpy(), d)
