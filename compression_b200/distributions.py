@@ -279,10 +279,22 @@ class _LocScale:
     return self.quantile(u.clamp(tiny, 1 - torch.finfo(self.dtype).eps / 2))
 
 
+def _float32_on_cpu(fn):
+  """torch's CPU kernels of the ndtr family have no float16 / bfloat16 variants (the CUDA ones do): 16-bit inputs on
+  the CPU go through float32 and come back in their own dtype."""
+
+  def wrapped(z):
+    if z.device.type == "cpu" and z.dtype in (torch.float16, torch.bfloat16):
+      return fn(z.float()).to(z.dtype)
+    return fn(z)
+
+  return staticmethod(wrapped)
+
+
 class Normal(_LocScale):
-  _std_cdf = staticmethod(torch.special.ndtr)
-  _std_log_cdf = staticmethod(torch.special.log_ndtr)
-  _std_quantile = staticmethod(torch.special.ndtri)
+  _std_cdf = _float32_on_cpu(torch.special.ndtr)
+  _std_log_cdf = _float32_on_cpu(torch.special.log_ndtr)
+  _std_quantile = _float32_on_cpu(torch.special.ndtri)
 
 
 class Logistic(_LocScale):

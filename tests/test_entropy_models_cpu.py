@@ -132,3 +132,53 @@ def test_deep_factorized_density_is_differentiable_in_its_input():
   # and under no_grad they still evaluate
   with torch.no_grad():
     assert d.prob(x).shape == (5, 3) and not d.log_prob(x).requires_grad
+
+
+def test_construction_argument_checks():
+  """continuous_batched_test.py:65-72: the coding unit must cover the prior's batch dimensions."""
+  noisy = tfc.NoisyLogistic(loc=0., scale=[[1.], [2.]])
+  for coding_rank in (0, 1):
+    with pytest.raises(ValueError):
+      tfc.ContinuousBatchedEntropyModel(noisy, coding_rank)
+  for coding_rank in (2, 3):
+    tfc.ContinuousBatchedEntropyModel(noisy, coding_rank)
+  with pytest.raises(ValueError):
+    tfc.ContinuousBatchedEntropyModel(tfc.NoisyNormal(loc=0., scale=1.), 1, tail_mass=1.5)
+
+
+def test_laplace_tail_mass_mixes_in_a_heavy_tail():
+  """continuous_batched_test.py:244-252 and continuous_base.py:298-334: with `laplace_tail_mass` the bit cost far
+  from the prior's mass follows the unit Laplace tail instead of the Gaussian one."""
+  noisy = tfc.NoisyNormal(loc=0., scale=1.)
+  assert tfc.ContinuousBatchedEntropyModel(noisy, 1, laplace_tail_mass=0.0).laplace_tail_mass == 0.0
+  em = tfc.ContinuousBatchedEntropyModel(noisy, 1, laplace_tail_mass=torch.tensor(1e-3))
+  assert float(em.laplace_tail_mass) == pytest.approx(1e-3)
+  lp = em._log_prob(noisy, torch.tensor(0.0))
+  assert lp.dtype == torch.float32
+  x = torch.tensor([0., 30., 60.])
+  with_tail, without = em._log_prob(noisy, x), tfc.ContinuousBatchedEntropyModel(noisy, 1)._log_prob(noisy, x)
+  assert torch.allclose(with_tail[0], without[0], atol=2e-3)           # at the mode the mixture barely matters
+  lap = tfc.NoisyLaplace(loc=0., scale=1.)
+  assert torch.allclose(with_tail[1:], np.log(1e-3) + lap.log_prob(x[1:]), atol=1e-4)
+  assert bool((with_tail[1:] > without[1:] + 100).all())
+  with pytest.raises(ValueError):
+    tfc.ContinuousBatchedEntropyModel(noisy, 1, laplace_tail_mass=1.0)._log_prob(noisy, x)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_dtypes_with_a_sixteen_bit_bottleneck(dtype):
+  """continuous_batched_test.py:197-216 without the coder: a float64 prior under a 16-bit bottleneck gives a
+  16-bit perturbed tensor and float64 bits; a prior of the bottleneck's own dtype works on the CPU too."""
+  noisy = tfc.NoisyNormal(loc=torch.tensor(.5, dtype=torch.float64), scale=torch.tensor(1., dtype=torch.float64),
+                          dtype=torch.float64)
+  em = tfc.ContinuousBatchedEntropyModel(noisy, 1, bottleneck_dtype=dtype)
+  assert em.bottleneck_dtype == dtype and em.prior.dtype == torch.float64
+  x = torch.randn(2, 5, generator=torch.Generator().manual_seed(1)).to(dtype)
+  x_tilde, bits = em(x)
+  assert x_tilde.dtype == dtype and float((x.float() - x_tilde.float()).abs().max()) <= .5 + 2e-2
+  assert bits.dtype == torch.float64 and bits.shape == (2,) and bool((bits >= 0).all())
+  assert em.quantize(x).dtype == dtype
+  for cls in (tfc.NoisyNormal, tfc.NoisyLogistic, tfc.NoisyLaplace):
+    em = tfc.ContinuousBatchedEntropyModel(cls(loc=0., scale=1., dtype=dtype), 1, bottleneck_dtype=dtype)
+    _, bits = em(x)
+    assert bits.dtype == dtype and bool(torch.isfinite(bits).all())
