@@ -1,6 +1,8 @@
 """CPU: the universal-quantisation entropy models' host logic (py/entropy_models/universal.py:30-62,147-211,446-528;
 cases from universal_test.py:29-58,121-150,349-375) and the counter-based noise-level stream that stands in for
 tf.random.stateless_uniform."""
+import math
+
 import numpy as np
 import pytest
 import torch
@@ -73,3 +75,47 @@ def test_indexed_model_indexes_are_clipped_flattened_with_the_noise_level_first(
     assert bits.shape == (2,) and float((x_hat - x).abs().max()) <= 0.5 + 1e-6
   with pytest.raises(ValueError):
     tfc.UniversalIndexedEntropyModel(tfc.NoisyLogistic, (5,), dict(loc=lambda i: i[..., 0]), coding_rank=0)
+
+
+def _mixture_model(expected_grads, coding_rank=2):
+  return tfc.UniversalIndexedEntropyModel(
+      tfc.NoisyLogisticMixture, index_ranges=(10, 10, 5),
+      parameter_fns=dict(loc=lambda i: i[..., 0:2] - 5, scale=lambda _: 1.,
+                         weight=lambda i: torch.softmax((i[..., 2:3] - 2) * torch.tensor([-1., 1.]), -1)),
+      coding_rank=coding_rank, expected_grads=expected_grads)
+
+
+def test_n_dimensional_indexes_with_a_mixture_prior():
+  """universal_test.py:152-167,377-417: three index dimensions parameterise a two-component logistic mixture; the
+  quantisation noise stays within half a bin and the bit estimate does not depend on `expected_grads`."""
+  em = _mixture_model(True, coding_rank=1)
+  assert em.coding_rank == 1 and float(em.laplace_tail_mass) == 0.0 and em.tail_mass == 2**-8
+  assert em.bottleneck_dtype == torch.float32
+  g = torch.Generator().manual_seed(0)
+  x = torch.randn(3, 2000, 16, generator=g)
+  indexes = (10 * torch.rand(3, 2000, 16, 3, generator=g)).to(torch.int32)
+  indexes[..., 2] //= 2
+  em_expected, em_plain = _mixture_model(True), _mixture_model(False)
+  x_hat, bits_expected = em_expected(x, indexes)
+  assert float((x - x_hat).abs().max()) <= .5
+  _, bits_plain = em_plain(x, indexes)
+  assert bits_expected.shape == (3,)
+  assert torch.allclose(bits_expected, bits_plain, rtol=0.01)
+  x = x.requires_grad_(True)
+  em_expected(x, indexes)[1].sum().backward()
+  assert x.grad is not None and bool(torch.isfinite(x.grad).all()) and float(x.grad.abs().sum()) > 0
+
+
+def test_laplace_tail_mass_bounds_the_cost_of_outliers():
+  """universal_test.py:94-119: with `laplace_tail_mass` an input far outside the prior costs about |x| / ln 2 bits
+  (the unit Laplace tail) instead of diverging, and nothing changes where the prior has its mass."""
+  prior = tfc.NoisyDeepFactorized(batch_shape=(1,))
+  em_tail = tfc.UniversalBatchedEntropyModel(prior, coding_rank=1, laplace_tail_mass=1e-3)
+  em_plain = tfc.UniversalBatchedEntropyModel(prior, coding_rank=1)
+  x = torch.tensor([1e3, 1e4, 1e5, 1e6])
+  _, bits = em_tail(x[..., None])
+  assert torch.allclose(bits, x / math.log(2.0), rtol=0.01)
+  x = torch.linspace(-10.0, 10.0, 50)
+  _, bits_tail = em_tail(x[..., None])
+  _, bits_plain = em_plain(x[..., None])
+  assert torch.allclose(bits_tail, bits_plain, rtol=0.01, atol=0.05)
