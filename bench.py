@@ -487,7 +487,8 @@ def main():
 
   def phase(name):
     faulthandler.cancel_dump_traceback_later()
-    faulthandler.dump_traceback_later(watchdog_s, exit=True)
+    if world > 1:   # a single process has nobody to leave waiting: no limit on its side measurements
+      faulthandler.dump_traceback_later(watchdog_s, exit=True)
     if os.environ.get("TFCB_BENCH_TRACE"):
       print(f"[bench rank {rank}] {name}", file=sys.stderr, flush=True)
 
