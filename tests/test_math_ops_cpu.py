@@ -128,3 +128,12 @@ def test_gdn_trainable_exponent_graph_keeps_the_fixed_special_cases(kw):
     eps = float(layer.epsilon.detach()) if callable(e) else e
     ref = gdn_oracle.gdn_reference(x, gamma, beta, layer.inverse, layer.rectify, a, eps)
     np.testing.assert_allclose(y.detach().double().numpy(), ref.numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_perturb_and_apply_expected_gradient_of_soft_round():
+  """math_ops_test.py:88-96: soft_round(x + 1/2) - soft_round(x - 1/2) == 1 for every x, so the expected gradient
+  of the soft-rounded, noise-perturbed signal is the identity's."""
+  x = torch.linspace(-2.0, 2.0, 200, requires_grad=True)
+  y = math_ops.perturb_and_apply(math_ops.soft_round, x, 7.0, expected_grads=True)[0]
+  y.sum().backward()
+  assert torch.allclose(x.grad, torch.ones_like(x.grad), atol=1e-5)
