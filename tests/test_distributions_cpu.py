@@ -96,3 +96,23 @@ def test_noisy_gradients_reach_the_parameters():
   dist = D.NoisyNormal(loc=loc, scale=scale)
   dist.log_prob(torch.tensor([0.0, 1.0, -2.5])).sum().backward()
   assert loc.grad is not None and scale.grad is not None and float(loc.grad.abs()) > 0 and float(scale.grad.abs()) > 0
+
+
+@pytest.mark.parametrize("cls", [D.NoisyNormal, D.NoisyLogistic, D.NoisyLaplace])
+def test_noisy_location_scale_family_contract(cls):
+  """uniform_noise_test.py:28-98 (LocationScaleTest): shapes, the unit-width uniform limit, sampling, tails, and the
+  statistics the noisy density does not define."""
+  assert cls(loc=3., scale=5.).batch_shape == () and cls(loc=[3., 2.], scale=5.).batch_shape == (2,)
+  dist = cls(loc=5.0, scale=1e-7)
+  assert torch.allclose(dist.prob(torch.linspace(4., 6., 10)), torch.tensor([0, 0, 0, 1, 1, 1, 1, 0, 0, 0.]), atol=1e-5)
+  s = cls(loc=0., scale=[3., 5.]).sample((5, 4), generator=torch.Generator().manual_seed(0))
+  assert s.shape == (5, 4, 2) and bool(torch.isfinite(s).all())
+  dist = cls(loc=10., scale=1.5)
+  assert float(dist._upper_tail(2**-8)) > float(dist._lower_tail(2**-8))
+  dist = cls(loc=1., scale=2.)
+  for call in (dist.mode, lambda: dist.quantile(.5), lambda: dist.survival_function(.5)):
+    with pytest.raises(NotImplementedError):
+      call()
+  # samples follow the density: the empirical mean of a wide distribution is its location
+  big = cls(loc=-4., scale=2.).sample((40000,), generator=torch.Generator().manual_seed(1))
+  assert abs(float(big.mean()) + 4.) < 0.08
