@@ -212,6 +212,16 @@ class DeepFactorized(nn.Module):
   def quantile(self, q):
     raise NotImplementedError
 
+  # no closed forms for these either (deep_factorized.py leaves the tfp defaults, which raise)
+  def mean(self):
+    raise NotImplementedError
+
+  def mode(self):
+    raise NotImplementedError
+
+  def sample(self, sample_shape=(), generator=None):
+    raise NotImplementedError
+
   def _quantization_offset(self):
     return estimate_tails(self._logits_cumulative, 0., self._batch_shape, self.dtype, self.device)
 

@@ -116,3 +116,27 @@ def test_noisy_location_scale_family_contract(cls):
   # samples follow the density: the empirical mean of a wide distribution is its location
   big = cls(loc=-4., scale=2.).sample((40000,), generator=torch.Generator().manual_seed(1))
   assert abs(float(big.mean()) + 4.) < 0.08
+
+
+def test_deep_factorized_contract():
+  """deep_factorized_test.py:32-70,81-106,126-143: defaults, broadcasting of a batch of densities over an input,
+  eight trainable variables, and the statistics that have no closed form."""
+  df = D.DeepFactorized()
+  assert df.batch_shape == () and tuple(df.num_filters) == (3, 3) and df.init_scale == 10
+  df = D.DeepFactorized(batch_shape=(2, 3))
+  x = torch.linspace(-5., 5., 20).reshape(4, 5, 1, 1)
+  for method in ("prob", "log_prob", "cdf", "log_cdf", "survival_function", "log_survival_function"):
+    assert getattr(df, method)(x).shape == (4, 5, 2, 3)
+  noisy = D.NoisyDeepFactorized(num_filters=(2, 3, 4))
+  assert noisy.batch_shape == () and tuple(noisy.base.num_filters) == (2, 3, 4)
+  assert noisy.prob(torch.randn(10)).shape == (10,)
+  noisy = D.NoisyDeepFactorized(batch_shape=(4, 3))
+  assert noisy.prob(torch.randn(10, 4, 3)).shape == (10, 4, 3)
+  noisy = D.NoisyDeepFactorized()
+  loss = -noisy.log_prob(torch.randn(20)).mean()
+  grads = torch.autograd.grad(loss, list(noisy.parameters()))
+  assert len(grads) == 8 and all(g is not None for g in grads)
+  assert float(D.upper_tail(noisy, 2**-8)) > float(D.lower_tail(noisy, 2**-8))
+  for call in (noisy.mode, noisy.mean, lambda: noisy.quantile(.5), lambda: noisy.survival_function(.5), noisy.sample):
+    with pytest.raises(NotImplementedError):
+      call()
