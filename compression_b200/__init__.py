@@ -11,7 +11,7 @@ from compression_b200._lib import InvalidArgumentError
 def __getattr__(name):  # lazy: importing the package must not require torch / the built library
   import importlib
   modules = ("gen_ops", "functional", "math_ops", "distributions", "entropy_models", "gdn", "packed_tensors",
-             "signal_conv", "models", "sharding", "run_length_models", "soft_round_layers")
+             "signal_conv", "models", "sharding", "run_length_models", "soft_round_layers", "layers", "ops")
   if name in modules:
     return importlib.import_module("compression_b200." + name)
   exported = {
@@ -39,6 +39,12 @@ def __getattr__(name):  # lazy: importing the package must not require torch / t
       "Logistic": "distributions", "Laplace": "distributions",
       "BLS2017Model": "models", "BMSHJ2018Model": "models", "MS2020Model": "models",
       "PowerLawEntropyModel": "run_length_models", "LaplaceEntropyModel": "run_length_models",
+      "create_range_encoder": "gen_ops", "create_range_decoder": "gen_ops", "entropy_encode_channel": "gen_ops",
+      "entropy_encode_index": "gen_ops", "entropy_encode_finalize": "gen_ops", "entropy_decode_channel": "gen_ops",
+      "entropy_decode_index": "gen_ops", "entropy_decode_finalize": "gen_ops", "pmf_to_quantized_cdf": "gen_ops",
+      "range_encode": "gen_ops", "range_decode": "gen_ops", "stochastic_round": "gen_ops",
+      "run_length_encode": "gen_ops", "run_length_decode": "gen_ops", "run_length_gamma_encode": "gen_ops",
+      "run_length_gamma_decode": "gen_ops",
   }
   if name in exported:
     return getattr(importlib.import_module("compression_b200." + exported[name]), name)
