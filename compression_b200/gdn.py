@@ -6,12 +6,13 @@ import torch
 from torch import nn
 
 from compression_b200 import functional as F
+from compression_b200.parameters import Parameter
 from compression_b200 import math_ops
 
 __all__ = ["GDN", "GDNParameter"]
 
 
-class GDNParameter(nn.Module):
+class GDNParameter(Parameter):
   """theta = max(v, sqrt(minimum + offset^2))^2 - offset^2 (parameters.py:186-269)."""
 
   def __init__(self, initial_value, name=None, minimum=0., offset=2**-18, shape=None, dtype=None):

@@ -16,6 +16,8 @@ import torch
 import torch.nn.functional as Fnn
 from torch import nn
 
+from compression_b200.parameters import Parameter
+
 __all__ = ["same_padding_for_kernel", "RDFTParameter", "SignalConv1D", "SignalConv2D", "SignalConv3D",
            "IdentityInitializer"]
 
@@ -54,7 +56,7 @@ def same_padding_for_kernel(shape, corr, strides_up=None):
   return [((padding[i][0] - 1) // strides_up[i] + 1, (padding[i][1] - 1) // strides_up[i] + 1) for i in range(rank)]
 
 
-class RDFTParameter(nn.Module):
+class RDFTParameter(Parameter):
   """Kernel stored as its real-input DFT over the spatial axes, split in real / imaginary parts and scaled by
   1/sqrt(prod(support)) (parameters.py:70-180).  `forward()` returns the kernel in (support..., in, out) layout."""
 

@@ -19,7 +19,7 @@ REFERENCE_ALL = {
     "entropy_models/universal.py": ["UniversalBatchedEntropyModel", "UniversalIndexedEntropyModel"],
     "layers/gdn.py": ["GDN"],
     "layers/initializers.py": ["IdentityInitializer"],
-    "layers/parameters.py": ["RDFTParameter", "GDNParameter"],
+    "layers/parameters.py": ["Parameter", "RDFTParameter", "GDNParameter"],
     "layers/signal_conv.py": ["SignalConv1D", "SignalConv2D", "SignalConv3D"],
     "layers/soft_round.py": ["SoftRound", "SoftRoundConditionalMean"],
     "ops/gen_ops.py": ["create_range_encoder", "create_range_decoder", "entropy_decode_channel", "entropy_decode_finalize",
