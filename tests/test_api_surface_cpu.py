@@ -1,11 +1,12 @@
 """CPU: every public name of the reference package resolves here (tensorflow_compression/__init__.py:17-40 star
 imports the `__all__` lists below), plus its four sub-namespaces.  Importing needs neither a GPU nor the built
-library; `Y4MDataset` (a tf.data source op, cc/kernels/y4m_dataset_kernels.cc) is the one name left out."""
+library."""
 import pytest
 
 import compression_b200 as tfc
 
 REFERENCE_ALL = {
+    "datasets/y4m_dataset.py": ["Y4MDataset"],
     "distributions/deep_factorized.py": ["DeepFactorized", "NoisyDeepFactorized"],
     "distributions/helpers.py": ["estimate_tails", "quantization_offset", "lower_tail", "upper_tail"],
     "distributions/round_adapters.py": ["MonotonicAdapter", "RoundAdapter", "NoisyRoundedNormal",
