@@ -470,8 +470,11 @@ class MixtureSameFamily:
     raise NotImplementedError("quantile is not implemented for MixtureSameFamily")
 
   def sample(self, sample_shape=(), generator=None):
-    x = self.components.sample(sample_shape, generator=generator)            # sample_shape + batch + [K]
-    x = x.expand(tuple(sample_shape) + self.batch_shape + x.shape[-1:])
+    x = self.components.sample(sample_shape, generator=generator)            # sample_shape + component batch
+    comp = tuple(self.components.batch_shape)
+    full = self.batch_shape + (max(comp[-1], self.probs.shape[-1]),)
+    x = x.reshape(tuple(sample_shape) + (1,) * (len(full) - len(comp)) + comp)
+    x = x.expand(tuple(sample_shape) + full)                                 # sample_shape + batch + [K]
     w = self.probs.expand(x.shape).reshape(-1, x.shape[-1])
     k = torch.multinomial(w, 1, generator=generator).reshape(x.shape[:-1] + (1,))
     return torch.gather(x, -1, k).squeeze(-1)

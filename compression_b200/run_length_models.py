@@ -85,7 +85,8 @@ class _RunLengthEntropyModel(torch.nn.Module):
       raise ValueError(f"`bottleneck` must have at least {self.coding_rank} dimensions.")
     shape = tuple(bottleneck.shape)
     strings_shape = shape if self.coding_rank == 0 else shape[:len(shape) - self.coding_rank]
-    symbols = torch.round(bottleneck).to(torch.int32).reshape(_prod(strings_shape), -1)
+    unit = _prod(shape[len(strings_shape):])
+    symbols = torch.round(bottleneck).to(torch.int32).reshape(_prod(strings_shape), unit)
     strings = np.empty(symbols.shape[0], dtype=object)
     for i in range(symbols.shape[0]):
       strings[i] = self.encode_fn(symbols[i])
